@@ -1,0 +1,699 @@
+// C ABI of the forward pass: context, plan (tensors + ops), execution.
+// Declared in include/cerberus_b200.h; bound from Python with ctypes (cerberus_b200/_lib.py).
+//
+// Replaces the reference's run_step closure (infer/base.py:51-53 -> models/run_desc.py:439-502
+// -> models/net_desc.py:144-200). The plan is a flat list of ops over NHWC tensors; Python
+// builds it once per batch shape from the model directory (cerberus_b200/plan.py).
+#include "../../include/cerberus_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "capi_internal.cuh"
+#include "conv_tc.cuh"
+#include "ops.cuh"
+
+namespace cerb {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+}  // namespace cerb
+
+using namespace cerb;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Tensor {
+  cerb_tensor_desc d;
+  void* plane[2] = {nullptr, nullptr};
+  size_t bytes = 0;
+};
+
+struct Step {
+  int kind = 0;
+  ConvKParams conv;
+  bool split = false;
+  // misc ops
+  ActRef a, b, c;
+  const uint8_t* u8_in = nullptr;
+  HeadParams head;
+  PClassParams pclass;
+};
+
+size_t dtype_size(int dt) {
+  switch (dt) {
+    case CERB_U8: return 1;
+    case CERB_F16: return 2;
+    case CERB_F32: return 4;
+    case CERB_I32: return 4;
+  }
+  return 0;
+}
+
+}  // namespace
+
+struct cerb_plan {
+  cerb_ctx* ctx = nullptr;
+  std::vector<Tensor> tensors;
+  std::vector<Step> steps;
+  uint8_t* blob = nullptr;
+  size_t blob_bytes = 0;
+  int prep_in_tensor = -1;
+};
+
+namespace {
+
+ActRef act_ref(const Tensor& t) {
+  ActRef a;
+  a.hi = static_cast<__half*>(t.plane[0]);
+  a.lo = static_cast<__half*>(t.plane[1]);
+  a.n = t.d.n;
+  a.h = t.d.h;
+  a.w = t.d.w;
+  a.c = t.d.c;
+  return a;
+}
+
+int encode_map(cerb_ctx* ctx, CUtensorMap* m, void* base, int rank, const cuuint64_t* dims,
+               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), base, dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(CERB_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] strides "
+                "[%llu,%llu,%llu] box [%u,%u,%u,%u]",
+                static_cast<int>(r), rank, (unsigned long long)dims[0],
+                (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                (unsigned long long)(rank > 3 ? dims[3] : 0), (unsigned long long)strides_bytes[0],
+                (unsigned long long)(rank > 2 ? strides_bytes[1] : 0),
+                (unsigned long long)(rank > 3 ? strides_bytes[2] : 0), box[0], box[1],
+                rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  }
+  return CERB_OK;
+}
+
+int floor_log2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+
+// Picks the 128-pixel box (BW x BH, both powers of two) that wastes the fewest MMA rows.
+int pick_box_w(int H, int W) {
+  long best_area = -1;
+  int best = 128;
+  for (int bw = 128; bw >= 1; bw >>= 1) {
+    const int bh = 128 / bw;
+    const long area = static_cast<long>((W + bw - 1) / bw) * bw * ((H + bh - 1) / bh) * bh;
+    if (best_area < 0 || area < best_area) {
+      best_area = area;
+      best = bw;
+    }
+  }
+  return best;
+}
+
+int pick_bn(int cout, long m_tiles, int num_sms) {
+  if (cout <= 128) return cout;
+  // Larger BN re-reads the activation slab fewer times; keep at least ~2 tiles per SM.
+  const int cands[2] = {256, 128};
+  for (int c : cands) {
+    if (cout % c != 0) continue;
+    if (m_tiles * (cout / c) >= 2L * num_sms) return c;
+  }
+  if (cout % 128 == 0) return 128;
+  if (cout % 64 == 0) return 64;
+  return 0;
+}
+
+int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
+  cerb_ctx* ctx = pl->ctx;
+  const int nt = static_cast<int>(pl->tensors.size());
+  if (op.in0 < 0 || op.in0 >= nt || op.out < 0 || op.out >= nt)
+    return fail(CERB_ERR_ARG, "conv: tensor id out of range");
+  const Tensor& in = pl->tensors[op.in0];
+  const Tensor& out = pl->tensors[op.out];
+  if (in.d.dtype != CERB_F16 || out.d.dtype != CERB_F16)
+    return fail(CERB_ERR_ARG, "conv: tensors must be fp16");
+  const bool split = ctx->precision == CERB_PREC_F16X2;
+  ConvKParams& p = st.conv;
+  memset(&p, 0, sizeof(p));
+  st.split = split;
+
+  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  if (in.d.n != N) return fail(CERB_ERR_ARG, "conv: batch mismatch");
+  if (op.cout <= 0 || op.cout % 16 != 0 || op.out_coff % 8 != 0 ||
+      op.out_coff + op.cout > out.d.c || out.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv: bad output channels (cout %d coff %d c %d)", op.cout,
+                op.out_coff, out.d.c);
+
+  int bw = op.box_w > 0 ? op.box_w : pick_box_w(H, W);
+  if (bw > 128 || (bw & (bw - 1)) != 0) return fail(CERB_ERR_ARG, "conv: bad box_w %d", bw);
+  const int bh = 128 / bw;
+  p.bw_log2 = floor_log2(bw);
+  p.n_img = N;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + bw - 1) / bw;
+  p.tiles_y = (H + bh - 1) / bh;
+  const long m_tiles = static_cast<long>(N) * p.tiles_x * p.tiles_y;
+  p.BN = pick_bn(op.cout, m_tiles, ctx->num_sms);
+  if (p.BN <= 0 || p.BN > 256 || p.BN % 16 != 0 || op.cout % p.BN != 0)
+    return fail(CERB_ERR_ARG, "conv: unsupported cout %d", op.cout);
+  p.n_ntiles = op.cout / p.BN;
+  p.n_tiles = static_cast<int>(m_tiles * p.n_ntiles);
+
+  const size_t es = 2;
+  int k_total = 0;
+  if (op.stem) {
+    // in = PREP tensor [N, H, W+8, 8]; one K chunk per filter row = 8 px x 8 ch window.
+    if (in.d.c != 8 || in.d.h != H || in.d.w != W + 8 || op.kh != 7 || op.kw != 7 ||
+        op.stride != 1 || op.pad != 3)
+      return fail(CERB_ERR_ARG, "conv: stem expects a 7x7 s1 p3 conv over a PREP tensor");
+    p.n_taps = 7;
+    p.n_chunks = 1;
+    for (int r = 0; r < 7; ++r) {
+      p.taps[r].map = 0;
+      p.taps[r].dx = 0;
+      p.taps[r].dy = static_cast<int8_t>(r - 3);
+    }
+    const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {8 * es, static_cast<cuuint64_t>(W + 8) * 8 * es,
+                                   static_cast<cuuint64_t>(H) * (W + 8) * 8 * es};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+    for (int pln = 0; pln < (split ? 2 : 1); ++pln) {
+      CUtensorMap* m = pln == 0 ? &p.in_hi[0] : &p.in_lo[0];
+      int rc = encode_map(ctx, m, in.plane[pln], 4, dims, strides, box);
+      if (rc) return rc;
+    }
+    k_total = 7 * 64;
+  } else {
+    const int s = op.stride;
+    if (s != 1 && s != 2) return fail(CERB_ERR_ARG, "conv: stride must be 1 or 2");
+    if (op.in_c <= 0 || op.in_c % 64 != 0 || op.in_coff % 8 != 0 ||
+        op.in_coff + op.in_c > in.d.c || in.d.c % 8 != 0)
+      return fail(CERB_ERR_ARG, "conv: bad input channels (in_c %d coff %d c %d)", op.in_c,
+                  op.in_coff, in.d.c);
+    const int eh = (in.d.h + 2 * op.pad - op.kh) / s + 1;
+    const int ew = (in.d.w + 2 * op.pad - op.kw) / s + 1;
+    if (eh != H || ew != W)
+      return fail(CERB_ERR_ARG, "conv: output is %dx%d but geometry gives %dx%d", H, W, eh, ew);
+    if (op.kh * op.kw > kConvMaxTaps) return fail(CERB_ERR_ARG, "conv: too many taps");
+    p.n_chunks = op.in_c / 64;
+    p.n_taps = op.kh * op.kw;
+    bool used[4] = {false, false, false, false};
+    for (int r = 0; r < op.kh; ++r) {
+      for (int q = 0; q < op.kw; ++q) {
+        ConvTap& t = p.taps[r * op.kw + q];
+        const int ty = r - op.pad, tx = q - op.pad;
+        if (s == 1) {
+          t.map = 0;
+          t.dy = static_cast<int8_t>(ty);
+          t.dx = static_cast<int8_t>(tx);
+        } else {
+          const int py = ((ty % 2) + 2) % 2, px = ((tx % 2) + 2) % 2;
+          t.map = static_cast<int8_t>(py * 2 + px);
+          t.dy = static_cast<int8_t>((ty - py) / 2);
+          t.dx = static_cast<int8_t>((tx - px) / 2);
+        }
+        used[t.map] = true;
+      }
+    }
+    for (int mi = 0; mi < 4; ++mi) {
+      if (!used[mi]) continue;
+      const int py = mi >> 1, px = mi & 1;
+      const int vh = (in.d.h - py + s - 1) / s, vw = (in.d.w - px + s - 1) / s;
+      if (vh <= 0 || vw <= 0) return fail(CERB_ERR_ARG, "conv: empty parity view");
+      const cuuint64_t dims[4] = {static_cast<cuuint64_t>(op.in_c), static_cast<cuuint64_t>(vw),
+                                  static_cast<cuuint64_t>(vh), static_cast<cuuint64_t>(N)};
+      const cuuint64_t strides[3] = {static_cast<cuuint64_t>(s) * in.d.c * es,
+                                     static_cast<cuuint64_t>(s) * in.d.w * in.d.c * es,
+                                     static_cast<cuuint64_t>(in.d.h) * in.d.w * in.d.c * es};
+      const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+      const size_t off = (static_cast<size_t>(py) * in.d.w + px) * in.d.c + op.in_coff;
+      for (int pln = 0; pln < (split ? 2 : 1); ++pln) {
+        CUtensorMap* m = pln == 0 ? &p.in_hi[mi] : &p.in_lo[mi];
+        int rc = encode_map(ctx, m, static_cast<__half*>(in.plane[pln]) + off, 4, dims, strides,
+                            box);
+        if (rc) return rc;
+      }
+    }
+    k_total = p.n_taps * op.in_c;
+  }
+
+  // weights [cout][k_total] fp16, K-major
+  if (op.w_off < 0 || static_cast<size_t>(op.w_off) + static_cast<size_t>(op.cout) * k_total * es >
+                          pl->blob_bytes || op.w_off % 16 != 0)
+    return fail(CERB_ERR_ARG, "conv: weight offset out of range");
+  if (split && (op.w_lo_off < 0 || static_cast<size_t>(op.w_lo_off) +
+                                           static_cast<size_t>(op.cout) * k_total * es >
+                                       pl->blob_bytes || op.w_lo_off % 16 != 0))
+    return fail(CERB_ERR_ARG, "conv: lo weight offset out of range");
+  {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(op.cout)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_total) * es};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.BN)};
+    int rc = encode_map(ctx, &p.w_hi, pl->blob + op.w_off, 2, dims, strides, box);
+    if (rc) return rc;
+    if (split) {
+      rc = encode_map(ctx, &p.w_lo, pl->blob + op.w_lo_off, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+  }
+  if (op.b_off >= 0) {
+    if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + op.cout * 4u > pl->blob_bytes)
+      return fail(CERB_ERR_ARG, "conv: bias offset out of range");
+    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+  }
+  p.out_hi = static_cast<__half*>(out.plane[0]);
+  p.out_lo = static_cast<__half*>(out.plane[1]);
+  p.out_cs = out.d.c;
+  p.out_coff = op.out_coff;
+  if (op.in1 >= 0) {
+    if (op.in1 >= nt) return fail(CERB_ERR_ARG, "conv: residual id out of range");
+    const Tensor& res = pl->tensors[op.in1];
+    if (res.d.n != N || res.d.h != H || res.d.w != W || res.d.c < op.cout || res.d.c % 8 != 0 ||
+        res.d.dtype != CERB_F16)
+      return fail(CERB_ERR_ARG, "conv: residual shape mismatch");
+    p.res_hi = static_cast<const __half*>(res.plane[0]);
+    p.res_lo = static_cast<const __half*>(res.plane[1]);
+    p.res_cs = res.d.c;
+    p.res_coff = 0;
+  }
+  p.relu = op.relu;
+  p.err_flag = ctx->err_flag_dev;
+  conv_tc_plan_pipeline(p, split);
+  return CERB_OK;
+}
+
+int check_id(const cerb_plan* pl, int id, const char* what) {
+  if (id < 0 || id >= static_cast<int>(pl->tensors.size()))
+    return fail(CERB_ERR_ARG, "%s: tensor id %d out of range", what, id);
+  return CERB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------ context
+extern "C" int cerb_ctx_create(int device, int precision, cerb_ctx** out) {
+  if (!out) return fail(CERB_ERR_ARG, "cerb_ctx_create: out is null");
+  *out = nullptr;
+  if (precision != CERB_PREC_F16 && precision != CERB_PREC_F16X2)
+    return fail(CERB_ERR_ARG, "cerb_ctx_create: unknown precision %d", precision);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(CERB_ERR_NO_DEVICE, "no CUDA device (%s); cerberus_b200 has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= count)
+    return fail(CERB_ERR_ARG, "cerb_ctx_create: device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  CERB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(CERB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                device, prop.major, prop.minor);
+  CERB_CUDA(cudaSetDevice(device));
+  cerb_ctx* ctx = new cerb_ctx();
+  ctx->device = device;
+  ctx->precision = precision;
+  ctx->num_sms = prop.multiProcessorCount;
+  CERB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CERB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->err_flag_host), sizeof(int) * 4,
+                          cudaHostAllocMapped));
+  memset(ctx->err_flag_host, 0, sizeof(int) * 4);
+  CERB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->err_flag_dev),
+                                     ctx->err_flag_host, 0));
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  CERB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+    return fail(CERB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  ctx->encode_tiled = fn;
+  *out = ctx;
+  return CERB_OK;
+}
+
+extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
+  for (void* p : ctx->scratch) cudaFree(p);
+  delete ctx;
+}
+
+extern "C" const char* cerb_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int cerb_ctx_sync(cerb_ctx* ctx) {
+  if (!ctx) return fail(CERB_ERR_ARG, "cerb_ctx_sync: null ctx");
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  const int flag = ctx->err_flag_host ? ctx->err_flag_host[0] : 0;
+  if (flag != 0) {
+    return fail(CERB_ERR_KERNEL, "kernel pipeline watchdog fired (code %d: %s)", flag,
+                flag == 1 ? "TMA producer waiting for a free smem stage"
+                : flag == 2 ? "MMA issuer waiting for a drained accumulator"
+                : flag == 3 ? "MMA issuer waiting for TMA data"
+                : flag == 4 ? "epilogue waiting for the accumulator"
+                            : "unknown");
+  }
+  if (e != cudaSuccess) return fail(CERB_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+  return CERB_OK;
+}
+
+extern "C" int64_t cerb_ctx_launch_count(cerb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* cerb_ctx_stream(cerb_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+
+// ------------------------------------------------------------------------ plan
+extern "C" void cerb_plan_destroy(cerb_plan* pl) {
+  if (!pl) return;
+  cudaSetDevice(pl->ctx->device);
+  for (Tensor& t : pl->tensors) {
+    if (t.plane[0]) cudaFree(t.plane[0]);
+    if (t.plane[1]) cudaFree(t.plane[1]);
+  }
+  if (pl->blob) cudaFree(pl->blob);
+  delete pl;
+}
+
+extern "C" int cerb_plan_create(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n_tensors,
+                                const cerb_op* ops, int n_ops, const void* weight_blob,
+                                size_t blob_bytes, cerb_plan** out) {
+  if (!ctx || !tensors || !ops || !out || n_tensors <= 0 || n_ops <= 0)
+    return fail(CERB_ERR_ARG, "cerb_plan_create: bad arguments");
+  *out = nullptr;
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  cerb_plan* pl = new cerb_plan();
+  pl->ctx = ctx;
+  int rc = CERB_OK;
+  auto bail = [&](int code) {
+    cerb_plan_destroy(pl);
+    return code;
+  };
+  const bool split = ctx->precision == CERB_PREC_F16X2;
+  pl->blob_bytes = blob_bytes;
+  if (blob_bytes > 0) {
+    if (cudaMalloc(reinterpret_cast<void**>(&pl->blob), blob_bytes) != cudaSuccess)
+      return bail(fail(CERB_ERR_CUDA, "cudaMalloc(%zu) for the weight blob failed", blob_bytes));
+    if (cudaMemcpy(pl->blob, weight_blob, blob_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(CERB_ERR_CUDA, "weight blob H2D copy failed"));
+  }
+  pl->tensors.resize(n_tensors);
+  for (int i = 0; i < n_tensors; ++i) {
+    Tensor& t = pl->tensors[i];
+    t.d = tensors[i];
+    const size_t es = dtype_size(t.d.dtype);
+    if (es == 0 || t.d.n <= 0 || t.d.h <= 0 || t.d.w <= 0 || t.d.c <= 0)
+      return bail(fail(CERB_ERR_ARG, "tensor %d: bad descriptor", i));
+    t.bytes = static_cast<size_t>(t.d.n) * t.d.h * t.d.w * t.d.c * es;
+    const int planes = (t.d.dtype == CERB_F16 && split) ? 2 : 1;
+    for (int pnum = 0; pnum < planes; ++pnum) {
+      cudaError_t e = cudaMalloc(&t.plane[pnum], t.bytes);
+      if (e != cudaSuccess)
+        return bail(fail(CERB_ERR_CUDA, "cudaMalloc(%zu) for tensor %d failed: %s", t.bytes, i,
+                         cudaGetErrorString(e)));
+      cudaMemsetAsync(t.plane[pnum], 0, t.bytes, ctx->stream);
+    }
+  }
+  pl->steps.resize(n_ops);
+  for (int i = 0; i < n_ops; ++i) {
+    const cerb_op& op = ops[i];
+    Step& st = pl->steps[i];
+    st.kind = op.kind;
+    switch (op.kind) {
+      case CERB_OP_PREP: {
+        if ((rc = check_id(pl, op.in0, "prep")) || (rc = check_id(pl, op.out, "prep")))
+          return bail(rc);
+        const Tensor& in = pl->tensors[op.in0];
+        const Tensor& o = pl->tensors[op.out];
+        if (in.d.dtype != CERB_U8 || in.d.c != 3 || o.d.dtype != CERB_F16 || o.d.c != 8 ||
+            o.d.w != in.d.w + 8 || o.d.h != in.d.h || o.d.n != in.d.n)
+          return bail(fail(CERB_ERR_ARG, "op %d: PREP expects u8 [N,H,W,3] -> f16 [N,H,W+8,8]", i));
+        st.u8_in = static_cast<const uint8_t*>(in.plane[0]);
+        st.a = act_ref(o);
+        pl->prep_in_tensor = op.in0;
+        break;
+      }
+      case CERB_OP_CONV:
+        if ((rc = build_conv(pl, op, st))) {
+          g_last_error = "op " + std::to_string(i) + ": " + g_last_error;
+          return bail(rc);
+        }
+        break;
+      case CERB_OP_MAXPOOL: {
+        if ((rc = check_id(pl, op.in0, "maxpool")) || (rc = check_id(pl, op.out, "maxpool")))
+          return bail(rc);
+        st.a = act_ref(pl->tensors[op.in0]);
+        st.b = act_ref(pl->tensors[op.out]);
+        if (st.b.h != (st.a.h + 1) / 2 || st.b.w != (st.a.w + 1) / 2 || st.a.c != st.b.c ||
+            st.a.c % 8 != 0 || st.a.n != st.b.n)
+          return bail(fail(CERB_ERR_ARG, "op %d: MAXPOOL shape mismatch", i));
+        break;
+      }
+      case CERB_OP_UPADD: {
+        if ((rc = check_id(pl, op.in0, "upadd")) || (rc = check_id(pl, op.in1, "upadd")) ||
+            (rc = check_id(pl, op.out, "upadd")))
+          return bail(rc);
+        st.a = act_ref(pl->tensors[op.in0]);  // skip
+        st.b = act_ref(pl->tensors[op.in1]);  // prev (low res)
+        st.c = act_ref(pl->tensors[op.out]);
+        // `prev` may be a channel slice of a wider tensor (fused first-stage convs).
+        if (st.a.h != 2 * st.b.h || st.a.w != 2 * st.b.w || st.c.h != st.a.h || st.c.w != st.a.w ||
+            st.a.c != st.c.c || st.a.c % 8 != 0 || op.in_coff % 8 != 0 ||
+            op.in_coff + st.a.c > st.b.c || st.a.n != st.b.n || st.a.n != st.c.n)
+          return bail(fail(CERB_ERR_ARG, "op %d: UPADD shape mismatch", i));
+        st.b.hi += op.in_coff;
+        if (st.b.lo) st.b.lo += op.in_coff;
+        break;
+      }
+      case CERB_OP_HEAD: {
+        if ((rc = check_id(pl, op.in0, "head")) || (rc = check_id(pl, op.out, "head")))
+          return bail(rc);
+        const Tensor& in = pl->tensors[op.in0];
+        const Tensor& cv = pl->tensors[op.out];
+        HeadParams& h = st.head;
+        memset(&h, 0, sizeof(h));
+        h.in = act_ref(in);
+        if (in.d.dtype != CERB_F16 || in.d.c != 96 || cv.d.dtype != CERB_F32 || cv.d.n != in.d.n ||
+            cv.d.h > in.d.h || cv.d.w > in.d.w || op.cout < 2 || op.cout > 8)
+          return bail(fail(CERB_ERR_ARG, "op %d: HEAD shape mismatch", i));
+        const int width = op.head_mode == CERB_HEAD_INST ? op.cout - 1 : 1;
+        if (op.out_coff < 0 || op.out_coff + width > cv.d.c)
+          return bail(fail(CERB_ERR_ARG, "op %d: HEAD canvas channels out of range", i));
+        if (op.w_off < 0 || op.b_off < 0 ||
+            static_cast<size_t>(op.w_off) + op.cout * 96 * 4u > blob_bytes ||
+            static_cast<size_t>(op.b_off) + op.cout * 4u > blob_bytes)
+          return bail(fail(CERB_ERR_ARG, "op %d: HEAD weight offsets out of range", i));
+        h.w = reinterpret_cast<const float*>(pl->blob + op.w_off);
+        h.b = reinterpret_cast<const float*>(pl->blob + op.b_off);
+        h.classes = op.cout;
+        h.mode = op.head_mode;
+        h.canvas = static_cast<float*>(cv.plane[0]);
+        h.oh = cv.d.h;
+        h.ow = cv.d.w;
+        h.canvas_c = cv.d.c;
+        h.canvas_coff = op.out_coff;
+        if (op.logits_out >= 0) {
+          if ((rc = check_id(pl, op.logits_out, "head logits"))) return bail(rc);
+          const Tensor& lg = pl->tensors[op.logits_out];
+          if (lg.d.dtype != CERB_F32 || lg.d.n != in.d.n || lg.d.h != in.d.h ||
+              lg.d.w != in.d.w || lg.d.c != op.cout)
+            return bail(fail(CERB_ERR_ARG, "op %d: HEAD logits tensor mismatch", i));
+          h.logits = static_cast<float*>(lg.plane[0]);
+        }
+        break;
+      }
+      case CERB_OP_PCLASS: {
+        if ((rc = check_id(pl, op.in0, "pclass")) || (rc = check_id(pl, op.out, "pclass")))
+          return bail(rc);
+        const Tensor& in = pl->tensors[op.in0];
+        const Tensor& cv = pl->tensors[op.out];
+        PClassParams& q = st.pclass;
+        memset(&q, 0, sizeof(q));
+        q.x4 = act_ref(in);
+        const size_t need = (512u + 512u + 256u * 512u + 256u + op.cout * 256u + op.cout) * 4u;
+        if (in.d.dtype != CERB_F16 || in.d.c != 512 || cv.d.dtype != CERB_F32 ||
+            cv.d.n != in.d.n || op.cout < 1 || op.cout > 16 || op.out_coff < 0 ||
+            op.out_coff >= cv.d.c || op.w_off < 0 ||
+            static_cast<size_t>(op.w_off) + need > blob_bytes)
+          return bail(fail(CERB_ERR_ARG, "op %d: PCLASS shape mismatch", i));
+        q.params = reinterpret_cast<const float*>(pl->blob + op.w_off);
+        q.classes = op.cout;
+        q.canvas = static_cast<float*>(cv.plane[0]);
+        q.oh = cv.d.h;
+        q.ow = cv.d.w;
+        q.canvas_c = cv.d.c;
+        q.canvas_coff = op.out_coff;
+        if (op.logits_out >= 0) {
+          if ((rc = check_id(pl, op.logits_out, "pclass logits"))) return bail(rc);
+          const Tensor& lg = pl->tensors[op.logits_out];
+          if (lg.d.dtype != CERB_F32 ||
+              static_cast<size_t>(lg.d.n) * lg.d.h * lg.d.w * lg.d.c !=
+                  static_cast<size_t>(in.d.n) * op.cout)
+            return bail(fail(CERB_ERR_ARG, "op %d: PCLASS logits tensor mismatch", i));
+          q.logits = static_cast<float*>(lg.plane[0]);
+        }
+        break;
+      }
+      default:
+        return bail(fail(CERB_ERR_ARG, "op %d: unknown kind %d", i, op.kind));
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return bail(fail(CERB_ERR_CUDA, "plan init: %s", cudaGetErrorString(e)));
+  *out = pl;
+  return CERB_OK;
+}
+
+namespace {
+cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  switch (st.kind) {
+    case CERB_OP_PREP:
+      e = launch_prep(st.u8_in, st.a.hi, st.a.n, st.a.h, st.a.w - 8, s);
+      if (e == cudaSuccess && st.a.lo != nullptr) {
+        // integers 0..255 are exact in fp16: the lo plane of the stem input is zero.
+        e = cudaMemsetAsync(st.a.lo, 0, static_cast<size_t>(st.a.n) * st.a.h * st.a.w * st.a.c * 2, s);
+      }
+      break;
+    case CERB_OP_CONV:
+      e = conv_tc_launch(st.conv, st.split, ctx->num_sms, s);
+      break;
+    case CERB_OP_MAXPOOL:
+      e = launch_maxpool(st.a, st.b, s);
+      break;
+    case CERB_OP_UPADD:
+      e = launch_upadd(st.a, st.b, st.c, s);
+      break;
+    case CERB_OP_HEAD:
+      e = launch_head(st.head, s);
+      break;
+    case CERB_OP_PCLASS:
+      e = launch_pclass(st.pclass, s);
+      break;
+  }
+  return e;
+}
+}  // namespace
+
+extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_on_device) {
+  if (!pl) return fail(CERB_ERR_ARG, "cerb_plan_run: null plan");
+  cerb_ctx* ctx = pl->ctx;
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (input_u8 != nullptr) {
+    if (pl->prep_in_tensor < 0) return fail(CERB_ERR_ARG, "cerb_plan_run: plan has no PREP op");
+    Tensor& t = pl->tensors[pl->prep_in_tensor];
+    CERB_CUDA(cudaMemcpyAsync(t.plane[0], input_u8, t.bytes,
+                              input_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                              s));
+  }
+  for (Step& st : pl->steps) {
+    cudaError_t e = launch_step(ctx, st, s);
+    if (e != cudaSuccess)
+      return fail(CERB_ERR_CUDA, "launch of op kind %d failed: %s", st.kind, cudaGetErrorString(e));
+    ctx->launches += 1;
+  }
+  return CERB_OK;
+}
+
+
+extern "C" int cerb_plan_num_ops(cerb_plan* pl) { return pl ? static_cast<int>(pl->steps.size()) : 0; }
+
+extern "C" int cerb_plan_profile(cerb_plan* pl, int reps, float* ms_per_op, int32_t* kinds) {
+  if (!pl || reps <= 0 || !ms_per_op) return fail(CERB_ERR_ARG, "cerb_plan_profile: bad arguments");
+  cerb_ctx* ctx = pl->ctx;
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t n = pl->steps.size();
+  std::vector<cudaEvent_t> ev((n + 1) * static_cast<size_t>(reps));
+  for (cudaEvent_t& e : ev) CERB_CUDA(cudaEventCreate(&e));
+  for (int r = 0; r < reps; ++r) {
+    cudaEvent_t* e = ev.data() + static_cast<size_t>(r) * (n + 1);
+    CERB_CUDA(cudaEventRecord(e[0], s));
+    for (size_t i = 0; i < n; ++i) {
+      cudaError_t le = launch_step(ctx, pl->steps[i], s);
+      if (le != cudaSuccess)
+        return fail(CERB_ERR_CUDA, "profile: launch of op %zu failed: %s", i, cudaGetErrorString(le));
+      ctx->launches += 1;
+      CERB_CUDA(cudaEventRecord(e[i + 1], s));
+    }
+  }
+  int rc = cerb_ctx_sync(ctx);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; ++i) {
+    double acc = 0.0;
+    for (int r = 0; r < reps; ++r) {
+      cudaEvent_t* e = ev.data() + static_cast<size_t>(r) * (n + 1);
+      float ms = 0.f;
+      CERB_CUDA(cudaEventElapsedTime(&ms, e[i], e[i + 1]));
+      acc += ms;
+    }
+    ms_per_op[i] = static_cast<float>(acc / reps);
+    if (kinds) kinds[i] = pl->steps[i].kind;
+  }
+  for (cudaEvent_t& e : ev) cudaEventDestroy(e);
+  return CERB_OK;
+}
+
+extern "C" void* cerb_plan_tensor_ptr(cerb_plan* pl, int tensor_id, int plane) {
+  if (!pl || tensor_id < 0 || tensor_id >= static_cast<int>(pl->tensors.size()) || plane < 0 ||
+      plane > 1)
+    return nullptr;
+  return pl->tensors[tensor_id].plane[plane];
+}
+
+extern "C" int cerb_plan_read_tensor(cerb_plan* pl, int tensor_id, int plane, void* host_dst,
+                                     size_t bytes) {
+  if (!pl || !host_dst) return fail(CERB_ERR_ARG, "cerb_plan_read_tensor: bad arguments");
+  void* p = cerb_plan_tensor_ptr(pl, tensor_id, plane);
+  if (!p) return fail(CERB_ERR_ARG, "cerb_plan_read_tensor: tensor %d plane %d absent", tensor_id, plane);
+  if (bytes != pl->tensors[tensor_id].bytes)
+    return fail(CERB_ERR_ARG, "cerb_plan_read_tensor: %zu bytes given, tensor holds %zu", bytes,
+                pl->tensors[tensor_id].bytes);
+  cudaSetDevice(pl->ctx->device);
+  cudaError_t e = cudaMemcpyAsync(host_dst, p, bytes, cudaMemcpyDeviceToHost, pl->ctx->stream);
+  if (e != cudaSuccess) return fail(CERB_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e));
+  return cerb_ctx_sync(pl->ctx);
+}
+
+extern "C" int cerb_plan_write_tensor(cerb_plan* pl, int tensor_id, int plane, const void* host_src,
+                                      size_t bytes) {
+  if (!pl || !host_src) return fail(CERB_ERR_ARG, "cerb_plan_write_tensor: bad arguments");
+  void* p = cerb_plan_tensor_ptr(pl, tensor_id, plane);
+  if (!p) return fail(CERB_ERR_ARG, "cerb_plan_write_tensor: tensor %d plane %d absent", tensor_id, plane);
+  if (bytes != pl->tensors[tensor_id].bytes)
+    return fail(CERB_ERR_ARG, "cerb_plan_write_tensor: %zu bytes given, tensor holds %zu", bytes,
+                pl->tensors[tensor_id].bytes);
+  cudaSetDevice(pl->ctx->device);
+  cudaError_t e = cudaMemcpyAsync(p, host_src, bytes, cudaMemcpyHostToDevice, pl->ctx->stream);
+  if (e != cudaSuccess) return fail(CERB_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e));
+  return cerb_ctx_sync(pl->ctx);
+}

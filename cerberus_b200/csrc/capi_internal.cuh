@@ -1,0 +1,35 @@
+// Shared between the translation units that implement include/cerberus_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/cerberus_b200.h"
+
+struct cerb_ctx {
+  int device = 0;
+  int precision = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  int* err_flag_host = nullptr;  // mapped pinned memory: readable even after a trapped kernel
+  int* err_flag_dev = nullptr;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved at run time (no libcuda link)
+  int64_t launches = 0;
+  std::vector<void*> scratch;  // device allocations owned by the ctx (post-proc workspaces)
+};
+
+namespace cerb {
+
+extern thread_local std::string g_last_error;
+int fail(int code, const char* fmt, ...);
+
+}  // namespace cerb
+
+#define CERB_CUDA(call)                                                                     \
+  do {                                                                                      \
+    cudaError_t cerb_e__ = (call);                                                          \
+    if (cerb_e__ != cudaSuccess)                                                            \
+      return cerb::fail(CERB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(cerb_e__)); \
+  } while (0)

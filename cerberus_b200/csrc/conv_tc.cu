@@ -1,0 +1,297 @@
+// tcgen05 / TMA implicit-GEMM convolution kernel. See conv_tc.cuh for the scheme.
+//
+// Replaces, for the hot path, every nn.Conv2d + BatchNorm2d(+ReLU)(+residual add) the
+// reference issues through cuDNN/ATen as separate kernels:
+//   models/backbone/resnet.py:32-48,81-97,195-200   (encoder convs, BN, ReLU, residual)
+//   models/utils/conv_layers.py:24-60               (decoder conv+bias -> BN -> ReLU)
+//   models/net_desc.py:52                           (conv_map 1x1)
+// BatchNorm is folded into weights/bias on load; bias, residual
+// add, ReLU and the fp16 (or hi/lo split) store are fused in the TMEM epilogue.
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace cerb {
+
+namespace {
+
+constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 fp16 channels
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM column offset between the two accumulator stages
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic smem base only promises 16.
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  const int stage_bytes = p.stage_bytes;
+  const int b_tile_bytes = p.BN * 128;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + n_stages;
+  uint64_t* tfull_bar = empty_bar + n_stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.in_hi[i]);
+    ptx::prefetch_tmap(&p.w_hi);
+    if (SPLIT) {
+      for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.in_lo[i]);
+      ptx::prefetch_tmap(&p.w_lo);
+    }
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_holder, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int n_ksteps = p.n_taps * p.n_chunks;
+  const int bw_mask = (1 << p.bw_log2) - 1;
+  const int BW = 1 << p.bw_log2;
+  const int BH = 128 >> p.bw_log2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (kATileBytes + b_tile_bytes);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_ntiles;
+        const int mt = tile / p.n_ntiles;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int img = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * BW, y0 = ty * BH;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const ConvTap tap = p.taps[t];
+          for (int c = 0; c < p.n_chunks; ++c) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+            uint8_t* sA = smem + stage * stage_bytes;
+            uint8_t* sB = sA + (SPLIT ? 2 : 1) * kATileBytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            ptx::tma_load_4d(sA, &p.in_hi[tap.map], &full_bar[stage], c * 64, x0 + tap.dx,
+                             y0 + tap.dy, img);
+            ptx::tma_load_2d(sB, &p.w_hi, &full_bar[stage], (t * p.n_chunks + c) * 64,
+                             nt * p.BN);
+            if (SPLIT) {
+              ptx::tma_load_4d(sA + kATileBytes, &p.in_lo[tap.map], &full_bar[stage], c * 64,
+                               x0 + tap.dx, y0 + tap.dy, img);
+              ptx::tma_load_2d(sB + b_tile_bytes, &p.w_lo, &full_bar[stage],
+                               (t * p.n_chunks + c) * 64, nt * p.BN);
+            }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(128, p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int ks = 0; ks < n_ksteps; ++ks) {
+          ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + (SPLIT ? 2 : 1) * kATileBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 16) per 64-channel slab
+            const uint64_t a_hi = ptx::umma_desc_sw128(a_addr + k * 32, 1024);
+            const uint64_t b_hi = ptx::umma_desc_sw128(b_addr + k * 32, 1024);
+            ptx::umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) != 0);
+            if (SPLIT) {
+              const uint64_t a_lo = ptx::umma_desc_sw128(a_addr + kATileBytes + k * 32, 1024);
+              const uint64_t b_lo = ptx::umma_desc_sw128(b_addr + b_tile_bytes + k * 32, 1024);
+              ptx::umma_f16(tmem_d, a_lo, b_hi, idesc, 1);
+              ptx::umma_f16(tmem_d, a_hi, b_lo, idesc, 1);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs retire
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int py = m >> p.bw_log2, px = m & bw_mask;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_ntiles;
+      const int mt = tile / p.n_ntiles;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int ox = tx * BW + px, oy = ty * BH + py;
+      const bool valid = (ox < p.W) && (oy < p.H);
+      const size_t pix = (static_cast<size_t>(img) * p.H + oy) * p.W + ox;
+      const int n0 = nt * p.BN;
+
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
+      for (int j = 0; j < p.BN; j += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + j, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (p.res_hi != nullptr) {
+            const size_t roff = pix * p.res_cs + p.res_coff + n0 + j;
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + roff);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(rh + i);
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                v[8 * i + 2 * e] += f.x; v[8 * i + 2 * e + 1] += f.y;
+              }
+            }
+            if (SPLIT) {
+              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + roff);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(rl + i);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h[e]);
+                  v[8 * i + 2 * e] += f.x; v[8 * i + 2 * e + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          }
+          const size_t ooff = pix * p.out_cs + p.out_coff + n0 + j;
+          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + ooff);
+          if (!SPLIT) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+              oh[i] = u;
+            }
+          } else {
+            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + ooff);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = v[8 * i + 2 * e], b = v[8 * i + 2 * e + 1];
+                const __half2 h = __floats2half2_rn(a, b);
+                const float2 hf = __half22float2(h);
+                hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[e] = pack_half2(a - hf.x, b - hf.y);
+              }
+              oh[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              ol[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+void conv_tc_plan_pipeline(ConvKParams& p, bool split) {
+  p.stage_bytes = (split ? 2 : 1) * (kATileBytes + p.BN * 128);
+  int n = (196 * 1024) / p.stage_bytes;
+  if (n > 8) n = 8;
+  if (n < 2) n = 2;
+  p.n_stages = n;
+}
+
+size_t conv_tc_smem_bytes(const ConvKParams& p) {
+  // tiles + barriers (+ tmem holder) + slack for the manual 1024-byte alignment.
+  // Always above half the SM's shared memory so that exactly one CTA (and one 512-column
+  // TMEM allocation) lives on an SM at a time.
+  size_t b = static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024;
+  if (b < 120 * 1024) b = 120 * 1024;
+  return b;
+}
+
+cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream) {
+  static bool attr_set[2] = {false, false};
+  auto kern = split ? conv_tc_kernel<true> : conv_tc_kernel<false>;
+  if (!attr_set[split ? 1 : 0]) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[split ? 1 : 0] = true;
+  }
+  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  kern<<<grid, kConvThreads, conv_tc_smem_bytes(p), stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace cerb

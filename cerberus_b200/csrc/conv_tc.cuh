@@ -1,0 +1,65 @@
+// Implicit-GEMM NHWC convolution on tcgen05 tensor cores (sm_100a).
+//
+// GEMM view: M = output pixels, N = Cout, K = taps * Cin.
+// One CTA tile = 128 output pixels (a BH x BW spatial box of one image) x BN output
+// channels. For every filter tap the 128 x 64-channel activation slab is fetched by ONE
+// 4-D TMA box load whose (x, y) coordinates are the tile origin shifted by the tap
+// offset; TMA zero-fills out-of-bounds pixels, which is exactly the convolution's zero
+// padding, so no im2col buffer ever exists. Stride-2 layers read four parity views of
+// the input (one tensor map per (y&1, x&1)), the 7x7 stem reads a pre-padded 8-channel
+// image through an overlapping-window tensor map (7 row taps x 64 = 8 px * 8 ch).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace cerb {
+
+constexpr int kConvMaxTaps = 16;
+constexpr int kConvThreads = 192;  // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2-5: epilogue
+
+struct ConvTap {
+  int8_t map;  // which input tensor map (parity view) this tap reads
+  int8_t dx;   // x offset added to the tile origin, in that view's pixel grid
+  int8_t dy;
+  int8_t pad;
+};
+
+struct ConvKParams {
+  CUtensorMap in_hi[4];
+  CUtensorMap in_lo[4];  // only read in split-precision mode
+  CUtensorMap w_hi;
+  CUtensorMap w_lo;
+  ConvTap taps[kConvMaxTaps];
+  int n_taps;
+  int n_chunks;  // Cin / 64 per tap
+  // output geometry
+  int n_img, H, W;
+  int bw_log2;  // tile box width = 1 << bw_log2, height = 128 >> bw_log2
+  int tiles_x, tiles_y, n_ntiles, n_tiles;
+  int BN;  // output channels per tile (multiple of 32, <= 256)
+  // epilogue
+  const float* bias;  // [Cout] fp32 (BN folded), may be null
+  __half* out_hi;
+  __half* out_lo;  // split-precision mode only
+  const __half* res_hi;
+  const __half* res_lo;
+  int out_cs;    // channel stride (elements per pixel) of the output tensor
+  int out_coff;  // channel offset inside the output tensor
+  int res_cs;
+  int res_coff;
+  int relu;
+  // pipeline
+  int n_stages;
+  int stage_bytes;
+  int* err_flag;
+};
+
+// Host side: encodes nothing, just launches. `split` selects the 3-MMA hi/lo mode.
+cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream);
+size_t conv_tc_smem_bytes(const ConvKParams& p);
+// Fills n_stages / stage_bytes for a given BN and mode.
+void conv_tc_plan_pipeline(ConvKParams& p, bool split);
+
+}  // namespace cerb

@@ -1,0 +1,346 @@
+// Bandwidth-bound operators of the forward pass: stem input preparation, max pool,
+// bilinear-x2 + skip add, classification-head tail and the Patch-Class branch.
+// All activations are NHWC fp16 (optionally hi+lo pairs); arithmetic is fp32.
+#include "ops.cuh"
+
+#include <cfloat>
+
+namespace cerb {
+namespace {
+
+__device__ __forceinline__ void load8(const __half* hi, const __half* lo, size_t off, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+  if (lo != nullptr) {
+    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lo + off));
+    const __half2* l = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(l[e]);
+      v[2 * e] += f.x;
+      v[2 * e + 1] += f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(__half* hi, __half* lo, size_t off, const float (&v)[8]) {
+  uint4 uh, ul;
+  uint32_t* ph = reinterpret_cast<uint32_t*>(&uh);
+  uint32_t* pl = reinterpret_cast<uint32_t*>(&ul);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    ph[e] = *reinterpret_cast<const uint32_t*>(&h);
+    if (lo != nullptr) {
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+      pl[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+  }
+  *reinterpret_cast<uint4*>(hi + off) = uh;
+  if (lo != nullptr) *reinterpret_cast<uint4*>(lo + off) = ul;
+}
+
+// ------------------------------------------------------------------ prep
+__global__ void prep_kernel(const uint8_t* __restrict__ in, __half* __restrict__ out, int n, int h,
+                            int w) {
+  const int wp = w + 8;
+  const size_t total = static_cast<size_t>(n) * h * wp;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xp = static_cast<int>(i % wp);
+    const size_t row = i / wp;  // n*h + y
+    const int x = xp - 3;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (x >= 0 && x < w) {
+      const uint8_t* px = in + (row * w + x) * 3;
+      const __half2 rg = __floats2half2_rn(static_cast<float>(px[0]), static_cast<float>(px[1]));
+      const __half2 b0 = __floats2half2_rn(static_cast<float>(px[2]), 0.0f);
+      u.x = *reinterpret_cast<const uint32_t*>(&rg);
+      u.y = *reinterpret_cast<const uint32_t*>(&b0);
+    }
+    reinterpret_cast<uint4*>(out)[i] = u;
+  }
+}
+
+// ------------------------------------------------------------------ maxpool
+__global__ void maxpool_kernel(ActRef in, ActRef out) {
+  const int cg = out.c >> 3;
+  const size_t total = static_cast<size_t>(out.n) * out.h * out.w * cg;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    size_t t = i / cg;
+    const int ox = static_cast<int>(t % out.w);
+    t /= out.w;
+    const int oy = static_cast<int>(t % out.h);
+    const int n = static_cast<int>(t / out.h);
+    float best_hi[8], best_lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best_hi[e] = -FLT_MAX; best_lo[e] = 0.0f; }
+    for (int r = 0; r < 3; ++r) {
+      const int y = 2 * oy + r - 1;
+      if (y < 0 || y >= in.h) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int x = 2 * ox + s - 1;
+        if (x < 0 || x >= in.w) continue;
+        const size_t off = ((static_cast<size_t>(n) * in.h + y) * in.w + x) * in.c + g * 8;
+        float vh[8], vl[8];
+        load8(in.hi, nullptr, off, vh);
+        if (in.lo != nullptr) {
+          load8(in.lo, nullptr, off, vl);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) vl[e] = 0.0f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          // (hi, lo) pairs order lexicographically because hi = round(value).
+          if (vh[e] > best_hi[e] || (vh[e] == best_hi[e] && vl[e] > best_lo[e])) {
+            best_hi[e] = vh[e];
+            best_lo[e] = vl[e];
+          }
+        }
+      }
+    }
+    const size_t ooff = ((static_cast<size_t>(n) * out.h + oy) * out.w + ox) * out.c + g * 8;
+    // hi and lo are copied verbatim (both already fp16-representable).
+    uint4 uh, ul;
+    uint32_t* ph = reinterpret_cast<uint32_t*>(&uh);
+    uint32_t* pl = reinterpret_cast<uint32_t*>(&ul);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 h = __floats2half2_rn(best_hi[2 * e], best_hi[2 * e + 1]);
+      const __half2 l = __floats2half2_rn(best_lo[2 * e], best_lo[2 * e + 1]);
+      ph[e] = *reinterpret_cast<const uint32_t*>(&h);
+      pl[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(out.hi + ooff) = uh;
+    if (out.lo != nullptr) *reinterpret_cast<uint4*>(out.lo + ooff) = ul;
+  }
+}
+
+// ------------------------------------------------------------------ upsample + add
+__global__ void upadd_kernel(ActRef skip, ActRef prev, ActRef out) {
+  const int cg = out.c >> 3;
+  const size_t total = static_cast<size_t>(out.n) * out.h * out.w * cg;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % cg);
+    size_t t = i / cg;
+    const int X = static_cast<int>(t % out.w);
+    t /= out.w;
+    const int Y = static_cast<int>(t % out.h);
+    const int n = static_cast<int>(t / out.h);
+    // src = (dst + 0.5) / 2 - 0.5, clamped at 0; second tap clamped at the last row/column.
+    const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.0f);
+    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f);
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = min(y0 + 1, prev.h - 1), x1 = min(x0 + 1, prev.w - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    const size_t base = static_cast<size_t>(n) * prev.h;
+    float p00[8], p01[8], p10[8], p11[8], sk[8], o[8];
+    load8(prev.hi, prev.lo, ((base + y0) * prev.w + x0) * prev.c + g * 8, p00);
+    load8(prev.hi, prev.lo, ((base + y0) * prev.w + x1) * prev.c + g * 8, p01);
+    load8(prev.hi, prev.lo, ((base + y1) * prev.w + x0) * prev.c + g * 8, p10);
+    load8(prev.hi, prev.lo, ((base + y1) * prev.w + x1) * prev.c + g * 8, p11);
+    const size_t ooff = ((static_cast<size_t>(n) * out.h + Y) * out.w + X) * out.c + g * 8;
+    load8(skip.hi, skip.lo, ((static_cast<size_t>(n) * skip.h + Y) * skip.w + X) * skip.c + g * 8,
+          sk);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float up = hy * (hx * p00[e] + lx * p01[e]) + ly * (hx * p10[e] + lx * p11[e]);
+      o[e] = sk[e] + up;
+    }
+    store8(out.hi, out.lo, ooff, o);
+  }
+}
+
+// ------------------------------------------------------------------ head tail
+constexpr int kHeadIn = 96;
+constexpr int kHeadMaxC = 8;
+
+__global__ void head_kernel(HeadParams p) {
+  __shared__ float sw[kHeadMaxC * kHeadIn];
+  __shared__ float sb[kHeadMaxC];
+  for (int i = threadIdx.x; i < p.classes * kHeadIn; i += blockDim.x) sw[i] = p.w[i];
+  if (threadIdx.x < p.classes) sb[threadIdx.x] = p.b[threadIdx.x];
+  __syncthreads();
+  const int H = p.in.h, W = p.in.w;
+  const int y_off = static_cast<int>((H - p.oh) * 0.5), x_off = static_cast<int>((W - p.ow) * 0.5);
+  const size_t total = static_cast<size_t>(p.in.n) * H * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float acc[kHeadMaxC];
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) acc[c] = 0.0f;
+    const size_t off = i * p.in.c;
+    for (int k = 0; k < kHeadIn; k += 8) {
+      float v[8];
+      load8(p.in.hi, p.in.lo, off + k, v);
+#pragma unroll
+      for (int c = 0; c < kHeadMaxC; ++c) {
+        if (c < p.classes) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[c] = fmaf(v[e], sw[c * kHeadIn + k + e], acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c)
+      if (c < p.classes) acc[c] += sb[c];
+    if (p.logits != nullptr) {
+      for (int c = 0; c < p.classes; ++c) p.logits[i * p.classes + c] = acc[c];
+    }
+    if (p.canvas == nullptr) continue;
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int n = static_cast<int>(i / (static_cast<size_t>(W) * H));
+    const int cy = y - y_off, cx = x - x_off;
+    if (cy < 0 || cy >= p.oh || cx < 0 || cx >= p.ow) continue;
+    // softmax over C in fp32 (models/run_desc.py:451-461)
+    float m = acc[0];
+#pragma unroll
+    for (int c = 1; c < kHeadMaxC; ++c)
+      if (c < p.classes) m = fmaxf(m, acc[c]);
+    float e[kHeadMaxC], sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) {
+      e[c] = (c < p.classes) ? expf(acc[c] - m) : 0.0f;
+      sum += e[c];
+    }
+    float* dst = p.canvas + ((static_cast<size_t>(n) * p.oh + cy) * p.ow + cx) * p.canvas_c +
+                 p.canvas_coff;
+    if (p.mode == 0) {
+      for (int c = 1; c < p.classes; ++c) dst[c - 1] = e[c] / sum;
+    } else {
+      int best = 0;
+      float bp = e[0] / sum;
+#pragma unroll
+      for (int c = 1; c < kHeadMaxC; ++c) {
+        if (c < p.classes) {
+          const float pc = e[c] / sum;
+          if (pc > bp) { bp = pc; best = c; }  // first maximum wins, as torch.argmax
+        }
+      }
+      dst[0] = static_cast<float>(best);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Patch-Class
+__global__ void pclass_kernel(PClassParams p) {
+  __shared__ float pooled[512];
+  __shared__ float hidden[256];
+  __shared__ float logit[16];
+  __shared__ int s_best;
+  const int n = blockIdx.x;
+  const int h4 = p.x4.h, w4 = p.x4.w;
+  int y0 = 0, x0 = 0, ch = h4, cw = w4;
+  if (h4 != 9 && w4 != 9) {  // models/net_desc.py:173 (note the `and`)
+    y0 = static_cast<int>((h4 - 9) * 0.5);
+    x0 = static_cast<int>((w4 - 9) * 0.5);
+    ch = 9;
+    cw = 9;
+  }
+  const float* bn_s = p.params;
+  const float* bn_b = bn_s + 512;
+  const float* W1 = bn_b + 512;
+  const float* b1 = W1 + 256 * 512;
+  const float* W2 = b1 + 256;
+  const float* b2 = W2 + p.classes * 256;
+  for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+    float s = 0.0f;
+    for (int y = 0; y < ch; ++y)
+      for (int x = 0; x < cw; ++x) {
+        const size_t off = ((static_cast<size_t>(n) * h4 + y0 + y) * w4 + x0 + x) * p.x4.c + c;
+        float v = __half2float(p.x4.hi[off]);
+        if (p.x4.lo != nullptr) v += __half2float(p.x4.lo[off]);
+        s += v;
+      }
+    const float mean = s / static_cast<float>(ch * cw);
+    pooled[c] = fmaxf(mean * bn_s[c] + bn_b[c], 0.0f);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 256; o += blockDim.x) {
+    float s = 0.0f;
+    const float* wr = W1 + static_cast<size_t>(o) * 512;
+    for (int k = 0; k < 512; ++k) s = fmaf(pooled[k], wr[k], s);
+    hidden[o] = fmaxf(s + b1[o], 0.0f);
+  }
+  __syncthreads();
+  if (threadIdx.x < p.classes) {
+    float s = 0.0f;
+    const float* wr = W2 + threadIdx.x * 256;
+    for (int k = 0; k < 256; ++k) s = fmaf(hidden[k], wr[k], s);
+    logit[threadIdx.x] = s + b2[threadIdx.x];
+    if (p.logits != nullptr) p.logits[n * p.classes + threadIdx.x] = logit[threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // argmax(softmax(x)) (models/run_desc.py:459-461): same softmax arithmetic as the heads.
+    float m = logit[0];
+    for (int c = 1; c < p.classes; ++c) m = fmaxf(m, logit[c]);
+    float sum = 0.0f;
+    for (int c = 0; c < p.classes; ++c) sum += expf(logit[c] - m);
+    int best = 0;
+    float bp = expf(logit[0] - m) / sum;
+    for (int c = 1; c < p.classes; ++c) {
+      const float pc = expf(logit[c] - m) / sum;
+      if (pc > bp) { bp = pc; best = c; }
+    }
+    s_best = best;
+  }
+  __syncthreads();
+  if (p.canvas != nullptr) {
+    const float v = static_cast<float>(s_best);
+    float* dst = p.canvas + static_cast<size_t>(n) * p.oh * p.ow * p.canvas_c + p.canvas_coff;
+    for (int i = threadIdx.x; i < p.oh * p.ow; i += blockDim.x) dst[static_cast<size_t>(i) * p.canvas_c] = v;
+  }
+}
+
+inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return static_cast<int>(g < cap ? (g == 0 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+cudaError_t launch_prep(const uint8_t* in_u8, __half* out, int n, int h, int w, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(n) * h * (w + 8);
+  prep_kernel<<<grid_for(total, 256), 256, 0, s>>>(in_u8, out, n, h, w);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool(ActRef in, ActRef out, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.c >> 3);
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upadd(ActRef skip, ActRef prev, ActRef out, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.c >> 3);
+  upadd_kernel<<<grid_for(total, 256), 256, 0, s>>>(skip, prev, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head(const HeadParams& p, cudaStream_t s) {
+  const size_t total = static_cast<size_t>(p.in.n) * p.in.h * p.in.w;
+  head_kernel<<<grid_for(total, 128), 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pclass(const PClassParams& p, cudaStream_t s) {
+  pclass_kernel<<<p.x4.n, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace cerb

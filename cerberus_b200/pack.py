@@ -1,0 +1,94 @@
+"""Weight folding and packing: reference state_dict -> one contiguous blob for the C ABI.
+
+Follows SURVEY.md Appendix D. Reference modules whose parameters are consumed here:
+  models/backbone/resnet.py:32-48,81-97,195-200  (conv / bn / downsample, no conv bias)
+  models/utils/conv_layers.py:24-60               (_ConvLayer: conv(bias) -> BN(eps 1e-5) -> ReLU)
+  models/net_desc.py:52,64-76                     (conv_map, Patch-Class head)
+  models/utils/net_layers.py:31-38                (classification head)
+BatchNorm (eval mode) is folded into the preceding convolution in float64, then the result
+is split into fp16 hi + fp16 lo planes (lo is only read in CERB_PREC_F16X2 mode).
+"""
+import numpy as np
+
+BN_EPS = 1e-5
+ALIGN = 256
+
+
+class BlobBuilder:
+    def __init__(self):
+        self._chunks = []
+        self._size = 0
+
+    def add(self, arr):
+        arr = np.ascontiguousarray(arr)
+        pad = (-self._size) % ALIGN
+        if pad:
+            self._chunks.append(b"\0" * pad)
+            self._size += pad
+        off = self._size
+        raw = arr.tobytes()
+        self._chunks.append(raw)
+        self._size += len(raw)
+        return off
+
+    def finish(self):
+        return np.frombuffer(b"".join(self._chunks), dtype=np.uint8).copy()
+
+
+def _np(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+def fold_bn(weight, bias, bn, eps=BN_EPS):
+    """conv -> BN(eval) as a single conv. weight [O,I,kh,kw]; bias [O] or None; bn = dict of
+    weight/bias/running_mean/running_var arrays (float64)."""
+    s = bn["weight"] / np.sqrt(bn["running_var"] + eps)
+    w = weight * s[:, None, None, None]
+    b0 = bias if bias is not None else np.zeros(weight.shape[0])
+    b = (b0 - bn["running_mean"]) * s + bn["bias"]
+    return w, b
+
+
+def bn_of(sd, prefix):
+    return {k: _np(sd[prefix + "." + k]) for k in ("weight", "bias", "running_mean", "running_var")}
+
+
+def split_f16(x):
+    """fp64/fp32 array -> (hi, lo) fp16 planes with hi + lo ~= x to ~22 bits."""
+    x = np.asarray(x, dtype=np.float64)
+    hi = x.astype(np.float16)
+    lo = (x - hi.astype(np.float64)).astype(np.float16)
+    return hi, lo
+
+
+def pack_conv(blob, w, b):
+    """w [O,I,kh,kw] float64 (BN folded) -> K-major [O][kh*kw][I] fp16 hi/lo; b -> fp32.
+    Returns dict(w_off, w_lo_off, b_off, cout, cin, kh, kw)."""
+    o, i, kh, kw = w.shape
+    km = np.transpose(w, (0, 2, 3, 1)).reshape(o, kh * kw * i)
+    hi, lo = split_f16(km)
+    out = {"w_off": blob.add(hi), "w_lo_off": blob.add(lo), "cout": o, "cin": i, "kh": kh, "kw": kw}
+    out["b_off"] = blob.add(b.astype(np.float32)) if b is not None else -1
+    return out
+
+
+def pack_stem(blob, w, b):
+    """Stem 7x7, 3->64. The device reads the image through an overlapping-window view of
+    the [N,H,W+8,8] PREP tensor: per filter row one K chunk of 64 = 8 pixels x 8 channels
+    (pixel 7 and channels 3..7 carry zero weights). `imgs / 255` (models/net_desc.py:147)
+    is folded into the weights."""
+    o, i, kh, kw = w.shape
+    assert (i, kh, kw) == (3, 7, 7)
+    w = w / 255.0
+    km = np.zeros((o, 7, 8, 8), dtype=np.float64)
+    km[:, :, :7, :3] = np.transpose(w, (0, 2, 3, 1))
+    hi, lo = split_f16(km.reshape(o, 7 * 64))
+    return {"w_off": blob.add(hi), "w_lo_off": blob.add(lo), "b_off": blob.add(b.astype(np.float32)),
+            "cout": o, "cin": 3, "kh": 7, "kw": 7}
+
+
+def strip_module_prefix(sd):
+    """infer/base.py:31-45: checkpoints saved from nn.DataParallel carry a 'module.' prefix."""
+    if all(k.startswith("module.") for k in sd.keys()):
+        return {k[len("module."):]: v for k, v in sd.items()}
+    return dict(sd)

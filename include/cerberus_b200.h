@@ -1,0 +1,133 @@
+/* cerberus_b200 — C ABI of the B200-native Cerberus inference hot path.
+ *
+ * The reference (TissueImageAnalytics/cerberus) is pure Python on top of PyTorch and
+ * scikit-image; it has no FFI of its own. This header is the drop-in boundary a
+ * maintainer binds with ctypes to replace, for the tiled
+ * inference path only:
+ *
+ *   B1  infer/base.py:51-53  run_step(input_batch, output_shape)
+ *         = models/run_desc.py:439-502 infer_step  ->  models/net_desc.py:144-200 forward
+ *       -> cerb_plan_create / cerb_plan_run / cerb_plan_read_*
+ *   B2  loader/postproc.py:383-407  PostProcInstErodedContourMap.post_process
+ *         (__proc_nuclei :352-381, __proc_gland :270-309, __proc_lumen :312-350)
+ *       -> cerb_postproc_nuclei / cerb_postproc_gland_lumen
+ *   a16 infer/tile.py:136-163  canvas stitch           -> cerb_stitch
+ *   a1/a2 infer/tile.py:43-106 + loader/infer_loader.py:57-69 (reflect pad + patch
+ *       slicing)                                        -> cerb_extract_patches
+ *
+ * Conventions: every function returns 0 on success or a negative cerb_status; nothing
+ * throws across the ABI; cerb_last_error() returns a thread-local, NUL-terminated
+ * description of the last failure. The caller owns all host buffers. A ctx owns its
+ * device buffers and one CUDA stream; a ctx is NOT thread-safe, different ctxs are
+ * independent. There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef CERBERUS_B200_H
+#define CERBERUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cerb_ctx cerb_ctx;
+typedef struct cerb_plan cerb_plan;
+
+enum cerb_status {
+  CERB_OK = 0,
+  CERB_ERR_CUDA = -1,     /* a CUDA runtime/driver call failed                        */
+  CERB_ERR_ARG = -2,      /* invalid argument / unsupported shape                     */
+  CERB_ERR_KERNEL = -3,   /* a kernel reported an internal error (pipeline watchdog)  */
+  CERB_ERR_NO_DEVICE = -4 /* no sm_100 device; this library has no CPU path           */
+};
+
+enum cerb_dtype { CERB_U8 = 0, CERB_F16 = 1, CERB_F32 = 2, CERB_I32 = 3 };
+
+/* Precision of the tensor-core path.
+ * CERB_PREC_F16   : fp16 operands, fp32 accumulation (throughput mode).
+ * CERB_PREC_F16X2 : every activation and weight carried as hi+lo fp16 pair, three MMAs per
+ *                   product (hi*hi + lo*hi + hi*lo), fp32 accumulation: ~fp32 accuracy, used
+ *                   for the 1e-3 logit gate against the fp32 reference. */
+enum cerb_precision { CERB_PREC_F16 = 0, CERB_PREC_F16X2 = 1 };
+
+/* NHWC tensor owned by a plan. `c` is the allocated channel count (pixel stride). */
+typedef struct cerb_tensor_desc {
+  int32_t n, h, w, c;
+  int32_t dtype; /* cerb_dtype; F16 tensors get a second (lo) plane in F16X2 mode */
+} cerb_tensor_desc;
+
+enum cerb_op_kind {
+  CERB_OP_PREP = 1,    /* u8 NHWC batch -> fp16 [N,H,W+8,8] zero-padded stem input (run_desc.py:440-441; /255 folded into stem weights, net_desc.py:147) */
+  CERB_OP_CONV = 2,    /* conv + folded BN + bias (+residual) (+ReLU)                   */
+  CERB_OP_MAXPOOL = 3, /* 3x3 s2 p1 (resnet.py:201)                                     */
+  CERB_OP_UPADD = 4,   /* out = skip + bilinear2x(prev), align_corners=False (net_layers.py:45-46, net_desc.py:185-188) */
+  CERB_OP_HEAD = 5,    /* 1x1 96->C (+bias), softmax / argmax / centre crop into the patch canvas (net_layers.py:36-38, run_desc.py:451-491) */
+  CERB_OP_PCLASS = 6   /* Patch-Class branch (net_desc.py:64-76,169-180) + argmax broadcast (run_desc.py:459-461,479-486) */
+};
+
+enum cerb_head_mode {
+  CERB_HEAD_INST = 0, /* softmax, drop channel 0 -> C-1 float channels */
+  CERB_HEAD_TYPE = 1  /* argmax(softmax) -> 1 channel holding the class index as float */
+};
+
+/* One step of a plan. Unused fields are 0 / -1. Weight offsets are byte offsets into the
+ * packed blob handed to cerb_plan_create (layout documented in cerberus_b200/pack.py). */
+typedef struct cerb_op {
+  int32_t kind;
+  int32_t in0;      /* input tensor id                                                  */
+  int32_t in1;      /* CONV: residual tensor id or -1; UPADD: low-res `prev` tensor id  */
+  int32_t out;      /* output tensor id                                                 */
+  int32_t in_coff;  /* CONV: first input channel read from in0; UPADD: first channel of in1 */
+  int32_t in_c;     /* CONV: number of input channels (multiple of 64; stem: 8)         */
+  int32_t out_coff; /* CONV/HEAD/PCLASS: first output channel written                   */
+  int32_t cout;     /* CONV: output channels; HEAD: classes C; PCLASS: classes          */
+  int32_t kh, kw, stride, pad;
+  int32_t relu;
+  int32_t stem;       /* CONV: 1 = 7x7 stem reading the PREP tensor                     */
+  int32_t head_mode;  /* HEAD: cerb_head_mode                                           */
+  int32_t logits_out; /* HEAD/PCLASS: tensor id receiving raw fp32 logits, or -1        */
+  int64_t w_off;      /* CONV: fp16 hi weights [cout][K]; HEAD/PCLASS: fp32 params      */
+  int64_t w_lo_off;   /* CONV: fp16 lo weights (F16X2 mode), else -1                    */
+  int64_t b_off;      /* fp32 bias [cout], or -1                                        */
+  int32_t box_w;      /* CONV: tile box width override (power of two <= 128), 0 = auto  */
+  int32_t reserved[3];
+} cerb_op;
+
+/* ---- context ------------------------------------------------------------------- */
+int cerb_ctx_create(int device, int precision, cerb_ctx** out);
+void cerb_ctx_destroy(cerb_ctx* ctx);
+const char* cerb_last_error(void);
+int cerb_ctx_sync(cerb_ctx* ctx);
+/* Number of kernels this library launched on ctx since creation (bench's gpu_launches). */
+int64_t cerb_ctx_launch_count(cerb_ctx* ctx);
+/* Raw CUDA stream handle (cudaStream_t) of the ctx, for event timing by the caller. */
+void* cerb_ctx_stream(cerb_ctx* ctx);
+
+/* ---- plan: one compiled forward for a fixed [N,H,W] batch shape ------------------ */
+int cerb_plan_create(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n_tensors,
+                     const cerb_op* ops, int n_ops, const void* weight_blob, size_t blob_bytes,
+                     cerb_plan** out);
+void cerb_plan_destroy(cerb_plan* plan);
+/* Runs every op. `input_u8` is the [N,H,W,3] uint8 batch for the PREP op's in0 tensor:
+ * host memory when input_on_device == 0 (copied H2D on the ctx stream inside the call),
+ * device memory otherwise. Asynchronous with respect to the host; pair with cerb_ctx_sync
+ * or a cerb_plan_read_* call (which synchronises). */
+int cerb_plan_run(cerb_plan* plan, const uint8_t* input_u8, int input_on_device);
+int cerb_plan_num_ops(cerb_plan* plan);
+/* Evidence for bench.py's roofline: runs the plan `reps` times on its current input with a
+ * CUDA event recorded on the ctx stream after every op and returns the mean device time per
+ * op in milliseconds (`ms_per_op[cerb_plan_num_ops]`, `kinds` optional). Synchronous. */
+int cerb_plan_profile(cerb_plan* plan, int reps, float* ms_per_op, int32_t* kinds);
+/* Device pointer of a plan tensor (plane 0 = hi / only plane, 1 = lo). */
+void* cerb_plan_tensor_ptr(cerb_plan* plan, int tensor_id, int plane);
+/* Synchronous D2H copy of a whole tensor plane into `host_dst` (`bytes` must match). */
+int cerb_plan_read_tensor(cerb_plan* plan, int tensor_id, int plane, void* host_dst, size_t bytes);
+/* Synchronous H2D copy into a tensor plane (tests feed intermediate activations). */
+int cerb_plan_write_tensor(cerb_plan* plan, int tensor_id, int plane, const void* host_src,
+                           size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CERBERUS_B200_H */

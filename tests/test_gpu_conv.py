@@ -1,0 +1,120 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution against torch fp32 conv2d of the
+same fp16-rounded operands (the only floating-point kernel family: torch fp32 reference)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cerberus_b200 import _lib
+from cerberus_b200.engine import Context, ForwardPlan
+from cerberus_b200.pack import BlobBuilder, pack_conv, pack_stem
+from tests.util import MiniModel, MiniSpec, f16, nchw_to_nhwc, nhwc_to_nchw
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n, h, w, cin, cout, k, stride, residual, relu
+    (2, 32, 32, 64, 64, 3, 1, False, True),     # layer1-like
+    (1, 128, 128, 64, 64, 3, 1, True, True),    # full-width rows, residual
+    (2, 64, 64, 64, 128, 3, 2, False, True),    # stride-2 parity views
+    (2, 64, 64, 64, 128, 1, 2, False, False),   # downsample 1x1 s2
+    (1, 16, 16, 512, 256, 1, 1, False, False),  # conv_map
+    (2, 28, 28, 256, 256, 3, 1, True, True),    # non power-of-two map (448 input), partial tiles
+    (1, 32, 32, 256, 1280, 3, 1, False, True),  # fused first decoder stage (5 decoders)
+    (1, 64, 64, 64, 96, 1, 1, False, True),     # head hidden layer, BN = 96
+    (3, 16, 16, 512, 512, 3, 1, True, True),    # layer4: K = 4608
+    (1, 48, 80, 128, 64, 3, 1, False, True),    # non-square
+]
+
+
+def _run_case(precision, n, h, w, cin, cout, k, stride, residual, relu, seed=0):
+    rng = np.random.RandomState(seed)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((cout, cin, k, k)) * (1.0 / np.sqrt(cin * k * k))).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, cout).astype(np.float32)
+    oh = (h + 2 * (k // 2) - k) // stride + 1
+    ow = (w + 2 * (k // 2) - k) // stride + 1
+    res = rng.standard_normal((n, oh, ow, cout)).astype(np.float32) if residual else None
+    if precision == "f16":
+        x = f16(x).astype(np.float32)
+        wt = f16(wt).astype(np.float32)
+        if res is not None:
+            res = f16(res).astype(np.float32)
+    blob = BlobBuilder()
+    layer = pack_conv(blob, wt.astype(np.float64), b.astype(np.float64))
+    spec = MiniSpec()
+    t_in = spec._tensor("in", n, h, w, cin)
+    t_out = spec._tensor("out", n, oh, ow, cout)
+    t_res = spec._tensor("res", n, oh, ow, cout) if residual else -1
+    spec._conv(layer, t_in, t_out, relu=int(relu), stride=stride, residual=t_res)
+    ctx = Context(0, precision)
+    plan = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
+
+    def put(tid, a):
+        hi = a.astype(np.float16)
+        plan.write(tid, hi, 0)
+        if precision == "f16x2":
+            plan.write(tid, (a - hi.astype(np.float32)).astype(np.float16), 1)
+
+    put(t_in, x)
+    if residual:
+        put(t_res, res)
+    plan.run()
+    got = plan.read(t_out).astype(np.float32)
+    ref = F.conv2d(torch.from_numpy(nhwc_to_nchw(x)).double(), torch.from_numpy(wt).double(),
+                   torch.from_numpy(b).double(), stride=stride, padding=k // 2)
+    if residual:
+        ref = ref + torch.from_numpy(nhwc_to_nchw(res)).double()
+    if relu:
+        ref = F.relu(ref)
+    ref = nchw_to_nhwc(ref.numpy())
+    plan.close()
+    ctx.close()
+    return got, ref
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_f16(case, built_lib):
+    got, ref = _run_case("f16", *case)
+    # fp32 accumulation of exact fp16 products; output rounded to fp16 (rel 2^-11)
+    err = np.abs(got - ref)
+    tol = 2e-3 * np.abs(ref) + 2e-3
+    assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_f16x2(case, built_lib):
+    got, ref = _run_case("f16x2", *case)
+    err = np.abs(got - ref)
+    tol = 2e-5 * np.abs(ref) + 5e-5
+    assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+def test_stem(built_lib):
+    """7x7 stride-1 stem through the overlapping-window PREP view (resnet.py:195-200)."""
+    rng = np.random.RandomState(3)
+    n, h, w = 2, 64, 96
+    img = rng.randint(0, 256, size=(n, h, w, 3)).astype(np.uint8)
+    wt = (rng.standard_normal((64, 3, 7, 7)) * 0.08).astype(np.float64)
+    b = rng.uniform(-0.5, 0.5, 64)
+    for precision, tol in (("f16", 4e-3), ("f16x2", 1e-4)):
+        blob = BlobBuilder()
+        layer = pack_stem(blob, wt, b)
+        spec = MiniSpec()
+        t_in = spec._tensor("input", n, h, w, 3, _lib.CERB_U8)
+        t_prep = spec._tensor("prep", n, h, w + 8, 8)
+        t_out = spec._tensor("x0", n, h, w, 64)
+        spec._op(_lib.OP_PREP, in0=t_in, out=t_prep)
+        spec._conv(layer, t_prep, t_out, relu=1, stem=1)
+        ctx = Context(0, precision)
+        plan = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
+        plan.write(t_in, img)
+        plan.run()
+        got = plan.read(t_out).astype(np.float32)
+        ref = F.relu(F.conv2d(torch.from_numpy(nhwc_to_nchw(img.astype(np.float64))) / 255.0,
+                              torch.from_numpy(wt), torch.from_numpy(b), padding=3))
+        ref = nchw_to_nhwc(ref.numpy())
+        err = np.abs(got - ref)
+        assert np.all(err <= tol * np.abs(ref) + tol), "%s: max err %g" % (precision, err.max())
+        plan.close()
+        ctx.close()
