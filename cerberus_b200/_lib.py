@@ -31,7 +31,7 @@ class Op(ctypes.Structure):
         ("pad", ctypes.c_int32), ("relu", ctypes.c_int32), ("stem", ctypes.c_int32),
         ("head_mode", ctypes.c_int32), ("logits_out", ctypes.c_int32),
         ("w_off", ctypes.c_int64), ("w_lo_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
-        ("box_w", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
+        ("box_w", ctypes.c_int32), ("w_shift", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2),
     ]
 
 
@@ -56,6 +56,29 @@ _SIGNATURES = {
                                              ctypes.c_void_p, ctypes.c_size_t]),
     "cerb_plan_write_tensor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_void_p, ctypes.c_size_t]),
+    "cerb_extract_patches": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
+    "cerb_stitch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
+    "cerb_postproc_nuclei": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "cerb_postproc_gland_lumen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                 ctypes.c_void_p, ctypes.c_int]),
+    "cerb_mask_lumen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_size_t]),
+    "cerb_ellipse_rows": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int32),
+                                         ctypes.POINTER(ctypes.c_int32)]),
+    "cerb_dev_alloc": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_size_t]),
+    "cerb_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "cerb_memcpy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_size_t, ctypes.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

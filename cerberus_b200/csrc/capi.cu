@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -307,6 +308,8 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
     p.res_coff = 0;
   }
   p.relu = op.relu;
+  if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv: w_shift out of range");
+  p.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
   conv_tc_plan_pipeline(p, split);
   return CERB_OK;

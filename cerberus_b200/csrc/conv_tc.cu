@@ -174,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
         if (valid) {
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.acc_scale;
           if (p.bias != nullptr) {
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + j);
 #pragma unroll

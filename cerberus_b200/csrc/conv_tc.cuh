@@ -41,6 +41,7 @@ struct ConvKParams {
   int BN;  // output channels per tile (multiple of 32, <= 256)
   // epilogue
   const float* bias;  // [Cout] fp32 (BN folded), may be null
+  float acc_scale;    // 2^-w_shift: weights are stored pre-scaled by a power of two
   __half* out_hi;
   __half* out_lo;  // split-precision mode only
   const __half* res_hi;

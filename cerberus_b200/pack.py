@@ -61,13 +61,24 @@ def split_f16(x):
     return hi, lo
 
 
+def weight_shift(w):
+    """Power-of-two pre-scale: max|w * 2^shift| lands in [256, 512], far from fp16 subnormals
+    (so the lo plane keeps its precision) and far from overflow."""
+    m = float(np.max(np.abs(w)))
+    if m == 0.0 or not np.isfinite(m):
+        return 0
+    return int(np.clip(np.floor(np.log2(512.0 / m)), -60, 60))
+
+
 def pack_conv(blob, w, b):
     """w [O,I,kh,kw] float64 (BN folded) -> K-major [O][kh*kw][I] fp16 hi/lo; b -> fp32.
     Returns dict(w_off, w_lo_off, b_off, cout, cin, kh, kw)."""
     o, i, kh, kw = w.shape
     km = np.transpose(w, (0, 2, 3, 1)).reshape(o, kh * kw * i)
-    hi, lo = split_f16(km)
-    out = {"w_off": blob.add(hi), "w_lo_off": blob.add(lo), "cout": o, "cin": i, "kh": kh, "kw": kw}
+    sh = weight_shift(km)
+    hi, lo = split_f16(np.ldexp(km, sh))
+    out = {"w_off": blob.add(hi), "w_lo_off": blob.add(lo), "cout": o, "cin": i, "kh": kh, "kw": kw,
+           "w_shift": sh}
     out["b_off"] = blob.add(b.astype(np.float32)) if b is not None else -1
     return out
 
@@ -82,9 +93,10 @@ def pack_stem(blob, w, b):
     w = w / 255.0
     km = np.zeros((o, 7, 8, 8), dtype=np.float64)
     km[:, :, :7, :3] = np.transpose(w, (0, 2, 3, 1))
-    hi, lo = split_f16(km.reshape(o, 7 * 64))
+    sh = weight_shift(km)
+    hi, lo = split_f16(np.ldexp(km.reshape(o, 7 * 64), sh))
     return {"w_off": blob.add(hi), "w_lo_off": blob.add(lo), "b_off": blob.add(b.astype(np.float32)),
-            "cout": o, "cin": 3, "kh": 7, "kw": 7}
+            "cout": o, "cin": 3, "kh": 7, "kw": 7, "w_shift": sh}
 
 
 def strip_module_prefix(sd):

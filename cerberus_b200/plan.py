@@ -243,7 +243,7 @@ class PlanSpec:
     def _op(self, kind, **kw):
         d = dict(kind=kind, in0=-1, in1=-1, out=-1, in_coff=0, in_c=0, out_coff=0, cout=0, kh=0,
                  kw=0, stride=0, pad=0, relu=0, stem=0, head_mode=0, logits_out=-1, w_off=-1,
-                 w_lo_off=-1, b_off=-1, box_w=0)
+                 w_lo_off=-1, b_off=-1, box_w=0, w_shift=0)
         d.update(kw)
         self.ops.append(d)
 
@@ -252,7 +252,7 @@ class PlanSpec:
         self._op(_lib.OP_CONV, in0=src, in1=residual, out=dst, in_coff=in_coff,
                  in_c=(8 if stem else layer["cin"]), out_coff=0, cout=layer["cout"], kh=k, kw=k,
                  stride=stride, pad=k // 2, relu=relu, stem=stem, w_off=layer["w_off"],
-                 w_lo_off=layer["w_lo_off"], b_off=layer["b_off"])
+                 w_lo_off=layer["w_lo_off"], b_off=layer["b_off"], w_shift=layer.get("w_shift", 0))
 
     def conv_flops(self):
         """Algorithmic conv FLOPs (2*M*N*K, no padding / zero-weight credit) of one batch."""

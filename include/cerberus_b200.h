@@ -12,6 +12,7 @@
  *         (__proc_nuclei :352-381, __proc_gland :270-309, __proc_lumen :312-350)
  *       -> cerb_postproc_nuclei / cerb_postproc_gland_lumen
  *   a16 infer/tile.py:136-163  canvas stitch           -> cerb_stitch
+ *   a19 infer/tile.py:187-191  lumen *= (gland > 0)    -> cerb_mask_lumen
  *   a1/a2 infer/tile.py:43-106 + loader/infer_loader.py:57-69 (reflect pad + patch
  *       slicing)                                        -> cerb_extract_patches
  *
@@ -91,7 +92,9 @@ typedef struct cerb_op {
   int64_t w_lo_off;   /* CONV: fp16 lo weights (F16X2 mode), else -1                    */
   int64_t b_off;      /* fp32 bias [cout], or -1                                        */
   int32_t box_w;      /* CONV: tile box width override (power of two <= 128), 0 = auto  */
-  int32_t reserved[3];
+  int32_t w_shift;    /* CONV: weights are stored multiplied by 2^w_shift (keeps the fp16 lo plane out
+                         of the subnormal range); the epilogue multiplies the accumulator by 2^-w_shift */
+  int32_t reserved[2];
 } cerb_op;
 
 /* ---- context ------------------------------------------------------------------- */
@@ -126,6 +129,54 @@ int cerb_plan_read_tensor(cerb_plan* plan, int tensor_id, int plane, void* host_
 /* Synchronous H2D copy into a tensor plane (tests feed intermediate activations). */
 int cerb_plan_write_tensor(cerb_plan* plan, int tensor_id, int plane, const void* host_src,
                            size_t bytes);
+
+/* ---- tile plumbing (a1/a2/a16) --------------------------------------------------------
+ * `flags` bit 0: the input buffer is device memory; bit 1: the output buffer is device
+ * memory. Host outputs make the call synchronous. */
+
+/* infer/tile.py:64-69 (np.pad "reflect", multi-bounce when the pad exceeds the image) fused
+ * with loader/infer_loader.py:57-69 (patch slicing): out[i] = padded[tl[i] : tl[i] + (ph,pw)]
+ * without materialising the padded image. img: u8 [H,W,3]; tl_yx: HOST int32 [n][2], top-left
+ * of each patch in padded coordinates (info_list[:,0,0] of _prepare_patching); out: u8
+ * [n,ph,pw,3]. */
+int cerb_extract_patches(cerb_ctx* ctx, const uint8_t* img, int H, int W, int pad_t, int pad_l,
+                         const int32_t* tl_yx, int n, int ph, int pw, uint8_t* out, int flags);
+
+/* infer/tile.py:136-163: canvas[tl : tl + (oh,ow)] += patch (in list order), count likewise,
+ * canvas / (count + 1e-8), crop [src_y : src_y + out_h, src_x : src_x + out_w].
+ * patches: f32 [n,oh,ow,C]; tl_yx: HOST int32 [n][2] (output top-left in canvas coordinates);
+ * out: f32 [out_h,out_w,C]. */
+int cerb_stitch(cerb_ctx* ctx, const float* patches, int n, int oh, int ow, int C,
+                const int32_t* tl_yx, int canvas_h, int canvas_w, int src_y, int src_x, int out_h,
+                int out_w, float* out, int flags);
+
+/* ---- instance post-processing (a17-a19), loader/postproc.py:383-407 -------------------
+ * canvas: f32 [n,H,W,C]; channels ch0 (inner) and ch0+1 (contour) of the tissue are read
+ * (idx_dict[tissue + "-INST"][0]). labels_out: int32 [n,H,W]. Same `flags` as above. */
+
+/* __proc_nuclei (:352-381). any_fg_out (nullable, int32 [n]) is 0 for images whose
+ * pre-erosion mask is empty: the reference returns a float64 zero map for those. */
+int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, int H, int W, int C, int ch0,
+                         int32_t* labels_out, int32_t* any_fg_out, int flags);
+
+enum cerb_tissue { CERB_TISSUE_GLAND = 0, CERB_TISSUE_LUMEN = 1 };
+/* __proc_gland (:270-309) / __proc_lumen (:312-350); ds_factor as in the reference
+ * (structuring element size int((ksize_-1)*ds), min object size int(1000|150 * ds^2)). The
+ * reference returns float64 maps; convert at the binding. */
+int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int n, int H, int W, int C,
+                              int ch0, int tissue, double ds_factor, int32_t* labels_out,
+                              int flags);
+
+/* infer/tile.py:187-191: lumen *= (gland > 0), both device int32 label maps. */
+int cerb_mask_lumen(cerb_ctx* ctx, int32_t* lumen_dev, const int32_t* gland_dev, size_t elems);
+
+/* cv2.getStructuringElement(MORPH_ELLIPSE, (k,k)) as row runs [j1[i], j2[i]) (1 <= k <= 32). */
+int cerb_ellipse_rows(int k, int32_t* j1, int32_t* j2);
+
+/* Device scratch helpers for callers that keep data resident between calls. */
+void* cerb_dev_alloc(cerb_ctx* ctx, size_t bytes);
+int cerb_dev_free(cerb_ctx* ctx, void* p);
+int cerb_memcpy(cerb_ctx* ctx, void* dst, const void* src, size_t bytes, int kind /*1 H2D, 2 D2H, 3 D2D*/);
 
 #ifdef __cplusplus
 }

