@@ -184,6 +184,7 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   p.tiles_y = (H + bh - 1) / bh;
   const long m_tiles = static_cast<long>(N) * p.tiles_x * p.tiles_y;
   p.BN = pick_bn(op.cout, m_tiles, ctx->num_sms);
+  if (split && p.BN > 128) p.BN = 128;  // three TMEM accumulators per tile in split mode
   if (p.BN <= 0 || p.BN > 256 || p.BN % 16 != 0 || op.cout % p.BN != 0)
     return fail(CERB_ERR_ARG, "conv: unsupported cout %d", op.cout);
   p.n_ntiles = op.cout / p.BN;

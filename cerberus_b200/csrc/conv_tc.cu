@@ -17,6 +17,13 @@ namespace {
 constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 fp16 channels
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM column offset between the two accumulator stages
+// Split-precision mode (BN <= 128): ONE accumulator stage made of three TMEM accumulators.
+// The tensor core truncates the fp32 accumulator on every MMA, an error proportional to
+// |acc| per instruction; keeping the small cross terms (lo*hi + hi*lo) out of the big hi*hi
+// accumulator and alternating hi*hi between two accumulators cuts that error ~6x. The
+// epilogue adds the three in fp32 (round-to-nearest).
+constexpr int kSplitMain1 = 128;
+constexpr int kSplitCross = 256;
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -69,6 +76,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  constexpr int kAccStages = SPLIT ? 1 : 2;
   const int n_ksteps = p.n_taps * p.n_chunks;
   const int bw_mask = (1 << p.bw_log2) - 1;
   const int BW = 1 << p.bw_log2;
@@ -130,19 +138,22 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
           for (int k = 0; k < 4; ++k) {  // 4 x (K = 16) per 64-channel slab
             const uint64_t a_hi = ptx::umma_desc_sw128(a_addr + k * 32, 1024);
             const uint64_t b_hi = ptx::umma_desc_sw128(b_addr + k * 32, 1024);
-            ptx::umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) != 0);
-            if (SPLIT) {
+            if (!SPLIT) {
+              ptx::umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) != 0);
+            } else {
               const uint64_t a_lo = ptx::umma_desc_sw128(a_addr + kATileBytes + k * 32, 1024);
               const uint64_t b_lo = ptx::umma_desc_sw128(b_addr + b_tile_bytes + k * 32, 1024);
-              ptx::umma_f16(tmem_d, a_lo, b_hi, idesc, 1);
-              ptx::umma_f16(tmem_d, a_hi, b_lo, idesc, 1);
+              ptx::umma_f16(tmem_d + ((k & 1) ? kSplitMain1 : 0), a_hi, b_hi, idesc,
+                            (ks != 0) || (k >= 2));
+              ptx::umma_f16(tmem_d + kSplitCross, a_lo, b_hi, idesc, (ks | k) != 0);
+              ptx::umma_f16(tmem_d + kSplitCross, a_hi, b_lo, idesc, 1);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs retire
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
+        acc = (acc + 1) % kAccStages;
         if (acc == 0) acc_phase ^= 1;
       }
     }
@@ -169,12 +180,23 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
       for (int j = 0; j < p.BN; j += 32) {
         uint32_t r[32];
+        float v[32];
         ptx::tmem_ld32(taddr + j, r);
         ptx::tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        if (SPLIT) {
+          uint32_t r1[32], r2[32];
+          ptx::tmem_ld32(taddr + kSplitMain1 + j, r1);
+          ptx::tmem_ld32(taddr + kSplitCross + j, r2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = ((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) *
+                   p.acc_scale;
+        } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.acc_scale;
+        }
+        if (valid) {
           if (p.bias != nullptr) {
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + j);
 #pragma unroll
@@ -248,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
+      acc = (acc + 1) % kAccStages;
       if (acc == 0) acc_phase ^= 1;
     }
   }

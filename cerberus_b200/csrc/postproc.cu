@@ -104,16 +104,19 @@ __global__ void k_filter_small(uint8_t* __restrict__ fg, const int* __restrict__
 // One block per image: rank[p] = 1 + number of surviving roots before p (raster order) for
 // root pixels; count[img] = number of components.
 __global__ void k_rank_roots(const uint8_t* __restrict__ fg, const int* __restrict__ L,
-                             int* __restrict__ rank, int* __restrict__ count, int hw) {
+                             int* __restrict__ rank, int* __restrict__ count,
+                             int* __restrict__ has_bg, int hw) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
   const size_t base = static_cast<size_t>(blockIdx.x) * hw;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
+  int any_bg = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int start = 0; start < hw; start += blockDim.x) {
     const int p = start + threadIdx.x;
     const int flag = (p < hw && fg[base + p] && L[base + p] == p) ? 1 : 0;
+    if (p < hw && !fg[base + p]) any_bg = 1;
     int v = flag;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -138,7 +141,11 @@ __global__ void k_rank_roots(const uint8_t* __restrict__ fg, const int* __restri
     if (threadIdx.x == 0) carry += warp_sums[nwarps - 1];
     __syncthreads();
   }
-  if (threadIdx.x == 0) count[blockIdx.x] = carry;
+  any_bg = __syncthreads_or(any_bg);
+  if (threadIdx.x == 0) {
+    count[blockIdx.x] = carry;
+    if (has_bg != nullptr) has_bg[blockIdx.x] = any_bg;
+  }
 }
 
 __global__ void k_apply_rank(const uint8_t* __restrict__ fg, const int* __restrict__ L,
@@ -389,13 +396,17 @@ __device__ __forceinline__ uint32_t bits_at(const uint32_t* row, int nwords, int
 // One block per (instance, image): crop (bbox +- 2k unless that would cross the border),
 // dilate inside the crop, fill holes inside the crop, paint max id.
 __global__ void __launch_bounds__(kThreads)
-k_gl_instance(const int* __restrict__ lab, const int* __restrict__ count, const int* __restrict__ bb,
+k_gl_instance(const int* __restrict__ lab, const int* __restrict__ count,
+              const int* __restrict__ has_bg, const int* __restrict__ bb,
               int* __restrict__ out, int H, int W, int max_inst, EllipseRows ell, int smem_words,
               int* __restrict__ err) {
   extern __shared__ uint32_t bitmem[];
   const int img = blockIdx.y;
   const int id = blockIdx.x + 1;
   if (id > count[img]) return;
+  // Reference quirk (loader/postproc.py:291,332): np.unique(inst_lab)[1:] drops the smallest
+  // label assuming it is the background; an image without any background pixel loses id 1.
+  if (id == 1 && !has_bg[img]) return;
   const int hw = H * W;
   const int* L = lab + static_cast<size_t>(img) * hw;
   int* O = out + static_cast<size_t>(img) * hw;
@@ -700,7 +711,7 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
   ctx->launches += 2;
   // :377 label -> raster-order ids
   cc_label(ctx, ws, mrk, n, H, W, 0);
-  k_rank_roots<<<n, 1024, 0, s>>>(mrk, ws->L, ws->rank, ws->count, hw);
+  k_rank_roots<<<n, 1024, 0, s>>>(mrk, ws->L, ws->rank, ws->count, nullptr, hw);
   k_apply_rank<<<g, kThreads, 0, s>>>(mrk, ws->L, ws->rank, ws->lab, hw);
   k_mask_markers<<<g, kThreads, 0, s>>>(ws->lab, msk, hw);
   // :378 watershed(-inner, marker, mask)
@@ -743,7 +754,8 @@ extern "C" int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int
   k_gl_threshold<<<g, kThreads, 0, s>>>(dcanvas, C, ch0, thr, fg, hw);
   ctx->launches += 1;
   cc_label(ctx, ws, fg, n, H, W, min_size > 0 ? min_size : 0);
-  k_rank_roots<<<n, 1024, 0, s>>>(fg, ws->L, ws->rank, ws->count, hw);
+  // ws->any_fg doubles as the per-image "has a background pixel" flag here
+  k_rank_roots<<<n, 1024, 0, s>>>(fg, ws->L, ws->rank, ws->count, ws->any_fg, hw);
   k_apply_rank<<<g, kThreads, 0, s>>>(fg, ws->L, ws->rank, ws->lab, hw);
   ctx->launches += 2;
   int max_inst = min_size > 1 ? hw / min_size + 1 : hw;
@@ -766,7 +778,8 @@ extern "C" int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int
     attr_set = true;
   }
   k_gl_instance<<<dim3(max_inst, n), kThreads, static_cast<size_t>(smem_words) * 4, s>>>(
-      ws->lab, ws->count, ws->bb, out, H, W, max_inst, ell, smem_words, ctx->err_flag_dev + 1);
+      ws->lab, ws->count, ws->any_fg, ws->bb, out, H, W, max_inst, ell, smem_words,
+      ctx->err_flag_dev + 1);
   ctx->launches += 3;
   return finish(ctx, out, labels_out, static_cast<size_t>(n) * hw, flags & 2);
 }

@@ -238,3 +238,40 @@ def _gaussian_blur(f, sigma):
         g = np.pad(f, pad, mode="symmetric")
         f = np.apply_along_axis(lambda v: np.convolve(v, k, mode="valid"), axis, g)
     return f
+
+
+def adversarial_field(h, w, seed=0, big=False):
+    """Piecewise-constant (inner, contour) maps drawn from a small value set: plateaus and
+    exact threshold hits (0.5, 0.55) everywhere, blobs touching the borders, holes, specks of
+    a few pixels. Stresses tie-breaking in the watershed heap, the strict `>` thresholds, the
+    size filters and the crop rules. Values are multiples of 1/64 (exact in fp32).
+    Returns float32 [h,w,2]."""
+    rng = np.random.RandomState(seed)
+    inner = np.zeros((h, w), dtype=np.float32)
+    cnt = np.zeros((h, w), dtype=np.float32)
+    yy, xx = np.mgrid[0:h, 0:w]
+    vals = np.array([0.25, 0.5, 0.515625, 0.546875, 0.5625, 0.625, 0.75, 1.0], dtype=np.float32)
+    n_blobs = rng.randint(6, 14)
+    for _ in range(n_blobs):
+        cy, cx = rng.randint(-4, h + 4), rng.randint(-4, w + 4)
+        if big:
+            ry, rx = rng.randint(8, max(9, h // 3)), rng.randint(8, max(9, w // 3))
+        else:
+            ry, rx = rng.randint(1, max(2, h // 6)), rng.randint(1, max(2, w // 6))
+        d = ((yy - cy) / float(ry)) ** 2 + ((xx - cx) / float(rx)) ** 2
+        if rng.rand() < 0.3:  # rectangle instead of ellipse
+            d = np.maximum(np.abs(yy - cy) / float(ry), np.abs(xx - cx) / float(rx))
+        ring = (d <= 1.0) & (d > 0.6)
+        core = d <= 0.6
+        cnt[ring] = rng.choice([0.25, 0.5, 0.53125, 0.75, 0.90625])
+        inner[ring] = rng.choice([0.0, 0.0, 0.25, 0.5])
+        inner[core] = rng.choice(vals)
+        cnt[core] = rng.choice([0.0, 0.0, 0.0, 0.25])
+        if rng.rand() < 0.4:  # a hole inside the core
+            hole = d <= rng.choice([0.05, 0.15, 0.3])
+            inner[hole] = rng.choice([0.0, 0.25, 0.5])
+    for _ in range(rng.randint(5, 20)):  # specks around the size-filter limits
+        y0, x0 = rng.randint(0, h), rng.randint(0, w)
+        sh, sw = rng.randint(1, 4), rng.randint(1, 5)
+        inner[y0:y0 + sh, x0:x0 + sw] = rng.choice([0.5625, 1.0])
+    return np.stack([inner, cnt], axis=-1)

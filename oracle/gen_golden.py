@@ -70,6 +70,73 @@ def gen_forward():
         print("wrote", path, os.path.getsize(path))
 
 
+POSTPROC_IDX = {"Lumen-INST": [0, 2], "Gland-INST": [2, 4], "Nuclei-INST": [4, 6],
+                "Nuclei-TYPE": [6, 7], "Gland-TYPE": [7, 8], "Patch-Class": [8, 9]}
+POSTPROC_CH = {"Lumen": 0, "Gland": 2, "Nuclei": 4}
+
+
+def postproc_cases():
+    """(name, tissue, ds, field) — fields are quantised to multiples of 2^-12 so that the
+    stored uint16 copy reproduces the float32 input exactly."""
+    from cerberus_b200 import synth
+    cases = []
+
+    def q(f):
+        return (np.round(f * 4096.0) / 4096.0).astype(np.float32)
+
+    for seed in range(3):
+        for tissue in ("Nuclei", "Gland", "Lumen"):
+            cases.append(("smooth_s%d" % seed, tissue, 1.0, q(synth.postproc_field(256, 256, tissue, seed))))
+    for tissue in ("Nuclei", "Gland", "Lumen"):
+        cases.append(("smooth_ds05", tissue, 0.5, q(synth.postproc_field(256, 256, tissue, 7))))
+        cases.append(("rect_s3", tissue, 1.0, q(synth.postproc_field(192, 320, tissue, 3))))
+    for seed in range(6):
+        cases.append(("adv_s%d" % seed, "Nuclei", 1.0, synth.adversarial_field(64, 80, seed)))
+        cases.append(("adv_s%d" % seed, "Lumen", 1.0, synth.adversarial_field(96, 128, seed + 50, big=True)))
+        cases.append(("adv_s%d" % seed, "Gland", 1.0, synth.adversarial_field(160, 200, seed + 100, big=True)))
+        cases.append(("adv_ds05_s%d" % seed, "Gland", 0.5, synth.adversarial_field(96, 128, seed + 150, big=True)))
+        cases.append(("adv_ds05_s%d" % seed, "Lumen", 0.5, synth.adversarial_field(64, 80, seed + 200, big=True)))
+    cases.append(("empty", "Nuclei", 1.0, np.zeros((32, 48, 2), np.float32)))
+    cases.append(("empty", "Gland", 1.0, np.zeros((32, 48, 2), np.float32)))
+    cases.append(("empty", "Lumen", 1.0, np.zeros((32, 48, 2), np.float32)))
+    full = np.zeros((40, 56, 2), np.float32)
+    full[..., 0] = 1.0
+    cases.append(("full", "Nuclei", 1.0, full))
+    cases.append(("full", "Gland", 1.0, np.tile(full, (2, 2, 1))))
+    cases.append(("full", "Lumen", 1.0, full))
+    thin = np.zeros((24, 40, 2), np.float32)  # mask erodes to nothing: watershed on an empty mask
+    thin[10:12, 5:35, 0] = 1.0
+    cases.append(("thin", "Nuclei", 1.0, thin))
+    return cases
+
+
+def gen_postproc():
+    from oracle import postproc_oracle as po
+    ref_shim.install(po)
+    from loader.postproc import PostProcInstErodedContourMap as PP
+    rec = {}
+    names = []
+    for name, tissue, ds, field in postproc_cases():
+        key = "%s/%s" % (name, tissue)
+        raw = np.zeros(field.shape[:2] + (9,), np.float32)
+        c0 = POSTPROC_CH[tissue]
+        raw[..., c0:c0 + 2] = field
+        inst, _ = PP.post_process(raw, POSTPROC_IDX, tissue, ds)
+        qf = np.round(field * 4096.0)
+        assert np.array_equal((qf / 4096.0).astype(np.float32), field), key
+        rec[key + "/field_q12"] = qf.astype(np.uint16)
+        rec[key + "/inst"] = inst.astype(np.uint16)
+        assert inst.max() < 65536
+        rec[key + "/dtype"] = np.array(str(inst.dtype))
+        rec[key + "/ds"] = np.array(ds)
+        names.append(key)
+        print(key, field.shape, "instances", int(inst.max()), inst.dtype)
+    rec["names"] = np.array(names)
+    path = os.path.join(GOLD, "postproc.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["forward", "patching", "postproc", "stitch"]
