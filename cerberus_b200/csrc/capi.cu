@@ -389,6 +389,15 @@ extern "C" int cerb_ctx_sync(cerb_ctx* ctx) {
                             : "unknown");
   }
   if (e != cudaSuccess) return fail(CERB_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+  const int pp = ctx->err_flag_host ? ctx->err_flag_host[1] : 0;
+  if (pp != 0) {
+    ctx->err_flag_host[1] = 0;
+    return fail(CERB_ERR_KERNEL,
+                pp == 10   ? "postproc: more instances than the size filter allows"
+                : pp == 11 ? "postproc: an instance crop does not fit in shared memory"
+                           : "postproc: kernel error %d",
+                pp);
+  }
   return CERB_OK;
 }
 
