@@ -137,6 +137,93 @@ def gen_postproc():
     print("wrote", path, os.path.getsize(path))
 
 
+PATCHING_CASES = [(256, 256, 448, 144), (256, 256, 256, 256), (300, 517, 448, 144), (40, 60, 448, 144),
+                  (500, 333, 256, 256)]
+
+
+def gen_patching():
+    """infer/tile.py:43-106 on seeded images: the patch grid and hashes of the padded image
+    (multi-bounce reflect when the pad exceeds the image: 40x60 with a 152/… pad)."""
+    import hashlib
+    ref_shim.install()
+    from infer.tile import _prepare_patching
+    rec = {"cases": np.array(PATCHING_CASES)}
+    for (h, w, i, o) in PATCHING_CASES:
+        img = np.random.RandomState(h * 1000 + w).randint(0, 256, (h, w, 3)).astype(np.uint8)
+        padded, info, src_pos = _prepare_patching(img, i, o, 0)
+        key = "%dx%d_%d_%d" % (h, w, i, o)
+        rec[key + "/info"] = info.astype(np.int32)
+        rec[key + "/src_pos"] = np.array(src_pos)
+        rec[key + "/padded_shape"] = np.array(padded.shape)
+        rec[key + "/padded_sha1"] = np.array(hashlib.sha1(np.ascontiguousarray(padded).tobytes()).hexdigest())
+        # three patches as the loader slices them (infer_loader.py:57-69)
+        sel = [0, info.shape[0] // 3, info.shape[0] - 1]
+        rec[key + "/sel"] = np.array(sel)
+        rec[key + "/patch_sha1"] = np.array([
+            hashlib.sha1(np.ascontiguousarray(
+                padded[info[k, 0, 0, 0]:info[k, 0, 1, 0], info[k, 0, 0, 1]:info[k, 0, 1, 1]]).tobytes()).hexdigest()
+            for k in sel])
+        print(key, info.shape, padded.shape)
+    path = os.path.join(GOLD, "patching.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path))
+
+
+def tile_case_inputs(seed=0, h=300, w=380, in_size=448, out_size=144):
+    """Synthetic per-patch network outputs cut from smooth fields, in the list-of-dicts format
+    of models/run_desc.py:494-502, for infer/tile.py:_post_process_patches."""
+    from cerberus_b200 import synth
+    from cerberus_b200.infer.tile import patch_grid
+    info, src_pos, (padt, padb, padl, padr) = patch_grid(h, w, in_size, out_size, 0)
+    H, W = h + padt + padb, w + padl + padr
+    q = lambda f: (np.round(f * 4096.0) / 4096.0).astype(np.float32)
+    rng = np.random.RandomState(seed)
+    heads = {
+        "Nuclei-INST": q(synth.postproc_field(H, W, "Nuclei", seed)),
+        "Nuclei-TYPE": rng.randint(0, 7, (H // 16 + 1, W // 16 + 1)).repeat(16, 0).repeat(16, 1)[:H, :W].astype(np.int64),
+        "Gland-INST": q(synth.postproc_field(H, W, "Gland", seed + 1)),
+        "Gland-TYPE": rng.randint(0, 3, (H // 32 + 1, W // 32 + 1)).repeat(32, 0).repeat(32, 1)[:H, :W].astype(np.int64),
+        "Lumen-INST": q(synth.postproc_field(H, W, "Lumen", seed + 2)),
+        "Patch-Class": rng.randint(0, 9, (H // 64 + 1, W // 64 + 1)).repeat(64, 0).repeat(64, 1)[:H, :W].astype(np.float32),
+    }
+    plist = []
+    for k in range(info.shape[0]):
+        (oy0, ox0), (oy1, ox1) = info[k, 1]
+        pdata = {name: np.ascontiguousarray(v[oy0:oy1, ox0:ox1]) for name, v in heads.items()}
+        plist.append((pdata, (info[k, 1, 0], info[k, 1, 1]), 0))
+    image_info = {"src_pos": src_pos, "src_shape": (h, w), "name": "case%d" % seed,
+                  "src_image": np.zeros((h, w, 3), np.uint8)}
+    return plist, image_info
+
+
+def gen_stitch():
+    """infer/tile.py:109-212 (_post_process_patches) end to end on synthetic patch outputs."""
+    from cerberus_b200 import synth
+    from oracle import postproc_oracle as po
+    ref_shim.install(po)
+    from infer.tile import _post_process_patches
+    margs = synth.model_args()
+    codes = dict(synth.DEFAULT_REQ_TARGET_CODE)
+    rec = {}
+    for seed in (0, 1):
+        plist, image_info = tile_case_inputs(seed)
+        name, _, inst, info, types, pclass = _post_process_patches(
+            plist, image_info, codes, ["gland", "lumen", "nuclei", "patch-class"], margs)
+        for t, m in inst.items():
+            rec["s%d/inst/%s" % (seed, t)] = m.astype(np.uint16)
+            rec["s%d/inst_dtype/%s" % (seed, t)] = np.array(str(m.dtype))
+            rec["s%d/ids/%s" % (seed, t)] = np.array(sorted(int(k) for k in info[t].keys()))
+            rec["s%d/types/%s" % (seed, t)] = np.array([info[t][k].get("type", -1) for k in sorted(info[t].keys())])
+            rec["s%d/centroids/%s" % (seed, t)] = np.array([info[t][k]["centroid"] for k in sorted(info[t].keys())]).reshape(-1, 2)
+            if types[t] is not None:
+                rec["s%d/type_map/%s" % (seed, t)] = types[t].astype(np.uint8)
+        rec["s%d/pclass" % seed] = pclass.astype(np.uint8)
+        print(seed, {t: int(m.max()) for t, m in inst.items()})
+    path = os.path.join(GOLD, "tile_postproc.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["forward", "patching", "postproc", "stitch"]

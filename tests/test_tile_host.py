@@ -1,0 +1,106 @@
+"""CPU: host-side tile logic (patch grid, reflect padding, CLI parsing, plan building, C-ABI
+symbol table) against golden vectors produced by the reference's infer/tile.py."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cerberus_b200 import _lib, synth
+from cerberus_b200.cli import parse_usage
+from cerberus_b200.infer.tile import _prepare_patching, patch_grid
+from cerberus_b200.plan import PackedModel, PlanSpec, canvas_layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_prepare_patching_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "patching.npz"))
+    for (h, w, i, o) in g["cases"]:
+        key = "%dx%d_%d_%d" % (h, w, i, o)
+        img = np.random.RandomState(h * 1000 + w).randint(0, 256, (h, w, 3)).astype(np.uint8)
+        padded, info, src_pos = _prepare_patching(img, int(i), int(o), 0)
+        assert np.array_equal(info, g[key + "/info"]), key
+        assert list(src_pos) == list(g[key + "/src_pos"])
+        assert tuple(padded.shape) == tuple(g[key + "/padded_shape"])
+        assert hashlib.sha1(np.ascontiguousarray(padded).tobytes()).hexdigest() == str(g[key + "/padded_sha1"])
+        info2, _, _ = patch_grid(int(h), int(w), int(i), int(o), 0)
+        assert np.array_equal(info2, info)
+        # duplicate grid quirk (tile.py:90-103): second half repeats the first
+        half = info.shape[0] // 2
+        assert np.array_equal(info[:half], info[half:])
+
+
+def test_canvas_layout_matches_tile_py():
+    idx, n = canvas_layout(synth.DEFAULT_DECODER_KWARGS)
+    assert n == 9
+    assert idx == {"Lumen-INST": [0, 2], "Gland-INST": [2, 4], "Nuclei-INST": [4, 6],
+                   "Nuclei-TYPE": [6, 7], "Gland-TYPE": [7, 8], "Patch-Class": [8, 9]}
+
+
+def test_plan_flops_match_survey(six_head_sd):
+    """121.128 GFLOP per 256^2 tile (6 heads), 370.953 @448^2, 54.891 enc+Nuclei."""
+    m = PackedModel(six_head_sd, synth.model_args())
+    assert abs(PlanSpec(m, 1, 256, 256, 256, 256).conv_flops() / 1e9 - 121.128) < 1e-3
+    assert abs(PlanSpec(m, 1, 448, 448, 144, 144).conv_flops() / 1e9 - 370.953) < 1e-3
+    sd1 = synth.make_state_dict(["Nuclei"], seed=0)
+    m1 = PackedModel(sd1, synth.model_args(["Nuclei"]))
+    assert abs(PlanSpec(m1, 1, 256, 256, 256, 256).conv_flops() / 1e9 - 54.891) < 1e-3
+
+
+def test_plan_never_writes_a_conv_input_in_place(six_head_sd):
+    m = PackedModel(six_head_sd, synth.model_args())
+    s = PlanSpec(m, 2, 256, 256, 256, 256)
+    for op in s.ops:
+        if op["kind"] == _lib.OP_CONV:
+            assert op["out"] != op["in0"] and op["out"] != op["in1"]
+    # skip features x0..x3 are never overwritten after they are produced
+    last_write = {}
+    for i, op in enumerate(s.ops):
+        last_write[op["out"]] = i
+    for name in ("x0", "x1", "x2", "x3", "x4"):
+        tid = s.named[name]
+        readers = [i for i, op in enumerate(s.ops) if tid in (op["in0"], op["in1"])]
+        assert max(readers) > last_write[tid] or name == "x4"
+
+
+def test_rejects_other_backbones(six_head_sd):
+    args = dict(synth.model_args(), encoder_backbone_name="resnet50")
+    with pytest.raises(ValueError):
+        PackedModel(six_head_sd, args)
+
+
+def test_module_prefix_is_stripped(six_head_sd):
+    """infer/base.py:31-45: DataParallel checkpoints."""
+    sd = {"module." + k: v for k, v in six_head_sd.items()}
+    a = PackedModel(sd, synth.model_args())
+    b = PackedModel(six_head_sd, synth.model_args())
+    assert np.array_equal(a.blob, b.blob)
+
+
+def test_cli_parser_has_reference_flags_and_defaults():
+    doc = open(os.path.join(ROOT, "run_infer_tile.py")).read().split('"""')[1]
+    a = parse_usage(doc, ["--model=/m", "--input_dir", "/in"])
+    assert a["--gpu"] == "0" and a["--batch_size"] == "10" and a["--patch_input_shape"] == "448"
+    assert a["--patch_output_shape"] == "144" and a["--output_dir"] == "output/"
+    assert a["--nr_inference_workers"] == "0" and a["--model"] == "/m" and a["--input_dir"] == "/in"
+
+
+def test_library_loads_and_exports_every_header_symbol(built_lib):
+    """No GPU needed: the .so loads (static cudart, no libcuda link) and exports every function
+    include/cerberus_b200.h declares; compute entry points fail loudly without a device."""
+    hdr = open(os.path.join(ROOT, "include", "cerberus_b200.h")).read()
+    declared = set(re.findall(r"\b(cerb_\w+)\s*\(", hdr))
+    declared -= {"cerb_status", "cerb_dtype"}
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    import torch
+    if not torch.cuda.is_available():
+        h = ctypes.c_void_p()
+        rc = built_lib.cerb_ctx_create(0, 0, ctypes.byref(h))
+        assert rc == -4 and b"no CPU path" in built_lib.cerb_last_error()
