@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "capi_internal.cuh"
+#include "conv64.cuh"
 #include "conv_tc.cuh"
 #include "ops.cuh"
 
@@ -54,6 +55,8 @@ struct Tensor {
 struct Step {
   int kind = 0;
   ConvKParams conv;
+  Conv64Params c64;
+  bool use64 = false;
   bool split = false;
   // misc ops
   ActRef a, b, c;
@@ -152,6 +155,72 @@ int pick_bn(int cout, long m_tiles, int num_sms) {
   return 0;
 }
 
+int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
+  cerb_ctx* ctx = pl->ctx;
+  const Tensor& in = pl->tensors[op.in0];
+  const Tensor& out = pl->tensors[op.out];
+  Conv64Params& p = st.c64;
+  memset(&p, 0, sizeof(p));
+  st.use64 = true;
+  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  p.mode = ctx->conv64_mode;
+  p.n_img = N;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + conv64_tile_w() - 1) / conv64_tile_w();
+  p.tiles_y = (H + conv64_tile_h() - 1) / conv64_tile_h();
+  p.n_tiles = N * p.tiles_x * p.tiles_y;
+  conv64_plan(p);
+  const size_t es = 2;
+  if (op.in_coff % 8 != 0 || op.in_coff + 64 > in.d.c || in.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv64: bad input channels");
+  {
+    const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * in.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * in.d.c * es};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(conv64_box_w(p.mode)),
+                               static_cast<cuuint32_t>(conv64_tile_h() + 2), 1};
+    int rc = encode_map(ctx, &p.in_map, static_cast<__half*>(in.plane[0]) + op.in_coff, 4, dims,
+                        strides, box);
+    if (rc) return rc;
+  }
+  if (op.w_off < 0 || op.w_off % 16 != 0 ||
+      static_cast<size_t>(op.w_off) + 64u * 576u * es > pl->blob_bytes)
+    return fail(CERB_ERR_ARG, "conv64: weight offset out of range");
+  {
+    const cuuint64_t dims[2] = {576, 64};
+    const cuuint64_t strides[1] = {576 * es};
+    const cuuint32_t box[2] = {64, 64};
+    int rc = encode_map(ctx, &p.w_map, pl->blob + op.w_off, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (op.b_off >= 0) {
+    if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + 64 * 4u > pl->blob_bytes)
+      return fail(CERB_ERR_ARG, "conv64: bias offset out of range");
+    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+  }
+  p.out = static_cast<__half*>(out.plane[0]);
+  p.out_cs = out.d.c;
+  p.out_coff = op.out_coff;
+  if (op.in1 >= 0) {
+    if (op.in1 >= static_cast<int>(pl->tensors.size()))
+      return fail(CERB_ERR_ARG, "conv64: residual id out of range");
+    const Tensor& res = pl->tensors[op.in1];
+    if (res.d.n != N || res.d.h != H || res.d.w != W || res.d.c < 64 || res.d.c % 8 != 0 ||
+        res.d.dtype != CERB_F16)
+      return fail(CERB_ERR_ARG, "conv64: residual shape mismatch");
+    p.res = static_cast<const __half*>(res.plane[0]);
+    p.res_cs = res.d.c;
+  }
+  p.relu = op.relu;
+  if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64: w_shift out of range");
+  p.acc_scale = ldexpf(1.0f, -op.w_shift);
+  p.err_flag = ctx->err_flag_dev;
+  return CERB_OK;
+}
+
 int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   cerb_ctx* ctx = pl->ctx;
   const int nt = static_cast<int>(pl->tensors.size());
@@ -173,6 +242,10 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
     return fail(CERB_ERR_ARG, "conv: bad output channels (cout %d coff %d c %d)", op.cout,
                 op.out_coff, out.d.c);
 
+  if (!split && !op.stem && ctx->conv64_mode >= 0 && op.kh == 3 && op.kw == 3 && op.stride == 1 &&
+      op.pad == 1 && op.in_c == 64 && op.cout == 64 && in.d.h == H && in.d.w == W) {
+    return build_conv64(pl, op, st);
+  }
   int bw = op.box_w > 0 ? op.box_w : pick_box_w(H, W);
   if (bw > 128 || (bw & (bw - 1)) != 0) return fail(CERB_ERR_ARG, "conv: bad box_w %d", bw);
   const int bh = 128 / bw;
@@ -401,6 +474,16 @@ extern "C" int cerb_ctx_sync(cerb_ctx* ctx) {
   return CERB_OK;
 }
 
+extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return fail(CERB_ERR_ARG, "cerb_ctx_set_option: bad arguments");
+  if (strcmp(name, "conv64_mode") == 0) {
+    if (value < -1 || value > 2) return fail(CERB_ERR_ARG, "conv64_mode must be -1, 0, 1 or 2");
+    ctx->conv64_mode = value;
+    return CERB_OK;
+  }
+  return fail(CERB_ERR_ARG, "cerb_ctx_set_option: unknown option %s", name);
+}
+
 extern "C" int64_t cerb_ctx_launch_count(cerb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* cerb_ctx_stream(cerb_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 
@@ -597,7 +680,8 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
       }
       break;
     case CERB_OP_CONV:
-      e = conv_tc_launch(st.conv, st.split, ctx->num_sms, s);
+      e = st.use64 ? conv64_launch(st.c64, ctx->num_sms, s)
+                   : conv_tc_launch(st.conv, st.split, ctx->num_sms, s);
       break;
     case CERB_OP_MAXPOOL:
       e = launch_maxpool(st.a, st.b, s);

@@ -1,0 +1,276 @@
+// 3x3 stride-1 64->64 convolution specialised for the full-resolution layers.
+//
+// These layers (layer1 of the encoder and the u2/u1 stages of the five decoders:
+// models/backbone/resnet.py:202, models/utils/net_layers.py:25-26) are 40 % of all FLOPs
+//  and have N = 64, K = 576: the generic kernel re-reads every
+// activation pixel nine times (once per tap) and the 72 KB of weights once per 128-pixel
+// tile from L2, which caps it at the L2 bandwidth (~1/3 of the tensor pipe, measured). Here
+//   * the 9 x [64 x 64] weights are loaded ONCE per persistent CTA and stay in shared memory,
+//   * each 16 x 8 pixel tile loads its input halo once and the nine taps are nine shared-
+//     memory matrix descriptors into that halo (no im2col, no re-read).
+// Three halo layouts are implemented because the descriptor semantics for a start address
+// that is not aligned to the 1024-byte swizzle period could only be settled on hardware:
+//   mode 0: three x-shifted copies of an 18 x 8 pixel slab (every descriptor 1024-aligned);
+//   mode 1: one 18 x 10 slab, taps are byte offsets into it (swizzle on absolute address bits);
+//   mode 2: one 18 x 16 slab (1024-byte row-group pitch), x taps via the descriptor's
+//           base_offset field.
+// tests/test_gpu_conv.py runs all three against the fp32 reference; capi.cu uses the mode
+// selected by cerb_ctx_set_option(ctx, "conv64_mode", m).
+#include "conv64.cuh"
+#include "ptx.cuh"
+
+namespace cerb {
+
+namespace {
+
+constexpr int kWBytes = 9 * 64 * 128;  // resident weights: 9 taps x 64 rows x 128 B
+constexpr int kTileW = 8, kTileH = 16;
+constexpr int kTmemCols = 128;  // 2 accumulator stages x 64 columns
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kConv64Threads, 1)
+conv64_kernel(const __grid_constant__ Conv64Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  const int stage_bytes = p.stage_bytes;
+
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + kWBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + n_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + n_stages;
+  uint64_t* tfull_bar = empty_bar + n_stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.in_map);
+    ptx::prefetch_tmap(&p.w_map);
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 4);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_holder, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: one 2-D box per tap
+      ptx::mbar_arrive_expect_tx(w_bar, kWBytes);
+      for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * 8192, &p.w_map, w_bar, t * 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_per_img;
+        const int rem = tile - img * tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int x0 = tx * kTileW - 1, y0 = ty * kTileH - 1;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 21);
+        uint8_t* dst = sA + stage * stage_bytes;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+        if (p.mode == 0) {
+          for (int s = 0; s < 3; ++s)
+            ptx::tma_load_4d(dst + s * p.copy_bytes, &p.in_map, &full_bar[stage], 0, x0 + s, y0, img);
+        } else {
+          ptx::tma_load_4d(dst, &p.in_map, &full_bar[stage], 0, x0, y0, img);
+        }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(128, 64);
+      ptx::mbar_wait(w_bar, 0, p.err_flag, 22);
+      ptx::tc_fence_after();
+      const uint32_t w_addr = ptx::smem_u32(sW);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 23);
+        ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 24);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 64;
+        const uint32_t a_base = ptx::smem_u32(sA + stage * stage_bytes);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int r = t / 3, s = t - 3 * r;
+          uint32_t a_addr, boff = 0;
+          if (p.mode == 0) {
+            a_addr = a_base + s * p.copy_bytes + r * (kTileW * 128);
+          } else {
+            a_addr = a_base + (r * p.pitch_px + s) * 128;
+            if (p.mode == 2) boff = (a_addr >> 7) & 7;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 32, p.sbo_bytes, boff);
+            const uint64_t bd = ptx::umma_desc_sw128(w_addr + t * 8192 + k * 32, 1024);
+            ptx::umma_f16(tmem_d, ad, bd, idesc, (t | k) != 0);
+          }
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        ptx::umma_commit(&tfull_bar[acc]);
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int py = m >> 3, px = m & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int ox = tx * kTileW + px, oy = ty * kTileH + py;
+      const bool valid = (ox < p.W) && (oy < p.H);
+      const size_t pix = (static_cast<size_t>(img) * p.H + oy) * p.W + ox;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 25);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 64;
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(taddr, r0);
+      ptx::tmem_ld32(taddr + 32, r1);
+      ptx::tmem_ld_wait();
+      // the accumulator is in registers: release it before the global-memory epilogue
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (valid) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = __uint_as_float(half == 0 ? r0[i] : r1[i]) * p.acc_scale;
+          const int j = half * 32;
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (p.res != nullptr) {
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res + pix * p.res_cs + j);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(rh + i);
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h[e]);
+                v[8 * i + 2 * e] += f.x; v[8 * i + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          }
+          uint4* oh = reinterpret_cast<uint4*>(p.out + pix * p.out_cs + p.out_coff + j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+            oh[i] = u;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+void conv64_plan(Conv64Params& p) {
+  // halo rows = kTileH + 2 = 18
+  if (p.mode == 0) {
+    p.pitch_px = kTileW;
+    p.copy_bytes = 18 * kTileW * 128;  // 18 KB, a multiple of 1024
+    p.stage_bytes = 3 * p.copy_bytes;
+    p.tx_bytes = 3 * p.copy_bytes;
+    p.sbo_bytes = 1024;
+  } else if (p.mode == 1) {
+    p.pitch_px = kTileW + 2;
+    p.copy_bytes = 18 * p.pitch_px * 128;  // 23040
+    p.stage_bytes = 23 * 1024;             // padded to the swizzle period
+    p.tx_bytes = p.copy_bytes;
+    p.sbo_bytes = p.pitch_px * 128;
+  } else {
+    p.pitch_px = 16;
+    p.copy_bytes = 18 * 16 * 128;
+    p.stage_bytes = p.copy_bytes;
+    p.tx_bytes = p.copy_bytes;
+    p.sbo_bytes = 16 * 128;
+  }
+  int n = (200 * 1024 - kWBytes) / p.stage_bytes;
+  if (n > 4) n = 4;
+  if (n < 2) n = 2;
+  p.n_stages = n;
+}
+
+int conv64_box_w(int mode) { return mode == 0 ? kTileW : (mode == 1 ? kTileW + 2 : 16); }
+int conv64_tile_w() { return kTileW; }
+int conv64_tile_h() { return kTileH; }
+
+size_t conv64_smem_bytes(const Conv64Params& p) {
+  return static_cast<size_t>(kWBytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024;
+}
+
+cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+  conv64_kernel<<<grid, kConv64Threads, conv64_smem_bytes(p), stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace cerb

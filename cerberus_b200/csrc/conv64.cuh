@@ -1,0 +1,36 @@
+// 64->64 3x3 stride-1 convolution with resident weights and halo reuse (see conv64.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace cerb {
+
+constexpr int kConv64Threads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+struct Conv64Params {
+  CUtensorMap in_map;  // [64 ch, W, H, N], box {64, conv64_box_w(mode), 18, 1}
+  CUtensorMap w_map;   // [576, 64], box {64, 64}
+  int mode;            // halo layout, see conv64.cu
+  int n_img, H, W;
+  int tiles_x, tiles_y, n_tiles;
+  const float* bias;
+  float acc_scale;
+  __half* out;
+  const __half* res;
+  int out_cs, out_coff, res_cs;
+  int relu;
+  // filled by conv64_plan
+  int pitch_px, copy_bytes, stage_bytes, tx_bytes, sbo_bytes, n_stages;
+  int* err_flag;
+};
+
+void conv64_plan(Conv64Params& p);
+int conv64_box_w(int mode);
+int conv64_tile_w();
+int conv64_tile_h();
+size_t conv64_smem_bytes(const Conv64Params& p);
+cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t stream);
+
+}  // namespace cerb

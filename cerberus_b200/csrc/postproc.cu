@@ -342,6 +342,151 @@ k_watershed(const float* __restrict__ val, const uint8_t* __restrict__ msk, int*
   }
 }
 
+// ---- fast path: images of <= 65536 pixels keep the label map (u16) and the upper 13 levels of
+// the heap in shared memory; (value, age) is packed into one order-preserving 64-bit key so a
+// heap node is one 8-byte load and one integer compare. Same algorithm, same heap layout.
+constexpr int kWsThreads = 128;
+constexpr int kWsHeapSmem = 8191;       // 13 levels
+constexpr uint16_t kWsOutside = 0xFFFF;  // not in the mask
+
+__device__ __forceinline__ uint64_t ws_key(float v, uint32_t age) {
+  uint32_t u = __float_as_uint(v);
+  if ((u << 1) == 0) u = 0;  // -0.0 == +0.0 for the reference's float compare
+  u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+  return (static_cast<uint64_t>(u) << 32) | age;
+}
+
+struct Heap64 {
+  uint64_t* sk;
+  uint16_t* si;
+  uint64_t* gk;
+  int* gi;
+  __device__ __forceinline__ uint64_t key(int i) const { return i < kWsHeapSmem ? sk[i] : gk[i]; }
+  __device__ __forceinline__ int idx(int i) const { return i < kWsHeapSmem ? si[i] : gi[i]; }
+  __device__ __forceinline__ void set(int i, uint64_t k, int ix) const {
+    if (i < kWsHeapSmem) { sk[i] = k; si[i] = static_cast<uint16_t>(ix); }
+    else { gk[i] = k; gi[i] = ix; }
+  }
+  __device__ __forceinline__ void push(int& n, uint64_t k, int ix) const {
+    int c = n++;
+    while (c > 0) {
+      const int parent = (c - 1) >> 1;
+      const uint64_t pk = key(parent);
+      if (!(k < pk)) break;
+      set(c, pk, idx(parent));
+      c = parent;
+    }
+    set(c, k, ix);
+  }
+  __device__ __forceinline__ int pop(int& n) const {
+    const int top = idx(0);
+    --n;
+    if (n == 0) return top;
+    const uint64_t xk = key(n);
+    const int xi = idx(n);
+    int i = 0;
+    for (;;) {
+      const int l = 2 * i + 1;
+      if (l >= n) break;
+      const int r = l + 1;
+      const uint64_t lk = key(l);
+      const uint64_t rk = r < n ? key(r) : ~0ull;
+      int s = i;
+      uint64_t sk_ = xk;
+      if (lk < xk) { s = l; sk_ = lk; }
+      if (rk < sk_) { s = r; sk_ = rk; }
+      if (s == i) break;
+      set(i, sk_, idx(s));
+      i = s;
+    }
+    set(i, xk, xi);
+    return top;
+  }
+};
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
+                 int* __restrict__ out, uint64_t* __restrict__ heap_k, int* __restrict__ heap_i,
+                 int* __restrict__ list_idx, float* __restrict__ list_val, int H, int W) {
+  extern __shared__ __align__(16) uint8_t ws_smem[];
+  __shared__ int s_warp[kWsThreads / 32];
+  __shared__ int s_carry;
+  const int hw = H * W;
+  uint64_t* sk = reinterpret_cast<uint64_t*>(ws_smem);
+  uint16_t* lab16 = reinterpret_cast<uint16_t*>(ws_smem + sizeof(uint64_t) * kWsHeapSmem + 8);
+  uint16_t* si = lab16 + ((hw + 7) & ~7);
+  const size_t base = static_cast<size_t>(blockIdx.x) * hw;
+  const float* v = val + base;
+  const uint8_t* m = msk + base;
+  int* o = out + base;
+  int* lidx = list_idx + base;
+  float* lval = list_val + base;
+  // parallel: stage labels, compact the marker pixels in raveled order
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int start = 0; start < hw; start += kWsThreads) {
+    const int p = start + threadIdx.x;
+    int flag = 0;
+    if (p < hw) {
+      const int l = o[p];  // markers * mask (k_mask_markers)
+      lab16[p] = m[p] ? static_cast<uint16_t>(l) : kWsOutside;
+      flag = l != 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_carry;
+    for (int w2 = 0; w2 < warp; ++w2) before += s_warp[w2];
+    if (flag) {
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      lidx[pos] = p;
+      lval[pos] = v[p];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w2 = 0; w2 < kWsThreads / 32; ++w2) t += s_warp[w2];
+      s_carry += t;
+    }
+    __syncthreads();
+  }
+  const int n_markers = s_carry;
+  __threadfence_block();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Heap64 h{sk, si, heap_k + base, heap_i + base};
+    int n = 0;
+    for (int j = 0; j < n_markers; ++j) h.push(n, ws_key(lval[j], 0u), lidx[j]);
+    uint32_t age = 1;
+    while (n > 0) {
+      const int ei = h.pop(n);
+      const int x = ei % W;
+      const uint16_t lab = lab16[ei];
+      // neighbour order of _offsets_to_raveled_neighbors (connectivity 1): -W, -1, +1, +W
+      const int q0 = ei - W, q1 = ei - 1, q2 = ei + 1, q3 = ei + W;
+      const bool c0 = q0 >= 0 && lab16[q0] == 0;
+      const bool c1 = x > 0 && lab16[q1] == 0;
+      const bool c2 = x < W - 1 && lab16[q2] == 0;
+      const bool c3 = q3 < hw && lab16[q3] == 0;
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      if (c0) v0 = __ldg(v + q0);
+      if (c1) v1 = __ldg(v + q1);
+      if (c2) v2 = __ldg(v + q2);
+      if (c3) v3 = __ldg(v + q3);
+      if (c0) { ++age; lab16[q0] = lab; h.push(n, ws_key(v0, age), q0); }
+      if (c1) { ++age; lab16[q1] = lab; h.push(n, ws_key(v1, age), q1); }
+      if (c2) { ++age; lab16[q2] = lab; h.push(n, ws_key(v2, age), q2); }
+      if (c3) { ++age; lab16[q3] = lab; h.push(n, ws_key(v3, age), q3); }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < hw; p += kWsThreads) {
+    const uint16_t l = lab16[p];
+    o[p] = l == kWsOutside ? 0 : static_cast<int>(l);
+  }
+}
+
 // ------------------------------------------------------------------ gland / lumen
 // loader/postproc.py:277-286 / :319-327
 __global__ void k_gl_threshold(const float* __restrict__ canvas, int C, int ch0, float thr,
@@ -519,6 +664,7 @@ struct Workspace {
   int *L = nullptr, *size = nullptr, *rank = nullptr, *lab = nullptr;
   float *val = nullptr, *heap_v = nullptr;
   int *heap_a = nullptr, *heap_i = nullptr;
+  unsigned long long* heap_k = nullptr;
   int *count = nullptr, *any_fg = nullptr;
   float* canvas = nullptr;
   size_t canvas_elems = 0;
@@ -572,6 +718,7 @@ int ensure_ws(cerb_ctx* ctx, Workspace*& ws, int n, int hw) {
     GROW(m0, uint8_t) GROW(m1, uint8_t) GROW(m2, uint8_t)
     GROW(L, int) GROW(size, int) GROW(rank, int) GROW(lab, int)
     GROW(val, float) GROW(heap_v, float) GROW(heap_a, int) GROW(heap_i, int)
+    GROW(heap_k, unsigned long long)
 #undef GROW
     ws->pixels = need;
   }
@@ -715,7 +862,20 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
   k_apply_rank<<<g, kThreads, 0, s>>>(mrk, ws->L, ws->rank, ws->lab, hw);
   k_mask_markers<<<g, kThreads, 0, s>>>(ws->lab, msk, hw);
   // :378 watershed(-inner, marker, mask)
-  k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W);
+  if (hw <= 65536) {
+    const size_t smem = sizeof(uint64_t) * kWsHeapSmem + 8 + 2u * ((hw + 7) & ~7) + 2u * kWsHeapSmem + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CERB_CUDA(cudaFuncSetAttribute(k_watershed_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     220 * 1024));
+      attr_set = true;
+    }
+    k_watershed_smem<<<n, kWsThreads, smem, s>>>(ws->val, msk, ws->lab,
+                                                 reinterpret_cast<uint64_t*>(ws->heap_k), ws->heap_i,
+                                                 ws->rank, ws->heap_v, H, W);
+  } else {
+    k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W);
+  }
   ctx->launches += 4;
   if (any_fg_out) {
     CERB_CUDA(cudaMemcpyAsync(any_fg_out, ws->any_fg, sizeof(int) * n,

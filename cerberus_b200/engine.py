@@ -29,6 +29,10 @@ class Context:
         _lib.check(self.lib.cerb_ctx_create(device, prec, ctypes.byref(h)), "cerb_ctx_create")
         self.handle = h
 
+    def set_option(self, name, value):
+        _lib.check(self.lib.cerb_ctx_set_option(self.handle, name.encode(), int(value)),
+                   "cerb_ctx_set_option")
+
     def sync(self):
         _lib.check(self.lib.cerb_ctx_sync(self.handle), "cerb_ctx_sync")
 

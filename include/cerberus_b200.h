@@ -102,6 +102,9 @@ int cerb_ctx_create(int device, int precision, cerb_ctx** out);
 void cerb_ctx_destroy(cerb_ctx* ctx);
 const char* cerb_last_error(void);
 int cerb_ctx_sync(cerb_ctx* ctx);
+/* Tuning knobs applied to plans created afterwards. "conv64_mode": -1 = generic kernel for every
+ * convolution, 0/1/2 = halo layout of the 64->64 3x3 kernel (csrc/conv64.cu). */
+int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value);
 /* Number of kernels this library launched on ctx since creation (bench's gpu_launches). */
 int64_t cerb_ctx_launch_count(cerb_ctx* ctx);
 /* Raw CUDA stream handle (cudaStream_t) of the ctx, for event timing by the caller. */
