@@ -164,6 +164,7 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
   st.use64 = true;
   const int H = out.d.h, W = out.d.w, N = out.d.n;
   p.mode = ctx->conv64_mode;
+  p.debug = ctx->conv64_debug;
   p.n_img = N;
   p.H = H;
   p.W = W;
@@ -479,6 +480,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
   if (strcmp(name, "conv64_mode") == 0) {
     if (value < -1 || value > 2) return fail(CERB_ERR_ARG, "conv64_mode must be -1, 0, 1 or 2");
     ctx->conv64_mode = value;
+    return CERB_OK;
+  }
+  if (strcmp(name, "conv64_debug") == 0) {
+    ctx->conv64_debug = value;
     return CERB_OK;
   }
   return fail(CERB_ERR_ARG, "cerb_ctx_set_option: unknown option %s", name);

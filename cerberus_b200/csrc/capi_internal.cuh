@@ -17,6 +17,7 @@ struct cerb_ctx {
   int* err_flag_dev = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved at run time (no libcuda link)
   int64_t launches = 0;
+  int conv64_debug = 0;
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout
   std::vector<void*> scratch;  // device allocations owned by the ctx (post-proc workspaces)
 };

@@ -105,7 +105,17 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       const uint32_t idesc = ptx::umma_idesc_f16(128, 64);
       ptx::mbar_wait(w_bar, 0, p.err_flag, 22);
       ptx::tc_fence_after();
-      const uint32_t w_addr = ptx::smem_u32(sW);
+      const uint64_t a_d0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), p.sbo_bytes, 0);
+      const uint64_t b_d0 = ptx::umma_desc_sw128(ptx::smem_u32(sW), 1024, 0);
+      const uint32_t a_hi = static_cast<uint32_t>(a_d0 >> 32), a_lo0 = static_cast<uint32_t>(a_d0);
+      const uint32_t b_hi = static_cast<uint32_t>(b_d0 >> 32), b_lo0 = static_cast<uint32_t>(b_d0);
+      uint32_t tap_off[9];  // byte offset of tap (r, s) inside a stage, in 16-byte units
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int r = t / 3, s = t - 3 * r;
+        tap_off[t] = static_cast<uint32_t>(
+            (p.mode == 0 ? s * p.copy_bytes + r * (kTileW * 128) : (r * p.pitch_px + s) * 128) >> 4);
+      }
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -115,22 +125,18 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
         ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 24);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 64;
-        const uint32_t a_base = ptx::smem_u32(sA + stage * stage_bytes);
+        // descriptor low words: only the 14-bit start-address field changes between MMAs
+        const uint32_t a_lo = a_lo0 + static_cast<uint32_t>((stage * stage_bytes) >> 4);
+        const int n_taps = (p.debug & 2) ? 1 : 9;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const int r = t / 3, s = t - 3 * r;
-          uint32_t a_addr, boff = 0;
-          if (p.mode == 0) {
-            a_addr = a_base + s * p.copy_bytes + r * (kTileW * 128);
-          } else {
-            a_addr = a_base + (r * p.pitch_px + s) * 128;
-            if (p.mode == 2) boff = (a_addr >> 7) & 7;
-          }
+          if (t < n_taps) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 32, p.sbo_bytes, boff);
-            const uint64_t bd = ptx::umma_desc_sw128(w_addr + t * 8192 + k * 32, 1024);
-            ptx::umma_f16(tmem_d, ad, bd, idesc, (t | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + tap_off[t] + 2 * k);
+              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + t * 512 + 2 * k);
+              ptx::umma_f16(tmem_d, ad, bd, idesc, (t | k) != 0);
+            }
           }
         }
         ptx::umma_commit(&empty_bar[stage]);
@@ -164,7 +170,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      if (valid) {
+      if (valid && !(p.debug & 4)) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float v[32];
@@ -205,7 +211,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
             u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
             u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
             u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
-            oh[i] = u;
+            if (!(p.debug & 1)) oh[i] = u;
           }
         }
       }

@@ -21,6 +21,7 @@ struct Conv64Params {
   const __half* res;
   int out_cs, out_coff, res_cs;
   int relu;
+  int debug;  // attribution experiments: 1 = no global stores, 2 = one tap only, 4 = no epilogue math
   // filled by conv64_plan
   int pitch_px, copy_bytes, stage_bytes, tx_bytes, sbo_bytes, n_stages;
   int* err_flag;

@@ -342,79 +342,96 @@ k_watershed(const float* __restrict__ val, const uint8_t* __restrict__ msk, int*
   }
 }
 
-// ---- fast path: images of <= 65536 pixels keep the label map (u16) and the upper 13 levels of
-// the heap in shared memory; (value, age) is packed into one order-preserving 64-bit key so a
-// heap node is one 8-byte load and one integer compare. Same algorithm, same heap layout.
+// ---- fast path: images of <= 65536 pixels keep the label map (u16) and the first kWsHeapSmem
+// heap nodes in shared memory. A heap node is ONE 64-bit word [value:32 | age:16 | pixel:16]:
+// the value is mapped to an order-preserving unsigned, ages fit 16 bits (at most 65535
+// non-marker pushes), and the comparison looks at the upper 48 bits only, so equal
+// (value, age) pairs still compare "not smaller" exactly like the reference. Same algorithm,
+// same heap layout; the sift-down reads children and grandchildren together (two levels per
+// shared-memory round trip) and the neighbours' values are fetched before the sift-down.
 constexpr int kWsThreads = 128;
-constexpr int kWsHeapSmem = 8191;       // 13 levels
+constexpr int kWsHeapSmem = 11000;
 constexpr uint16_t kWsOutside = 0xFFFF;  // not in the mask
 
-__device__ __forceinline__ uint64_t ws_key(float v, uint32_t age) {
+__device__ __forceinline__ uint64_t ws_entry(float v, uint32_t age, int pix) {
   uint32_t u = __float_as_uint(v);
   if ((u << 1) == 0) u = 0;  // -0.0 == +0.0 for the reference's float compare
   u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;
-  return (static_cast<uint64_t>(u) << 32) | age;
+  const uint32_t a16 = age == 0 ? 0u : age - 1u;  // ages start at 2 (watershed_raveled)
+  return (static_cast<uint64_t>(u) << 32) | (static_cast<uint64_t>(a16) << 16) |
+         static_cast<uint32_t>(pix);
 }
 
 struct Heap64 {
-  uint64_t* sk;
-  uint16_t* si;
-  uint64_t* gk;
-  int* gi;
-  __device__ __forceinline__ uint64_t key(int i) const { return i < kWsHeapSmem ? sk[i] : gk[i]; }
-  __device__ __forceinline__ int idx(int i) const { return i < kWsHeapSmem ? si[i] : gi[i]; }
-  __device__ __forceinline__ void set(int i, uint64_t k, int ix) const {
-    if (i < kWsHeapSmem) { sk[i] = k; si[i] = static_cast<uint16_t>(ix); }
-    else { gk[i] = k; gi[i] = ix; }
+  uint64_t* s;
+  uint64_t* g;
+  __device__ __forceinline__ uint64_t get(int i) const { return i < kWsHeapSmem ? s[i] : g[i]; }
+  __device__ __forceinline__ uint64_t get_or_max(int i, int n) const {
+    return i < n ? get(i) : ~0ull;
   }
-  __device__ __forceinline__ void push(int& n, uint64_t k, int ix) const {
+  __device__ __forceinline__ void set(int i, uint64_t e) const {
+    if (i < kWsHeapSmem) s[i] = e; else g[i] = e;
+  }
+  __device__ __forceinline__ void push(int& n, uint64_t e) const {
     int c = n++;
+    const uint64_t k = e >> 16;
     while (c > 0) {
       const int parent = (c - 1) >> 1;
-      const uint64_t pk = key(parent);
-      if (!(k < pk)) break;
-      set(c, pk, idx(parent));
+      const uint64_t pe = get(parent);
+      if (!(k < (pe >> 16))) break;
+      set(c, pe);
       c = parent;
     }
-    set(c, k, ix);
+    set(c, e);
   }
-  __device__ __forceinline__ int pop(int& n) const {
-    const int top = idx(0);
+  // removes the root (the caller has already read it)
+  __device__ __forceinline__ void remove_top(int& n) const {
     --n;
-    if (n == 0) return top;
-    const uint64_t xk = key(n);
-    const int xi = idx(n);
+    if (n == 0) return;
+    const uint64_t x = get(n);
+    const uint64_t xk = x >> 16;
     int i = 0;
     for (;;) {
       const int l = 2 * i + 1;
       if (l >= n) break;
-      const int r = l + 1;
-      const uint64_t lk = key(l);
-      const uint64_t rk = r < n ? key(r) : ~0ull;
-      int s = i;
-      uint64_t sk_ = xk;
-      if (lk < xk) { s = l; sk_ = lk; }
-      if (rk < sk_) { s = r; sk_ = rk; }
-      if (s == i) break;
-      set(i, sk_, idx(s));
-      i = s;
+      const uint64_t c0 = get(l), c1 = get_or_max(l + 1, n);
+      const int gl = 2 * l + 1;
+      const uint64_t g0 = get_or_max(gl, n), g1 = get_or_max(gl + 1, n);
+      const uint64_t g2 = get_or_max(gl + 2, n), g3 = get_or_max(gl + 3, n);
+      // level 1: smallest of (x, left, right); x wins ties, left wins over right
+      int s1 = -1;
+      uint64_t sk = xk;
+      if ((c0 >> 16) < sk) { s1 = 0; sk = c0 >> 16; }
+      if ((c1 >> 16) < sk) { s1 = 1; sk = c1 >> 16; }
+      if (s1 < 0) break;
+      set(i, s1 ? c1 : c0);
+      i = l + s1;
+      // level 2 with the grandchildren already in registers
+      const int l2 = 2 * i + 1;
+      if (l2 >= n) break;
+      const uint64_t d0 = s1 ? g2 : g0, d1 = s1 ? g3 : g1;
+      int s2 = -1;
+      sk = xk;
+      if ((d0 >> 16) < sk) { s2 = 0; sk = d0 >> 16; }
+      if ((d1 >> 16) < sk) { s2 = 1; sk = d1 >> 16; }
+      if (s2 < 0) break;
+      set(i, s2 ? d1 : d0);
+      i = l2 + s2;
     }
-    set(i, xk, xi);
-    return top;
+    set(i, x);
   }
 };
 
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
-                 int* __restrict__ out, uint64_t* __restrict__ heap_k, int* __restrict__ heap_i,
+                 int* __restrict__ out, uint64_t* __restrict__ heap_k,
                  int* __restrict__ list_idx, float* __restrict__ list_val, int H, int W) {
   extern __shared__ __align__(16) uint8_t ws_smem[];
   __shared__ int s_warp[kWsThreads / 32];
   __shared__ int s_carry;
   const int hw = H * W;
-  uint64_t* sk = reinterpret_cast<uint64_t*>(ws_smem);
-  uint16_t* lab16 = reinterpret_cast<uint16_t*>(ws_smem + sizeof(uint64_t) * kWsHeapSmem + 8);
-  uint16_t* si = lab16 + ((hw + 7) & ~7);
+  uint64_t* sh = reinterpret_cast<uint64_t*>(ws_smem);
+  uint16_t* lab16 = reinterpret_cast<uint16_t*>(ws_smem + sizeof(uint64_t) * kWsHeapSmem);
   const size_t base = static_cast<size_t>(blockIdx.x) * hw;
   const float* v = val + base;
   const uint8_t* m = msk + base;
@@ -455,12 +472,12 @@ k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
   __threadfence_block();
   __syncthreads();
   if (threadIdx.x == 0) {
-    Heap64 h{sk, si, heap_k + base, heap_i + base};
+    Heap64 h{sh, heap_k + base};
     int n = 0;
-    for (int j = 0; j < n_markers; ++j) h.push(n, ws_key(lval[j], 0u), lidx[j]);
+    for (int j = 0; j < n_markers; ++j) h.push(n, ws_entry(lval[j], 0u, lidx[j]));
     uint32_t age = 1;
     while (n > 0) {
-      const int ei = h.pop(n);
+      const int ei = static_cast<int>(h.get(0) & 0xFFFFu);
       const int x = ei % W;
       const uint16_t lab = lab16[ei];
       // neighbour order of _offsets_to_raveled_neighbors (connectivity 1): -W, -1, +1, +W
@@ -470,14 +487,15 @@ k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
       const bool c2 = x < W - 1 && lab16[q2] == 0;
       const bool c3 = q3 < hw && lab16[q3] == 0;
       float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-      if (c0) v0 = __ldg(v + q0);
+      if (c0) v0 = __ldg(v + q0);  // in flight during the sift-down
       if (c1) v1 = __ldg(v + q1);
       if (c2) v2 = __ldg(v + q2);
       if (c3) v3 = __ldg(v + q3);
-      if (c0) { ++age; lab16[q0] = lab; h.push(n, ws_key(v0, age), q0); }
-      if (c1) { ++age; lab16[q1] = lab; h.push(n, ws_key(v1, age), q1); }
-      if (c2) { ++age; lab16[q2] = lab; h.push(n, ws_key(v2, age), q2); }
-      if (c3) { ++age; lab16[q3] = lab; h.push(n, ws_key(v3, age), q3); }
+      h.remove_top(n);
+      if (c0) { ++age; lab16[q0] = lab; h.push(n, ws_entry(v0, age, q0)); }
+      if (c1) { ++age; lab16[q1] = lab; h.push(n, ws_entry(v1, age, q1)); }
+      if (c2) { ++age; lab16[q2] = lab; h.push(n, ws_entry(v2, age, q2)); }
+      if (c3) { ++age; lab16[q3] = lab; h.push(n, ws_entry(v3, age, q3)); }
     }
   }
   __syncthreads();
@@ -863,16 +881,16 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
   k_mask_markers<<<g, kThreads, 0, s>>>(ws->lab, msk, hw);
   // :378 watershed(-inner, marker, mask)
   if (hw <= 65536) {
-    const size_t smem = sizeof(uint64_t) * kWsHeapSmem + 8 + 2u * ((hw + 7) & ~7) + 2u * kWsHeapSmem + 16;
+    const size_t smem = sizeof(uint64_t) * kWsHeapSmem + 2u * ((hw + 7) & ~7) + 16;
     static bool attr_set = false;
     if (!attr_set) {
       CERB_CUDA(cudaFuncSetAttribute(k_watershed_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     220 * 1024));
+                                     226 * 1024));
       attr_set = true;
     }
     k_watershed_smem<<<n, kWsThreads, smem, s>>>(ws->val, msk, ws->lab,
-                                                 reinterpret_cast<uint64_t*>(ws->heap_k), ws->heap_i,
-                                                 ws->rank, ws->heap_v, H, W);
+                                                 reinterpret_cast<uint64_t*>(ws->heap_k), ws->rank,
+                                                 ws->heap_v, H, W);
   } else {
     k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W);
   }

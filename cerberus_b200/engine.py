@@ -5,6 +5,7 @@ PyTorch is used for `torch.load` of the checkpoint only; all device work goes th
 libcerberus_b200.so (hand-written sm_100a kernels). There is no CPU fallback.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -28,6 +29,9 @@ class Context:
         h = ctypes.c_void_p()
         _lib.check(self.lib.cerb_ctx_create(device, prec, ctypes.byref(h)), "cerb_ctx_create")
         self.handle = h
+        # halo layout of the 64->64 3x3 kernel (csrc/conv64.cu): 1 = single halo slab addressed
+        # through shifted descriptors (validated on B200, tools/conv64_modes.py); -1 = generic kernel
+        self.set_option("conv64_mode", int(os.environ.get("CERB_CONV64_MODE", "1")))
 
     def set_option(self, name, value):
         _lib.check(self.lib.cerb_ctx_set_option(self.handle, name.encode(), int(value)),

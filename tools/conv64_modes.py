@@ -70,6 +70,16 @@ def child(mode):
     fl = 2.0 * n * h * w * 64 * 576
     print("mode %d: %s, 256x256 64->64 batch 32: %.4f ms = %.1f TFLOP/s" % (
         mode, "PASS" if ok_all else "FAIL", ms, fl / ms / 1e9))
+    if mode >= 0:
+        for dbg, what in ((1, "no global stores"), (4, "no epilogue math/stores"), (2, "one tap only"),
+                          (6, "one tap, no epilogue"), (3, "one tap, no stores")):
+            ctx.set_option("conv64_debug", dbg)
+            pl2 = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
+            pl2.run(); ctx.sync()
+            ms2 = profile_ops(pl2, reps=10)[0][1]
+            print("   mode %d debug %d (%s): %.4f ms" % (mode, dbg, what, ms2))
+            pl2.close()
+        ctx.set_option("conv64_debug", 0)
 
 
 if __name__ == "__main__":
