@@ -215,29 +215,9 @@ def run_ours(args):
 
     margs = synth.model_args()
     # rank 0 folds + packs the checkpoint; the packed blob is NCCL-broadcast once
-    if rank == 0:
-        sd = synth.make_state_dict(seed=0)
-        model = PackedModel(sd, margs)
-    if world > 1:
-        nbytes = torch.tensor([model.blob.nbytes if rank == 0 else 0], device="cuda", dtype=torch.int64)
-        dist.broadcast(nbytes, 0)
-        if rank == 0:
-            blob_t = torch.from_numpy(model.blob).cuda()
-            objs = [{"layers": model.layers, "idx": model.idx_dict, "canvas_c": model.canvas_c,
-                     "seg": model.seg_decoders, "pc": model.has_pclass}]
-        else:
-            blob_t = torch.empty(int(nbytes.item()), dtype=torch.uint8, device="cuda")
-            objs = [None]
-        dist.broadcast(blob_t, 0)
-        dist.broadcast_object_list(objs, 0)
-        if rank != 0:
-            model = PackedModel.__new__(PackedModel)
-            model.decoder_kwargs = margs["decoder_kwargs"]
-            model.considered_tasks = margs["considered_tasks"]
-            model.layers, model.idx_dict = objs[0]["layers"], objs[0]["idx"]
-            model.canvas_c, model.seg_decoders, model.has_pclass = objs[0]["canvas_c"], objs[0]["seg"], objs[0]["pc"]
-            model.blob = blob_t.cpu().numpy()
-        del blob_t
+    from cerberus_b200.dist import broadcast_packed_model
+    model = PackedModel(synth.make_state_dict(seed=0), margs) if rank == 0 else None
+    model = broadcast_packed_model(model, margs, rank, world, torch.device("cuda", local_rank))
 
     B = args.batch
     ctx = Context(local_rank, args.precision)

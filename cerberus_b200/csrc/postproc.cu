@@ -350,7 +350,7 @@ k_watershed(const float* __restrict__ val, const uint8_t* __restrict__ msk, int*
 // same heap layout; the sift-down reads children and grandchildren together (two levels per
 // shared-memory round trip) and the neighbours' values are fetched before the sift-down.
 constexpr int kWsThreads = 128;
-constexpr int kWsHeapSmem = 11000;
+constexpr int kWsHeapSmem = 10500;
 constexpr uint16_t kWsOutside = 0xFFFF;  // not in the mask
 
 __device__ __forceinline__ uint64_t ws_entry(float v, uint32_t age, int pix) {
@@ -422,9 +422,117 @@ struct Heap64 {
   }
 };
 
+// Warp-cooperative version of the same heap (same array layout after every operation). One
+// GPU thread retires roughly one dependent instruction every 4-6 cycles, so the sequential
+// sift loops above cost ~2000 cycles per queue operation. Here warp 0 owns the heap:
+//  * push: the ancestor chain of the new leaf is known in advance ((c+1) >> d), so lane d loads
+//    ancestor d+1, every lane compares with the new key at once, a ballot gives the number of
+//    moves, the moves are independent stores;
+//  * pop: the hole follows the "smaller child" path, which does not depend on the element being
+//    re-inserted; one byte per node caches "the right child is strictly smaller", so the path
+//    is a chase over bytes, after which lanes load the path entries in parallel, a ballot finds
+//    where the re-inserted element stops, and the moves are independent stores.
+// The cached bytes of the touched nodes are recomputed in parallel from the moved entries and
+// their (untouched) siblings. All arguments are warp-uniform; every lane must call.
+struct WarpHeap {
+  uint64_t* s;
+  uint64_t* g;
+  uint8_t* sb;
+  uint8_t* gb;
+  int lane;
+  __device__ __forceinline__ uint64_t get(int i) const { return i < kWsHeapSmem ? s[i] : g[i]; }
+  __device__ __forceinline__ void set(int i, uint64_t e) const {
+    if (i < kWsHeapSmem) s[i] = e; else g[i] = e;
+  }
+  __device__ __forceinline__ int getb(int i) const { return i < kWsHeapSmem ? sb[i] : gb[i]; }
+  __device__ __forceinline__ void setb(int i, int b) const {
+    if (i < kWsHeapSmem) sb[i] = static_cast<uint8_t>(b); else gb[i] = static_cast<uint8_t>(b);
+  }
+
+  __device__ __forceinline__ void push(int& n, uint64_t e) const {
+    const int c = n;
+    n = c + 1;
+    const int dep = 31 - __clz(c + 1);  // depth of the new leaf; ancestors d = 1..dep
+    const uint64_t k = e >> 16;
+    const int d = lane;
+    const int a_d = ((c + 1) >> d) - 1;        // ancestor d levels up (d = 0: the leaf slot)
+    const int a_p = ((c + 1) >> (d + 1)) - 1;  // its parent
+    const bool has_parent = d < dep;
+    uint64_t P = 0;
+    if (has_parent) P = get(a_p);
+    const unsigned mv = __ballot_sync(0xffffffffu, has_parent && (k < (P >> 16)));
+    const int t = __ffs(~mv) - 1;  // number of moves (the predicate is monotone along the chain)
+    // sibling of a_d (child of a_p on the chain); needed by lanes d <= t with a parent
+    uint64_t S = 0;
+    bool sib_exists = false;
+    const bool upd = has_parent && d <= t;
+    const bool is_left = (a_d & 1) != 0;
+    if (upd) {
+      const int sib = is_left ? a_d + 1 : a_d - 1;
+      sib_exists = sib < n;
+      if (sib_exists) S = get(sib);
+    }
+    __syncwarp();
+    if (d < t) set(a_d, P);
+    if (d == t) set(a_d, e);
+    if (upd) {
+      const uint64_t nc = (d < t ? P : e) >> 16;  // new content of slot a_d
+      const int bit = is_left ? (sib_exists && ((S >> 16) < nc)) : (nc < (S >> 16));
+      setb(a_p, bit);
+    }
+    __syncwarp();
+  }
+
+  // Removes the root (the caller has already read it).
+  __device__ __forceinline__ void remove_top(int& n) const {
+    n = n - 1;
+    if (n == 0) return;
+    const uint64_t x = get(n);
+    const uint64_t xk = x >> 16;
+    if (lane == 0 && (n & 1) == 0) setb((n - 1) >> 1, 0);  // the last node was a right child
+    __syncwarp();
+    int c = 0, my_c = 0, my_child = 0, D = 0;
+    for (;;) {
+      const int l = 2 * c + 1;
+      if (l >= n) break;
+      const int ch = l + getb(c);
+      if (lane == D) { my_c = c; my_child = ch; }
+      c = ch;
+      ++D;
+    }
+    const int d = lane;
+    uint64_t E = 0;
+    if (d < D) E = get(my_child);
+    const unsigned mv = __ballot_sync(0xffffffffu, d < D && ((E >> 16) < xk));
+    const int t = __ffs(~mv) - 1;
+    const uint64_t E_next = __shfl_down_sync(0xffffffffu, E, 1);
+    uint64_t S = 0;
+    bool sib_exists = false;
+    const bool is_left = (my_child & 1) != 0;
+    if (d < t) {
+      const int sib = is_left ? my_child + 1 : my_child - 1;
+      sib_exists = sib < n;
+      if (sib_exists) S = get(sib);
+    }
+    __syncwarp();
+    if (d < t) set(my_c, E);
+    if (t < D) {
+      if (d == t) set(my_c, x);
+    } else if (d == 0) {
+      set(c, x);  // the hole reached a leaf
+    }
+    if (d < t) {
+      const uint64_t nc = (d + 1 < t ? E_next : x) >> 16;  // new content of slot my_child
+      const int bit = is_left ? (sib_exists && ((S >> 16) < nc)) : (nc < (S >> 16));
+      setb(my_c, bit);
+    }
+    __syncwarp();
+  }
+};
+
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
-                 int* __restrict__ out, uint64_t* __restrict__ heap_k,
+                 int* __restrict__ out, uint64_t* __restrict__ heap_k, uint8_t* __restrict__ heap_b,
                  int* __restrict__ list_idx, float* __restrict__ list_val, int H, int W) {
   extern __shared__ __align__(16) uint8_t ws_smem[];
   __shared__ int s_warp[kWsThreads / 32];
@@ -432,6 +540,7 @@ k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
   const int hw = H * W;
   uint64_t* sh = reinterpret_cast<uint64_t*>(ws_smem);
   uint16_t* lab16 = reinterpret_cast<uint16_t*>(ws_smem + sizeof(uint64_t) * kWsHeapSmem);
+  uint8_t* sbits = ws_smem + sizeof(uint64_t) * kWsHeapSmem + 2u * ((hw + 7) & ~7);
   const size_t base = static_cast<size_t>(blockIdx.x) * hw;
   const float* v = val + base;
   const uint8_t* m = msk + base;
@@ -471,31 +580,42 @@ k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
   const int n_markers = s_carry;
   __threadfence_block();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    Heap64 h{sh, heap_k + base};
+  if (warp == 0) {
+    WarpHeap h{sh, heap_k + base, sbits, heap_b + base, lane};
     int n = 0;
-    for (int j = 0; j < n_markers; ++j) h.push(n, ws_entry(lval[j], 0u, lidx[j]));
+    for (int j0 = 0; j0 < n_markers; j0 += 32) {
+      const int j = j0 + lane;
+      uint64_t mine = 0;
+      if (j < n_markers) mine = ws_entry(lval[j], 0u, lidx[j]);
+      const int cnt = min(32, n_markers - j0);
+      for (int k = 0; k < cnt; ++k) h.push(n, __shfl_sync(0xffffffffu, mine, k));
+    }
     uint32_t age = 1;
     while (n > 0) {
       const int ei = static_cast<int>(h.get(0) & 0xFFFFu);
       const int x = ei % W;
       const uint16_t lab = lab16[ei];
-      // neighbour order of _offsets_to_raveled_neighbors (connectivity 1): -W, -1, +1, +W
-      const int q0 = ei - W, q1 = ei - 1, q2 = ei + 1, q3 = ei + W;
-      const bool c0 = q0 >= 0 && lab16[q0] == 0;
-      const bool c1 = x > 0 && lab16[q1] == 0;
-      const bool c2 = x < W - 1 && lab16[q2] == 0;
-      const bool c3 = q3 < hw && lab16[q3] == 0;
-      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-      if (c0) v0 = __ldg(v + q0);  // in flight during the sift-down
-      if (c1) v1 = __ldg(v + q1);
-      if (c2) v2 = __ldg(v + q2);
-      if (c3) v3 = __ldg(v + q3);
+      // neighbour order of _offsets_to_raveled_neighbors (connectivity 1): -W, -1, +1, +W;
+      // lane k < 4 examines neighbour k and fetches its value while the root is removed
+      int q = ei;
+      bool ok = false;
+      if (lane == 0) { q = ei - W; ok = q >= 0; }
+      if (lane == 1) { q = ei - 1; ok = x > 0; }
+      if (lane == 2) { q = ei + 1; ok = x < W - 1; }
+      if (lane == 3) { q = ei + W; ok = q < hw; }
+      ok = ok && lab16[q] == 0;
+      float vq = 0.f;
+      if (ok) vq = __ldg(v + q);
+      const unsigned todo = __ballot_sync(0xffffffffu, ok);
       h.remove_top(n);
-      if (c0) { ++age; lab16[q0] = lab; h.push(n, ws_entry(v0, age, q0)); }
-      if (c1) { ++age; lab16[q1] = lab; h.push(n, ws_entry(v1, age, q1)); }
-      if (c2) { ++age; lab16[q2] = lab; h.push(n, ws_entry(v2, age, q2)); }
-      if (c3) { ++age; lab16[q3] = lab; h.push(n, ws_entry(v3, age, q3)); }
+      for (int k = 0; k < 4; ++k) {
+        if (!((todo >> k) & 1u)) continue;
+        ++age;
+        const int qk = __shfl_sync(0xffffffffu, q, k);
+        const float vk = __shfl_sync(0xffffffffu, vq, k);
+        if (lane == 0) lab16[qk] = lab;
+        h.push(n, ws_entry(vk, age, qk));  // push ends with __syncwarp
+      }
     }
   }
   __syncthreads();
@@ -881,7 +1001,7 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
   k_mask_markers<<<g, kThreads, 0, s>>>(ws->lab, msk, hw);
   // :378 watershed(-inner, marker, mask)
   if (hw <= 65536) {
-    const size_t smem = sizeof(uint64_t) * kWsHeapSmem + 2u * ((hw + 7) & ~7) + 16;
+    const size_t smem = sizeof(uint64_t) * kWsHeapSmem + 2u * ((hw + 7) & ~7) + kWsHeapSmem + 16;
     static bool attr_set = false;
     if (!attr_set) {
       CERB_CUDA(cudaFuncSetAttribute(k_watershed_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -889,8 +1009,8 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
       attr_set = true;
     }
     k_watershed_smem<<<n, kWsThreads, smem, s>>>(ws->val, msk, ws->lab,
-                                                 reinterpret_cast<uint64_t*>(ws->heap_k), ws->rank,
-                                                 ws->heap_v, H, W);
+                                                 reinterpret_cast<uint64_t*>(ws->heap_k), ws->m0,
+                                                 ws->rank, ws->heap_v, H, W);
   } else {
     k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W);
   }
