@@ -31,7 +31,8 @@ class Op(ctypes.Structure):
         ("pad", ctypes.c_int32), ("relu", ctypes.c_int32), ("stem", ctypes.c_int32),
         ("head_mode", ctypes.c_int32), ("logits_out", ctypes.c_int32),
         ("w_off", ctypes.c_int64), ("w_lo_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
-        ("box_w", ctypes.c_int32), ("w_shift", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2),
+        ("box_w", ctypes.c_int32), ("w_shift", ctypes.c_int32), ("aux_classes", ctypes.c_int32),
+        ("reserved", ctypes.c_int32), ("aux_w_off", ctypes.c_int64), ("aux_b_off", ctypes.c_int64),
     ]
 
 
@@ -76,6 +77,8 @@ _SIGNATURES = {
                                        ctypes.c_size_t]),
     "cerb_ellipse_rows": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32)]),
+    "cerb_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "cerb_host_free": (None, [ctypes.c_void_p]),
     "cerb_dev_alloc": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_size_t]),
     "cerb_dev_free": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "cerb_memcpy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

@@ -229,19 +229,31 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
     return fail(CERB_ERR_ARG, "conv: tensor id out of range");
   const Tensor& in = pl->tensors[op.in0];
   const Tensor& out = pl->tensors[op.out];
-  if (in.d.dtype != CERB_F16 || out.d.dtype != CERB_F16)
-    return fail(CERB_ERR_ARG, "conv: tensors must be fp16");
+  const bool fused_head = op.aux_classes > 0;
+  if (in.d.dtype != CERB_F16 || out.d.dtype != (fused_head ? CERB_F32 : CERB_F16))
+    return fail(CERB_ERR_ARG, "conv: tensors must be fp16 (fp32 canvas for a fused head)");
   const bool split = ctx->precision == CERB_PREC_F16X2;
   ConvKParams& p = st.conv;
   memset(&p, 0, sizeof(p));
   st.split = split;
 
-  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  // a fused head writes the (centre-cropped) canvas; its geometry is the input's
+  const int H = fused_head ? in.d.h : out.d.h, W = fused_head ? in.d.w : out.d.w, N = out.d.n;
   if (in.d.n != N) return fail(CERB_ERR_ARG, "conv: batch mismatch");
-  if (op.cout <= 0 || op.cout % 16 != 0 || op.out_coff % 8 != 0 ||
-      op.out_coff + op.cout > out.d.c || out.d.c % 8 != 0)
+  if (fused_head) {
+    const int width = op.head_mode == CERB_HEAD_INST ? op.aux_classes - 1 : 1;
+    if (op.cout != 96 || op.kh != 1 || op.kw != 1 || op.stride != 1 || op.stem || op.in1 >= 0 ||
+        op.aux_classes < 2 || op.aux_classes > 8 || out.d.h > H || out.d.w > W || op.out_coff < 0 ||
+        op.out_coff + width > out.d.c || op.aux_w_off < 0 || op.aux_b_off < 0 ||
+        op.aux_w_off % 16 != 0 ||
+        static_cast<size_t>(op.aux_w_off) + op.aux_classes * 96 * 4u > pl->blob_bytes ||
+        static_cast<size_t>(op.aux_b_off) + op.aux_classes * 4u > pl->blob_bytes)
+      return fail(CERB_ERR_ARG, "conv: bad fused-head description");
+  } else if (op.cout <= 0 || op.cout % 16 != 0 || op.out_coff % 8 != 0 ||
+             op.out_coff + op.cout > out.d.c || out.d.c % 8 != 0) {
     return fail(CERB_ERR_ARG, "conv: bad output channels (cout %d coff %d c %d)", op.cout,
                 op.out_coff, out.d.c);
+  }
 
   if (!split && !op.stem && ctx->conv64_mode >= 0 && op.kh == 3 && op.kw == 3 && op.stride == 1 &&
       op.pad == 1 && op.in_c == 64 && op.cout == 64 && in.d.h == H && in.d.w == W) {
@@ -367,10 +379,30 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
       return fail(CERB_ERR_ARG, "conv: bias offset out of range");
     p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
   }
-  p.out_hi = static_cast<__half*>(out.plane[0]);
-  p.out_lo = static_cast<__half*>(out.plane[1]);
-  p.out_cs = out.d.c;
-  p.out_coff = op.out_coff;
+  if (fused_head) {
+    p.head_w = reinterpret_cast<const float*>(pl->blob + op.aux_w_off);
+    p.head_b = reinterpret_cast<const float*>(pl->blob + op.aux_b_off);
+    p.head_classes = op.aux_classes;
+    p.head_mode = op.head_mode;
+    p.canvas = static_cast<float*>(out.plane[0]);
+    p.oh = out.d.h;
+    p.ow = out.d.w;
+    p.canvas_c = out.d.c;
+    p.canvas_coff = op.out_coff;
+    if (op.logits_out >= 0) {
+      if (op.logits_out >= nt) return fail(CERB_ERR_ARG, "conv: logits id out of range");
+      const Tensor& lg = pl->tensors[op.logits_out];
+      if (lg.d.dtype != CERB_F32 || lg.d.n != N || lg.d.h != H || lg.d.w != W ||
+          lg.d.c != op.aux_classes)
+        return fail(CERB_ERR_ARG, "conv: fused-head logits tensor mismatch");
+      p.logits = static_cast<float*>(lg.plane[0]);
+    }
+  } else {
+    p.out_hi = static_cast<__half*>(out.plane[0]);
+    p.out_lo = static_cast<__half*>(out.plane[1]);
+    p.out_cs = out.d.c;
+    p.out_coff = op.out_coff;
+  }
   if (op.in1 >= 0) {
     if (op.in1 >= nt) return fail(CERB_ERR_ARG, "conv: residual id out of range");
     const Tensor& res = pl->tensors[op.in1];
@@ -480,6 +512,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
   if (strcmp(name, "conv64_mode") == 0) {
     if (value < -1 || value > 2) return fail(CERB_ERR_ARG, "conv64_mode must be -1, 0, 1 or 2");
     ctx->conv64_mode = value;
+    return CERB_OK;
+  }
+  if (strcmp(name, "ws_mode") == 0) {
+    ctx->ws_mode = value;
     return CERB_OK;
   }
   if (strcmp(name, "conv64_debug") == 0) {

@@ -8,6 +8,7 @@
 // BatchNorm is folded into weights/bias on load; bias, residual
 // add, ReLU and the fp16 (or hi/lo split) store are fused in the TMEM epilogue.
 #include "conv_tc.cuh"
+#include "head_tail.cuh"
 #include "ptx.cuh"
 
 namespace cerb {
@@ -49,6 +50,12 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   uint64_t* tfull_bar = empty_bar + n_stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // [C][96] fp32 when the head tail is fused (16-byte aligned for float4 reads)
+  float* s_head_w = reinterpret_cast<float*>(
+      (reinterpret_cast<uintptr_t>(tmem_holder + 1) + 15) & ~static_cast<uintptr_t>(15));
+  if (p.head_classes > 0) {
+    for (int i = threadIdx.x; i < p.head_classes * 96; i += blockDim.x) s_head_w[i] = p.head_w[i];
+  }
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.in_hi[i]);
@@ -178,6 +185,9 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
+      float hacc[kHeadMaxC];
+#pragma unroll
+      for (int c = 0; c < kHeadMaxC; ++c) hacc[c] = 0.0f;
       for (int j = 0; j < p.BN; j += 32) {
         uint32_t r[32];
         float v[32];
@@ -236,6 +246,24 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
           }
+          if (p.head_classes > 0) {
+            // fused 1x1 96 -> C of the classification head: this thread owns the whole pixel
+#pragma unroll
+            for (int c = 0; c < kHeadMaxC; ++c) {
+              if (c < p.head_classes) {
+                const float4* w4 = reinterpret_cast<const float4*>(s_head_w + c * 96 + j);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 w = w4[i];
+                  hacc[c] = fmaf(v[4 * i + 0], w.x, hacc[c]);
+                  hacc[c] = fmaf(v[4 * i + 1], w.y, hacc[c]);
+                  hacc[c] = fmaf(v[4 * i + 2], w.z, hacc[c]);
+                  hacc[c] = fmaf(v[4 * i + 3], w.w, hacc[c]);
+                }
+              }
+            }
+            continue;
+          }
           const size_t ooff = pix * p.out_cs + p.out_coff + n0 + j;
           uint4* oh = reinterpret_cast<uint4*>(p.out_hi + ooff);
           if (!SPLIT) {
@@ -270,6 +298,18 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (p.head_classes > 0 && valid) {
+#pragma unroll
+        for (int c = 0; c < kHeadMaxC; ++c)
+          if (c < p.head_classes) hacc[c] += __ldg(p.head_b + c);
+        const int y_off = static_cast<int>((p.H - p.oh) * 0.5), x_off = static_cast<int>((p.W - p.ow) * 0.5);
+        const int cy = oy - y_off, cx = ox - x_off;
+        float* dst = nullptr;
+        if (cy >= 0 && cy < p.oh && cx >= 0 && cx < p.ow)
+          dst = p.canvas + ((static_cast<size_t>(img) * p.oh + cy) * p.ow + cx) * p.canvas_c + p.canvas_coff;
+        head_tail(hacc, p.head_classes, p.head_mode,
+                  p.logits != nullptr ? p.logits + pix * p.head_classes : nullptr, dst);
+      }
       acc = (acc + 1) % kAccStages;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -287,7 +327,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
 
 void conv_tc_plan_pipeline(ConvKParams& p, bool split) {
   p.stage_bytes = (split ? 2 : 1) * (kATileBytes + p.BN * 128);
-  int n = (196 * 1024) / p.stage_bytes;
+  int n = (192 * 1024) / p.stage_bytes;
   if (n > 8) n = 8;
   if (n < 2) n = 2;
   p.n_stages = n;
@@ -297,7 +337,7 @@ size_t conv_tc_smem_bytes(const ConvKParams& p) {
   // tiles + barriers (+ tmem holder) + slack for the manual 1024-byte alignment.
   // Always above half the SM's shared memory so that exactly one CTA (and one 512-column
   // TMEM allocation) lives on an SM at a time.
-  size_t b = static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024;
+  size_t b = static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 + 3200;
   if (b < 120 * 1024) b = 120 * 1024;
   return b;
 }

@@ -51,6 +51,13 @@ struct ConvKParams {
   int res_cs;
   int res_coff;
   int relu;
+  // fused classification-head tail (head_classes > 0): see CERB_OP_CONV.aux_classes
+  const float* head_w;   // [C][96] fp32
+  const float* head_b;   // [C]
+  int head_classes, head_mode;
+  float* canvas;         // [N, oh, ow, canvas_c]
+  float* logits;         // optional [N, H, W, C]
+  int oh, ow, canvas_c, canvas_coff;
   // pipeline
   int n_stages;
   int stage_bytes;

@@ -41,7 +41,7 @@ cudaError_t launch_head(const HeadParams& p, cudaStream_t s);
 
 struct PClassParams {
   ActRef x4;            // [N,h4,w4,512] encoder bottom features
-  const float* params;  // bn1 scale[512], bn1 shift[512], W1[256][512], b1[256], W2[C][256], b2[C]
+  const float* params;  // bn1 scale[512], bn1 shift[512], W1^T[512][256], b1[256], W2[C][256], b2[C]
   int classes;
   float* logits;        // optional [N,C]
   float* canvas;        // [N,oh,ow,canvas_c]

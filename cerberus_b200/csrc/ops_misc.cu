@@ -127,39 +127,53 @@ __global__ void maxpool_kernel(ActRef in, ActRef out) {
 }
 
 // ------------------------------------------------------------------ upsample + add
+// out = skip + bilinear_x2(prev), align_corners=False. One thread produces a 2x2 block of
+// output pixels (X in {2i+1, 2i+2}, Y in {2j+1, 2j+2}, i/j from -1) for 8 channels: the four
+// outputs share the same four `prev` taps, so `prev` is read once instead of four times.
+// Per-output arithmetic is identical to the direct form (src = (dst + 0.5) / 2 - 0.5 clamped).
 __global__ void upadd_kernel(ActRef skip, ActRef prev, ActRef out) {
   const int cg = out.c >> 3;
-  const size_t total = static_cast<size_t>(out.n) * out.h * out.w * cg;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % cg);
-    size_t t = i / cg;
-    const int X = static_cast<int>(t % out.w);
-    t /= out.w;
-    const int Y = static_cast<int>(t % out.h);
-    const int n = static_cast<int>(t / out.h);
-    // src = (dst + 0.5) / 2 - 0.5, clamped at 0; second tap clamped at the last row/column.
-    const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.0f);
-    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f);
-    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
-    const int y1 = min(y0 + 1, prev.h - 1), x1 = min(x0 + 1, prev.w - 1);
-    const float ly = sy - y0, lx = sx - x0;
-    const float hy = 1.0f - ly, hx = 1.0f - lx;
-    const size_t base = static_cast<size_t>(n) * prev.h;
-    float p00[8], p01[8], p10[8], p11[8], sk[8], o[8];
-    load8(prev.hi, prev.lo, ((base + y0) * prev.w + x0) * prev.c + g * 8, p00);
-    load8(prev.hi, prev.lo, ((base + y0) * prev.w + x1) * prev.c + g * 8, p01);
-    load8(prev.hi, prev.lo, ((base + y1) * prev.w + x0) * prev.c + g * 8, p10);
-    load8(prev.hi, prev.lo, ((base + y1) * prev.w + x1) * prev.c + g * 8, p11);
-    const size_t ooff = ((static_cast<size_t>(n) * out.h + Y) * out.w + X) * out.c + g * 8;
-    load8(skip.hi, skip.lo, ((static_cast<size_t>(n) * skip.h + Y) * skip.w + X) * skip.c + g * 8,
-          sk);
+  const int pw = prev.w + 1, ph = prev.h + 1;  // pair grid
+  const size_t total = static_cast<size_t>(out.n) * ph * pw * cg;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % cg);
+    size_t t = idx / cg;
+    const int i = static_cast<int>(t % pw) - 1;
+    t /= pw;
+    const int j = static_cast<int>(t % ph) - 1;
+    const int n = static_cast<int>(t / ph);
+    const int x0 = max(i, 0), x1 = min(i + 1, prev.w - 1);
+    const int y0 = max(j, 0), y1 = min(j + 1, prev.h - 1);
+    const size_t pb = static_cast<size_t>(n) * prev.h;
+    float p00[8], p01[8], p10[8], p11[8];
+    load8(prev.hi, prev.lo, ((pb + y0) * prev.w + x0) * prev.c + g * 8, p00);
+    load8(prev.hi, prev.lo, ((pb + y0) * prev.w + x1) * prev.c + g * 8, p01);
+    load8(prev.hi, prev.lo, ((pb + y1) * prev.w + x0) * prev.c + g * 8, p10);
+    load8(prev.hi, prev.lo, ((pb + y1) * prev.w + x1) * prev.c + g * 8, p11);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float up = hy * (hx * p00[e] + lx * p01[e]) + ly * (hx * p10[e] + lx * p11[e]);
-      o[e] = sk[e] + up;
+    for (int dy = 0; dy < 2; ++dy) {
+      const int Y = 2 * j + 1 + dy;
+      if (Y < 0 || Y >= out.h) continue;
+      const float ly = (j < 0) ? 0.0f : (dy == 0 ? 0.25f : 0.75f);
+      const float hy = 1.0f - ly;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int X = 2 * i + 1 + dx;
+        if (X < 0 || X >= out.w) continue;
+        const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
+        const float hx = 1.0f - lx;
+        const size_t off = ((static_cast<size_t>(n) * out.h + Y) * out.w + X) * out.c + g * 8;
+        float sk[8], o[8];
+        load8(skip.hi, skip.lo, ((static_cast<size_t>(n) * skip.h + Y) * skip.w + X) * skip.c + g * 8, sk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float up = hy * (hx * p00[e] + lx * p01[e]) + ly * (hx * p10[e] + lx * p11[e]);
+          o[e] = sk[e] + up;
+        }
+        store8(out.hi, out.lo, off, o);
+      }
     }
-    store8(out.hi, out.lo, ooff, o);
   }
 }
 
@@ -271,8 +285,8 @@ __global__ void pclass_kernel(PClassParams p) {
   __syncthreads();
   for (int o = threadIdx.x; o < 256; o += blockDim.x) {
     float s = 0.0f;
-    const float* wr = W1 + static_cast<size_t>(o) * 512;
-    for (int k = 0; k < 512; ++k) s = fmaf(pooled[k], wr[k], s);
+    // W1 is packed transposed ([512][256]) so that a warp reads consecutive floats
+    for (int k = 0; k < 512; ++k) s = fmaf(pooled[k], W1[static_cast<size_t>(k) * 256 + o], s);
     hidden[o] = fmaxf(s + b1[o], 0.0f);
   }
   __syncthreads();
@@ -327,7 +341,7 @@ cudaError_t launch_maxpool(ActRef in, ActRef out, cudaStream_t s) {
 }
 
 cudaError_t launch_upadd(ActRef skip, ActRef prev, ActRef out, cudaStream_t s) {
-  const size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.c >> 3);
+  const size_t total = static_cast<size_t>(out.n) * (prev.h + 1) * (prev.w + 1) * (out.c >> 3);
   upadd_kernel<<<grid_for(total, 256), 256, 0, s>>>(skip, prev, out);
   return cudaGetLastError();
 }

@@ -533,8 +533,10 @@ struct WarpHeap {
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
                  int* __restrict__ out, uint64_t* __restrict__ heap_k, uint8_t* __restrict__ heap_b,
-                 int* __restrict__ list_idx, float* __restrict__ list_val, int H, int W) {
+                 int* __restrict__ list_idx, float* __restrict__ list_val,
+                 const int* __restrict__ run_flag, int H, int W) {
   extern __shared__ __align__(16) uint8_t ws_smem[];
+  if (run_flag != nullptr && run_flag[blockIdx.x] == 0) return;  // the fast path handled this image
   __shared__ int s_warp[kWsThreads / 32];
   __shared__ int s_carry;
   const int hw = H * W;
@@ -620,6 +622,197 @@ k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
   }
   __syncthreads();
   for (int p = threadIdx.x; p < hw; p += kWsThreads) {
+    const uint16_t l = lab16[p];
+    o[p] = l == kWsOutside ? 0 : static_cast<int>(l);
+  }
+}
+
+// ---- component-parallel fast path. Inside one 4-connected component of the mask the order of
+// queue events depends only on that component's own entries: non-marker entries carry unique,
+// monotonically assigned ages, so the pop order restricted to a component is a total order on
+// its own keys - unless two of its marker pixels have bit-equal values (age 0 ties are resolved
+// by the global heap layout). Marker pixels without an unlabeled in-mask neighbour push nothing
+// and are inert. So: one thread per mask component floods it with a private heap holding only
+// its boundary markers; markers leave the queue in non-decreasing value order, so a tie shows
+// up as two consecutive marker pops with equal values - the tile is then handed, untouched, to
+// the exact whole-tile emulation above (k_watershed_smem). Results are identical either way.
+constexpr int kWcThreads = 256;
+constexpr int kWcPool = 9000;     // heap entries (8 bytes) in shared memory
+constexpr int kWcMaxComp = 1024;
+
+__global__ void __launch_bounds__(kWcThreads, 1)
+k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
+                 const int* __restrict__ Lroot, const int* __restrict__ csize,
+                 int* __restrict__ out, int* __restrict__ aux_map, int* __restrict__ slow_flag, int H,
+                 int W) {
+  extern __shared__ __align__(16) uint8_t ws_smem[];
+  __shared__ int s_warp_cnt[kWcThreads / 32], s_warp_sz[kWcThreads / 32];
+  __shared__ int s_ncomp, s_total, s_unsafe;
+  const int hw = H * W;
+  uint64_t* pool = reinterpret_cast<uint64_t*>(ws_smem);
+  uint16_t* lab16 = reinterpret_cast<uint16_t*>(ws_smem + sizeof(uint64_t) * kWcPool);
+  int* c_off = reinterpret_cast<int*>(ws_smem + sizeof(uint64_t) * kWcPool + 2u * ((hw + 7) & ~7));
+  int* c_cnt = c_off + kWcMaxComp;
+  const size_t base = static_cast<size_t>(blockIdx.x) * hw;
+  const float* v = val + base;
+  const uint8_t* m = msk + base;
+  const int* L = Lroot + base;
+  const int* sz = csize + base;
+  int* o = out + base;
+  int* amap = aux_map + base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_ncomp = 0; s_total = 0; s_unsafe = 0; }
+  // A: stage the label map; clear the per-root "has a marker" flag
+  for (int p = tid; p < hw; p += kWcThreads) {
+    const bool in = m[p] != 0;
+    lab16[p] = in ? static_cast<uint16_t>(o[p]) : kWsOutside;
+    if (in && L[p] == p) amap[p] = 0;
+  }
+  __syncthreads();
+  for (int p = tid; p < hw; p += kWcThreads) {
+    const uint16_t l = lab16[p];
+    if (l != 0 && l != kWsOutside) amap[L[p]] = 1;
+  }
+  __syncthreads();
+  // B: number the components that own markers (raster order) and carve the heap pool
+  for (int start = 0; start < hw; start += kWcThreads) {
+    const int p = start + tid;
+    int flag = 0, size = 0;
+    if (p < hw && m[p] && L[p] == p) {
+      if (amap[p]) { flag = 1; size = sz[p]; } else amap[p] = -1;
+    }
+    int c = flag, a = size;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int tc = __shfl_up_sync(0xffffffffu, c, d), ta = __shfl_up_sync(0xffffffffu, a, d);
+      if (lane >= d) { c += tc; a += ta; }
+    }
+    if (lane == 31) { s_warp_cnt[warp] = c; s_warp_sz[warp] = a; }
+    __syncthreads();
+    int bc = s_ncomp, ba = s_total;
+    for (int w2 = 0; w2 < warp; ++w2) { bc += s_warp_cnt[w2]; ba += s_warp_sz[w2]; }
+    if (flag) {
+      const int k = bc + c - 1;
+      if (k < kWcMaxComp) { c_off[k] = ba + a - size; c_cnt[k] = 0; }
+      amap[p] = k;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tc = 0, ta = 0;
+      for (int w2 = 0; w2 < kWcThreads / 32; ++w2) { tc += s_warp_cnt[w2]; ta += s_warp_sz[w2]; }
+      s_ncomp += tc;
+      s_total += ta;
+    }
+    __syncthreads();
+  }
+  const int ncomp = s_ncomp;
+  const bool fits = ncomp <= kWcMaxComp && s_total <= kWcPool;
+  if (fits) {
+    // C: boundary markers go straight into their component's heap slice (arbitrary order)
+    for (int p = tid; p < hw; p += kWcThreads) {
+      const uint16_t l = lab16[p];
+      if (l == 0 || l == kWsOutside) continue;
+      const int x = p % W;
+      const bool b = (p >= W && lab16[p - W] == 0) || (x > 0 && lab16[p - 1] == 0) ||
+                     (x < W - 1 && lab16[p + 1] == 0) || (p + W < hw && lab16[p + W] == 0);
+      if (!b) continue;
+      const int k = amap[L[p]];
+      const int slot = c_off[k] + atomicAdd(&c_cnt[k], 1);
+      pool[slot] = ws_entry(v[p], 0u, p);
+    }
+    __syncthreads();
+    // D: one thread per component
+    for (int k = tid; k < ncomp; k += kWcThreads) {
+      uint64_t* hp = pool + c_off[k];
+      int n = c_cnt[k];
+      for (int j = 1; j < n; ++j) {  // in-place build by successive pushes
+        const uint64_t e = hp[j];
+        const uint64_t ek = e >> 16;
+        int c = j;
+        while (c > 0) {
+          const int parent = (c - 1) >> 1;
+          const uint64_t pe = hp[parent];
+          if (!(ek < (pe >> 16))) break;
+          hp[c] = pe;
+          c = parent;
+        }
+        hp[c] = e;
+      }
+      uint32_t age = 1;
+      uint64_t last_marker = ~0ull;
+      bool tie = false;
+      while (n > 0) {
+        const uint64_t top = hp[0];
+        const int ei = static_cast<int>(top & 0xFFFFu);
+        if (((top >> 16) & 0xFFFFu) == 0) {  // a marker entry (age 0)
+          if ((top >> 32) == last_marker) { tie = true; break; }
+          last_marker = top >> 32;
+        }
+        const int x = ei % W;
+        const uint16_t lab = lab16[ei];
+        const int q0 = ei - W, q1 = ei - 1, q2 = ei + 1, q3 = ei + W;
+        const bool c0 = q0 >= 0 && lab16[q0] == 0;
+        const bool c1 = x > 0 && lab16[q1] == 0;
+        const bool c2 = x < W - 1 && lab16[q2] == 0;
+        const bool c3 = q3 < hw && lab16[q3] == 0;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        if (c0) v0 = __ldg(v + q0);
+        if (c1) v1 = __ldg(v + q1);
+        if (c2) v2 = __ldg(v + q2);
+        if (c3) v3 = __ldg(v + q3);
+        // remove the root
+        --n;
+        if (n > 0) {
+          const uint64_t xe = hp[n];
+          const uint64_t xk = xe >> 16;
+          int i = 0;
+          for (;;) {
+            const int l = 2 * i + 1;
+            if (l >= n) break;
+            const uint64_t le = hp[l];
+            const uint64_t re = (l + 1 < n) ? hp[l + 1] : ~0ull;
+            int sidx = i;
+            uint64_t sk = xk, se = xe;
+            if ((le >> 16) < sk) { sidx = l; sk = le >> 16; se = le; }
+            if ((re >> 16) < sk) { sidx = l + 1; sk = re >> 16; se = re; }
+            if (sidx == i) break;
+            hp[i] = se;
+            i = sidx;
+          }
+          hp[i] = xe;
+        }
+#define CERB_WC_PUSH(cond, vv, qq)                                  \
+        if (cond) {                                                     \
+          ++age;                                                        \
+          lab16[qq] = lab;                                              \
+          const uint64_t e = ws_entry(vv, age, qq);                     \
+          const uint64_t ek = e >> 16;                                  \
+          int c = n++;                                                  \
+          while (c > 0) {                                               \
+            const int parent = (c - 1) >> 1;                            \
+            const uint64_t pe = hp[parent];                             \
+            if (!(ek < (pe >> 16))) break;                              \
+            hp[c] = pe;                                                 \
+            c = parent;                                                 \
+          }                                                             \
+          hp[c] = e;                                                    \
+        }
+        CERB_WC_PUSH(c0, v0, q0)
+        CERB_WC_PUSH(c1, v1, q1)
+        CERB_WC_PUSH(c2, v2, q2)
+        CERB_WC_PUSH(c3, v3, q3)
+#undef CERB_WC_PUSH
+      }
+      if (tie) s_unsafe = 1;
+    }
+  }
+  __syncthreads();
+  if (!fits || s_unsafe) {
+    if (tid == 0) slow_flag[blockIdx.x] = 1;  // `out` still holds markers * mask
+    return;
+  }
+  if (tid == 0) slow_flag[blockIdx.x] = 0;
+  for (int p = tid; p < hw; p += kWcThreads) {
     const uint16_t l = lab16[p];
     o[p] = l == kWsOutside ? 0 : static_cast<int>(l);
   }
@@ -984,7 +1177,6 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
   k_nuc_threshold<<<g, kThreads, 0, s>>>(dcanvas, C, ch0, msk0, mrk, ws->val, ws->any_fg, hw);
   k_erode_cross<<<g, kThreads, 0, s>>>(msk0, msk, H, W);
   ctx->launches += 2;
-  cc_label(ctx, ws, msk, n, H, W, 8);  // :366-368
   cc_label(ctx, ws, mrk, n, H, W, 4);  // :370-373
   // :375-376 binary_fill_holes(marker)
   uint8_t* bg = msk0;  // msk0 is dead after the erosion
@@ -998,6 +1190,8 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
   cc_label(ctx, ws, mrk, n, H, W, 0);
   k_rank_roots<<<n, 1024, 0, s>>>(mrk, ws->L, ws->rank, ws->count, nullptr, hw);
   k_apply_rank<<<g, kThreads, 0, s>>>(mrk, ws->L, ws->rank, ws->lab, hw);
+  // :366-368 (done last so that ws->L / ws->size describe the mask components for the watershed)
+  cc_label(ctx, ws, msk, n, H, W, 8);
   k_mask_markers<<<g, kThreads, 0, s>>>(ws->lab, msk, hw);
   // :378 watershed(-inner, marker, mask)
   if (hw <= 65536) {
@@ -1008,9 +1202,23 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
                                      226 * 1024));
       attr_set = true;
     }
+    const size_t smem_c = sizeof(uint64_t) * kWcPool + 2u * ((hw + 7) & ~7) + 8u * kWcMaxComp + 16;
+    static bool attr_c = false;
+    if (!attr_c) {
+      CERB_CUDA(cudaFuncSetAttribute(k_watershed_comp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     226 * 1024));
+      attr_c = true;
+    }
+    const bool fast = (ctx->ws_mode != 1);
+    if (fast) {
+      k_watershed_comp<<<n, kWcThreads, smem_c, s>>>(ws->val, msk, ws->L, ws->size, ws->lab,
+                                                     ws->heap_a, ws->count, H, W);
+      ctx->launches += 1;
+    }
     k_watershed_smem<<<n, kWsThreads, smem, s>>>(ws->val, msk, ws->lab,
                                                  reinterpret_cast<uint64_t*>(ws->heap_k), ws->m0,
-                                                 ws->rank, ws->heap_v, H, W);
+                                                 ws->rank, ws->heap_v, fast ? ws->count : nullptr, H,
+                                                 W);
   } else {
     k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W);
   }

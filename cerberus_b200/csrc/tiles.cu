@@ -63,6 +63,20 @@ __global__ void k_stitch(const float* __restrict__ patches, int n, int oh, int o
 
 }  // namespace
 
+extern "C" void* cerb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    fail(CERB_ERR_CUDA, "cerb_host_alloc(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void cerb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 extern "C" void* cerb_dev_alloc(cerb_ctx* ctx, size_t bytes) {
   if (!ctx || bytes == 0) return nullptr;
   cudaSetDevice(ctx->device);

@@ -32,7 +32,16 @@ class DevicePostProc:
                 _lib.check(-1, "cerb_dev_alloc")
             self.dev[t] = p
         self.any_fg = np.zeros(n, dtype=np.int32)
-        self.host = {t: np.empty((n, h, w), dtype=np.int32) for t in self.tissues}
+        # pinned host buffers: the label maps are the step's result (D2H every step)
+        self._pinned = {}
+        self.host = {}
+        for t in self.tissues:
+            hp = lib.cerb_host_alloc(self.nbytes)
+            if not hp:
+                _lib.check(-1, "cerb_host_alloc")
+            self._pinned[t] = hp
+            buf = (ctypes.c_int32 * (n * h * w)).from_address(hp)
+            self.host[t] = np.frombuffer(buf, dtype=np.int32).reshape(n, h, w)
         self.d2h_bytes = len(self.tissues) * self.nbytes
 
     def run(self, plan):
@@ -69,3 +78,7 @@ class DevicePostProc:
         for p in self.dev.values():
             self.ctx.lib.cerb_dev_free(self.ctx.handle, ctypes.c_void_p(p))
         self.dev = {}
+        self.host = {}
+        for hp in self._pinned.values():
+            self.ctx.lib.cerb_host_free(ctypes.c_void_p(hp))
+        self._pinned = {}

@@ -123,7 +123,7 @@ class PackedModel:
             w2 = _np(sd[p + ".conv2.weight"])
             b2 = _np(sd[p + ".conv2.bias"])
             ncls = w2.shape[0]
-            params = np.concatenate([s1, sh1, w1.reshape(256, 512).ravel(), b1,
+            params = np.concatenate([s1, sh1, w1.reshape(256, 512).T.ravel(), b1,
                                      w2.reshape(ncls, 256).ravel(), b2]).astype(np.float32)
             L["pclass"] = {"w_off": blob.add(params), "classes": ncls}
         self.blob = blob.finish()
@@ -132,7 +132,7 @@ class PackedModel:
 class PlanSpec:
     """Tensors + ops for one batch shape. Pure host data (testable without a GPU)."""
 
-    def __init__(self, model, n, h, w, out_h, out_w, want_logits=False):
+    def __init__(self, model, n, h, w, out_h, out_w, want_logits=False, fuse_head=True):
         if h % 16 or w % 16:
             raise ValueError("input size must be a multiple of 16 (got %dx%d)" % (h, w))
         if out_h > h or out_w > w:
@@ -202,7 +202,7 @@ class PlanSpec:
             s0 = T("s0", n, h, w, 64)
             a0 = T("a0", n, h, w, 64)
             b0 = T("b0", n, h, w, 64)
-            hid = T("hid", n, h, w, 96)
+            hid = T("hid", n, h, w, 96) if not fuse_head else -1
             for di, d in enumerate(model.seg_decoders):
                 self._conv(L["dec.%s.0.1" % d], u4a, u4b, relu=1, in_coff=di * 256)
                 self._op(_lib.OP_UPADD, in0=x2, in1=u4b, out=s2)
@@ -214,7 +214,6 @@ class PlanSpec:
                 self._op(_lib.OP_UPADD, in0=x0, in1=b1, out=s0)
                 self._conv(L["dec.%s.3.0" % d], s0, a0, relu=1)
                 self._conv(L["dec.%s.3.1" % d], a0, b0, relu=1)
-                self._conv(L["head.%s.hidden" % d], b0, hid, relu=1)
                 ho = L["head.%s.out" % d]
                 key = HEAD_NAME_MAP[d]
                 lo, hi_ = model.idx_dict[key]
@@ -223,8 +222,16 @@ class PlanSpec:
                     lg = T("logits." + key, n, h, w, ho["classes"], _lib.CERB_F32)
                     self.logit_tensors[key] = lg
                 mode = _lib.HEAD_INST if ho["clf"] == "INST" else _lib.HEAD_TYPE
-                self._op(_lib.OP_HEAD, in0=hid, out=canvas, out_coff=lo, cout=ho["classes"],
-                         head_mode=mode, logits_out=lg, w_off=ho["w_off"], b_off=ho["b_off"])
+                if fuse_head:
+                    # 1x1 64->96 + BN + ReLU + 1x1 96->C + softmax/argmax/crop in ONE kernel: the
+                    # 96-channel hidden tensor never exists in HBM
+                    self._conv(L["head.%s.hidden" % d], b0, canvas, relu=1, out_coff=lo,
+                               aux_classes=ho["classes"], aux_w_off=ho["w_off"],
+                               aux_b_off=ho["b_off"], head_mode=mode, logits_out=lg)
+                else:
+                    self._conv(L["head.%s.hidden" % d], b0, hid, relu=1)
+                    self._op(_lib.OP_HEAD, in0=hid, out=canvas, out_coff=lo, cout=ho["classes"],
+                             head_mode=mode, logits_out=lg, w_off=ho["w_off"], b_off=ho["b_off"])
         if model.has_pclass:
             pc = L["pclass"]
             lg = -1
@@ -243,25 +250,29 @@ class PlanSpec:
     def _op(self, kind, **kw):
         d = dict(kind=kind, in0=-1, in1=-1, out=-1, in_coff=0, in_c=0, out_coff=0, cout=0, kh=0,
                  kw=0, stride=0, pad=0, relu=0, stem=0, head_mode=0, logits_out=-1, w_off=-1,
-                 w_lo_off=-1, b_off=-1, box_w=0, w_shift=0)
+                 w_lo_off=-1, b_off=-1, box_w=0, w_shift=0, aux_classes=0, aux_w_off=-1,
+                 aux_b_off=-1)
         d.update(kw)
         self.ops.append(d)
 
-    def _conv(self, layer, src, dst, relu, stride=1, residual=-1, stem=0, in_coff=0):
+    def _conv(self, layer, src, dst, relu, stride=1, residual=-1, stem=0, in_coff=0, out_coff=0,
+              **extra):
         k = layer["kh"]
         self._op(_lib.OP_CONV, in0=src, in1=residual, out=dst, in_coff=in_coff,
-                 in_c=(8 if stem else layer["cin"]), out_coff=0, cout=layer["cout"], kh=k, kw=k,
-                 stride=stride, pad=k // 2, relu=relu, stem=stem, w_off=layer["w_off"],
-                 w_lo_off=layer["w_lo_off"], b_off=layer["b_off"], w_shift=layer.get("w_shift", 0))
+                 in_c=(8 if stem else layer["cin"]), out_coff=out_coff, cout=layer["cout"], kh=k,
+                 kw=k, stride=stride, pad=k // 2, relu=relu, stem=stem, w_off=layer["w_off"],
+                 w_lo_off=layer["w_lo_off"], b_off=layer["b_off"], w_shift=layer.get("w_shift", 0),
+                 **extra)
 
     def conv_flops(self):
         """Algorithmic conv FLOPs (2*M*N*K, no padding / zero-weight credit) of one batch."""
         total = 0
         for op in self.ops:
             if op["kind"] == _lib.OP_CONV:
-                _, n, h, w, _, _ = self.tensors[op["out"]]
+                _, n, h, w, _, _ = self.tensors[op["in0"] if op["aux_classes"] else op["out"]]
                 cin = 3 if op["stem"] else op["in_c"]
                 total += 2 * n * h * w * op["cout"] * op["kh"] * op["kw"] * cin
+                total += 2 * n * h * w * op["aux_classes"] * 96
             elif op["kind"] == _lib.OP_HEAD:
                 _, n, h, w, _, _ = self.tensors[op["in0"]]
                 total += 2 * n * h * w * op["cout"] * 96

@@ -94,7 +94,13 @@ typedef struct cerb_op {
   int32_t box_w;      /* CONV: tile box width override (power of two <= 128), 0 = auto  */
   int32_t w_shift;    /* CONV: weights are stored multiplied by 2^w_shift (keeps the fp16 lo plane out
                          of the subnormal range); the epilogue multiplies the accumulator by 2^-w_shift */
-  int32_t reserved[2];
+  int32_t aux_classes; /* CONV: > 0 fuses the classification-head tail into the epilogue: this conv is
+                          the 1x1 64->96 hidden layer (+BN+ReLU), `out` is the fp32 CANVAS tensor, and
+                          the 1x1 96->aux_classes (+bias) + softmax / argmax / centre crop of CERB_OP_HEAD
+                          run per pixel in registers; head_mode / logits_out / out_coff as for HEAD */
+  int32_t reserved;
+  int64_t aux_w_off;   /* fp32 [aux_classes][96] */
+  int64_t aux_b_off;   /* fp32 [aux_classes] */
 } cerb_op;
 
 /* ---- context ------------------------------------------------------------------- */
@@ -175,6 +181,10 @@ int cerb_mask_lumen(cerb_ctx* ctx, int32_t* lumen_dev, const int32_t* gland_dev,
 
 /* cv2.getStructuringElement(MORPH_ELLIPSE, (k,k)) as row runs [j1[i], j2[i]) (1 <= k <= 32). */
 int cerb_ellipse_rows(int k, int32_t* j1, int32_t* j2);
+
+/* Pinned (page-locked) host memory for fast asynchronous H2D / D2H copies. */
+void* cerb_host_alloc(size_t bytes);
+void cerb_host_free(void* p);
 
 /* Device scratch helpers for callers that keep data resident between calls. */
 void* cerb_dev_alloc(cerb_ctx* ctx, size_t bytes);
