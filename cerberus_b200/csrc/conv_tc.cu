@@ -165,13 +165,18 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------ epilogue (2 groups x 4 warps)
+    // Group g owns accumulator stage g and every second tile of this CTA, so two epilogues run
+    // concurrently (layers with a short K loop are epilogue-bound with a single group).
     const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int py = m >> p.bw_log2, px = m & bw_mask;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int acc = grp;
+    uint32_t use = 0;
+    for (int tile = blockIdx.x + grp * gridDim.x; grp < kAccStages && tile < p.n_tiles;
+         tile += kAccStages * gridDim.x, ++use) {
+      const uint32_t acc_phase = use & 1;
       const int nt = tile % p.n_ntiles;
       const int mt = tile / p.n_ntiles;
       const int tx = mt % p.tiles_x;
@@ -310,8 +315,6 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
         head_tail(hacc, p.head_classes, p.head_mode,
                   p.logits != nullptr ? p.logits + pix * p.head_classes : nullptr, dst);
       }
-      acc = (acc + 1) % kAccStages;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 

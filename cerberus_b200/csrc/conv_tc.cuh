@@ -17,7 +17,8 @@
 namespace cerb {
 
 constexpr int kConvMaxTaps = 16;
-constexpr int kConvThreads = 192;  // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2-5: epilogue
+// warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2-5 / 6-9: epilogue groups 0 / 1
+constexpr int kConvThreads = 320;
 
 struct ConvTap {
   int8_t map;  // which input tensor map (parity view) this tap reads
