@@ -103,6 +103,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_rate(args, seconds, batch):
     """The reference's CPU path (oracle restatement: models/run_desc.py:439-502 +
     loader/postproc.py post_process) on this host's cores. Returns (tiles/s, cores, sample)."""
@@ -112,6 +119,7 @@ def cpu_reference_rate(args, seconds, batch):
     margs = synth.model_args()
     sd = synth.make_state_dict(seed=0)
     tiles = synth.synthetic_tiles(batch, TILE, TILE, seed=123)
+    torch.set_num_threads(host_cores())  # torchrun exports OMP_NUM_THREADS=1
     cores = torch.get_num_threads()
     post = None
     if not args.no_postproc:
@@ -152,6 +160,7 @@ def run_reference(args):
     sd = synth.make_state_dict(seed=0)
     b = args.ref_batch
     tiles = synth.synthetic_tiles(b, TILE, TILE, seed=123)
+    torch.set_num_threads(host_cores())  # torchrun exports OMP_NUM_THREADS=1
     post = None
     if not args.no_postproc:
         try:

@@ -131,7 +131,7 @@ __global__ void maxpool_kernel(ActRef in, ActRef out) {
 // output pixels (X in {2i+1, 2i+2}, Y in {2j+1, 2j+2}, i/j from -1) for 8 channels: the four
 // outputs share the same four `prev` taps, so `prev` is read once instead of four times.
 // Per-output arithmetic is identical to the direct form (src = (dst + 0.5) / 2 - 0.5 clamped).
-__global__ void upadd_kernel(ActRef skip, ActRef prev, ActRef out) {
+__global__ void __launch_bounds__(256, 4) upadd_kernel(ActRef skip, ActRef prev, ActRef out) {
   const int cg = out.c >> 3;
   const int pw = prev.w + 1, ph = prev.h + 1;  // pair grid
   const size_t total = static_cast<size_t>(out.n) * ph * pw * cg;

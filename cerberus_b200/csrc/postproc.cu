@@ -59,15 +59,30 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 }
 
 // fg: [n][hw] bytes (0/1). L: [n][hw].
+// Initial label = first pixel of the horizontal run inside the warp's 32-pixel segment (found
+// with one ballot), so a run is a depth-1 tree before any atomic is issued.
 __global__ void k_cc_init(const uint8_t* __restrict__ fg, int* __restrict__ L, int* __restrict__ size,
-                          int hw) {
+                          int hw, int W) {
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
-    L[base + p] = fg[base + p] ? p : -1;
-    size[base + p] = 0;
+  const int lane = threadIdx.x & 31;
+  const int hw_up = (hw + 31) & ~31;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw_up; p += gridDim.x * blockDim.x) {
+    const bool inb = p < hw;
+    const bool f = inb && fg[base + p];
+    const bool prev_f = __shfl_up_sync(0xffffffffu, f ? 1 : 0, 1) != 0;
+    const bool cont = f && lane > 0 && prev_f && (p % W) != 0;  // continues the previous lane's run
+    const unsigned breaks = ~__ballot_sync(0xffffffffu, cont);
+    if (inb) {
+      const int start = 31 - __clz(breaks & (0xffffffffu >> (31 - lane)));
+      L[base + p] = f ? p - (lane - start) : -1;
+      size[base + p] = 0;
+    }
   }
 }
 
+// Unions that the run initialisation has not already implied: the horizontal link across a
+// 32-pixel segment boundary, and the vertical link unless the left and upper-left neighbours
+// are both foreground (then the link was made one pixel to the left).
 __global__ void k_cc_merge(const uint8_t* __restrict__ fg, int* __restrict__ L, int H, int W) {
   const int hw = H * W;
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
@@ -76,8 +91,11 @@ __global__ void k_cc_merge(const uint8_t* __restrict__ fg, int* __restrict__ L, 
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
     if (!f[p]) continue;
     const int x = p % W;
-    if (x > 0 && f[p - 1]) uf_union(l, p, p - 1);
-    if (p >= W && f[p - W]) uf_union(l, p, p - W);
+    const bool left = x > 0 && f[p - 1];
+    if (left && (p & 31) == 0) uf_union(l, p, p - 1);
+    if (p >= W && f[p - W]) {
+      if (!(left && f[p - W - 1])) uf_union(l, p, p - W);
+    }
   }
 }
 
@@ -1075,7 +1093,7 @@ dim3 grid2(int hw, int n) {
 void cc_label(cerb_ctx* ctx, Workspace* ws, uint8_t* fg, int n, int H, int W, int min_size) {
   const int hw = H * W;
   cudaStream_t s = ctx->stream;
-  k_cc_init<<<grid2(hw, n), kThreads, 0, s>>>(fg, ws->L, ws->size, hw);
+  k_cc_init<<<grid2(hw, n), kThreads, 0, s>>>(fg, ws->L, ws->size, hw, W);
   k_cc_merge<<<grid2(hw, n), kThreads, 0, s>>>(fg, ws->L, H, W);
   k_cc_flatten_count<<<grid2(hw, n), kThreads, 0, s>>>(fg, ws->L, ws->size, hw);
   ctx->launches += 3;
