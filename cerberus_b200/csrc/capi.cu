@@ -84,6 +84,10 @@ struct cerb_plan {
   uint8_t* blob = nullptr;
   size_t blob_bytes = 0;
   int prep_in_tensor = -1;
+  // the op list is launch-bound on the host (~100 small launches): it is captured into a CUDA
+  // graph on the second run (the first run doubles as warm-up / attribute setup) and replayed
+  cudaGraphExec_t graph_exec = nullptr;
+  int runs = 0;
 };
 
 namespace {
@@ -514,6 +518,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     ctx->conv64_mode = value;
     return CERB_OK;
   }
+  if (strcmp(name, "use_graphs") == 0) {
+    ctx->use_graphs = value != 0;
+    return CERB_OK;
+  }
   if (strcmp(name, "ws_mode") == 0) {
     ctx->ws_mode = value;
     return CERB_OK;
@@ -537,6 +545,7 @@ extern "C" void cerb_plan_destroy(cerb_plan* pl) {
     if (t.plane[1]) cudaFree(t.plane[1]);
   }
   if (pl->blob) cudaFree(pl->blob);
+  if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   delete pl;
 }
 
@@ -753,11 +762,37 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
                               input_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                               s));
   }
+  if (pl->graph_exec != nullptr) {
+    CERB_CUDA(cudaGraphLaunch(pl->graph_exec, s));
+    ctx->launches += static_cast<int64_t>(pl->steps.size());
+    return CERB_OK;
+  }
+  const bool capture = ctx->use_graphs && pl->runs >= 1;
+  if (capture) CERB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   for (Step& st : pl->steps) {
     cudaError_t e = launch_step(ctx, st, s);
-    if (e != cudaSuccess)
+    if (e != cudaSuccess) {
+      if (capture) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(s, &g);
+        if (g) cudaGraphDestroy(g);
+      }
       return fail(CERB_ERR_CUDA, "launch of op kind %d failed: %s", st.kind, cudaGetErrorString(e));
-    ctx->launches += 1;
+    }
+    if (!capture) ctx->launches += 1;
+  }
+  pl->runs += 1;
+  if (capture) {
+    cudaGraph_t g = nullptr;
+    CERB_CUDA(cudaStreamEndCapture(s, &g));
+    cudaError_t e = cudaGraphInstantiate(&pl->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      pl->graph_exec = nullptr;
+      return fail(CERB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    CERB_CUDA(cudaGraphLaunch(pl->graph_exec, s));
+    ctx->launches += static_cast<int64_t>(pl->steps.size());
   }
   return CERB_OK;
 }

@@ -17,6 +17,7 @@ struct cerb_ctx {
   int* err_flag_dev = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved at run time (no libcuda link)
   int64_t launches = 0;
+  bool use_graphs = true;  // replay the forward op list as a CUDA graph
   int conv64_debug = 0;
   int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout

@@ -17,7 +17,7 @@ namespace {
 
 constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 fp16 channels
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;  // TMEM column offset between the two accumulator stages
+constexpr int kMaxAcc = 4;  // accumulator stages (= epilogue warp groups): 512 TMEM columns / n_acc each
 // Split-precision mode (BN <= 128): ONE accumulator stage made of three TMEM accumulators.
 // The tensor core truncates the fp32 accumulator on every MMA, an error proportional to
 // |acc| per instruction; keeping the small cross terms (lo*hi + hi*lo) out of the big hi*hi
@@ -31,8 +31,8 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <bool SPLIT>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <bool SPLIT, int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic smem base only promises 16.
@@ -48,8 +48,8 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
   uint64_t* empty_bar = full_bar + n_stages;
   uint64_t* tfull_bar = empty_bar + n_stages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kMaxAcc;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAcc);
   // [C][96] fp32 when the head tail is fused (16-byte aligned for float4 reads)
   float* s_head_w = reinterpret_cast<float*>(
       (reinterpret_cast<uintptr_t>(tmem_holder + 1) + 15) & ~static_cast<uintptr_t>(15));
@@ -68,7 +68,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxAcc; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
       ptx::mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
     }
@@ -83,7 +83,8 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  constexpr int kAccStages = SPLIT ? 1 : 2;
+  const int kAccStages = SPLIT ? 1 : p.n_acc;
+  const int kAccStride = SPLIT ? 512 : 512 / p.n_acc;
   const int n_ksteps = p.n_taps * p.n_chunks;
   const int bw_mask = (1 << p.bw_log2) - 1;
   const int BW = 1 << p.bw_log2;
@@ -329,6 +330,9 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
 }  // namespace
 
 void conv_tc_plan_pipeline(ConvKParams& p, bool split) {
+  // epilogue-bound layers (one or two K steps per tile) get four accumulator stages / epilogue
+  // groups when the tile is narrow enough for 4 x BN TMEM columns
+  p.n_acc = (!split && p.BN <= 128 && p.n_taps * p.n_chunks <= 2) ? 4 : 2;
   p.stage_bytes = (split ? 2 : 1) * (kATileBytes + p.BN * 128);
   int n = (192 * 1024) / p.stage_bytes;
   if (n > 8) n = 8;
@@ -346,16 +350,20 @@ size_t conv_tc_smem_bytes(const ConvKParams& p) {
 }
 
 cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream) {
-  static bool attr_set[2] = {false, false};
-  auto kern = split ? conv_tc_kernel<true> : conv_tc_kernel<false>;
-  if (!attr_set[split ? 1 : 0]) {
+  static bool attr_set[3] = {false, false, false};
+  const int variant = split ? 2 : (p.n_acc == 4 ? 1 : 0);
+  void (*kern)(ConvKParams) = variant == 2   ? conv_tc_kernel<true, 192>
+                              : variant == 1 ? conv_tc_kernel<false, 576>
+                                             : conv_tc_kernel<false, 320>;
+  if (!attr_set[variant]) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set[split ? 1 : 0] = true;
+    attr_set[variant] = true;
   }
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-  kern<<<grid, kConvThreads, conv_tc_smem_bytes(p), stream>>>(p);
+  const int threads = 64 + 128 * (split ? 1 : p.n_acc);
+  kern<<<grid, threads, conv_tc_smem_bytes(p), stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -18,7 +18,7 @@ namespace cerb {
 
 constexpr int kConvMaxTaps = 16;
 // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2-5 / 6-9: epilogue groups 0 / 1
-constexpr int kConvThreads = 320;
+constexpr int kConvThreads = 576;  // launch bound; the launch uses 64 + 128 * n_acc threads
 
 struct ConvTap {
   int8_t map;  // which input tensor map (parity view) this tap reads
@@ -60,6 +60,7 @@ struct ConvKParams {
   float* logits;         // optional [N, H, W, C]
   int oh, ow, canvas_c, canvas_coff;
   // pipeline
+  int n_acc;  // accumulator stages = epilogue groups (2 or 4; split mode always 1)
   int n_stages;
   int stage_bytes;
   int* err_flag;
