@@ -32,7 +32,7 @@ class Op(ctypes.Structure):
         ("head_mode", ctypes.c_int32), ("logits_out", ctypes.c_int32),
         ("w_off", ctypes.c_int64), ("w_lo_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
         ("box_w", ctypes.c_int32), ("w_shift", ctypes.c_int32), ("aux_classes", ctypes.c_int32),
-        ("reserved", ctypes.c_int32), ("aux_w_off", ctypes.c_int64), ("aux_b_off", ctypes.c_int64),
+        ("up_prev1", ctypes.c_int32), ("aux_w_off", ctypes.c_int64), ("aux_b_off", ctypes.c_int64),
     ]
 
 

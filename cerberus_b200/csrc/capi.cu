@@ -219,6 +219,19 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
     p.res = static_cast<const __half*>(res.plane[0]);
     p.res_cs = res.d.c;
   }
+  if (op.up_prev1 > 0) {
+    const int pid = op.up_prev1 - 1;
+    if (pid >= static_cast<int>(pl->tensors.size()))
+      return fail(CERB_ERR_ARG, "conv64: up_prev id out of range");
+    const Tensor& pv = pl->tensors[pid];
+    if (pv.d.dtype != CERB_F16 || pv.d.n != N || pv.d.h * 2 != H || pv.d.w * 2 != W || pv.d.c < 64 ||
+        pv.d.c % 8 != 0 || op.in_coff != 0)
+      return fail(CERB_ERR_ARG, "conv64: fused upsample+add shape mismatch");
+    p.up_skip = static_cast<const __half*>(in.plane[0]);
+    p.up_prev = static_cast<const __half*>(pv.plane[0]);
+    p.up_skip_cs = in.d.c;
+    p.up_prev_cs = pv.d.c;
+  }
   p.relu = op.relu;
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64: w_shift out of range");
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
@@ -259,10 +272,13 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
                 op.out_coff, out.d.c);
   }
 
-  if (!split && !op.stem && ctx->conv64_mode >= 0 && op.kh == 3 && op.kw == 3 && op.stride == 1 &&
-      op.pad == 1 && op.in_c == 64 && op.cout == 64 && in.d.h == H && in.d.w == W) {
-    return build_conv64(pl, op, st);
-  }
+  const bool conv64_ok = !split && !op.stem && !fused_head && ctx->conv64_mode >= 0 && op.kh == 3 &&
+                         op.kw == 3 && op.stride == 1 && op.pad == 1 && op.in_c == 64 &&
+                         op.cout == 64 && in.d.h == H && in.d.w == W;
+  if (op.up_prev1 > 0 && !(conv64_ok && ctx->conv64_mode == 1))
+    return fail(CERB_ERR_ARG, "conv: fused upsample+add needs the 64->64 3x3 kernel (conv64_mode 1, "
+                "CERB_PREC_F16)");
+  if (conv64_ok) return build_conv64(pl, op, st);
   int bw = op.box_w > 0 ? op.box_w : pick_box_w(H, W);
   if (bw > 128 || (bw & (bw - 1)) != 0) return fail(CERB_ERR_ARG, "conv: bad box_w %d", bw);
   const int bh = 128 / bw;

@@ -26,13 +26,14 @@ namespace {
 constexpr int kWBytes = 9 * 64 * 128;  // resident weights: 9 taps x 64 rows x 128 B
 constexpr int kTileW = 8, kTileH = 16;
 constexpr int kTmemCols = 128;  // 2 accumulator stages x 64 columns
+constexpr int kUpGroupThreads = 128;
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kConv64Threads, 1)
+__global__ void __launch_bounds__(kConv64ThreadsUp, 1)
 conv64_kernel(const __grid_constant__ Conv64Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -55,7 +56,8 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     ptx::prefetch_tmap(&p.in_map);
     ptx::prefetch_tmap(&p.w_map);
     for (int s = 0; s < n_stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      // fused upsample+add: the 128 threads of one producer group arrive instead of a TMA
+      ptx::mbar_init(&full_bar[s], p.up_prev != nullptr ? kUpGroupThreads : 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -83,7 +85,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * 8192, &p.w_map, w_bar, t * 64, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; p.up_prev == nullptr && tile < p.n_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img;
         const int rem = tile - img * tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -145,6 +147,87 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+    }
+  } else if (warp >= 6) {
+    // ---------------------------------------------------- fused `skip + bilinear_x2(prev)` producer
+    // (models/net_desc.py:185-188). Two groups of four warps build alternate tiles' halos
+    // directly in the swizzled shared-memory layout the MMA descriptors expect, so the summed
+    // tensor never exists in HBM. Arithmetic and fp16 rounding are those of upadd_kernel.
+    const int grp = (warp - 6) >> 2;
+    const int gtid = threadIdx.x - (6 + 4 * grp) * 32;
+    const int PH = p.H >> 1, PW = p.W >> 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int stage = it % n_stages;
+      const uint32_t phase = (it / n_stages) & 1;
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int x0 = tx * kTileW - 1, y0 = ty * kTileH - 1;
+      ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 26);
+      uint8_t* dst = sA + stage * stage_bytes;
+      const __half* skip_img = p.up_skip + static_cast<size_t>(img) * p.H * p.W * p.up_skip_cs;
+      const __half* prev_img = p.up_prev + static_cast<size_t>(img) * PH * PW * p.up_prev_cs;
+      constexpr int kTasks = 18 * 10 * 8;  // halo pixels x 16-byte channel chunks
+      for (int t0 = gtid; t0 < kTasks; t0 += kUpGroupThreads * 3) {
+        uint4 sk[3], q00[3], q01[3], q10[3], q11[3];
+        float lyv[3], lxv[3];
+        bool inside[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int t = t0 + u * kUpGroupThreads;
+          const int h = t >> 3, c = t & 7;
+          const int hy = h / 10, hx = h - hy * 10;
+          const int Y = y0 + hy, X = x0 + hx;
+          inside[u] = t < kTasks && Y >= 0 && Y < p.H && X >= 0 && X < p.W;
+          sk[u] = q00[u] = q01[u] = q10[u] = q11[u] = make_uint4(0, 0, 0, 0);
+          lyv[u] = lxv[u] = 0.f;
+          if (inside[u]) {
+            const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.0f);
+            const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f);
+            const int py0 = static_cast<int>(sy), px0 = static_cast<int>(sx);
+            const int py1 = min(py0 + 1, PH - 1), px1 = min(px0 + 1, PW - 1);
+            lyv[u] = sy - py0;
+            lxv[u] = sx - px0;
+            sk[u] = __ldg(reinterpret_cast<const uint4*>(
+                skip_img + (static_cast<size_t>(Y) * p.W + X) * p.up_skip_cs + c * 8));
+            const __half* pb = prev_img + c * 8;
+            q00[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py0) * PW + px0) * p.up_prev_cs));
+            q01[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py0) * PW + px1) * p.up_prev_cs));
+            q10[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py1) * PW + px0) * p.up_prev_cs));
+            q11[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py1) * PW + px1) * p.up_prev_cs));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int t = t0 + u * kUpGroupThreads;
+          if (t >= kTasks) continue;
+          const int h = t >> 3, c = t & 7;
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (inside[u]) {
+            const float ly = lyv[u], lx = lxv[u], hy_ = 1.0f - ly, hx_ = 1.0f - lx;
+            const __half2* s2 = reinterpret_cast<const __half2*>(&sk[u]);
+            const __half2* a2 = reinterpret_cast<const __half2*>(&q00[u]);
+            const __half2* b2 = reinterpret_cast<const __half2*>(&q01[u]);
+            const __half2* c2 = reinterpret_cast<const __half2*>(&q10[u]);
+            const __half2* d2 = reinterpret_cast<const __half2*>(&q11[u]);
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 s = __half22float2(s2[e]), a = __half22float2(a2[e]), b = __half22float2(b2[e]);
+              const float2 cc = __half22float2(c2[e]), d = __half22float2(d2[e]);
+              const float ux = hy_ * (hx_ * a.x + lx * b.x) + ly * (hx_ * cc.x + lx * d.x);
+              const float uy = hy_ * (hx_ * a.y + lx * b.y) + ly * (hx_ * cc.y + lx * d.y);
+              ow[e] = pack_half2(s.x + ux, s.y + uy);
+            }
+          }
+          // 128-byte swizzle: 16-byte chunk c of row h lives at chunk (c ^ (h & 7))
+          *reinterpret_cast<uint4*>(dst + h * 128 + ((c ^ (h & 7)) << 4)) = o;
+        }
+      }
+      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor-core proxy
+      ptx::mbar_arrive(&full_bar[stage]);
     }
   } else {
     const int q = warp & 3;
@@ -275,7 +358,8 @@ cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t strea
     attr_set = true;
   }
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-  conv64_kernel<<<grid, kConv64Threads, conv64_smem_bytes(p), stream>>>(p);
+  const int threads = p.up_prev != nullptr ? kConv64ThreadsUp : 192;
+  conv64_kernel<<<grid, threads, conv64_smem_bytes(p), stream>>>(p);
   return cudaGetLastError();
 }
 

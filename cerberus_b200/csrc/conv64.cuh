@@ -7,7 +7,9 @@
 
 namespace cerb {
 
-constexpr int kConv64Threads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+// warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue, warps 6-13: fused upsample+add producers
+constexpr int kConv64Threads = 192;
+constexpr int kConv64ThreadsUp = 448;
 
 struct Conv64Params {
   CUtensorMap in_map;  // [64 ch, W, H, N], box {64, conv64_box_w(mode), 18, 1}
@@ -21,6 +23,10 @@ struct Conv64Params {
   const __half* res;
   int out_cs, out_coff, res_cs;
   int relu;
+  // fused input: A = up_skip + bilinear_x2(up_prev) instead of a TMA load of in_map (mode 1 only)
+  const __half* up_skip;
+  const __half* up_prev;
+  int up_skip_cs, up_prev_cs;
   int debug;  // attribution experiments: 1 = no global stores, 2 = one tap only, 4 = no epilogue math
   // filled by conv64_plan
   int pitch_px, copy_bytes, stage_bytes, tx_bytes, sbo_bytes, n_stages;

@@ -31,11 +31,14 @@ class Context:
         self.handle = h
         # halo layout of the 64->64 3x3 kernel (csrc/conv64.cu): 1 = single halo slab addressed
         # through shifted descriptors (validated on B200, tools/conv64_modes.py); -1 = generic kernel
-        self.set_option("conv64_mode", int(os.environ.get("CERB_CONV64_MODE", "1")))
+        self.conv64_mode = int(os.environ.get("CERB_CONV64_MODE", "1"))
+        self.set_option("conv64_mode", self.conv64_mode)
 
     def set_option(self, name, value):
         _lib.check(self.lib.cerb_ctx_set_option(self.handle, name.encode(), int(value)),
                    "cerb_ctx_set_option")
+        if name == "conv64_mode":
+            self.conv64_mode = int(value)
 
     def sync(self):
         _lib.check(self.lib.cerb_ctx_sync(self.handle), "cerb_ctx_sync")
@@ -66,7 +69,11 @@ class ForwardPlan:
     def __init__(self, ctx, model, n, h, w, out_h, out_w, want_logits=False, spec=None):
         self.ctx = ctx
         self.model = model
-        self.spec = spec if spec is not None else PlanSpec(model, n, h, w, out_h, out_w, want_logits)
+        if spec is None:
+            # the upsample+add fusion lives in the fp16 64->64 kernel (conv64_mode 1)
+            fuse_up = ctx.precision == "f16" and ctx.conv64_mode == 1
+            spec = PlanSpec(model, n, h, w, out_h, out_w, want_logits, fuse_upadd=fuse_up)
+        self.spec = spec
         td, ops = self.spec.c_arrays()
         blob = model.blob
         h_ = ctypes.c_void_p()

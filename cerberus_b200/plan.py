@@ -132,7 +132,8 @@ class PackedModel:
 class PlanSpec:
     """Tensors + ops for one batch shape. Pure host data (testable without a GPU)."""
 
-    def __init__(self, model, n, h, w, out_h, out_w, want_logits=False, fuse_head=True):
+    def __init__(self, model, n, h, w, out_h, out_w, want_logits=False, fuse_head=True,
+                 fuse_upadd=False):
         if h % 16 or w % 16:
             raise ValueError("input size must be a multiple of 16 (got %dx%d)" % (h, w))
         if out_h > h or out_w > w:
@@ -196,10 +197,10 @@ class PlanSpec:
             s2 = T("s2", n, hs[2], ws[2], 128)
             a2 = T("a2", n, hs[2], ws[2], 128)
             b2 = T("b2", n, hs[2], ws[2], 64)
-            s1 = T("s1", n, hs[1], ws[1], 64)
+            s1 = T("s1", n, hs[1], ws[1], 64) if not fuse_upadd else -1
             a1 = T("a1", n, hs[1], ws[1], 64)
             b1 = T("b1", n, hs[1], ws[1], 64)
-            s0 = T("s0", n, h, w, 64)
+            s0 = T("s0", n, h, w, 64) if not fuse_upadd else -1
             a0 = T("a0", n, h, w, 64)
             b0 = T("b0", n, h, w, 64)
             hid = T("hid", n, h, w, 96) if not fuse_head else -1
@@ -208,11 +209,17 @@ class PlanSpec:
                 self._op(_lib.OP_UPADD, in0=x2, in1=u4b, out=s2)
                 self._conv(L["dec.%s.1.0" % d], s2, a2, relu=1)
                 self._conv(L["dec.%s.1.1" % d], a2, b2, relu=1)
-                self._op(_lib.OP_UPADD, in0=x1, in1=b2, out=s1)
-                self._conv(L["dec.%s.2.0" % d], s1, a1, relu=1)
+                if fuse_upadd:  # s1 = x1 + up(b2) is built inside the conv's producer
+                    self._conv(L["dec.%s.2.0" % d], x1, a1, relu=1, up_prev1=b2 + 1)
+                else:
+                    self._op(_lib.OP_UPADD, in0=x1, in1=b2, out=s1)
+                    self._conv(L["dec.%s.2.0" % d], s1, a1, relu=1)
                 self._conv(L["dec.%s.2.1" % d], a1, b1, relu=1)
-                self._op(_lib.OP_UPADD, in0=x0, in1=b1, out=s0)
-                self._conv(L["dec.%s.3.0" % d], s0, a0, relu=1)
+                if fuse_upadd:
+                    self._conv(L["dec.%s.3.0" % d], x0, a0, relu=1, up_prev1=b1 + 1)
+                else:
+                    self._op(_lib.OP_UPADD, in0=x0, in1=b1, out=s0)
+                    self._conv(L["dec.%s.3.0" % d], s0, a0, relu=1)
                 self._conv(L["dec.%s.3.1" % d], a0, b0, relu=1)
                 ho = L["head.%s.out" % d]
                 key = HEAD_NAME_MAP[d]
@@ -251,7 +258,7 @@ class PlanSpec:
         d = dict(kind=kind, in0=-1, in1=-1, out=-1, in_coff=0, in_c=0, out_coff=0, cout=0, kh=0,
                  kw=0, stride=0, pad=0, relu=0, stem=0, head_mode=0, logits_out=-1, w_off=-1,
                  w_lo_off=-1, b_off=-1, box_w=0, w_shift=0, aux_classes=0, aux_w_off=-1,
-                 aux_b_off=-1)
+                 aux_b_off=-1, up_prev1=0)
         d.update(kw)
         self.ops.append(d)
 

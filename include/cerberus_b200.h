@@ -98,7 +98,9 @@ typedef struct cerb_op {
                           the 1x1 64->96 hidden layer (+BN+ReLU), `out` is the fp32 CANVAS tensor, and
                           the 1x1 96->aux_classes (+bias) + softmax / argmax / centre crop of CERB_OP_HEAD
                           run per pixel in registers; head_mode / logits_out / out_coff as for HEAD */
-  int32_t reserved;
+  int32_t up_prev1;    /* CONV (64->64 3x3 s1, CERB_PREC_F16 only): tensor id + 1 of a half-resolution
+                          tensor `prev`; the conv then reads  in0 + bilinear_x2(prev)  (the UPADD op fused
+                          into the conv's producer, the sum is never written to HBM). 0 = none */
   int64_t aux_w_off;   /* fp32 [aux_classes][96] */
   int64_t aux_b_off;   /* fp32 [aux_classes] */
 } cerb_op;

@@ -119,3 +119,45 @@ def test_stem(built_lib):
         assert np.all(err <= tol * np.abs(ref) + tol), "%s: max err %g" % (precision, err.max())
         plan.close()
         ctx.close()
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 16), (2, 48, 40), (1, 128, 128)])
+def test_conv64_fused_upsample_add(shape, built_lib):
+    """conv64 with the UPADD op fused into its producer: conv(skip + bilinear_x2(prev)) with
+    align_corners=False (models/net_desc.py:185-188, net_layers.py:45-46); also checks it against
+    the unfused upadd kernel + conv (same fp16 rounding of the sum -> identical output)."""
+    n, h, w = shape
+    rng = np.random.RandomState(5)
+    skip = f16(rng.standard_normal((n, h, w, 64))).astype(np.float32)
+    prev = f16(rng.standard_normal((n, h // 2, w // 2, 64))).astype(np.float32)
+    wt = f16(rng.standard_normal((64, 64, 3, 3)) / 24.0).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, 64).astype(np.float32)
+    blob = BlobBuilder()
+    layer = pack_conv(blob, wt.astype(np.float64), b.astype(np.float64))
+    outs = []
+    for fused in (True, False):
+        spec = MiniSpec()
+        t_skip = spec._tensor("skip", n, h, w, 64)
+        t_prev = spec._tensor("prev", n, h // 2, w // 2, 64)
+        t_out = spec._tensor("out", n, h, w, 64)
+        if fused:
+            spec._conv(layer, t_skip, t_out, relu=1, up_prev1=t_prev + 1)
+        else:
+            t_sum = spec._tensor("sum", n, h, w, 64)
+            spec._op(_lib.OP_UPADD, in0=t_skip, in1=t_prev, out=t_sum)
+            spec._conv(layer, t_sum, t_out, relu=1)
+        ctx = Context(0, "f16")
+        plan = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
+        plan.write(t_skip, skip.astype(np.float16))
+        plan.write(t_prev, prev.astype(np.float16))
+        plan.run()
+        outs.append(plan.read(t_out).astype(np.float32))
+        plan.close()
+        ctx.close()
+    assert np.array_equal(outs[0], outs[1]), "fused and unfused paths differ: %g" % np.abs(outs[0] - outs[1]).max()
+    up = F.interpolate(torch.from_numpy(nhwc_to_nchw(prev)), scale_factor=2, mode="bilinear", align_corners=False)
+    s = (torch.from_numpy(nhwc_to_nchw(skip)) + up).half().double()
+    ref = F.relu(F.conv2d(s, torch.from_numpy(wt).double(), torch.from_numpy(b).double(), padding=1))
+    ref = nchw_to_nhwc(ref.numpy())
+    err = np.abs(outs[0] - ref)
+    assert np.all(err <= 4e-3 * np.abs(ref) + 4e-3), err.max()
