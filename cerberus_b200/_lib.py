@@ -77,6 +77,12 @@ _SIGNATURES = {
                                        ctypes.c_size_t]),
     "cerb_ellipse_rows": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32)]),
+    "cerb_copy_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_size_t, ctypes.c_int]),
+    "cerb_stream_order": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cerb_copy_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cerb_copy_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cerb_copy_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "cerb_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "cerb_host_free": (None, [ctypes.c_void_p]),
     "cerb_dev_alloc": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_size_t]),

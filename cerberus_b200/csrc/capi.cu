@@ -175,7 +175,6 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
   p.tiles_x = (W + conv64_tile_w() - 1) / conv64_tile_w();
   p.tiles_y = (H + conv64_tile_h() - 1) / conv64_tile_h();
   p.n_tiles = N * p.tiles_x * p.tiles_y;
-  conv64_plan(p);
   const size_t es = 2;
   if (op.in_coff % 8 != 0 || op.in_coff + 64 > in.d.c || in.d.c % 8 != 0)
     return fail(CERB_ERR_ARG, "conv64: bad input channels");
@@ -232,6 +231,7 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
     p.up_skip_cs = in.d.c;
     p.up_prev_cs = pv.d.c;
   }
+  conv64_plan(p);  // after up_prev is known: the fused producer needs staging shared memory
   p.relu = op.relu;
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64: w_shift out of range");
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
@@ -476,6 +476,11 @@ extern "C" int cerb_ctx_create(int device, int precision, cerb_ctx** out) {
   ctx->precision = precision;
   ctx->num_sms = prop.multiProcessorCount;
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CERB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CERB_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i)
+    CERB_CUDA(cudaEventCreateWithFlags(&ctx->slot_event[i], cudaEventDisableTiming));
+  CERB_CUDA(cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming));
   CERB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->err_flag_host), sizeof(int) * 4,
                           cudaHostAllocMapped));
   memset(ctx->err_flag_host, 0, sizeof(int) * 4);
@@ -495,6 +500,11 @@ extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->slot_event[i]) cudaEventDestroy(ctx->slot_event[i]);
+  if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
   for (void* p : ctx->scratch) cudaFree(p);
   delete ctx;
@@ -547,6 +557,50 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     return CERB_OK;
   }
   return fail(CERB_ERR_ARG, "cerb_ctx_set_option: unknown option %s", name);
+}
+
+extern "C" int cerb_copy_async(cerb_ctx* ctx, void* dst, const void* src, size_t bytes, int kind) {
+  if (!ctx || !dst || !src || (kind != 1 && kind != 2))
+    return fail(CERB_ERR_ARG, "cerb_copy_async: bad arguments");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  CERB_CUDA(cudaMemcpyAsync(dst, src, bytes,
+                            kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                            kind == 1 ? ctx->up_stream : ctx->copy_stream));
+  return CERB_OK;
+}
+
+extern "C" int cerb_copy_mark(cerb_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 3) return fail(CERB_ERR_ARG, "cerb_copy_mark: bad arguments");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  CERB_CUDA(cudaEventRecord(ctx->slot_event[slot], ctx->copy_stream));
+  return CERB_OK;
+}
+
+extern "C" int cerb_copy_wait(cerb_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 3) return fail(CERB_ERR_ARG, "cerb_copy_wait: bad arguments");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  CERB_CUDA(cudaEventSynchronize(ctx->slot_event[slot]));
+  const int flag = ctx->err_flag_host ? ctx->err_flag_host[0] : 0;
+  if (flag != 0) return fail(CERB_ERR_KERNEL, "kernel pipeline watchdog fired (code %d)", flag);
+  return CERB_OK;
+}
+
+extern "C" int cerb_stream_order(cerb_ctx* ctx, int copy_waits_for_compute) {
+  if (!ctx) return fail(CERB_ERR_ARG, "cerb_stream_order: null ctx");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t from = copy_waits_for_compute ? ctx->stream : ctx->up_stream;
+  cudaStream_t to = copy_waits_for_compute ? ctx->copy_stream : ctx->stream;
+  CERB_CUDA(cudaEventRecord(ctx->order_event, from));
+  CERB_CUDA(cudaStreamWaitEvent(to, ctx->order_event, 0));
+  return CERB_OK;
+}
+
+extern "C" int cerb_copy_sync(cerb_ctx* ctx) {
+  if (!ctx) return fail(CERB_ERR_ARG, "cerb_copy_sync: null ctx");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  CERB_CUDA(cudaStreamSynchronize(ctx->up_stream));
+  CERB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  return CERB_OK;
 }
 
 extern "C" int64_t cerb_ctx_launch_count(cerb_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -13,6 +13,10 @@ struct cerb_ctx {
   int precision = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H copies overlapped with compute
+  cudaStream_t up_stream = nullptr;    // H2D copies overlapped with compute
+  cudaEvent_t order_event = nullptr;
+  cudaEvent_t slot_event[4] = {nullptr, nullptr, nullptr, nullptr};
   int* err_flag_host = nullptr;  // mapped pinned memory: readable even after a trapped kernel
   int* err_flag_dev = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved at run time (no libcuda link)

@@ -27,6 +27,7 @@ constexpr int kWBytes = 9 * 64 * 128;  // resident weights: 9 taps x 64 rows x 1
 constexpr int kTileW = 8, kTileH = 16;
 constexpr int kTmemCols = 128;  // 2 accumulator stages x 64 columns
 constexpr int kUpGroupThreads = 128;
+constexpr int kUpStageBytes = (18 * 10 + 10 * 6) * 128;  // skip halo + prev patch, per producer group
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -156,6 +157,10 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     const int grp = (warp - 6) >> 2;
     const int gtid = threadIdx.x - (6 + 4 * grp) * 32;
     const int PH = p.H >> 1, PW = p.W >> 1;
+    // per-group staging: the raw skip halo (18x10 px) and the prev patch (10x6 px), fetched with
+    // cp.async so that every 16-byte request of a tile is in flight at once
+    uint8_t* stS = sA + n_stages * stage_bytes + 256 + grp * kUpStageBytes;
+    uint8_t* stP = stS + 18 * 10 * 128;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
@@ -165,69 +170,65 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       const int rem = tile - img * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int x0 = tx * kTileW - 1, y0 = ty * kTileH - 1;
-      ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 26);
-      uint8_t* dst = sA + stage * stage_bytes;
+      const int pby = ty * (kTileH / 2) - 1, pbx = tx * (kTileW / 2) - 1;  // prev patch origin
       const __half* skip_img = p.up_skip + static_cast<size_t>(img) * p.H * p.W * p.up_skip_cs;
       const __half* prev_img = p.up_prev + static_cast<size_t>(img) * PH * PW * p.up_prev_cs;
-      constexpr int kTasks = 18 * 10 * 8;  // halo pixels x 16-byte channel chunks
-      for (int t0 = gtid; t0 < kTasks; t0 += kUpGroupThreads * 3) {
-        uint4 sk[3], q00[3], q01[3], q10[3], q11[3];
-        float lyv[3], lxv[3];
-        bool inside[3];
+      constexpr int kSkipTasks = 18 * 10 * 8;  // halo pixels x 16-byte channel chunks
+      constexpr int kPrevTasks = 10 * 6 * 8;
+      for (int t = gtid; t < kSkipTasks; t += kUpGroupThreads) {
+        const int h = t >> 3, c = t & 7;
+        const int hy = h / 10, hx = h - hy * 10;
+        const int Y = y0 + hy, X = x0 + hx;
+        if (Y >= 0 && Y < p.H && X >= 0 && X < p.W)
+          ptx::cp_async16(stS + t * 16, skip_img + (static_cast<size_t>(Y) * p.W + X) * p.up_skip_cs + c * 8);
+      }
+      for (int t = gtid; t < kPrevTasks; t += kUpGroupThreads) {
+        const int h = t >> 3, c = t & 7;
+        const int ly_ = h / 6, lx_ = h - ly_ * 6;
+        const int py = min(max(pby + ly_, 0), PH - 1), px = min(max(pbx + lx_, 0), PW - 1);
+        ptx::cp_async16(stP + t * 16, prev_img + (static_cast<size_t>(py) * PW + px) * p.up_prev_cs + c * 8);
+      }
+      ptx::cp_async_wait_all();
+      ptx::named_bar_sync(1 + grp, kUpGroupThreads);  // the whole group's copies have landed
+      ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 26);
+      uint8_t* dst = sA + stage * stage_bytes;
+      for (int t = gtid; t < kSkipTasks; t += kUpGroupThreads) {
+        const int h = t >> 3, c = t & 7;
+        const int hy = h / 10, hx = h - hy * 10;
+        const int Y = y0 + hy, X = x0 + hx;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (Y >= 0 && Y < p.H && X >= 0 && X < p.W) {
+          const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.0f);
+          const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f);
+          const int py0 = static_cast<int>(sy), px0 = static_cast<int>(sx);
+          const int py1 = min(py0 + 1, PH - 1), px1 = min(px0 + 1, PW - 1);
+          const float ly = sy - py0, lx = sx - px0, hy_ = 1.0f - ly, hx_ = 1.0f - lx;
+          const uint4 sk = *reinterpret_cast<const uint4*>(stS + t * 16);
+          const uint4 q00 = *reinterpret_cast<const uint4*>(stP + (((py0 - pby) * 6 + (px0 - pbx)) * 8 + c) * 16);
+          const uint4 q01 = *reinterpret_cast<const uint4*>(stP + (((py0 - pby) * 6 + (px1 - pbx)) * 8 + c) * 16);
+          const uint4 q10 = *reinterpret_cast<const uint4*>(stP + (((py1 - pby) * 6 + (px0 - pbx)) * 8 + c) * 16);
+          const uint4 q11 = *reinterpret_cast<const uint4*>(stP + (((py1 - pby) * 6 + (px1 - pbx)) * 8 + c) * 16);
+          const __half2* s2 = reinterpret_cast<const __half2*>(&sk);
+          const __half2* a2 = reinterpret_cast<const __half2*>(&q00);
+          const __half2* b2 = reinterpret_cast<const __half2*>(&q01);
+          const __half2* c2 = reinterpret_cast<const __half2*>(&q10);
+          const __half2* d2 = reinterpret_cast<const __half2*>(&q11);
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int t = t0 + u * kUpGroupThreads;
-          const int h = t >> 3, c = t & 7;
-          const int hy = h / 10, hx = h - hy * 10;
-          const int Y = y0 + hy, X = x0 + hx;
-          inside[u] = t < kTasks && Y >= 0 && Y < p.H && X >= 0 && X < p.W;
-          sk[u] = q00[u] = q01[u] = q10[u] = q11[u] = make_uint4(0, 0, 0, 0);
-          lyv[u] = lxv[u] = 0.f;
-          if (inside[u]) {
-            const float sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.0f);
-            const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f);
-            const int py0 = static_cast<int>(sy), px0 = static_cast<int>(sx);
-            const int py1 = min(py0 + 1, PH - 1), px1 = min(px0 + 1, PW - 1);
-            lyv[u] = sy - py0;
-            lxv[u] = sx - px0;
-            sk[u] = __ldg(reinterpret_cast<const uint4*>(
-                skip_img + (static_cast<size_t>(Y) * p.W + X) * p.up_skip_cs + c * 8));
-            const __half* pb = prev_img + c * 8;
-            q00[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py0) * PW + px0) * p.up_prev_cs));
-            q01[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py0) * PW + px1) * p.up_prev_cs));
-            q10[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py1) * PW + px0) * p.up_prev_cs));
-            q11[u] = __ldg(reinterpret_cast<const uint4*>(pb + (static_cast<size_t>(py1) * PW + px1) * p.up_prev_cs));
+          for (int e = 0; e < 4; ++e) {
+            const float2 sv = __half22float2(s2[e]), av = __half22float2(a2[e]), bv = __half22float2(b2[e]);
+            const float2 cv = __half22float2(c2[e]), dv = __half22float2(d2[e]);
+            const float ux = hy_ * (hx_ * av.x + lx * bv.x) + ly * (hx_ * cv.x + lx * dv.x);
+            const float uy = hy_ * (hx_ * av.y + lx * bv.y) + ly * (hx_ * cv.y + lx * dv.y);
+            ow[e] = pack_half2(sv.x + ux, sv.y + uy);
           }
         }
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int t = t0 + u * kUpGroupThreads;
-          if (t >= kTasks) continue;
-          const int h = t >> 3, c = t & 7;
-          uint4 o = make_uint4(0, 0, 0, 0);
-          if (inside[u]) {
-            const float ly = lyv[u], lx = lxv[u], hy_ = 1.0f - ly, hx_ = 1.0f - lx;
-            const __half2* s2 = reinterpret_cast<const __half2*>(&sk[u]);
-            const __half2* a2 = reinterpret_cast<const __half2*>(&q00[u]);
-            const __half2* b2 = reinterpret_cast<const __half2*>(&q01[u]);
-            const __half2* c2 = reinterpret_cast<const __half2*>(&q10[u]);
-            const __half2* d2 = reinterpret_cast<const __half2*>(&q11[u]);
-            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 s = __half22float2(s2[e]), a = __half22float2(a2[e]), b = __half22float2(b2[e]);
-              const float2 cc = __half22float2(c2[e]), d = __half22float2(d2[e]);
-              const float ux = hy_ * (hx_ * a.x + lx * b.x) + ly * (hx_ * cc.x + lx * d.x);
-              const float uy = hy_ * (hx_ * a.y + lx * b.y) + ly * (hx_ * cc.y + lx * d.y);
-              ow[e] = pack_half2(s.x + ux, s.y + uy);
-            }
-          }
-          // 128-byte swizzle: 16-byte chunk c of row h lives at chunk (c ^ (h & 7))
-          *reinterpret_cast<uint4*>(dst + h * 128 + ((c ^ (h & 7)) << 4)) = o;
-        }
+        // 128-byte swizzle: 16-byte chunk c of row h lives at chunk (c ^ (h & 7))
+        *reinterpret_cast<uint4*>(dst + h * 128 + ((c ^ (h & 7)) << 4)) = o;
       }
       ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor-core proxy
       ptx::mbar_arrive(&full_bar[stage]);
+      ptx::named_bar_sync(1 + grp, kUpGroupThreads);  // staging may be overwritten by the next tile
     }
   } else {
     const int q = warp & 3;
@@ -335,7 +336,7 @@ void conv64_plan(Conv64Params& p) {
     p.tx_bytes = p.copy_bytes;
     p.sbo_bytes = 16 * 128;
   }
-  int n = (200 * 1024 - kWBytes) / p.stage_bytes;
+  int n = (200 * 1024 - kWBytes - (p.up_prev != nullptr ? 2 * kUpStageBytes : 0)) / p.stage_bytes;
   if (n > 4) n = 4;
   if (n < 2) n = 2;
   p.n_stages = n;
@@ -346,7 +347,8 @@ int conv64_tile_w() { return kTileW; }
 int conv64_tile_h() { return kTileH; }
 
 size_t conv64_smem_bytes(const Conv64Params& p) {
-  return static_cast<size_t>(kWBytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024;
+  return static_cast<size_t>(kWBytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 +
+         (p.up_prev != nullptr ? 2 * kUpStageBytes : 0);
 }
 
 cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t stream) {

@@ -803,6 +803,9 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
         if (cond) {                                                     \
           ++age;                                                        \
           lab16[qq] = lab;                                              \
+          /* the rows above / below will be read when qq is popped */   \
+          if (qq >= W) asm volatile("prefetch.global.L1 [%0];" ::"l"(v + qq - W));       \
+          if (qq + W < hw) asm volatile("prefetch.global.L1 [%0];" ::"l"(v + qq + W));   \
           const uint64_t e = ws_entry(vv, age, qq);                     \
           const uint64_t ek = e >> 16;                                  \
           int c = n++;                                                  \

@@ -188,8 +188,9 @@ def canvas_to_step_outputs(canvas, model):
 class Engine:
     """Model directory -> run_step. Plans are cached per (N,H,W,out) shape."""
 
-    def __init__(self, state_dict, model_args, device=0, precision="f16"):
-        self.model = PackedModel(state_dict, model_args)
+    def __init__(self, state_dict, model_args, device=0, precision="f16", packed=None):
+        """`packed`: an already folded + packed model (e.g. received by broadcast_packed_model)."""
+        self.model = packed if packed is not None else PackedModel(state_dict, model_args)
         self.ctx = Context(device, precision)
         self._plans = {}
 

@@ -82,3 +82,86 @@ class DevicePostProc:
         for hp in self._pinned.values():
             self.ctx.lib.cerb_host_free(ctypes.c_void_p(hp))
         self._pinned = {}
+
+
+class TilePipeline:
+    """Public streaming API for batches of independent tiles whose network output covers the
+    tile (the bench workload): host uint8 batch in -> host int32 label maps out, with the H2D of
+    batch k+1 and the D2H of batch k-1 overlapped with the compute of batch k on the ctx's
+    upload / download streams (cerb_copy_async / cerb_stream_order / cerb_copy_mark).
+
+        pipe = TilePipeline(engine, n, h, w)
+        for batch in batches:            # uint8 [n,h,w,3]
+            done = pipe.submit(batch)    # -> labels of the PREVIOUS batch (None for the first)
+        last = pipe.flush()
+
+    Returned dicts {tissue: int32 [n,h,w]} are views of pinned buffers that stay valid until the
+    second-next submit()."""
+
+    def __init__(self, engine, n, h, w, ds_factor=1.0):
+        self.ctx, self.model = engine.ctx, engine.model
+        self.lib = self.ctx.lib
+        self.plan = engine.plan_for(n, h, w, h, w)
+        self.n, self.h, self.w = n, h, w
+        self.in_bytes = n * h * w * 3
+        # two result slots: D2H of batch k-1 overlaps the compute of batch k
+        self.post = [DevicePostProc(self.ctx, self.model, n, h, w, ds_factor) for _ in range(2)]
+        # three input slots: the upload of batch k never races the read of batch k-1 / k-2
+        self.stage_host, self.stage_dev, self._views = [], [], []
+        for _ in range(3):
+            hp = self.lib.cerb_host_alloc(self.in_bytes)
+            dp = self.lib.cerb_dev_alloc(self.ctx.handle, self.in_bytes)
+            if not hp or not dp:
+                _lib.check(-1, "TilePipeline staging allocation")
+            self.stage_host.append(hp)
+            self.stage_dev.append(dp)
+            buf = (ctypes.c_uint8 * self.in_bytes).from_address(hp)
+            self._views.append(np.frombuffer(buf, dtype=np.uint8).reshape(n, h, w, 3))
+        self.k = 0
+        self.pending = None  # result slot whose D2H is in flight
+        self.h2d_bytes = self.in_bytes
+        self.d2h_bytes = self.post[0].d2h_bytes
+
+    def submit(self, batch_u8):
+        lib, ctx = self.lib, self.ctx
+        s_in, s_out = self.k % 3, self.k & 1
+        np.copyto(self._views[s_in], batch_u8)  # pageable -> pinned (host memcpy)
+        _lib.check(lib.cerb_copy_async(ctx.handle, ctypes.c_void_p(self.stage_dev[s_in]),
+                                       ctypes.c_void_p(self.stage_host[s_in]), self.in_bytes, 1),
+                   "cerb_copy_async")
+        _lib.check(lib.cerb_stream_order(ctx.handle, 0), "cerb_stream_order")  # compute waits for H2D
+        self.plan.run(device_ptr=self.stage_dev[s_in])
+        post = self.post[s_out]
+        post.run(self.plan)
+        _lib.check(lib.cerb_stream_order(ctx.handle, 1), "cerb_stream_order")  # D2H waits for compute
+        for t in post.tissues:
+            _lib.check(lib.cerb_copy_async(ctx.handle, post.host[t].ctypes.data_as(ctypes.c_void_p),
+                                           ctypes.c_void_p(post.dev[t]), post.nbytes, 2),
+                       "cerb_copy_async")
+        _lib.check(lib.cerb_copy_mark(ctx.handle, s_out), "cerb_copy_mark")
+        done = None
+        if self.pending is not None:  # results of the previous batch (its D2H was queued earlier)
+            _lib.check(lib.cerb_copy_wait(ctx.handle, self.pending), "cerb_copy_wait")
+            done = self.post[self.pending].host
+        self.pending = s_out
+        self.k += 1
+        return done
+
+    def flush(self):
+        if self.pending is None:
+            return None
+        _lib.check(self.lib.cerb_copy_wait(self.ctx.handle, self.pending), "cerb_copy_wait")
+        self.ctx.sync()
+        out = self.post[self.pending].host
+        self.pending = None
+        return out
+
+    def close(self):
+        self.flush()
+        for p in self.post:
+            p.close()
+        for hp in self.stage_host:
+            self.lib.cerb_host_free(ctypes.c_void_p(hp))
+        for dp in self.stage_dev:
+            self.lib.cerb_dev_free(self.ctx.handle, ctypes.c_void_p(dp))
+        self.stage_host, self.stage_dev = [], []

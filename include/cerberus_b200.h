@@ -184,6 +184,22 @@ int cerb_mask_lumen(cerb_ctx* ctx, int32_t* lumen_dev, const int32_t* gland_dev,
 /* cv2.getStructuringElement(MORPH_ELLIPSE, (k,k)) as row runs [j1[i], j2[i]) (1 <= k <= 32). */
 int cerb_ellipse_rows(int k, int32_t* j1, int32_t* j2);
 
+/* ---- copy stream: overlap host<->device traffic of step k+1 / k-1 with the compute of step k.
+ * Each ctx owns an upload stream and a download stream used only by these calls.
+ *   cerb_copy_async : cudaMemcpyAsync, kind 1 = H2D on the upload stream, 2 = D2H on the download
+ *                     stream; host memory should come from cerb_host_alloc.
+ *   cerb_stream_order(ctx, 0): later work on the COMPUTE stream waits for everything queued so far
+ *                     on the upload stream; (ctx, 1): later work on the DOWNLOAD stream waits for
+ *                     the compute stream.
+ *   cerb_copy_mark / cerb_copy_wait : record an event (slot 0..3) on the download stream / block
+ *                     the host until it has fired.
+ *   cerb_copy_sync  : blocks the host until both copy streams are idle. */
+int cerb_copy_async(cerb_ctx* ctx, void* dst, const void* src, size_t bytes, int kind);
+int cerb_stream_order(cerb_ctx* ctx, int download_waits_for_compute);
+int cerb_copy_mark(cerb_ctx* ctx, int slot);
+int cerb_copy_wait(cerb_ctx* ctx, int slot);
+int cerb_copy_sync(cerb_ctx* ctx);
+
 /* Pinned (page-locked) host memory for fast asynchronous H2D / D2H copies. */
 void* cerb_host_alloc(size_t bytes);
 void cerb_host_free(void* p);

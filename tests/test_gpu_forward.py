@@ -127,3 +127,33 @@ def test_device_pipeline_matches_oracle_pipeline(built_lib, six_head_sd):
         assert np.array_equal(labels2[t], labels[t])
     post.close()
     eng.close()
+
+
+def test_tile_pipeline_streams_batches_in_order(built_lib, six_head_sd):
+    """TilePipeline (overlapped H2D / compute / D2H) returns, one submit late, exactly what the
+    synchronous path produces for each batch."""
+    from cerberus_b200.pipeline import DevicePostProc, TilePipeline
+    args = synth.model_args()
+    n = 4
+    batches = [synth.synthetic_tiles(n, 256, 256, seed=30 + i) for i in range(4)]
+    eng = Engine(six_head_sd, args, precision="f16")
+    plan = eng.plan_for(n, 256, 256, 256, 256)
+    post = DevicePostProc(eng.ctx, eng.model, n, 256, 256)
+    want = []
+    for b in batches:
+        plan.run(b)
+        want.append({t: v.copy() for t, v in post.run_to_host(plan).items()})
+    post.close()
+    pipe = TilePipeline(eng, n, 256, 256)
+    got = []
+    for b in batches:
+        r = pipe.submit(b)
+        if r is not None:
+            got.append({t: v.copy() for t, v in r.items()})
+    got.append({t: v.copy() for t, v in pipe.flush().items()})
+    assert len(got) == len(want)
+    for g, w_ in zip(got, want):
+        for t in w_:
+            assert np.array_equal(g[t], w_[t]), t
+    pipe.close()
+    eng.close()
