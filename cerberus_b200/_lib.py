@@ -80,6 +80,7 @@ _SIGNATURES = {
     "cerb_copy_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_size_t, ctypes.c_int]),
     "cerb_stream_order": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cerb_ctx_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "cerb_copy_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cerb_copy_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cerb_copy_sync": (ctypes.c_int, [ctypes.c_void_p]),

@@ -595,6 +595,15 @@ extern "C" int cerb_stream_order(cerb_ctx* ctx, int copy_waits_for_compute) {
   return CERB_OK;
 }
 
+extern "C" int cerb_ctx_wait(cerb_ctx* waiter, cerb_ctx* signal) {
+  if (!waiter || !signal || waiter->device != signal->device)
+    return fail(CERB_ERR_ARG, "cerb_ctx_wait: both contexts must live on the same device");
+  CERB_CUDA(cudaSetDevice(waiter->device));
+  CERB_CUDA(cudaEventRecord(signal->order_event, signal->stream));
+  CERB_CUDA(cudaStreamWaitEvent(waiter->stream, signal->order_event, 0));
+  return CERB_OK;
+}
+
 extern "C" int cerb_copy_sync(cerb_ctx* ctx) {
   if (!ctx) return fail(CERB_ERR_ARG, "cerb_copy_sync: null ctx");
   CERB_CUDA(cudaSetDevice(ctx->device));

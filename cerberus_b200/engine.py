@@ -70,8 +70,11 @@ class ForwardPlan:
         self.ctx = ctx
         self.model = model
         if spec is None:
-            # the upsample+add fusion lives in the fp16 64->64 kernel (conv64_mode 1)
-            fuse_up = ctx.precision == "f16" and ctx.conv64_mode == 1
+            # The upsample+add fusion (fp16 64->64 kernel, conv64_mode 1) is exact but measured
+            # SLOWER than upadd_kernel + conv64 on B200 (0.38 vs 0.34 ms per 256^2 layer: its eight
+            # producer warps are instruction-bound), so it is opt-in.
+            fuse_up = (ctx.precision == "f16" and ctx.conv64_mode == 1
+                       and os.environ.get("CERB_FUSE_UPADD", "0") == "1")
             spec = PlanSpec(model, n, h, w, out_h, out_w, want_logits, fuse_upadd=fuse_up)
         self.spec = spec
         td, ops = self.spec.c_arrays()

@@ -44,10 +44,11 @@ class DevicePostProc:
             self.host[t] = np.frombuffer(buf, dtype=np.int32).reshape(n, h, w)
         self.d2h_bytes = len(self.tissues) * self.nbytes
 
-    def run(self, plan):
-        """Asynchronous: leaves int32 label maps in device buffers."""
+    def run(self, plan, canvas_ptr=None):
+        """Asynchronous: leaves int32 label maps in device buffers. `canvas_ptr`: device address
+        of a [n,h,w,C] float32 canvas to read instead of the plan's own canvas tensor."""
         lib, ctx = self.ctx.lib, self.ctx
-        canvas = plan.tensor_ptr(plan.spec.canvas)
+        canvas = canvas_ptr if canvas_ptr is not None else plan.tensor_ptr(plan.spec.canvas)
         C = self.model.canvas_c
         for t in self.tissues:
             ch0 = self.model.idx_dict[t + "-INST"][0]
@@ -86,9 +87,14 @@ class DevicePostProc:
 
 class TilePipeline:
     """Public streaming API for batches of independent tiles whose network output covers the
-    tile (the bench workload): host uint8 batch in -> host int32 label maps out, with the H2D of
-    batch k+1 and the D2H of batch k-1 overlapped with the compute of batch k on the ctx's
-    upload / download streams (cerb_copy_async / cerb_stream_order / cerb_copy_mark).
+    tile (the bench workload): host uint8 batch in -> host int32 label maps out. Four streams
+    are kept busy at once:
+        upload   : H2D of batch k+1                         (engine ctx, cerb_copy_async kind 1)
+        compute  : forward of batch k, canvas -> slot copy  (engine ctx)
+        post     : post-processing of batch k-1             (a second ctx on the same device)
+        download : D2H of the label maps of batch k-1       (second ctx, cerb_copy_async kind 2)
+    The post-processing kernels are latency-bound (one block per image / instance), so running
+    them next to the next batch's convolutions hides most of their time.
 
         pipe = TilePipeline(engine, n, h, w)
         for batch in batches:            # uint8 [n,h,w,3]
@@ -99,13 +105,23 @@ class TilePipeline:
     second-next submit()."""
 
     def __init__(self, engine, n, h, w, ds_factor=1.0):
+        from .engine import Context
         self.ctx, self.model = engine.ctx, engine.model
         self.lib = self.ctx.lib
+        self.pctx = Context(self.ctx.device, self.ctx.precision)  # post-processing + download
         self.plan = engine.plan_for(n, h, w, h, w)
         self.n, self.h, self.w = n, h, w
         self.in_bytes = n * h * w * 3
-        # two result slots: D2H of batch k-1 overlaps the compute of batch k
-        self.post = [DevicePostProc(self.ctx, self.model, n, h, w, ds_factor) for _ in range(2)]
+        self.canvas_bytes = n * h * w * self.model.canvas_c * 4
+        # two result slots (canvas copy + label maps): batch k-1 is post-processed / downloaded
+        # while batch k is computed
+        self.post = [DevicePostProc(self.pctx, self.model, n, h, w, ds_factor) for _ in range(2)]
+        self.canvas_copy = []
+        for _ in range(2):
+            cp = self.lib.cerb_dev_alloc(self.ctx.handle, self.canvas_bytes)
+            if not cp:
+                _lib.check(-1, "TilePipeline canvas allocation")
+            self.canvas_copy.append(cp)
         # three input slots: the upload of batch k never races the read of batch k-1 / k-2
         self.stage_host, self.stage_dev, self._views = [], [], []
         for _ in range(3):
@@ -122,46 +138,76 @@ class TilePipeline:
         self.h2d_bytes = self.in_bytes
         self.d2h_bytes = self.post[0].d2h_bytes
 
-    def submit(self, batch_u8):
-        lib, ctx = self.lib, self.ctx
+    def submit(self, batch_u8=None, device_ptr=None, download=True):
+        """Queues one batch. batch_u8: host uint8 [n,h,w,3]; or device_ptr: address of a batch
+        already resident in HBM (no upload). download=False leaves the label maps on the device
+        (self.post[slot].dev) and returns None."""
+        lib, ctx, pctx = self.lib, self.ctx, self.pctx
         s_in, s_out = self.k % 3, self.k & 1
-        np.copyto(self._views[s_in], batch_u8)  # pageable -> pinned (host memcpy)
-        _lib.check(lib.cerb_copy_async(ctx.handle, ctypes.c_void_p(self.stage_dev[s_in]),
-                                       ctypes.c_void_p(self.stage_host[s_in]), self.in_bytes, 1),
-                   "cerb_copy_async")
-        _lib.check(lib.cerb_stream_order(ctx.handle, 0), "cerb_stream_order")  # compute waits for H2D
-        self.plan.run(device_ptr=self.stage_dev[s_in])
+        if device_ptr is None:
+            np.copyto(self._views[s_in], batch_u8)  # pageable -> pinned (host memcpy)
+            _lib.check(lib.cerb_copy_async(ctx.handle, ctypes.c_void_p(self.stage_dev[s_in]),
+                                           ctypes.c_void_p(self.stage_host[s_in]), self.in_bytes, 1),
+                       "cerb_copy_async")
+            _lib.check(lib.cerb_stream_order(ctx.handle, 0), "cerb_stream_order")  # compute waits H2D
+            device_ptr = self.stage_dev[s_in]
+        self.plan.run(device_ptr=device_ptr)
+        # canvas -> slot copy on the compute stream, after the post-processing that last read the
+        # slot (batch k-2; waiting for the post stream's tail also covers batch k-1, which is far
+        # shorter than the forward that has just been queued)
+        _lib.check(lib.cerb_ctx_wait(ctx.handle, pctx.handle), "cerb_ctx_wait")
+        _lib.check(lib.cerb_memcpy(ctx.handle, ctypes.c_void_p(self.canvas_copy[s_out]),
+                                   ctypes.c_void_p(self.plan.tensor_ptr(self.plan.spec.canvas)),
+                                   self.canvas_bytes, 3), "cerb_memcpy")
+        _lib.check(lib.cerb_ctx_wait(pctx.handle, ctx.handle), "cerb_ctx_wait")  # post waits compute
         post = self.post[s_out]
-        post.run(self.plan)
-        _lib.check(lib.cerb_stream_order(ctx.handle, 1), "cerb_stream_order")  # D2H waits for compute
+        post.run(self.plan, canvas_ptr=self.canvas_copy[s_out])
+        if not download:
+            self.k += 1
+            return None
+        _lib.check(lib.cerb_stream_order(pctx.handle, 1), "cerb_stream_order")  # D2H waits for post
         for t in post.tissues:
-            _lib.check(lib.cerb_copy_async(ctx.handle, post.host[t].ctypes.data_as(ctypes.c_void_p),
+            _lib.check(lib.cerb_copy_async(pctx.handle, post.host[t].ctypes.data_as(ctypes.c_void_p),
                                            ctypes.c_void_p(post.dev[t]), post.nbytes, 2),
                        "cerb_copy_async")
-        _lib.check(lib.cerb_copy_mark(ctx.handle, s_out), "cerb_copy_mark")
+        _lib.check(lib.cerb_copy_mark(pctx.handle, s_out), "cerb_copy_mark")
         done = None
         if self.pending is not None:  # results of the previous batch (its D2H was queued earlier)
-            _lib.check(lib.cerb_copy_wait(ctx.handle, self.pending), "cerb_copy_wait")
+            _lib.check(lib.cerb_copy_wait(pctx.handle, self.pending), "cerb_copy_wait")
             done = self.post[self.pending].host
         self.pending = s_out
         self.k += 1
         return done
 
+    def join_streams(self):
+        """Makes the compute stream wait for the post stream (for timing with one end event)."""
+        _lib.check(self.lib.cerb_ctx_wait(self.ctx.handle, self.pctx.handle), "cerb_ctx_wait")
+
     def flush(self):
         if self.pending is None:
+            self.ctx.sync()
+            self.pctx.sync()
             return None
-        _lib.check(self.lib.cerb_copy_wait(self.ctx.handle, self.pending), "cerb_copy_wait")
+        _lib.check(self.lib.cerb_copy_wait(self.pctx.handle, self.pending), "cerb_copy_wait")
         self.ctx.sync()
+        self.pctx.sync()
         out = self.post[self.pending].host
         self.pending = None
         return out
+
+    @property
+    def launch_count(self):
+        return self.ctx.launch_count + self.pctx.launch_count
 
     def close(self):
         self.flush()
         for p in self.post:
             p.close()
+        for cp in self.canvas_copy:
+            self.lib.cerb_dev_free(self.ctx.handle, ctypes.c_void_p(cp))
         for hp in self.stage_host:
             self.lib.cerb_host_free(ctypes.c_void_p(hp))
         for dp in self.stage_dev:
             self.lib.cerb_dev_free(self.ctx.handle, ctypes.c_void_p(dp))
-        self.stage_host, self.stage_dev = [], []
+        self.stage_host, self.stage_dev, self.canvas_copy = [], [], []
+        self.pctx.close()

@@ -200,6 +200,11 @@ int cerb_copy_mark(cerb_ctx* ctx, int slot);
 int cerb_copy_wait(cerb_ctx* ctx, int slot);
 int cerb_copy_sync(cerb_ctx* ctx);
 
+/* Cross-context ordering on one device: work queued later on `waiter`'s compute stream waits for
+ * everything queued so far on `signal`'s compute stream (lets a second ctx run the
+ * post-processing of batch k while the first runs the forward of batch k+1). */
+int cerb_ctx_wait(cerb_ctx* waiter, cerb_ctx* signal);
+
 /* Pinned (page-locked) host memory for fast asynchronous H2D / D2H copies. */
 void* cerb_host_alloc(size_t bytes);
 void cerb_host_free(void* p);
