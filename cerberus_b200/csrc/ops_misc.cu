@@ -70,7 +70,9 @@ __global__ void prep_kernel(const uint8_t* __restrict__ in, __half* __restrict__
 }
 
 // ------------------------------------------------------------------ maxpool
-__global__ void maxpool_kernel(ActRef in, ActRef out) {
+// fp16 throughput mode: the maximum of fp16 values is exact, so the nine taps are loaded as raw
+// 16-byte words (all issued before the first compare) and reduced with packed __hmax2.
+__global__ void __launch_bounds__(256, 2) maxpool_kernel(ActRef in, ActRef out) {
   const int cg = out.c >> 3;
   const size_t total = static_cast<size_t>(out.n) * out.h * out.w * cg;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -81,6 +83,33 @@ __global__ void maxpool_kernel(ActRef in, ActRef out) {
     t /= out.w;
     const int oy = static_cast<int>(t % out.h);
     const int n = static_cast<int>(t / out.h);
+    const size_t ooff = ((static_cast<size_t>(n) * out.h + oy) * out.w + ox) * out.c + g * 8;
+    if (in.lo == nullptr) {
+      uint4 tap[9];
+      bool ok[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int y = 2 * oy + k / 3 - 1, x = 2 * ox + k % 3 - 1;
+        ok[k] = y >= 0 && y < in.h && x >= 0 && x < in.w;
+        if (ok[k])
+          tap[k] = __ldg(reinterpret_cast<const uint4*>(
+              in.hi + ((static_cast<size_t>(n) * in.h + y) * in.w + x) * in.c + g * 8));
+      }
+      // the centre tap (k = 4) is always inside the image
+      __half2 best[4];
+      const __half2* c4 = reinterpret_cast<const __half2*>(&tap[4]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) best[e] = c4[e];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if (k == 4 || !ok[k]) continue;
+        const __half2* h = reinterpret_cast<const __half2*>(&tap[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) best[e] = __hmax2(best[e], h[e]);
+      }
+      *reinterpret_cast<uint4*>(out.hi + ooff) = *reinterpret_cast<const uint4*>(best);
+      continue;
+    }
     float best_hi[8], best_lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { best_hi[e] = -FLT_MAX; best_lo[e] = 0.0f; }
@@ -93,12 +122,7 @@ __global__ void maxpool_kernel(ActRef in, ActRef out) {
         const size_t off = ((static_cast<size_t>(n) * in.h + y) * in.w + x) * in.c + g * 8;
         float vh[8], vl[8];
         load8(in.hi, nullptr, off, vh);
-        if (in.lo != nullptr) {
-          load8(in.lo, nullptr, off, vl);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) vl[e] = 0.0f;
-        }
+        load8(in.lo, nullptr, off, vl);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           // (hi, lo) pairs order lexicographically because hi = round(value).
@@ -109,7 +133,6 @@ __global__ void maxpool_kernel(ActRef in, ActRef out) {
         }
       }
     }
-    const size_t ooff = ((static_cast<size_t>(n) * out.h + oy) * out.w + ox) * out.c + g * 8;
     // hi and lo are copied verbatim (both already fp16-representable).
     uint4 uh, ul;
     uint32_t* ph = reinterpret_cast<uint32_t*>(&uh);
@@ -122,7 +145,7 @@ __global__ void maxpool_kernel(ActRef in, ActRef out) {
       pl[e] = *reinterpret_cast<const uint32_t*>(&l);
     }
     *reinterpret_cast<uint4*>(out.hi + ooff) = uh;
-    if (out.lo != nullptr) *reinterpret_cast<uint4*>(out.lo + ooff) = ul;
+    *reinterpret_cast<uint4*>(out.lo + ooff) = ul;
   }
 }
 
@@ -131,7 +154,7 @@ __global__ void maxpool_kernel(ActRef in, ActRef out) {
 // output pixels (X in {2i+1, 2i+2}, Y in {2j+1, 2j+2}, i/j from -1) for 8 channels: the four
 // outputs share the same four `prev` taps, so `prev` is read once instead of four times.
 // Per-output arithmetic is identical to the direct form (src = (dst + 0.5) / 2 - 0.5 clamped).
-__global__ void __launch_bounds__(256, 4) upadd_kernel(ActRef skip, ActRef prev, ActRef out) {
+__global__ void __launch_bounds__(256, 2) upadd_kernel(ActRef skip, ActRef prev, ActRef out) {
   const int cg = out.c >> 3;
   const int pw = prev.w + 1, ph = prev.h + 1;  // pair grid
   const size_t total = static_cast<size_t>(out.n) * ph * pw * cg;
@@ -151,28 +174,34 @@ __global__ void __launch_bounds__(256, 4) upadd_kernel(ActRef skip, ActRef prev,
     load8(prev.hi, prev.lo, ((pb + y0) * prev.w + x1) * prev.c + g * 8, p01);
     load8(prev.hi, prev.lo, ((pb + y1) * prev.w + x0) * prev.c + g * 8, p10);
     load8(prev.hi, prev.lo, ((pb + y1) * prev.w + x1) * prev.c + g * 8, p11);
+    // all eight 16-byte loads (4 prev taps above, 4 skip pixels here) are issued before any
+    // arithmetic so that they are in flight together
+    float sk[4][8];
+    bool ok[4];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int Y = 2 * j + 1 + dy;
-      if (Y < 0 || Y >= out.h) continue;
+    for (int k = 0; k < 4; ++k) {
+      const int Y = 2 * j + 1 + (k >> 1), X = 2 * i + 1 + (k & 1);
+      ok[k] = Y >= 0 && Y < out.h && X >= 0 && X < out.w;
+      if (ok[k]) {
+        load8(skip.hi, skip.lo, ((static_cast<size_t>(n) * skip.h + Y) * skip.w + X) * skip.c + g * 8, sk[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const int dy = k >> 1, dx = k & 1;
+      const int Y = 2 * j + 1 + dy, X = 2 * i + 1 + dx;
       const float ly = (j < 0) ? 0.0f : (dy == 0 ? 0.25f : 0.75f);
       const float hy = 1.0f - ly;
+      const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
+      const float hx = 1.0f - lx;
+      float o[8];
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int X = 2 * i + 1 + dx;
-        if (X < 0 || X >= out.w) continue;
-        const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
-        const float hx = 1.0f - lx;
-        const size_t off = ((static_cast<size_t>(n) * out.h + Y) * out.w + X) * out.c + g * 8;
-        float sk[8], o[8];
-        load8(skip.hi, skip.lo, ((static_cast<size_t>(n) * skip.h + Y) * skip.w + X) * skip.c + g * 8, sk);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float up = hy * (hx * p00[e] + lx * p01[e]) + ly * (hx * p10[e] + lx * p11[e]);
-          o[e] = sk[e] + up;
-        }
-        store8(out.hi, out.lo, off, o);
+      for (int e = 0; e < 8; ++e) {
+        const float up = hy * (hx * p00[e] + lx * p01[e]) + ly * (hx * p10[e] + lx * p11[e]);
+        o[e] = sk[k][e] + up;
       }
+      store8(out.hi, out.lo, ((static_cast<size_t>(n) * out.h + Y) * out.w + X) * out.c + g * 8, o);
     }
   }
 }
@@ -273,6 +302,7 @@ __global__ void pclass_kernel(PClassParams p) {
   for (int c = threadIdx.x; c < 512; c += blockDim.x) {
     float s = 0.0f;
     for (int y = 0; y < ch; ++y)
+#pragma unroll 9
       for (int x = 0; x < cw; ++x) {
         const size_t off = ((static_cast<size_t>(n) * h4 + y0 + y) * w4 + x0 + x) * p.x4.c + c;
         float v = __half2float(p.x4.hi[off]);
@@ -286,7 +316,8 @@ __global__ void pclass_kernel(PClassParams p) {
   for (int o = threadIdx.x; o < 256; o += blockDim.x) {
     float s = 0.0f;
     // W1 is packed transposed ([512][256]) so that a warp reads consecutive floats
-    for (int k = 0; k < 512; ++k) s = fmaf(pooled[k], W1[static_cast<size_t>(k) * 256 + o], s);
+#pragma unroll 16
+    for (int k = 0; k < 512; ++k) s = fmaf(pooled[k], __ldg(W1 + static_cast<size_t>(k) * 256 + o), s);
     hidden[o] = fmaxf(s + b1[o], 0.0f);
   }
   __syncthreads();
