@@ -507,6 +507,7 @@ extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
   if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
   for (void* p : ctx->scratch) cudaFree(p);
+  if (ctx->postproc_ws && ctx->postproc_ws_free) ctx->postproc_ws_free(ctx->postproc_ws);
   delete ctx;
 }
 

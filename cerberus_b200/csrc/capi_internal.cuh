@@ -26,6 +26,8 @@ struct cerb_ctx {
   int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout
   std::vector<void*> scratch;  // device allocations owned by the ctx (post-proc workspaces)
+  void* postproc_ws = nullptr;             // csrc/postproc.cu Workspace, created on first use
+  void (*postproc_ws_free)(void*) = nullptr;
 };
 
 namespace cerb {

@@ -149,7 +149,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && p.up_prev != nullptr) {
     // ---------------------------------------------------- fused `skip + bilinear_x2(prev)` producer
     // (models/net_desc.py:185-188). Two groups of four warps build alternate tiles' halos
     // directly in the swizzled shared-memory layout the MMA descriptors expect, so the summed
@@ -231,12 +231,18 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       ptx::named_bar_sync(1 + grp, kUpGroupThreads);  // staging may be overwritten by the next tile
     }
   } else {
+    // epilogue: warps 2-5 drain accumulator stage 0 (even tiles of this CTA); without the fused
+    // producer, warps 6-9 drain stage 1 (odd tiles) so that two tiles' epilogues overlap
+    const int egrp = (warp - 2) >> 2;
+    const bool two_groups = p.up_prev == nullptr;
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int py = m >> 3, px = m & 7;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      if (two_groups && (it & 1) != egrp) continue;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
       const int img = tile / tiles_per_img;
       const int rem = tile - img * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -299,8 +305,6 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
           }
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -360,7 +364,7 @@ cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t strea
     attr_set = true;
   }
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-  const int threads = p.up_prev != nullptr ? kConv64ThreadsUp : 192;
+  const int threads = p.up_prev != nullptr ? kConv64ThreadsUp : kConv64Threads;
   conv64_kernel<<<grid, threads, conv64_smem_bytes(p), stream>>>(p);
   return cudaGetLastError();
 }

@@ -7,8 +7,9 @@
 
 namespace cerb {
 
-// warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue, warps 6-13: fused upsample+add producers
-constexpr int kConv64Threads = 192;
+// warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5 (+ 6-9): epilogue groups; with the fused
+// upsample+add input, warps 6-13 are its producers and only warps 2-5 run the epilogue
+constexpr int kConv64Threads = 320;
 constexpr int kConv64ThreadsUp = 448;
 
 struct Conv64Params {

@@ -206,6 +206,76 @@ __global__ void __launch_bounds__(256, 2) upadd_kernel(ActRef skip, ActRef prev,
   }
 }
 
+// fp16 throughput-mode variant (no lo planes). Same 2x2-block decomposition and the same fp32
+// expression per output as upadd_kernel, but laid out for bandwidth: blockIdx.y = (image, pair
+// row), threads = (pair column, 8-channel group), so there is no index division chain, all
+// offsets are 32-bit, and the eight 16-byte loads of a thread are issued before any arithmetic.
+__device__ __forceinline__ void cvt8(const uint4& u, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+}
+
+__global__ void __launch_bounds__(288) upadd_f16_kernel(
+    const __half* __restrict__ skip, int skip_c, const __half* __restrict__ prev, int prev_c,
+    __half* __restrict__ out, int out_c, int PH, int PW, int cg_shift, int ipb) {
+  const int cg = 1 << cg_shift;
+  const int g = threadIdx.x & (cg - 1);
+  const int i = blockIdx.x * ipb + (threadIdx.x >> cg_shift) - 1;  // pair column, -1 .. PW-1
+  if (i >= PW) return;
+  const int ph = PH + 1;
+  const int n = blockIdx.y / ph;
+  const int j = blockIdx.y - n * ph - 1;  // pair row, -1 .. PH-1
+  const int H = 2 * PH, W = 2 * PW;
+  const int x0 = max(i, 0), x1 = min(i + 1, PW - 1);
+  const int y0 = max(j, 0), y1 = min(j + 1, PH - 1);
+  const uint32_t pb = static_cast<uint32_t>(n) * PH;
+  const uint32_t gc = g * 8;
+  const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y0) * PW + x0) * prev_c + gc));
+  const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y0) * PW + x1) * prev_c + gc));
+  const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y1) * PW + x0) * prev_c + gc));
+  const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y1) * PW + x1) * prev_c + gc));
+  const int Y0 = 2 * j + 1, X0 = 2 * i + 1;
+  const bool oky[2] = {Y0 >= 0, Y0 + 1 < H};
+  const bool okx[2] = {X0 >= 0, X0 + 1 < W};
+  const uint32_t pix00 = (static_cast<uint32_t>(n) * H + Y0) * W + X0;  // may wrap; used only when valid
+  uint4 sk[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sk[k] = make_uint4(0, 0, 0, 0);
+    if (oky[k >> 1] && okx[k & 1])
+      sk[k] = __ldg(reinterpret_cast<const uint4*>(skip + (pix00 + (k >> 1) * W + (k & 1)) * skip_c + gc));
+  }
+  float p00[8], p01[8], p10[8], p11[8];
+  cvt8(q00, p00); cvt8(q01, p01); cvt8(q10, p10); cvt8(q11, p11);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dy = k >> 1, dx = k & 1;
+    if (!(oky[dy] && okx[dx])) continue;
+    const float ly = (j < 0) ? 0.0f : (dy == 0 ? 0.25f : 0.75f);
+    const float hy = 1.0f - ly;
+    const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
+    const float hx = 1.0f - lx;
+    float s[8];
+    cvt8(sk[k], s);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float u0 = hy * (hx * p00[2 * e] + lx * p01[2 * e]) + ly * (hx * p10[2 * e] + lx * p11[2 * e]);
+      const float u1 = hy * (hx * p00[2 * e + 1] + lx * p01[2 * e + 1]) +
+                       ly * (hx * p10[2 * e + 1] + lx * p11[2 * e + 1]);
+      const __half2 h = __floats2half2_rn(s[2 * e] + u0, s[2 * e + 1] + u1);
+      ow[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(out + (pix00 + dy * W + dx) * out_c + gc) = o;
+  }
+}
+
 // ------------------------------------------------------------------ head tail
 constexpr int kHeadIn = 96;
 constexpr int kHeadMaxC = 8;
@@ -372,6 +442,21 @@ cudaError_t launch_maxpool(ActRef in, ActRef out, cudaStream_t s) {
 }
 
 cudaError_t launch_upadd(ActRef skip, ActRef prev, ActRef out, cudaStream_t s) {
+  const int cg = out.c >> 3;
+  const size_t out_elems = static_cast<size_t>(out.n) * out.h * out.w * out.c;
+  const size_t skip_elems = static_cast<size_t>(out.n) * out.h * out.w * skip.c;
+  if (skip.lo == nullptr && prev.lo == nullptr && out.lo == nullptr && (cg & (cg - 1)) == 0 && cg <= 32 &&
+      out_elems < (1ull << 31) && skip_elems < (1ull << 31) && out.h == 2 * prev.h && out.w == 2 * prev.w) {
+    int cg_shift = 0;
+    while ((1 << cg_shift) < cg) ++cg_shift;
+    const int pw = prev.w + 1;
+    const int nblk = (pw * cg + 255) / 256;
+    const int ipb = (pw + nblk - 1) / nblk;  // pair columns per block; ipb * cg <= 256 + cg
+    dim3 grid(nblk, out.n * (prev.h + 1));
+    upadd_f16_kernel<<<grid, ipb * cg, 0, s>>>(skip.hi, skip.c, prev.hi, prev.c, out.hi, out.c, prev.h,
+                                               prev.w, cg_shift, ipb);
+    return cudaGetLastError();
+  }
   const size_t total = static_cast<size_t>(out.n) * (prev.h + 1) * (prev.w + 1) * (out.c >> 3);
   upadd_kernel<<<grid_for(total, 256), 256, 0, s>>>(skip, prev, out);
   return cudaGetLastError();

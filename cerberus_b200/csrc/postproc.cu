@@ -1030,31 +1030,32 @@ Workspace* g_ws_for(cerb_ctx* ctx);
 template <typename T>
 cudaError_t grow(cerb_ctx* ctx, T*& p, size_t& cap_elems, size_t need) {
   if (need <= cap_elems && p != nullptr) return cudaSuccess;
-  // old buffer stays owned by ctx->scratch until the ctx is destroyed (grow-only workspace)
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, need * sizeof(T));
   if (e != cudaSuccess) return e;
+  if (p != nullptr) {
+    // the outgrown buffer may still be read by queued kernels: cudaFree synchronises the device
+    for (size_t i = 0; i < ctx->scratch.size(); ++i)
+      if (ctx->scratch[i] == p) {
+        ctx->scratch.erase(ctx->scratch.begin() + i);
+        break;
+      }
+    cudaFree(p);
+  }
   ctx->scratch.push_back(q);
   p = static_cast<T*>(q);
   cap_elems = need;
   return cudaSuccess;
 }
 
-struct WsHolder {
-  cerb_ctx* ctx;
-  Workspace ws;
-};
-constexpr int kMaxCtx = 64;
-WsHolder g_holders[kMaxCtx];
-int g_nholders = 0;
-
+// The workspace lives and dies with its ctx (a table keyed by the ctx address would hand a stale
+// workspace, full of freed pointers, to a later ctx allocated at the same address).
 Workspace* g_ws_for(cerb_ctx* ctx) {
-  for (int i = 0; i < g_nholders; ++i)
-    if (g_holders[i].ctx == ctx) return &g_holders[i].ws;
-  if (g_nholders >= kMaxCtx) return nullptr;
-  g_holders[g_nholders].ctx = ctx;
-  g_holders[g_nholders].ws = Workspace();
-  return &g_holders[g_nholders++].ws;
+  if (ctx->postproc_ws == nullptr) {
+    ctx->postproc_ws = new Workspace();
+    ctx->postproc_ws_free = [](void* w) { delete static_cast<Workspace*>(w); };
+  }
+  return static_cast<Workspace*>(ctx->postproc_ws);
 }
 
 int ensure_ws(cerb_ctx* ctx, Workspace*& ws, int n, int hw) {
@@ -1065,7 +1066,6 @@ int ensure_ws(cerb_ctx* ctx, Workspace*& ws, int n, int hw) {
     size_t c;
 #define GROW(field, type)                                                              \
   c = 0;                                                                               \
-  ws->field = nullptr;                                                                 \
   CERB_CUDA(grow<type>(ctx, ws->field, c, need));
     GROW(m0, uint8_t) GROW(m1, uint8_t) GROW(m2, uint8_t)
     GROW(L, int) GROW(size, int) GROW(rank, int) GROW(lab, int)
@@ -1076,10 +1076,8 @@ int ensure_ws(cerb_ctx* ctx, Workspace*& ws, int n, int hw) {
   }
   if (static_cast<size_t>(n) > ws->count_cap) {
     size_t c = 0;
-    ws->count = nullptr;
     CERB_CUDA(grow<int>(ctx, ws->count, c, static_cast<size_t>(n)));
     c = 0;
-    ws->any_fg = nullptr;
     CERB_CUDA(grow<int>(ctx, ws->any_fg, c, static_cast<size_t>(n)));
     ws->count_cap = n;
   }
