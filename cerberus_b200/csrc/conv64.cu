@@ -80,19 +80,26 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp walks the loop and ONE elected lane issues: a branch on `lane == 0` makes
+    // ptxas wrap every uniform-datapath instruction (UTMALDG, UTCHMMA) in an ELECT/BRA.U.ANY
+    // serialisation loop, which costs ~78 cycles per MMA (tools/umma_bench.cu, profiles/).
+    const bool leader = ptx::elect_one() != 0;
+    if (leader) {
       // resident weights: one 2-D box per tap
       ptx::mbar_arrive_expect_tx(w_bar, kWBytes);
+#pragma unroll
       for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * 8192, &p.w_map, w_bar, t * 64, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; p.up_prev == nullptr && tile < p.n_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_per_img;
-        const int rem = tile - img * tiles_per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int x0 = tx * kTileW - 1, y0 = ty * kTileH - 1;
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 21);
-        uint8_t* dst = sA + stage * stage_bytes;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; p.up_prev == nullptr && tile < p.n_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int x0 = tx * kTileW - 1, y0 = ty * kTileH - 1;
+      ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 21);
+      uint8_t* dst = sA + stage * stage_bytes;
+      if (leader) {
         ptx::mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
         if (p.mode == 0) {
           for (int s = 0; s < 3; ++s)
@@ -100,54 +107,54 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
         } else {
           ptx::tma_load_4d(dst, &p.in_map, &full_bar[stage], 0, x0, y0, img);
         }
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16(128, 64);
-      ptx::mbar_wait(w_bar, 0, p.err_flag, 22);
-      ptx::tc_fence_after();
-      const uint64_t a_d0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), p.sbo_bytes, 0);
-      const uint64_t b_d0 = ptx::umma_desc_sw128(ptx::smem_u32(sW), 1024, 0);
-      const uint32_t a_hi = static_cast<uint32_t>(a_d0 >> 32), a_lo0 = static_cast<uint32_t>(a_d0);
-      const uint32_t b_hi = static_cast<uint32_t>(b_d0 >> 32), b_lo0 = static_cast<uint32_t>(b_d0);
-      uint32_t tap_off[9];  // byte offset of tap (r, s) inside a stage, in 16-byte units
+    const bool leader = ptx::elect_one() != 0;
+    const uint32_t idesc = ptx::umma_idesc_f16(128, 64);
+    ptx::mbar_wait(w_bar, 0, p.err_flag, 22);
+    ptx::tc_fence_after();
+    const uint64_t a_d0 = ptx::umma_desc_sw128(ptx::smem_u32(sA), p.sbo_bytes, 0);
+    const uint64_t b_d0 = ptx::umma_desc_sw128(ptx::smem_u32(sW), 1024, 0);
+    const uint32_t a_hi = static_cast<uint32_t>(a_d0 >> 32), a_lo0 = static_cast<uint32_t>(a_d0);
+    const uint32_t b_hi = static_cast<uint32_t>(b_d0 >> 32), b_lo0 = static_cast<uint32_t>(b_d0);
+    uint32_t tap_off[9];  // byte offset of tap (r, s) inside a stage, in 16-byte units
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int r = t / 3, s = t - 3 * r;
-        tap_off[t] = static_cast<uint32_t>(
-            (p.mode == 0 ? s * p.copy_bytes + r * (kTileW * 128) : (r * p.pitch_px + s) * 128) >> 4);
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 23);
-        ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 24);
-        ptx::tc_fence_after();
+    for (int t = 0; t < 9; ++t) {
+      const int r = t / 3, s = t - 3 * r;
+      tap_off[t] = static_cast<uint32_t>(
+          (p.mode == 0 ? s * p.copy_bytes + r * (kTileW * 128) : (r * p.pitch_px + s) * 128) >> 4);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 23);
+      ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 24);
+      ptx::tc_fence_after();
+      if (leader) {
         const uint32_t tmem_d = tmem_base + acc * 64;
         // descriptor low words: only the 14-bit start-address field changes between MMAs
         const uint32_t a_lo = a_lo0 + static_cast<uint32_t>((stage * stage_bytes) >> 4);
-        const int n_taps = (p.debug & 2) ? 1 : 9;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          if (t < n_taps) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + tap_off[t] + 2 * k);
-              const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + t * 512 + 2 * k);
-              ptx::umma_f16(tmem_d, ad, bd, idesc, (t | k) != 0);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + tap_off[t] + 2 * k);
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo0 + t * 512 + 2 * k);
+            ptx::umma_f16(tmem_d, ad, bd, idesc, (t | k) != 0);
           }
         }
         ptx::umma_commit(&empty_bar[stage]);
         ptx::umma_commit(&tfull_bar[acc]);
-        if (++stage == n_stages) { stage = 0; phase ^= 1; }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
+      __syncwarp();
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 6 && p.up_prev != nullptr) {
     // ---------------------------------------------------- fused `skip + bilinear_x2(prev)` producer

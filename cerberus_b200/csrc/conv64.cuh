@@ -28,7 +28,7 @@ struct Conv64Params {
   const __half* up_skip;
   const __half* up_prev;
   int up_skip_cs, up_prev_cs;
-  int debug;  // attribution experiments: 1 = no global stores, 2 = one tap only, 4 = no epilogue math
+  int debug;  // attribution experiments: 1 = no global stores, 4 = no epilogue math
   // filled by conv64_plan
   int pitch_px, copy_bytes, stage_bytes, tx_bytes, sbo_bytes, n_stages;
   int* err_flag;

@@ -92,21 +92,25 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (kATileBytes + b_tile_bytes);
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_ntiles;
-        const int mt = tile / p.n_ntiles;
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int img = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * BW, y0 = ty * BH;
-        for (int t = 0; t < p.n_taps; ++t) {
-          const ConvTap tap = p.taps[t];
-          for (int c = 0; c < p.n_chunks; ++c) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+    // The whole warp walks the loops and ONE elected lane issues: a branch on `lane == 0` makes
+    // ptxas wrap every uniform-datapath instruction (UTMALDG, UTCHMMA) in an ELECT/BRA.U.ANY
+    // serialisation loop (~78 cycles per instruction; tools/umma_bench.cu, profiles/).
+    const bool leader = ptx::elect_one() != 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (kATileBytes + b_tile_bytes);
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_ntiles;
+      const int mt = tile / p.n_ntiles;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int img = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * BW, y0 = ty * BH;
+      for (int t = 0; t < p.n_taps; ++t) {
+        const ConvTap tap = p.taps[t];
+        for (int c = 0; c < p.n_chunks; ++c) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+          if (leader) {
             uint8_t* sA = smem + stage * stage_bytes;
             uint8_t* sB = sA + (SPLIT ? 2 : 1) * kATileBytes;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -120,50 +124,56 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
               ptx::tma_load_2d(sB + b_tile_bytes, &p.w_lo, &full_bar[stage],
                                (t * p.n_chunks + c) * 64, nt * p.BN);
             }
-            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16(128, p.BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+    const bool leader = ptx::elect_one() != 0;
+    const uint32_t idesc = ptx::umma_idesc_f16(128, p.BN);
+    // descriptor of stage 0, k-step 0; only the 14-bit start-address field (16-byte units) moves
+    const uint64_t a_d0 = ptx::umma_desc_sw128(ptx::smem_u32(smem), 1024);
+    const uint32_t stage_u = static_cast<uint32_t>(stage_bytes >> 4);
+    const uint32_t b_off_u = static_cast<uint32_t>(((SPLIT ? 2 : 1) * kATileBytes) >> 4);
+    const uint32_t lo_a_u = static_cast<uint32_t>(kATileBytes >> 4);
+    const uint32_t lo_b_u = static_cast<uint32_t>(b_tile_bytes >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kAccStride;
+      for (int ks = 0; ks < n_ksteps; ++ks) {
+        ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * kAccStride;
-        for (int ks = 0; ks < n_ksteps; ++ks) {
-          ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + (SPLIT ? 2 : 1) * kATileBytes;
+        if (leader) {
+          const uint64_t a0 = a_d0 + static_cast<uint32_t>(stage) * stage_u;
+          const uint64_t b0 = a0 + b_off_u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x (K = 16) per 64-channel slab
-            const uint64_t a_hi = ptx::umma_desc_sw128(a_addr + k * 32, 1024);
-            const uint64_t b_hi = ptx::umma_desc_sw128(b_addr + k * 32, 1024);
             if (!SPLIT) {
-              ptx::umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) != 0);
+              ptx::umma_f16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (ks | k) != 0);
             } else {
-              const uint64_t a_lo = ptx::umma_desc_sw128(a_addr + kATileBytes + k * 32, 1024);
-              const uint64_t b_lo = ptx::umma_desc_sw128(b_addr + b_tile_bytes + k * 32, 1024);
-              ptx::umma_f16(tmem_d + ((k & 1) ? kSplitMain1 : 0), a_hi, b_hi, idesc,
+              ptx::umma_f16(tmem_d + ((k & 1) ? kSplitMain1 : 0), a0 + 2 * k, b0 + 2 * k, idesc,
                             (ks != 0) || (k >= 2));
-              ptx::umma_f16(tmem_d + kSplitCross, a_lo, b_hi, idesc, (ks | k) != 0);
-              ptx::umma_f16(tmem_d + kSplitCross, a_hi, b_lo, idesc, 1);
+              ptx::umma_f16(tmem_d + kSplitCross, a0 + lo_a_u + 2 * k, b0 + 2 * k, idesc, (ks | k) != 0);
+              ptx::umma_f16(tmem_d + kSplitCross, a0 + 2 * k, b0 + lo_b_u + 2 * k, idesc, 1);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs retire
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        acc = (acc + 1) % kAccStages;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
+      if (leader) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      acc = (acc + 1) % kAccStages;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ------------------------------------------------------------ epilogue (2 groups x 4 warps)
