@@ -205,9 +205,20 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
       return fail(CERB_ERR_ARG, "conv64: bias offset out of range");
     p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
   }
-  p.out = static_cast<__half*>(out.plane[0]);
-  p.out_cs = out.d.c;
-  p.out_coff = op.out_coff;
+  if (op.out_coff % 8 != 0 || op.out_coff + 64 > out.d.c || out.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv64: bad output channels");
+  {
+    const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(out.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * out.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * out.d.c * es};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(conv64_tile_w()),
+                               static_cast<cuuint32_t>(conv64_tile_h()), 1};
+    int rc = encode_map(ctx, &p.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, dims,
+                        strides, box);
+    if (rc) return rc;
+  }
   if (op.in1 >= 0) {
     if (op.in1 >= static_cast<int>(pl->tensors.size()))
       return fail(CERB_ERR_ARG, "conv64: residual id out of range");
@@ -215,8 +226,16 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
     if (res.d.n != N || res.d.h != H || res.d.w != W || res.d.c < 64 || res.d.c % 8 != 0 ||
         res.d.dtype != CERB_F16)
       return fail(CERB_ERR_ARG, "conv64: residual shape mismatch");
-    p.res = static_cast<const __half*>(res.plane[0]);
-    p.res_cs = res.d.c;
+    const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(res.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * res.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * res.d.c * es};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(conv64_tile_w()),
+                               static_cast<cuuint32_t>(conv64_tile_h()), 1};
+    int rc = encode_map(ctx, &p.res_map, res.plane[0], 4, dims, strides, box);
+    if (rc) return rc;
+    p.has_res = 1;
   }
   if (op.up_prev1 > 0) {
     const int pid = op.up_prev1 - 1;
@@ -236,6 +255,7 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64: w_shift out of range");
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
+  p.prof = ctx->prof_dev;
   return CERB_OK;
 }
 
@@ -438,6 +458,7 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv: w_shift out of range");
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
+  p.prof = ctx->prof_dev;
   conv_tc_plan_pipeline(p, split);
   return CERB_OK;
 }
@@ -506,6 +527,7 @@ extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
     if (ctx->slot_event[i]) cudaEventDestroy(ctx->slot_event[i]);
   if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
+  if (ctx->prof_dev) cudaFree(ctx->prof_dev);
   for (void* p : ctx->scratch) cudaFree(p);
   if (ctx->postproc_ws && ctx->postproc_ws_free) ctx->postproc_ws_free(ctx->postproc_ws);
   delete ctx;
@@ -555,6 +577,18 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
   }
   if (strcmp(name, "conv64_debug") == 0) {
     ctx->conv64_debug = value;
+    return CERB_OK;
+  }
+  if (strcmp(name, "kernel_prof") == 0) {
+    // plans created afterwards hand the 64->64 kernel a counter buffer (cerb_ctx_read_prof)
+    CERB_CUDA(cudaSetDevice(ctx->device));
+    if (value != 0 && ctx->prof_dev == nullptr) {
+      CERB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->prof_dev), kProfSlots * sizeof(long long)));
+      CERB_CUDA(cudaMemset(ctx->prof_dev, 0, kProfSlots * sizeof(long long)));
+    } else if (value == 0 && ctx->prof_dev != nullptr) {
+      cudaFree(ctx->prof_dev);
+      ctx->prof_dev = nullptr;
+    }
     return CERB_OK;
   }
   return fail(CERB_ERR_ARG, "cerb_ctx_set_option: unknown option %s", name);
@@ -610,6 +644,16 @@ extern "C" int cerb_copy_sync(cerb_ctx* ctx) {
   CERB_CUDA(cudaSetDevice(ctx->device));
   CERB_CUDA(cudaStreamSynchronize(ctx->up_stream));
   CERB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  return CERB_OK;
+}
+
+extern "C" int cerb_ctx_read_prof(cerb_ctx* ctx, int64_t* out, int n, int reset) {
+  if (!ctx || !out || n <= 0 || n > kProfSlots) return fail(CERB_ERR_ARG, "cerb_ctx_read_prof: bad arguments");
+  if (ctx->prof_dev == nullptr) return fail(CERB_ERR_ARG, "cerb_ctx_read_prof: option kernel_prof is off");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  CERB_CUDA(cudaStreamSynchronize(ctx->stream));
+  CERB_CUDA(cudaMemcpy(out, ctx->prof_dev, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (reset) CERB_CUDA(cudaMemset(ctx->prof_dev, 0, kProfSlots * sizeof(long long)));
   return CERB_OK;
 }
 

@@ -23,6 +23,7 @@ struct cerb_ctx {
   int64_t launches = 0;
   bool use_graphs = true;  // replay the forward op list as a CUDA graph
   int conv64_debug = 0;
+  long long* prof_dev = nullptr;  // [kProfSlots] in-kernel attribution counters (option "kernel_prof")
   int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout
   std::vector<void*> scratch;  // device allocations owned by the ctx (post-proc workspaces)
@@ -31,6 +32,8 @@ struct cerb_ctx {
 };
 
 namespace cerb {
+
+constexpr int kProfSlots = 256 * 16;
 
 extern thread_local std::string g_last_error;
 int fail(int code, const char* fmt, ...);

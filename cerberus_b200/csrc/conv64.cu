@@ -23,9 +23,15 @@ namespace cerb {
 
 namespace {
 
+// In-kernel attribution (Conv64Params::prof != nullptr): cycles a role spends in each wait.
+#define CERB_PROF_T0(var) const long long var = p.prof != nullptr ? clock64() : 0
+#define CERB_PROF_ADD(acc, var) \
+  do { if (p.prof != nullptr) acc += clock64() - var; } while (0)
+
 constexpr int kWBytes = 9 * 64 * 128;  // resident weights: 9 taps x 64 rows x 128 B
 constexpr int kTileW = 8, kTileH = 16;
 constexpr int kTmemCols = 128;  // 2 accumulator stages x 64 columns
+constexpr int kOutTileBytes = 128 * 128;  // 128 pixels x 64 fp16 channels
 constexpr int kUpGroupThreads = 128;
 constexpr int kUpStageBytes = (18 * 10 + 10 * 6) * 128;  // skip halo + prev patch, per producer group
 
@@ -45,17 +51,21 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
   const int stage_bytes = p.stage_bytes;
 
   uint8_t* sW = smem;
-  uint8_t* sA = smem + kWBytes;
+  uint8_t* sOut = smem + kWBytes;            // 2 x 16 KB output / residual staging (epilogue groups)
+  uint8_t* sA = sOut + 2 * kOutTileBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + n_stages * stage_bytes);
   uint64_t* empty_bar = full_bar + n_stages;
   uint64_t* tfull_bar = empty_bar + n_stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* w_bar = tempty_bar + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* res_bar = w_bar + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.in_map);
     ptx::prefetch_tmap(&p.w_map);
+    ptx::prefetch_tmap(&p.out_map);
+    if (p.has_res) ptx::prefetch_tmap(&p.res_map);
     for (int s = 0; s < n_stages; ++s) {
       // fused upsample+add: the 128 threads of one producer group arrive instead of a TMA
       ptx::mbar_init(&full_bar[s], p.up_prev != nullptr ? kUpGroupThreads : 1);
@@ -66,6 +76,8 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       ptx::mbar_init(&tempty_bar[s], 4);
     }
     ptx::mbar_init(w_bar, 1);
+    ptx::mbar_init(&res_bar[0], 1);
+    ptx::mbar_init(&res_bar[1], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -92,12 +104,15 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     }
     int stage = 0;
     uint32_t phase = 0;
+    long long prof_a = 0;
     for (int tile = blockIdx.x; p.up_prev == nullptr && tile < p.n_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img;
       const int rem = tile - img * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int x0 = tx * kTileW - 1, y0 = ty * kTileH - 1;
+      CERB_PROF_T0(t_pe);
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 21);
+      CERB_PROF_ADD(prof_a, t_pe);
       uint8_t* dst = sA + stage * stage_bytes;
       if (leader) {
         ptx::mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
@@ -111,6 +126,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       __syncwarp();
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
+    if (p.prof != nullptr && lane == 0) p.prof[blockIdx.x * 16 + 0] = prof_a;
   } else if (warp == 1) {
     const bool leader = ptx::elect_one() != 0;
     const uint32_t idesc = ptx::umma_idesc_f16(128, 64);
@@ -131,10 +147,17 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long prof_a = 0, prof_b = 0, prof_c = 0;
+    CERB_PROF_T0(t_all);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      CERB_PROF_T0(t_m0);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 23);
+      CERB_PROF_ADD(prof_a, t_m0);
+      CERB_PROF_T0(t_m1);
       ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 24);
+      CERB_PROF_ADD(prof_b, t_m1);
       ptx::tc_fence_after();
+      CERB_PROF_T0(t_m2);
       if (leader) {
         const uint32_t tmem_d = tmem_base + acc * 64;
         // descriptor low words: only the 14-bit start-address field changes between MMAs
@@ -152,9 +175,14 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
         ptx::umma_commit(&tfull_bar[acc]);
       }
       __syncwarp();
+      CERB_PROF_ADD(prof_c, t_m2);
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.prof != nullptr && lane == 0) {
+      long long* o = p.prof + blockIdx.x * 16;
+      o[1] = prof_a; o[2] = prof_b; o[3] = prof_c; o[8] = clock64() - t_all;
     }
   } else if (warp >= 6 && p.up_prev != nullptr) {
     // ---------------------------------------------------- fused `skip + bilinear_x2(prev)` producer
@@ -239,13 +267,23 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     }
   } else {
     // epilogue: warps 2-5 drain accumulator stage 0 (even tiles of this CTA); without the fused
-    // producer, warps 6-9 drain stage 1 (odd tiles) so that two tiles' epilogues overlap
+    // producer, warps 6-9 drain stage 1 (odd tiles) so that two tiles' epilogues overlap.
+    // A thread owns one pixel (= one TMEM lane = one 128-byte row of the output tile). Writing
+    // that row straight to global memory makes every warp store touch 32 different lines; the
+    // rows go to a swizzled shared-memory tile instead and ONE TMA store per tile writes whole
+    // lines (and clips partial tiles at the image border). The residual tile arrives in the same
+    // staging buffer by TMA while the MMAs of the tile are still running.
     const int egrp = (warp - 2) >> 2;
     const bool two_groups = p.up_prev == nullptr;
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int py = m >> 3, px = m & 7;
+    const int gtid = static_cast<int>(threadIdx.x) - (2 + 4 * egrp) * 32;
+    uint8_t* sO = sOut + egrp * kOutTileBytes;
+    uint8_t* my_row = sO + m * 128;
+    const int sw = m & 7;  // 128-byte swizzle: 16-byte chunk c of row m lives at chunk c ^ (m & 7)
+    uint32_t res_phase = 0;
     int it = 0;
+    long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0, prof_e = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       if (two_groups && (it & 1) != egrp) continue;
       const int acc = it & 1;
@@ -253,65 +291,94 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       const int img = tile / tiles_per_img;
       const int rem = tile - img * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int ox = tx * kTileW + px, oy = ty * kTileH + py;
-      const bool valid = (ox < p.W) && (oy < p.H);
-      const size_t pix = (static_cast<size_t>(img) * p.H + oy) * p.W + ox;
+      const int x0 = tx * kTileW, y0 = ty * kTileH;
+      CERB_PROF_T0(t_e0);
+      if (gtid == 0) {
+        ptx::bulk_wait_read<0>();  // the previous store of this group has drained the staging tile
+        if (p.has_res) {
+          ptx::mbar_arrive_expect_tx(&res_bar[egrp], kOutTileBytes);
+          ptx::tma_load_4d(sO, &p.res_map, &res_bar[egrp], 0, x0, y0, img);
+        }
+      }
+      CERB_PROF_ADD(prof_e, t_e0);
+      CERB_PROF_T0(t_e1);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 25);
+      CERB_PROF_ADD(prof_a, t_e1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 64;
       uint32_t r0[32], r1[32];
       ptx::tmem_ld32(taddr, r0);
       ptx::tmem_ld32(taddr + 32, r1);
       ptx::tmem_ld_wait();
-      // the accumulator is in registers: release it before the global-memory epilogue
+      // the accumulator is in registers: release it before the rest of the epilogue
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      if (valid && !(p.debug & 4)) {
+      if (p.debug & 4) continue;
+      CERB_PROF_T0(t_e2);
+      if (p.has_res) {
+        ptx::mbar_wait(&res_bar[egrp], res_phase, p.err_flag, 27);
+        res_phase ^= 1;
+      } else {
+        ptx::named_bar_sync(3 + egrp, 128);  // thread 0 has seen the staging tile drained
+      }
+      CERB_PROF_ADD(prof_b, t_e2);
+      CERB_PROF_T0(t_e3);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            v[i] = __uint_as_float(half == 0 ? r0[i] : r1[i]) * p.acc_scale;
-          const int j = half * 32;
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + j);
+        for (int i = 0; i < 32; ++i)
+          v[i] = __uint_as_float(half == 0 ? r0[i] : r1[i]) * p.acc_scale;
+        const int j = half * 32;
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + j);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-            }
-          }
-          if (p.res != nullptr) {
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res + pix * p.res_cs + j);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(rh + i);
-              const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h[e]);
-                v[8 * i + 2 * e] += f.x; v[8 * i + 2 * e + 1] += f.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-          }
-          uint4* oh = reinterpret_cast<uint4*>(p.out + pix * p.out_cs + p.out_coff + j);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
-            u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
-            u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
-            if (!(p.debug & 1)) oh[i] = u;
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
           }
         }
+        if (p.has_res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = *reinterpret_cast<const uint4*>(my_row + (((half * 4 + i) ^ sw) << 4));
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h[e]);
+              v[8 * i + 2 * e] += f.x; v[8 * i + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+          u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+          u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+          *reinterpret_cast<uint4*>(my_row + (((half * 4 + i) ^ sw) << 4)) = u;
+        }
       }
+      CERB_PROF_ADD(prof_c, t_e3);
+      CERB_PROF_T0(t_e4);
+      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+      ptx::named_bar_sync(3 + egrp, 128);
+      if (gtid == 0 && !(p.debug & 1)) {
+        ptx::tma_store_4d(&p.out_map, sO, 0, x0, y0, img);
+        ptx::bulk_commit_group();
+      }
+      CERB_PROF_ADD(prof_d, t_e4);
+    }
+    if (gtid == 0) ptx::bulk_wait_all<0>();
+    if (p.prof != nullptr && gtid == 0) {
+      long long* o = p.prof + blockIdx.x * 16 + (egrp == 0 ? 4 : 10);
+      o[0] = prof_a; o[1] = prof_b; o[2] = prof_c; o[3] = prof_d; o[5] = prof_e;
     }
   }
 
@@ -347,7 +414,7 @@ void conv64_plan(Conv64Params& p) {
     p.tx_bytes = p.copy_bytes;
     p.sbo_bytes = 16 * 128;
   }
-  int n = (200 * 1024 - kWBytes - (p.up_prev != nullptr ? 2 * kUpStageBytes : 0)) / p.stage_bytes;
+  int n = (224 * 1024 - kWBytes - 2 * kOutTileBytes - (p.up_prev != nullptr ? 2 * kUpStageBytes : 0)) / p.stage_bytes;
   if (n > 4) n = 4;
   if (n < 2) n = 2;
   p.n_stages = n;
@@ -358,7 +425,7 @@ int conv64_tile_w() { return kTileW; }
 int conv64_tile_h() { return kTileH; }
 
 size_t conv64_smem_bytes(const Conv64Params& p) {
-  return static_cast<size_t>(kWBytes) + static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 +
+  return static_cast<size_t>(kWBytes) + 2 * kOutTileBytes + static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 +
          (p.up_prev != nullptr ? 2 * kUpStageBytes : 0);
 }
 

@@ -15,14 +15,14 @@ constexpr int kConv64ThreadsUp = 448;
 struct Conv64Params {
   CUtensorMap in_map;  // [64 ch, W, H, N], box {64, conv64_box_w(mode), 18, 1}
   CUtensorMap w_map;   // [576, 64], box {64, 64}
+  CUtensorMap out_map; // output [64 ch, W, H, N], box {64, 8, 16, 1} (TMA store)
+  CUtensorMap res_map; // residual, same geometry (TMA load into the staging tile)
+  int has_res;
   int mode;            // halo layout, see conv64.cu
   int n_img, H, W;
   int tiles_x, tiles_y, n_tiles;
   const float* bias;
   float acc_scale;
-  __half* out;
-  const __half* res;
-  int out_cs, out_coff, res_cs;
   int relu;
   // fused input: A = up_skip + bilinear_x2(up_prev) instead of a TMA load of in_map (mode 1 only)
   const __half* up_skip;
@@ -32,6 +32,7 @@ struct Conv64Params {
   // filled by conv64_plan
   int pitch_px, copy_bytes, stage_bytes, tx_bytes, sbo_bytes, n_stages;
   int* err_flag;
+  long long* prof;  // optional [grid][16] per-role wait cycles (cerb_ctx_set_option "kernel_prof")
 };
 
 void conv64_plan(Conv64Params& p);

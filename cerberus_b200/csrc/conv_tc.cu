@@ -15,6 +15,11 @@ namespace cerb {
 
 namespace {
 
+// In-kernel attribution (ConvKParams::prof != nullptr): cycles a role spends in each phase.
+#define CERB_PROF_T0(var) const long long var = p.prof != nullptr ? clock64() : 0
+#define CERB_PROF_ADD(acc, var) \
+  do { if (p.prof != nullptr) acc += clock64() - var; } while (0)
+
 constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 fp16 channels
 constexpr int kTmemCols = 512;
 constexpr int kMaxAcc = 4;  // accumulator stages (= epilogue warp groups): 512 TMEM columns / n_acc each
@@ -25,6 +30,7 @@ constexpr int kMaxAcc = 4;  // accumulator stages (= epilogue warp groups): 512 
 // epilogue adds the three in fp32 (round-to-nearest).
 constexpr int kSplitMain1 = 128;
 constexpr int kSplitCross = 256;
+constexpr int kHeadA2Bytes = 2 * kATileBytes;  // hidden tile of one epilogue group: 2 slabs x 16 KB
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -45,16 +51,35 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   const int stage_bytes = p.stage_bytes;
   const int b_tile_bytes = p.BN * 128;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
+  // MMA tail (fp16 mode, fused classification head): per epilogue group a [128 x 96] fp16 hidden
+  // tile (two 128-byte-swizzled 64-channel slabs) and the [16 x 96] fp16 head weights, both
+  // K-major UMMA operands, sit between the pipeline stages and the barriers.
+  const bool mma_tail = !SPLIT && p.mma_tail != 0;
+  uint8_t* sA2 = smem + n_stages * stage_bytes;
+  uint8_t* sB2 = sA2 + kMaxAcc * kHeadA2Bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(mma_tail ? sB2 + 4096 : sA2);
   uint64_t* empty_bar = full_bar + n_stages;
   uint64_t* tfull_bar = empty_bar + n_stages;
   uint64_t* tempty_bar = tfull_bar + kMaxAcc;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAcc);
+  uint64_t* head_bar = reinterpret_cast<uint64_t*>(tmem_holder + 2);  // [kMaxAcc], MMA-tail mode
   // [C][96] fp32 when the head tail is fused (16-byte aligned for float4 reads)
   float* s_head_w = reinterpret_cast<float*>(
-      (reinterpret_cast<uintptr_t>(tmem_holder + 1) + 15) & ~static_cast<uintptr_t>(15));
+      (reinterpret_cast<uintptr_t>(head_bar + kMaxAcc) + 15) & ~static_cast<uintptr_t>(15));
   if (p.head_classes > 0) {
-    for (int i = threadIdx.x; i < p.head_classes * 96; i += blockDim.x) s_head_w[i] = p.head_w[i];
+    if (!mma_tail) {
+      for (int i = threadIdx.x; i < p.head_classes * 96; i += blockDim.x) s_head_w[i] = p.head_w[i];
+    } else {
+      // B2[n][k] = fp16(head_w[n][k]) for n < C, zero rows up to N = 16
+      for (int i = threadIdx.x; i < 16 * 96; i += blockDim.x) {
+        const int n = i / 96, k = i - n * 96;
+        const float w = n < p.head_classes ? p.head_w[n * 96 + k] : 0.0f;
+        const int slab = k >> 6, kk = k & 63;
+        *reinterpret_cast<__half*>(sB2 + slab * 2048 + n * 128 + ((((kk >> 3) ^ (n & 7))) << 4) +
+                                   (kk & 7) * 2) = __float2half_rn(w);
+      }
+      ptx::fence_proxy_async_smem();
+    }
   }
 
   if (warp == 0 && lane == 0) {
@@ -71,6 +96,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     for (int s = 0; s < kMaxAcc; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
       ptx::mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+      ptx::mbar_init(&head_bar[s], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -99,6 +125,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (kATileBytes + b_tile_bytes);
+    long long prof_a = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_ntiles;
       const int mt = tile / p.n_ntiles;
@@ -109,7 +136,9 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       for (int t = 0; t < p.n_taps; ++t) {
         const ConvTap tap = p.taps[t];
         for (int c = 0; c < p.n_chunks; ++c) {
+          CERB_PROF_T0(t_p0);
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+          CERB_PROF_ADD(prof_a, t_p0);
           if (leader) {
             uint8_t* sA = smem + stage * stage_bytes;
             uint8_t* sB = sA + (SPLIT ? 2 : 1) * kATileBytes;
@@ -130,6 +159,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
         }
       }
     }
+    if (p.prof != nullptr && lane == 0) p.prof[blockIdx.x * 16 + 0] = prof_a;
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const bool leader = ptx::elect_one() != 0;
@@ -144,13 +174,20 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long prof_a = 0, prof_b = 0, prof_c = 0;
+    CERB_PROF_T0(t_all);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      CERB_PROF_T0(t_m0);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+      CERB_PROF_ADD(prof_a, t_m0);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * kAccStride;
       for (int ks = 0; ks < n_ksteps; ++ks) {
+        CERB_PROF_T0(t_m1);
         ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+        CERB_PROF_ADD(prof_b, t_m1);
         ptx::tc_fence_after();
+        CERB_PROF_T0(t_m2);
         if (leader) {
           const uint64_t a0 = a_d0 + static_cast<uint32_t>(stage) * stage_u;
           const uint64_t b0 = a0 + b_off_u;
@@ -168,12 +205,17 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs retire
         }
         __syncwarp();
+        CERB_PROF_ADD(prof_c, t_m2);
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
       if (leader) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
       __syncwarp();
       acc = (acc + 1) % kAccStages;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.prof != nullptr && lane == 0) {
+      long long* o = p.prof + blockIdx.x * 16;
+      o[1] = prof_a; o[2] = prof_b; o[3] = prof_c; o[8] = clock64() - t_all;
     }
   } else {
     // ------------------------------------------------------------ epilogue (2 groups x 4 warps)
@@ -185,6 +227,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     const int py = m >> p.bw_log2, px = m & bw_mask;
     const int acc = grp;
     uint32_t use = 0;
+    long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
     for (int tile = blockIdx.x + grp * gridDim.x; grp < kAccStages && tile < p.n_tiles;
          tile += kAccStages * gridDim.x, ++use) {
       const uint32_t acc_phase = use & 1;
@@ -198,9 +241,97 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       const size_t pix = (static_cast<size_t>(img) * p.H + oy) * p.W + ox;
       const int n0 = nt * p.BN;
 
+      CERB_PROF_T0(t_e0);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      CERB_PROF_ADD(prof_a, t_e0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
+      CERB_PROF_T0(t_e1);
+      if (mma_tail) {
+        // ---- classification head on the tensor core: hidden = ReLU(acc + bias) -> fp16 tile in
+        // shared memory (A operand), logits = hidden x W2^T as six N = 16 MMAs into TMEM columns
+        // 96..111 of this accumulator stage (the main MMA, N = 96, never touches them).
+        uint8_t* a2 = sA2 + grp * kHeadA2Bytes;
+        const int sw = m & 7;
+#pragma unroll
+        for (int j = 0; j < 96; j += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(taddr + j, r);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.acc_scale;
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int cj = (j >> 3) + i;  // 16-byte chunk index inside the 96-channel row
+            uint4 u;
+            u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+            *reinterpret_cast<uint4*>(a2 + (cj >> 3) * kATileBytes + m * 128 + (((cj & 7) ^ sw) << 4)) = u;
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);  // main accumulator drained
+        CERB_PROF_ADD(prof_b, t_e1);
+        CERB_PROF_T0(t_e2);
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(1 + grp, 128);
+        if (q == 2) {  // first warp of the group (warps 2, 6, 10, 14 have warp & 3 == 2)
+          if (ptx::elect_one()) {
+            ptx::tc_fence_after();
+            const uint32_t idesc2 = ptx::umma_idesc_f16(128, 16);
+            const uint64_t ad = ptx::umma_desc_sw128(ptx::smem_u32(a2), 1024);
+            const uint64_t bd = ptx::umma_desc_sw128(ptx::smem_u32(sB2), 1024);
+            const uint32_t d2 = tmem_base + acc * kAccStride + 96;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              const uint32_t a_off = static_cast<uint32_t>(((k >> 2) * kATileBytes + (k & 3) * 32) >> 4);
+              const uint32_t b_off = static_cast<uint32_t>(((k >> 2) * 2048 + (k & 3) * 32) >> 4);
+              ptx::umma_f16(d2, ad + a_off, bd + b_off, idesc2, k != 0);
+            }
+            ptx::umma_commit(&head_bar[grp]);
+          }
+          __syncwarp();
+        }
+        ptx::mbar_wait(&head_bar[grp], acc_phase, p.err_flag, 5);
+        CERB_PROF_ADD(prof_c, t_e2);
+        CERB_PROF_T0(t_e3);
+        ptx::tc_fence_after();
+        uint32_t r8[8];
+        ptx::tmem_ld8(taddr + 96, r8);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        if (valid) {
+          float hacc[kHeadMaxC];
+#pragma unroll
+          for (int c = 0; c < kHeadMaxC; ++c)
+            hacc[c] = c < p.head_classes ? __uint_as_float(r8[c]) + __ldg(p.head_b + c) : 0.0f;
+          const int y_off = static_cast<int>((p.H - p.oh) * 0.5), x_off = static_cast<int>((p.W - p.ow) * 0.5);
+          const int cy = oy - y_off, cx = ox - x_off;
+          float* dst = nullptr;
+          if (cy >= 0 && cy < p.oh && cx >= 0 && cx < p.ow)
+            dst = p.canvas + ((static_cast<size_t>(img) * p.oh + cy) * p.ow + cx) * p.canvas_c + p.canvas_coff;
+          head_tail(hacc, p.head_classes, p.head_mode,
+                    p.logits != nullptr ? p.logits + pix * p.head_classes : nullptr, dst);
+        }
+        CERB_PROF_ADD(prof_d, t_e3);
+        continue;
+      }
       float hacc[kHeadMaxC];
 #pragma unroll
       for (int c = 0; c < kHeadMaxC; ++c) hacc[c] = 0.0f;
@@ -314,6 +445,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      CERB_PROF_ADD(prof_b, t_e1);
       if (p.head_classes > 0 && valid) {
 #pragma unroll
         for (int c = 0; c < kHeadMaxC; ++c)
@@ -326,6 +458,10 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
         head_tail(hacc, p.head_classes, p.head_mode,
                   p.logits != nullptr ? p.logits + pix * p.head_classes : nullptr, dst);
       }
+    }
+    if (p.prof != nullptr && (warp & 3) == 2 && lane == 0 && grp < 2) {
+      long long* o = p.prof + blockIdx.x * 16 + (grp == 0 ? 4 : 10);
+      o[0] = prof_a; o[1] = prof_b; o[2] = prof_c; o[3] = prof_d;
     }
   }
 
@@ -344,7 +480,10 @@ void conv_tc_plan_pipeline(ConvKParams& p, bool split) {
   // groups when the tile is narrow enough for 4 x BN TMEM columns
   p.n_acc = (!split && p.BN <= 128 && p.n_taps * p.n_chunks <= 2) ? 4 : 2;
   p.stage_bytes = (split ? 2 : 1) * (kATileBytes + p.BN * 128);
-  int n = (192 * 1024) / p.stage_bytes;
+  int budget = 192 * 1024;
+  p.mma_tail = (!split && p.head_classes > 0 && p.n_acc == 4 && p.BN == 96) ? 1 : 0;
+  if (p.mma_tail) budget = 224 * 1024 - kMaxAcc * kHeadA2Bytes - 4096;  // MMA tail staging
+  int n = budget / p.stage_bytes;
   if (n > 8) n = 8;
   if (n < 2) n = 2;
   p.n_stages = n;
@@ -355,6 +494,7 @@ size_t conv_tc_smem_bytes(const ConvKParams& p) {
   // Always above half the SM's shared memory so that exactly one CTA (and one 512-column
   // TMEM allocation) lives on an SM at a time.
   size_t b = static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 + 3200;
+  if (p.mma_tail) b += kMaxAcc * kHeadA2Bytes + 4096;
   if (b < 120 * 1024) b = 120 * 1024;
   return b;
 }

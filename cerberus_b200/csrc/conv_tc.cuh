@@ -63,7 +63,9 @@ struct ConvKParams {
   int n_acc;  // accumulator stages = epilogue groups (2 or 4; split mode always 1)
   int n_stages;
   int stage_bytes;
+  int mma_tail;  // fused head: 1x1 96 -> C on the tensor core (fp16 mode), else fp32 FMAs
   int* err_flag;
+  long long* prof;  // optional [grid][16] per-role cycle counters (option "kernel_prof")
 };
 
 // Host side: encodes nothing, just launches. `split` selects the 3-MMA hi/lo mode.

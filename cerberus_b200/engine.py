@@ -43,6 +43,12 @@ class Context:
     def sync(self):
         _lib.check(self.lib.cerb_ctx_sync(self.handle), "cerb_ctx_sync")
 
+    def read_prof(self, n_ctas=148, reset=True):
+        """Per-CTA wait-cycle counters of the last 64->64 launch (option kernel_prof): int64 [n_ctas,16]."""
+        buf = (ctypes.c_int64 * (n_ctas * 16))()
+        _lib.check(self.lib.cerb_ctx_read_prof(self.handle, buf, n_ctas * 16, int(reset)), "cerb_ctx_read_prof")
+        return np.frombuffer(buf, dtype=np.int64).reshape(n_ctas, 16).copy()
+
     @property
     def launch_count(self):
         return int(self.lib.cerb_ctx_launch_count(self.handle))

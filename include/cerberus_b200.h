@@ -113,6 +113,10 @@ int cerb_ctx_sync(cerb_ctx* ctx);
 /* Tuning knobs applied to plans created afterwards. "conv64_mode": -1 = generic kernel for every
  * convolution, 0/1/2 = halo layout of the 64->64 3x3 kernel (csrc/conv64.cu). */
 int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value);
+/* Attribution evidence (option "kernel_prof" = 1 before creating the plan): the 64->64 3x3 kernel
+ * stores, per CTA, 16 counters of clock cycles each role spent waiting (layout in csrc/conv64.cu;
+ * the last launch wins). Copies the first n counters (n <= 4096) and optionally zeroes them. */
+int cerb_ctx_read_prof(cerb_ctx* ctx, int64_t* out, int n, int reset);
 /* Number of kernels this library launched on ctx since creation (bench's gpu_launches). */
 int64_t cerb_ctx_launch_count(cerb_ctx* ctx);
 /* Raw CUDA stream handle (cudaStream_t) of the ctx, for event timing by the caller. */

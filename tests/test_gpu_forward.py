@@ -157,3 +157,35 @@ def test_tile_pipeline_streams_batches_in_order(built_lib, six_head_sd):
             assert np.array_equal(g[t], w_[t]), t
     pipe.close()
     eng.close()
+
+
+def test_fused_head_on_tensor_core_matches_fp32_head(built_lib, six_head_sd):
+    """fp16 mode: the fused head runs its 1x1 96->C on the tensor core (hidden tile and head
+    weights rounded to fp16, fp32 accumulation). It must agree with the unfused path (hidden
+    tensor in HBM as fp16, CERB_OP_HEAD in fp32 FMAs) to fp16-rounding accuracy of the head
+    weights, on every head and for a batch that does not fill the last tile row."""
+    from cerberus_b200.engine import Context, ForwardPlan
+    from cerberus_b200.plan import PackedModel, PlanSpec
+    args = synth.model_args()
+    model = PackedModel(six_head_sd, args)
+    tiles = synth.synthetic_tiles(3, 256, 256, seed=5)
+    ctx = Context(0, "f16")
+    out = []
+    for fuse in (True, False):
+        spec = PlanSpec(model, 3, 256, 256, 256, 256, want_logits=True, fuse_head=fuse)
+        plan = ForwardPlan(ctx, model, 3, 256, 256, 256, 256, spec=spec)
+        plan.run(tiles)
+        out.append(({k: v.copy() for k, v in plan.read_logits().items()}, plan.read_canvas().copy()))
+        plan.close()
+    ctx.close()
+    (lg_f, cv_f), (lg_u, cv_u) = out
+    for k in lg_u:
+        if k == "Patch-Class":
+            continue
+        err = float(np.abs(lg_f[k] - lg_u[k]).max())
+        scale = float(np.abs(lg_u[k]).max())
+        print("%s: fused-vs-unfused max-abs %.4g (logit scale %.3g)" % (k, err, scale))
+        assert err <= 4e-3 * max(scale, 1.0), (k, err, scale)
+    # probabilities written to the canvas agree as well
+    inst = [i for k, (a, b) in model.idx_dict.items() if k.endswith("-INST") for i in range(a, b)]
+    assert float(np.abs(cv_f[..., inst] - cv_u[..., inst]).max()) <= 5e-3
