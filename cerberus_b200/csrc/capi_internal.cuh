@@ -25,6 +25,8 @@ struct cerb_ctx {
   int conv64_debug = 0;
   long long* prof_dev = nullptr;  // [kProfSlots] in-kernel attribution counters (option "kernel_prof")
   int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only
+  int k_rotate = 1;     // per-CTA rotated K walk in conv3x3.cu (de-synchronises weight-slab reads)
+  int conv3_mode = 1;   // 0: generic kernel for the wide 3x3 layers; 1: conv3x3.cu (cout <= 512); 2: always
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout
   std::vector<void*> scratch;  // device allocations owned by the ctx (post-proc workspaces)
   void* postproc_ws = nullptr;             // csrc/postproc.cu Workspace, created on first use

@@ -281,6 +281,9 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     uint8_t* sO = sOut + egrp * kOutTileBytes;
     uint8_t* my_row = sO + m * 128;
     const int sw = m & 7;  // 128-byte swizzle: 16-byte chunk c of row m lives at chunk c ^ (m & 7)
+    // first warp of the group issues the TMA traffic through an elected lane (uniform branch:
+    // no ELECT/BRA.U.ANY serialisation loop around UTMALDG / UTMASTG)
+    const bool store_warp = q == 2;
     uint32_t res_phase = 0;
     int it = 0;
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0, prof_e = 0;
@@ -293,7 +296,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int x0 = tx * kTileW, y0 = ty * kTileH;
       CERB_PROF_T0(t_e0);
-      if (gtid == 0) {
+      if (store_warp && ptx::elect_one()) {
         ptx::bulk_wait_read<0>();  // the previous store of this group has drained the staging tile
         if (p.has_res) {
           ptx::mbar_arrive_expect_tx(&res_bar[egrp], kOutTileBytes);
@@ -369,13 +372,13 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       CERB_PROF_T0(t_e4);
       ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
       ptx::named_bar_sync(3 + egrp, 128);
-      if (gtid == 0 && !(p.debug & 1)) {
+      if (store_warp && !(p.debug & 1) && ptx::elect_one()) {
         ptx::tma_store_4d(&p.out_map, sO, 0, x0, y0, img);
         ptx::bulk_commit_group();
       }
       CERB_PROF_ADD(prof_d, t_e4);
     }
-    if (gtid == 0) ptx::bulk_wait_all<0>();
+    if (store_warp) ptx::bulk_wait_all<0>();  // only the elected lane has groups pending
     if (p.prof != nullptr && gtid == 0) {
       long long* o = p.prof + blockIdx.x * 16 + (egrp == 0 ? 4 : 10);
       o[0] = prof_a; o[1] = prof_b; o[2] = prof_c; o[3] = prof_d; o[5] = prof_e;

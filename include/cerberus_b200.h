@@ -111,7 +111,9 @@ void cerb_ctx_destroy(cerb_ctx* ctx);
 const char* cerb_last_error(void);
 int cerb_ctx_sync(cerb_ctx* ctx);
 /* Tuning knobs applied to plans created afterwards. "conv64_mode": -1 = generic kernel for every
- * convolution, 0/1/2 = halo layout of the 64->64 3x3 kernel (csrc/conv64.cu). */
+ * convolution, 0/1/2 = halo layout of the 64->64 3x3 kernel (csrc/conv64.cu). "conv3_mode": 0 =
+ * generic kernel for the wide 3x3 stride-1 layers, 1 (default) = halo kernel csrc/conv3x3.cu for
+ * Cout <= 512, 2 = for every Cout. "use_graphs", "ws_mode", "kernel_prof": see capi.cu. */
 int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value);
 /* Attribution evidence (option "kernel_prof" = 1 before creating the plan): the 64->64 3x3 kernel
  * stores, per CTA, 16 counters of clock cycles each role spent waiting (layout in csrc/conv64.cu;

@@ -24,6 +24,9 @@ CASES = [
     (1, 64, 64, 64, 96, 1, 1, False, True),     # head hidden layer, BN = 96
     (3, 16, 16, 512, 512, 3, 1, True, True),    # layer4: K = 4608
     (1, 48, 80, 128, 64, 3, 1, False, True),    # non-square
+    (2, 64, 64, 128, 128, 3, 1, False, True),   # layer2 / decoder u3: halo kernel, several regions per CTA
+    (5, 40, 24, 128, 128, 3, 1, True, False),   # partial regions in x and y, residual, no ReLU
+    (40, 16, 16, 256, 128, 3, 1, False, True),  # more work items than SMs, 4 chunks
 ]
 
 

@@ -36,6 +36,9 @@ def main():
     ctx = Context(0, "f16")
     ctx.set_option("kernel_prof", 1)
     ctx.set_option("use_graphs", 0)
+    for kv in os.environ.get("CERB_OPTS", "").split(","):
+        if "=" in kv:
+            ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     plan = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
     plan.write(ti, rng.standard_normal((n, h, w, cin)).astype(np.float16))
     if res:
@@ -55,7 +58,8 @@ def main():
         if generic:
             SLOTS[5:8] = ["epi0 ld+math(+sts)", "epi0 fence+bar+mma2+wait", "epi0 tail"]
             SLOTS[11:14] = ["epi1 ld+math(+sts)", "epi1 fence+bar+mma2+wait", "epi1 tail"]
-            SLOTS[9] = SLOTS[15] = "-"
+            SLOTS[9] = "mma wait A-halo (conv3x3)"
+            SLOTS[15] = "-"
         tot = c[:, 8].astype(np.float64)
         print("  per-CTA cycles (mean over %d CTAs; kernel total %.0f):" % (len(c), tot.mean()))
         for i, name in enumerate(SLOTS):
