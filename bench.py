@@ -346,7 +346,7 @@ def run_ours(args):
             tid = op["in0"] if op["aux_classes"] else op["out"]
             _, n_, h_, w_, _, _ = spec.tensors[tid]
             if (op["in_c"] == 64 and op["cout"] == 64 and op["kh"] == 3 and op["stride"] == 1
-                    and h_ == TILE and w_ == TILE and not op["stem"]):
+                    and h_ == TILE and w_ == TILE and not op["stem"] and not op["aux_classes"]):
                 dom_ms += ms_
                 dom_n += 1
                 dom_fl += 2.0 * n_ * h_ * w_ * 64 * 576

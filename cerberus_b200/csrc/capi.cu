@@ -169,7 +169,8 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
   Conv64Params& p = st.c64;
   memset(&p, 0, sizeof(p));
   st.use64 = true;
-  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  const bool tail = op.aux_classes > 0;  // fused classification head: `out` is the fp32 canvas
+  const int H = tail ? in.d.h : out.d.h, W = tail ? in.d.w : out.d.w, N = out.d.n;
   p.mode = ctx->conv64_mode;
   p.debug = ctx->conv64_debug;
   p.n_img = N;
@@ -208,9 +209,48 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
       return fail(CERB_ERR_ARG, "conv64: bias offset out of range");
     p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
   }
-  if (op.out_coff % 8 != 0 || op.out_coff + 64 > out.d.c || out.d.c % 8 != 0)
-    return fail(CERB_ERR_ARG, "conv64: bad output channels");
-  {
+  if (tail) {
+    const int width = op.head_mode == CERB_HEAD_INST ? op.aux_classes - 1 : 1;
+    const int nt = static_cast<int>(pl->tensors.size());
+    if (ctx->conv64_mode != 1 || op.in1 >= 0 || op.up_prev1 > 0 || op.aux_classes < 2 ||
+        op.aux_classes > 8 || out.d.dtype != CERB_F32 || out.d.h > H || out.d.w > W ||
+        op.out_coff < 0 || op.out_coff + width > out.d.c || op.tail_w_off < 0 ||
+        op.tail_w_off % 16 != 0 || op.tail_b_off < 0 || op.tail_b_off % 16 != 0 ||
+        op.aux_w_off < 0 || op.aux_b_off < 0 ||
+        static_cast<size_t>(op.tail_w_off) + 96u * 64u * es > pl->blob_bytes ||
+        static_cast<size_t>(op.tail_b_off) + 96u * 4u > pl->blob_bytes ||
+        static_cast<size_t>(op.aux_w_off) + op.aux_classes * 96 * 4u > pl->blob_bytes ||
+        static_cast<size_t>(op.aux_b_off) + op.aux_classes * 4u > pl->blob_bytes ||
+        op.tail_w_shift < -60 || op.tail_w_shift > 60)
+      return fail(CERB_ERR_ARG, "conv64: bad fused-head description");
+    const cuuint64_t dims[2] = {64, 96};
+    const cuuint64_t strides[1] = {64 * es};
+    const cuuint32_t box[2] = {64, 96};
+    int rc = encode_map(ctx, &p.w1_map, pl->blob + op.tail_w_off, 2, dims, strides, box);
+    if (rc) return rc;
+    p.has_tail = 1;
+    p.tail_b1 = reinterpret_cast<const float*>(pl->blob + op.tail_b_off);
+    p.tail_scale = ldexpf(1.0f, -op.tail_w_shift);
+    p.tail_w2 = reinterpret_cast<const float*>(pl->blob + op.aux_w_off);
+    p.tail_b2 = reinterpret_cast<const float*>(pl->blob + op.aux_b_off);
+    p.tail_classes = op.aux_classes;
+    p.tail_mode = op.head_mode;
+    p.canvas = static_cast<float*>(out.plane[0]);
+    p.oh = out.d.h;
+    p.ow = out.d.w;
+    p.canvas_c = out.d.c;
+    p.canvas_coff = op.out_coff;
+    if (op.logits_out >= 0) {
+      if (op.logits_out >= nt) return fail(CERB_ERR_ARG, "conv64: logits id out of range");
+      const Tensor& lg = pl->tensors[op.logits_out];
+      if (lg.d.dtype != CERB_F32 || lg.d.n != N || lg.d.h != H || lg.d.w != W ||
+          lg.d.c != op.aux_classes)
+        return fail(CERB_ERR_ARG, "conv64: fused-head logits tensor mismatch");
+      p.logits = static_cast<float*>(lg.plane[0]);
+    }
+  } else {
+    if (op.out_coff % 8 != 0 || op.out_coff + 64 > out.d.c || out.d.c % 8 != 0)
+      return fail(CERB_ERR_ARG, "conv64: bad output channels");
     const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                                 static_cast<cuuint64_t>(N)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(out.d.c) * es,
@@ -353,6 +393,13 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
     return fail(CERB_ERR_ARG, "conv: tensor id out of range");
   const Tensor& in = pl->tensors[op.in0];
   const Tensor& out = pl->tensors[op.out];
+  if (op.aux_classes > 0 && op.kh == 3) {
+    // 64->64 3x3 conv with the whole classification head fused behind it (csrc/conv64.cu)
+    if (ctx->precision != CERB_PREC_F16 || op.stem || op.kw != 3 || op.stride != 1 || op.pad != 1 ||
+        op.in_c != 64 || op.cout != 64 || in.d.dtype != CERB_F16 || in.d.n != out.d.n)
+      return fail(CERB_ERR_ARG, "conv: a fused head tail needs the 64->64 3x3 kernel in CERB_PREC_F16");
+    return build_conv64(pl, op, st);
+  }
   const bool fused_head = op.aux_classes > 0;
   if (in.d.dtype != CERB_F16 || out.d.dtype != (fused_head ? CERB_F32 : CERB_F16))
     return fail(CERB_ERR_ARG, "conv: tensors must be fp16 (fp32 canvas for a fused head)");

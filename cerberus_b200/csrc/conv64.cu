@@ -17,6 +17,7 @@
 // tests/test_gpu_conv.py runs all three against the fp32 reference; capi.cu uses the mode
 // selected by cerb_ctx_set_option(ctx, "conv64_mode", m).
 #include "conv64.cuh"
+#include "head_tail.cuh"
 #include "ptx.cuh"
 
 namespace cerb {
@@ -30,7 +31,11 @@ namespace {
 
 constexpr int kWBytes = 9 * 64 * 128;  // resident weights: 9 taps x 64 rows x 128 B
 constexpr int kTileW = 8, kTileH = 16;
-constexpr int kTmemCols = 128;  // 2 accumulator stages x 64 columns
+constexpr int kTmemCols = 128;      // 2 accumulator stages x 64 columns
+constexpr int kTmemColsTail = 512;  // + per epilogue group 96 (hidden) + 16 (logits) columns at 128 + 128 * group
+constexpr int kTailW1Bytes = 96 * 128;   // head hidden weights [96][64] fp16
+constexpr int kTailW2Bytes = 2 * 2048;   // head output weights [16][96] fp16, two 64-channel slabs
+constexpr int kTailBytes = kTailW1Bytes + kTailW2Bytes + 2 * 128 * 128;  // + second hidden slab per group
 constexpr int kOutTileBytes = 128 * 128;  // 128 pixels x 64 fp16 channels
 constexpr int kUpGroupThreads = 128;
 constexpr int kUpStageBytes = (18 * 10 + 10 * 6) * 128;  // skip halo + prev patch, per producer group
@@ -52,19 +57,25 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
 
   uint8_t* sW = smem;
   uint8_t* sOut = smem + kWBytes;            // 2 x 16 KB output / residual staging (epilogue groups)
-  uint8_t* sA = sOut + 2 * kOutTileBytes;
+  uint8_t* sTail = sOut + 2 * kOutTileBytes;  // fused head: W1 | W2 | second hidden slab per group
+  uint8_t* sW1 = sTail;
+  uint8_t* sW2 = sW1 + kTailW1Bytes;
+  uint8_t* sH1 = sW2 + kTailW2Bytes;
+  uint8_t* sA = sTail + (p.has_tail ? kTailBytes : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + n_stages * stage_bytes);
   uint64_t* empty_bar = full_bar + n_stages;
   uint64_t* tfull_bar = empty_bar + n_stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* w_bar = tempty_bar + 2;
   uint64_t* res_bar = w_bar + 1;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* tail_bar = res_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tail_bar + 2);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.in_map);
     ptx::prefetch_tmap(&p.w_map);
     ptx::prefetch_tmap(&p.out_map);
+    if (p.has_tail) ptx::prefetch_tmap(&p.w1_map);
     if (p.has_res) ptx::prefetch_tmap(&p.res_map);
     for (int s = 0; s < n_stages; ++s) {
       // fused upsample+add: the 128 threads of one producer group arrive instead of a TMA
@@ -78,11 +89,24 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     ptx::mbar_init(w_bar, 1);
     ptx::mbar_init(&res_bar[0], 1);
     ptx::mbar_init(&res_bar[1], 1);
+    ptx::mbar_init(&tail_bar[0], 1);
+    ptx::mbar_init(&tail_bar[1], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_holder, kTmemCols);
+    ptx::tmem_alloc(tmem_holder, p.has_tail ? kTmemColsTail : kTmemCols);
     ptx::tmem_relinquish();
+  }
+  if (p.has_tail) {
+    // W2[n][k] = fp16(tail_w2[n][k]) for n < C, zero rows up to N = 16 (K-major, 128-byte swizzle)
+    for (int i = threadIdx.x; i < 16 * 96; i += blockDim.x) {
+      const int n = i / 96, k = i - n * 96;
+      const float w = n < p.tail_classes ? p.tail_w2[n * 96 + k] : 0.0f;
+      const int slab = k >> 6, kk = k & 63;
+      *reinterpret_cast<__half*>(sW2 + slab * 2048 + n * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2) =
+          __float2half_rn(w);
+    }
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -98,9 +122,10 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     const bool leader = ptx::elect_one() != 0;
     if (leader) {
       // resident weights: one 2-D box per tap
-      ptx::mbar_arrive_expect_tx(w_bar, kWBytes);
+      ptx::mbar_arrive_expect_tx(w_bar, kWBytes + (p.has_tail ? kTailW1Bytes : 0));
 #pragma unroll
       for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * 8192, &p.w_map, w_bar, t * 64, 0);
+      if (p.has_tail) ptx::tma_load_2d(sW1, &p.w1_map, w_bar, 0, 0);
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -284,7 +309,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     // first warp of the group issues the TMA traffic through an elected lane (uniform branch:
     // no ELECT/BRA.U.ANY serialisation loop around UTMALDG / UTMASTG)
     const bool store_warp = q == 2;
-    uint32_t res_phase = 0;
+    uint32_t res_phase = 0, tail_phase = 0;
     int it = 0;
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0, prof_e = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -296,7 +321,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int x0 = tx * kTileW, y0 = ty * kTileH;
       CERB_PROF_T0(t_e0);
-      if (store_warp && ptx::elect_one()) {
+      if (!p.has_tail && store_warp && ptx::elect_one()) {
         ptx::bulk_wait_read<0>();  // the previous store of this group has drained the staging tile
         if (p.has_res) {
           ptx::mbar_arrive_expect_tx(&res_bar[egrp], kOutTileBytes);
@@ -370,11 +395,107 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       }
       CERB_PROF_ADD(prof_c, t_e3);
       CERB_PROF_T0(t_e4);
-      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store / the MMA
       ptx::named_bar_sync(3 + egrp, 128);
-      if (store_warp && !(p.debug & 1) && ptx::elect_one()) {
-        ptx::tma_store_4d(&p.out_map, sO, 0, x0, y0, img);
-        ptx::bulk_commit_group();
+      if (!p.has_tail) {
+        if (store_warp && !(p.debug & 1) && ptx::elect_one()) {
+          ptx::tma_store_4d(&p.out_map, sO, 0, x0, y0, img);
+          ptx::bulk_commit_group();
+        }
+        CERB_PROF_ADD(prof_d, t_e4);
+        continue;
+      }
+      // ---- fused classification head (models/utils/net_layers.py:31-38, run_desc.py:451-491):
+      // the tile just written is the A operand of the hidden 1x1 64 -> 96 (four N = 96 MMAs into
+      // this group's TMEM columns), whose ReLU output is the A operand of the 1x1 96 -> C (six
+      // N = 16 MMAs); the 64- and 96-channel tensors never exist in HBM.
+      const uint32_t d2 = tmem_base + 128 + egrp * 128;
+      const uint32_t t2addr = d2 + (static_cast<uint32_t>(q * 32) << 16);
+      if (store_warp) {
+        if (ptx::elect_one()) {
+          ptx::tc_fence_after();
+          const uint32_t idesc1 = ptx::umma_idesc_f16(128, 96);
+          const uint64_t ad = ptx::umma_desc_sw128(ptx::smem_u32(sO), 1024);
+          const uint64_t bd = ptx::umma_desc_sw128(ptx::smem_u32(sW1), 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_f16(d2, ad + 2 * k, bd + 2 * k, idesc1, k != 0);
+          ptx::umma_commit(&tail_bar[egrp]);
+        }
+        __syncwarp();
+      }
+      ptx::mbar_wait(&tail_bar[egrp], tail_phase, p.err_flag, 28);
+      tail_phase ^= 1;
+      ptx::tc_fence_after();
+      uint8_t* sH = sH1 + egrp * kOutTileBytes;  // channels 64..95 of the hidden tile
+#pragma unroll
+      for (int j = 0; j < 96; j += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(t2addr + j, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.tail_scale;
+        const float4* b4 = reinterpret_cast<const float4*>(p.tail_b1 + j);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          v[4 * i + 0] = fmaxf(v[4 * i + 0] + b.x, 0.0f);
+          v[4 * i + 1] = fmaxf(v[4 * i + 1] + b.y, 0.0f);
+          v[4 * i + 2] = fmaxf(v[4 * i + 2] + b.z, 0.0f);
+          v[4 * i + 3] = fmaxf(v[4 * i + 3] + b.w, 0.0f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cj = (j >> 3) + i;  // 16-byte chunk inside the 96-channel row
+          uint4 u;
+          u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+          u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+          u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+          uint8_t* base = cj < 8 ? sO : sH;
+          *reinterpret_cast<uint4*>(base + m * 128 + (((cj & 7) ^ sw) << 4)) = u;
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(3 + egrp, 128);
+      if (store_warp) {
+        if (ptx::elect_one()) {
+          ptx::tc_fence_after();
+          const uint32_t idesc2 = ptx::umma_idesc_f16(128, 16);
+          const uint64_t a0 = ptx::umma_desc_sw128(ptx::smem_u32(sO), 1024);
+          const uint64_t a1 = ptx::umma_desc_sw128(ptx::smem_u32(sH), 1024);
+          const uint64_t bd = ptx::umma_desc_sw128(ptx::smem_u32(sW2), 1024);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const uint64_t ad = (k < 4 ? a0 : a1) + 2 * (k & 3);
+            ptx::umma_f16(d2 + 96, ad, bd + static_cast<uint32_t>(((k >> 2) * 2048 + (k & 3) * 32) >> 4), idesc2, k != 0);
+          }
+          ptx::umma_commit(&tail_bar[egrp]);
+        }
+        __syncwarp();
+      }
+      ptx::mbar_wait(&tail_bar[egrp], tail_phase, p.err_flag, 29);
+      tail_phase ^= 1;
+      ptx::tc_fence_after();
+      uint32_t r8[8];
+      ptx::tmem_ld8(t2addr + 96, r8);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      const int ox = x0 + (m & 7), oy = y0 + (m >> 3);
+      if (ox < p.W && oy < p.H) {
+        float hacc[kHeadMaxC];
+#pragma unroll
+        for (int c = 0; c < kHeadMaxC; ++c)
+          hacc[c] = c < p.tail_classes ? __uint_as_float(r8[c]) + __ldg(p.tail_b2 + c) : 0.0f;
+        const int y_off = static_cast<int>((p.H - p.oh) * 0.5), x_off = static_cast<int>((p.W - p.ow) * 0.5);
+        const int cy = oy - y_off, cx = ox - x_off;
+        float* dst = nullptr;
+        if (cy >= 0 && cy < p.oh && cx >= 0 && cx < p.ow)
+          dst = p.canvas + ((static_cast<size_t>(img) * p.oh + cy) * p.ow + cx) * p.canvas_c + p.canvas_coff;
+        const size_t pix = (static_cast<size_t>(img) * p.H + oy) * p.W + ox;
+        head_tail(hacc, p.tail_classes, p.tail_mode,
+                  p.logits != nullptr ? p.logits + pix * p.tail_classes : nullptr, dst);
       }
       CERB_PROF_ADD(prof_d, t_e4);
     }
@@ -390,7 +511,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
   if (warp == 1) {
     __syncwarp();
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    ptx::tmem_dealloc(tmem_base, p.has_tail ? kTmemColsTail : kTmemCols);
   }
 }
 
@@ -417,7 +538,8 @@ void conv64_plan(Conv64Params& p) {
     p.tx_bytes = p.copy_bytes;
     p.sbo_bytes = 16 * 128;
   }
-  int n = (224 * 1024 - kWBytes - 2 * kOutTileBytes - (p.up_prev != nullptr ? 2 * kUpStageBytes : 0)) / p.stage_bytes;
+  int n = (224 * 1024 - kWBytes - 2 * kOutTileBytes - (p.has_tail ? kTailBytes : 0) -
+           (p.up_prev != nullptr ? 2 * kUpStageBytes : 0)) / p.stage_bytes;
   if (n > 4) n = 4;
   if (n < 2) n = 2;
   p.n_stages = n;
@@ -428,7 +550,8 @@ int conv64_tile_w() { return kTileW; }
 int conv64_tile_h() { return kTileH; }
 
 size_t conv64_smem_bytes(const Conv64Params& p) {
-  return static_cast<size_t>(kWBytes) + 2 * kOutTileBytes + static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 +
+  return static_cast<size_t>(kWBytes) + 2 * kOutTileBytes + (p.has_tail ? kTailBytes : 0) +
+         static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 +
          (p.up_prev != nullptr ? 2 * kUpStageBytes : 0);
 }
 

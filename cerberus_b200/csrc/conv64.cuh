@@ -18,6 +18,18 @@ struct Conv64Params {
   CUtensorMap out_map; // output [64 ch, W, H, N], box {64, 8, 16, 1} (TMA store)
   CUtensorMap res_map; // residual, same geometry (TMA load into the staging tile)
   int has_res;
+  // fused classification head (has_tail): hidden 1x1 64 -> 96 + BN + ReLU, 1x1 96 -> C, softmax /
+  // argmax / centre crop into the canvas; the conv's own 64-channel output is not stored
+  CUtensorMap w1_map;  // [64, 96] fp16 hidden weights, box {64, 96}
+  int has_tail;
+  const float* tail_b1;  // [96]
+  float tail_scale;      // 2^-w_shift of the hidden layer
+  const float* tail_w2;  // [C][96] fp32
+  const float* tail_b2;  // [C]
+  int tail_classes, tail_mode;
+  float* canvas;         // [N, oh, ow, canvas_c]
+  float* logits;         // optional [N, H, W, C]
+  int oh, ow, canvas_c, canvas_coff;
   int mode;            // halo layout, see conv64.cu
   int n_img, H, W;
   int tiles_x, tiles_y, n_tiles;

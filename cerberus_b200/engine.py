@@ -81,7 +81,15 @@ class ForwardPlan:
             # producer warps are instruction-bound), so it is opt-in.
             fuse_up = (ctx.precision == "f16" and ctx.conv64_mode == 1
                        and os.environ.get("CERB_FUSE_UPADD", "0") == "1")
-            spec = PlanSpec(model, n, h, w, out_h, out_w, want_logits, fuse_upadd=fuse_up)
+            # Last decoder conv + output head in one kernel (csrc/conv64.cu, fp16 mode only): exact
+            # to fp16 rounding and saves 2 x 268 MB of HBM traffic per decoder at batch 32, but
+            # measured SLOWER on B200 (0.315 ms vs 0.150 + 0.143 ms): the two tail MMAs of a tile queue
+            # behind the next tile's 36 main MMAs in the in-order tensor pipe and two epilogue groups
+            # cannot hide those round trips. Opt-in until the tail is software-pipelined.
+            fuse_tail = (ctx.precision == "f16" and ctx.conv64_mode == 1
+                         and os.environ.get("CERB_FUSE_TAIL", "0") == "1")
+            spec = PlanSpec(model, n, h, w, out_h, out_w, want_logits, fuse_upadd=fuse_up,
+                            fuse_tail=fuse_tail)
         self.spec = spec
         td, ops = self.spec.c_arrays()
         blob = model.blob

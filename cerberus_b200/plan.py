@@ -133,7 +133,7 @@ class PlanSpec:
     """Tensors + ops for one batch shape. Pure host data (testable without a GPU)."""
 
     def __init__(self, model, n, h, w, out_h, out_w, want_logits=False, fuse_head=True,
-                 fuse_upadd=False):
+                 fuse_upadd=False, fuse_tail=False):
         if h % 16 or w % 16:
             raise ValueError("input size must be a multiple of 16 (got %dx%d)" % (h, w))
         if out_h > h or out_w > w:
@@ -202,8 +202,8 @@ class PlanSpec:
             b1 = T("b1", n, hs[1], ws[1], 64)
             s0 = T("s0", n, h, w, 64) if not fuse_upadd else -1
             a0 = T("a0", n, h, w, 64)
-            b0 = T("b0", n, h, w, 64)
-            hid = T("hid", n, h, w, 96) if not fuse_head else -1
+            b0 = T("b0", n, h, w, 64) if not fuse_tail else -1
+            hid = T("hid", n, h, w, 96) if not (fuse_head or fuse_tail) else -1
             for di, d in enumerate(model.seg_decoders):
                 self._conv(L["dec.%s.0.1" % d], u4a, u4b, relu=1, in_coff=di * 256)
                 self._op(_lib.OP_UPADD, in0=x2, in1=u4b, out=s2)
@@ -220,7 +220,6 @@ class PlanSpec:
                 else:
                     self._op(_lib.OP_UPADD, in0=x0, in1=b1, out=s0)
                     self._conv(L["dec.%s.3.0" % d], s0, a0, relu=1)
-                self._conv(L["dec.%s.3.1" % d], a0, b0, relu=1)
                 ho = L["head.%s.out" % d]
                 key = HEAD_NAME_MAP[d]
                 lo, hi_ = model.idx_dict[key]
@@ -229,6 +228,17 @@ class PlanSpec:
                     lg = T("logits." + key, n, h, w, ho["classes"], _lib.CERB_F32)
                     self.logit_tensors[key] = lg
                 mode = _lib.HEAD_INST if ho["clf"] == "INST" else _lib.HEAD_TYPE
+                if fuse_tail:
+                    # last decoder conv + the whole output head in ONE kernel (fp16 mode): neither
+                    # the 64-channel decoder output nor the 96-channel hidden tensor touches HBM
+                    hd = L["head.%s.hidden" % d]
+                    self._conv(L["dec.%s.3.1" % d], a0, canvas, relu=1, out_coff=lo,
+                               aux_classes=ho["classes"], aux_w_off=ho["w_off"],
+                               aux_b_off=ho["b_off"], head_mode=mode, logits_out=lg,
+                               tail_w_off=hd["w_off"], tail_b_off=hd["b_off"],
+                               tail_w_shift=hd.get("w_shift", 0))
+                    continue
+                self._conv(L["dec.%s.3.1" % d], a0, b0, relu=1)
                 if fuse_head:
                     # 1x1 64->96 + BN + ReLU + 1x1 96->C + softmax/argmax/crop in ONE kernel: the
                     # 96-channel hidden tensor never exists in HBM
@@ -258,7 +268,7 @@ class PlanSpec:
         d = dict(kind=kind, in0=-1, in1=-1, out=-1, in_coff=0, in_c=0, out_coff=0, cout=0, kh=0,
                  kw=0, stride=0, pad=0, relu=0, stem=0, head_mode=0, logits_out=-1, w_off=-1,
                  w_lo_off=-1, b_off=-1, box_w=0, w_shift=0, aux_classes=0, aux_w_off=-1,
-                 aux_b_off=-1, up_prev1=0)
+                 aux_b_off=-1, up_prev1=0, tail_w_off=-1, tail_b_off=-1, tail_w_shift=0, reserved0=0)
         d.update(kw)
         self.ops.append(d)
 
@@ -280,6 +290,8 @@ class PlanSpec:
                 cin = 3 if op["stem"] else op["in_c"]
                 total += 2 * n * h * w * op["cout"] * op["kh"] * op["kw"] * cin
                 total += 2 * n * h * w * op["aux_classes"] * 96
+                if op["tail_w_off"] >= 0:
+                    total += 2 * n * h * w * 96 * 64
             elif op["kind"] == _lib.OP_HEAD:
                 _, n, h, w, _, _ = self.tensors[op["in0"]]
                 total += 2 * n * h * w * op["cout"] * 96

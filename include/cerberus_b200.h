@@ -103,6 +103,14 @@ typedef struct cerb_op {
                           into the conv's producer, the sum is never written to HBM). 0 = none */
   int64_t aux_w_off;   /* fp32 [aux_classes][96] */
   int64_t aux_b_off;   /* fp32 [aux_classes] */
+  /* CONV 64->64 3x3 s1 with aux_classes > 0 (CERB_PREC_F16 only): the WHOLE output head is fused
+   * behind the conv - hidden 1x1 64->96 (+BN+ReLU; fp16 weights [96][64] at tail_w_off, fp32 bias at
+   * tail_b_off, weight pre-scale tail_w_shift) and the aux_* tail; `out` is the fp32 CANVAS tensor and
+   * neither the conv's 64-channel output nor the hidden tensor is written to HBM. -1 = not used. */
+  int64_t tail_w_off;
+  int64_t tail_b_off;
+  int32_t tail_w_shift;
+  int32_t reserved0;
 } cerb_op;
 
 /* ---- context ------------------------------------------------------------------- */

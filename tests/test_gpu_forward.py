@@ -159,11 +159,12 @@ def test_tile_pipeline_streams_batches_in_order(built_lib, six_head_sd):
     eng.close()
 
 
-def test_fused_head_on_tensor_core_matches_fp32_head(built_lib, six_head_sd):
-    """fp16 mode: the fused head runs its 1x1 96->C on the tensor core (hidden tile and head
-    weights rounded to fp16, fp32 accumulation). It must agree with the unfused path (hidden
-    tensor in HBM as fp16, CERB_OP_HEAD in fp32 FMAs) to fp16-rounding accuracy of the head
-    weights, on every head and for a batch that does not fill the last tile row."""
+@pytest.mark.parametrize("variant", ["head_in_1x1", "head_behind_conv64"])
+def test_fused_head_on_tensor_core_matches_fp32_head(built_lib, six_head_sd, variant):
+    """fp16 mode: the fused heads run the 1x1 96->C (and, behind the last decoder conv, also the
+    hidden 1x1 64->96) on the tensor core with fp16-rounded hidden tiles / head weights and fp32
+    accumulation. They must agree with the unfused path (tensors in HBM as fp16, CERB_OP_HEAD in
+    fp32 FMAs) to fp16-rounding accuracy, on every head, for a batch that leaves CTAs idle."""
     from cerberus_b200.engine import Context, ForwardPlan
     from cerberus_b200.plan import PackedModel, PlanSpec
     args = synth.model_args()
@@ -172,7 +173,9 @@ def test_fused_head_on_tensor_core_matches_fp32_head(built_lib, six_head_sd):
     ctx = Context(0, "f16")
     out = []
     for fuse in (True, False):
-        spec = PlanSpec(model, 3, 256, 256, 256, 256, want_logits=True, fuse_head=fuse)
+        spec = PlanSpec(model, 3, 256, 256, 256, 256, want_logits=True,
+                        fuse_head=fuse and variant == "head_in_1x1",
+                        fuse_tail=fuse and variant == "head_behind_conv64")
         plan = ForwardPlan(ctx, model, 3, 256, 256, 256, 256, spec=spec)
         plan.run(tiles)
         out.append(({k: v.copy() for k, v in plan.read_logits().items()}, plan.read_canvas().copy()))
@@ -184,8 +187,28 @@ def test_fused_head_on_tensor_core_matches_fp32_head(built_lib, six_head_sd):
             continue
         err = float(np.abs(lg_f[k] - lg_u[k]).max())
         scale = float(np.abs(lg_u[k]).max())
-        print("%s: fused-vs-unfused max-abs %.4g (logit scale %.3g)" % (k, err, scale))
+        print("%s %s: fused-vs-unfused max-abs %.4g (logit scale %.3g)" % (variant, k, err, scale))
         assert err <= 4e-3 * max(scale, 1.0), (k, err, scale)
     # probabilities written to the canvas agree as well
     inst = [i for k, (a, b) in model.idx_dict.items() if k.endswith("-INST") for i in range(a, b)]
     assert float(np.abs(cv_f[..., inst] - cv_u[..., inst]).max()) <= 5e-3
+
+
+def test_fused_head_crops_and_partial_tiles(built_lib, six_head_sd):
+    """448 -> 144 centre crop (reference defaults, run_infer_tile.py:1-23) through the fused tail:
+    448 is not a multiple of the 16-row tile, so border tiles are partial."""
+    args = synth.model_args()
+    tiles = synth.synthetic_tiles(1, 448, 448, seed=3)
+    outs = []
+    for env in ("1", "0"):
+        import os
+        os.environ["CERB_FUSE_TAIL"] = env
+        eng = Engine(six_head_sd, args, precision="f16")
+        plan = eng.plan_for(1, 448, 448, 144, 144)
+        plan.run(tiles)
+        outs.append(plan.read_canvas().copy())
+        eng.close()
+    os.environ.pop("CERB_FUSE_TAIL", None)
+    inst = [i for k, (a, b) in eng.model.idx_dict.items() if k.endswith("-INST") for i in range(a, b)]
+    assert outs[0].shape == outs[1].shape == (1, 144, 144, eng.model.canvas_c)
+    assert float(np.abs(outs[0][..., inst] - outs[1][..., inst]).max()) <= 5e-3
