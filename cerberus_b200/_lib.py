@@ -34,7 +34,7 @@ class Op(ctypes.Structure):
         ("box_w", ctypes.c_int32), ("w_shift", ctypes.c_int32), ("aux_classes", ctypes.c_int32),
         ("up_prev1", ctypes.c_int32), ("aux_w_off", ctypes.c_int64), ("aux_b_off", ctypes.c_int64),
         ("tail_w_off", ctypes.c_int64), ("tail_b_off", ctypes.c_int64),
-        ("tail_w_shift", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("tail_w_shift", ctypes.c_int32), ("side", ctypes.c_int32),
     ]
 
 

@@ -60,6 +60,7 @@ struct Step {
   Conv3Params c3;
   bool use64 = false;
   bool use3 = false;
+  bool side = false;  // may overlap the ops that follow (nothing later in the plan reads its output)
   bool split = false;
   // misc ops
   ActRef a, b, c;
@@ -640,6 +641,8 @@ extern "C" int cerb_ctx_create(int device, int precision, cerb_ctx** out) {
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+  CERB_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  CERB_CUDA(cudaEventCreateWithFlags(&ctx->side_event, cudaEventDisableTiming));
   for (int i = 0; i < 4; ++i)
     CERB_CUDA(cudaEventCreateWithFlags(&ctx->slot_event[i], cudaEventDisableTiming));
   CERB_CUDA(cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming));
@@ -664,6 +667,8 @@ extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->side_event) cudaEventDestroy(ctx->side_event);
   for (int i = 0; i < 4; ++i)
     if (ctx->slot_event[i]) cudaEventDestroy(ctx->slot_event[i]);
   if (ctx->order_event) cudaEventDestroy(ctx->order_event);
@@ -867,6 +872,7 @@ extern "C" int cerb_plan_create(cerb_ctx* ctx, const cerb_tensor_desc* tensors, 
     const cerb_op& op = ops[i];
     Step& st = pl->steps[i];
     st.kind = op.kind;
+    st.side = op.side != 0;
     switch (op.kind) {
       case CERB_OP_PREP: {
         if ((rc = check_id(pl, op.in0, "prep")) || (rc = check_id(pl, op.out, "prep")))
@@ -1044,8 +1050,17 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
   }
   const bool capture = ctx->use_graphs && pl->runs >= 1;
   if (capture) CERB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  bool forked = false;
   for (Step& st : pl->steps) {
-    cudaError_t e = launch_step(ctx, st, s);
+    cudaStream_t ls = s;
+    if (capture && st.side) {
+      // graph branch: the op depends on everything queued so far and joins at the end of the plan
+      CERB_CUDA(cudaEventRecord(ctx->order_event, s));
+      CERB_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->order_event, 0));
+      ls = ctx->side_stream;
+      forked = true;
+    }
+    cudaError_t e = launch_step(ctx, st, ls);
     if (e != cudaSuccess) {
       if (capture) {
         cudaGraph_t g = nullptr;
@@ -1058,6 +1073,10 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
   }
   pl->runs += 1;
   if (capture) {
+    if (forked) {
+      CERB_CUDA(cudaEventRecord(ctx->side_event, ctx->side_stream));
+      CERB_CUDA(cudaStreamWaitEvent(s, ctx->side_event, 0));
+    }
     cudaGraph_t g = nullptr;
     CERB_CUDA(cudaStreamEndCapture(s, &g));
     cudaError_t e = cudaGraphInstantiate(&pl->graph_exec, g, 0);

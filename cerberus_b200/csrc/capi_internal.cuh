@@ -15,6 +15,8 @@ struct cerb_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H copies overlapped with compute
   cudaStream_t up_stream = nullptr;    // H2D copies overlapped with compute
+  cudaStream_t side_stream = nullptr;  // graph branch for ops flagged `side` (Patch-Class)
+  cudaEvent_t side_event = nullptr;
   cudaEvent_t order_event = nullptr;
   cudaEvent_t slot_event[4] = {nullptr, nullptr, nullptr, nullptr};
   int* err_flag_host = nullptr;  // mapped pinned memory: readable even after a trapped kernel

@@ -185,6 +185,16 @@ class PlanSpec:
 
         canvas = T("canvas", n, out_h, out_w, model.canvas_c, _lib.CERB_F32)
         self.canvas = canvas
+        if model.has_pclass:
+            # depends on x4 only and nothing in the plan reads its canvas channel: queued right
+            # after the encoder and flagged `side`, it overlaps the decoders in the replayed graph
+            pc = L["pclass"]
+            lg = -1
+            if want_logits:
+                lg = T("logits.Patch-Class", n, 1, 1, pc["classes"], _lib.CERB_F32)
+            self._op(_lib.OP_PCLASS, in0=x4, out=canvas, out_coff=model.idx_dict["Patch-Class"][0],
+                     cout=pc["classes"], logits_out=lg, w_off=pc["w_off"], side=1)
+            pclass_logits = lg
         D = len(model.seg_decoders)
         if D:
             f4 = T("conv_map", n, hs[4], ws[4], 256)
@@ -249,14 +259,8 @@ class PlanSpec:
                     self._conv(L["head.%s.hidden" % d], b0, hid, relu=1)
                     self._op(_lib.OP_HEAD, in0=hid, out=canvas, out_coff=lo, cout=ho["classes"],
                              head_mode=mode, logits_out=lg, w_off=ho["w_off"], b_off=ho["b_off"])
-        if model.has_pclass:
-            pc = L["pclass"]
-            lg = -1
-            if want_logits:
-                lg = T("logits.Patch-Class", n, 1, 1, pc["classes"], _lib.CERB_F32)
-                self.logit_tensors["Patch-Class"] = lg
-            self._op(_lib.OP_PCLASS, in0=x4, out=canvas, out_coff=model.idx_dict["Patch-Class"][0],
-                     cout=pc["classes"], logits_out=lg, w_off=pc["w_off"])
+        if model.has_pclass and want_logits:
+            self.logit_tensors["Patch-Class"] = pclass_logits
 
     # -- helpers
     def _tensor(self, name, n, h, w, c, dtype=_lib.CERB_F16):
@@ -268,7 +272,7 @@ class PlanSpec:
         d = dict(kind=kind, in0=-1, in1=-1, out=-1, in_coff=0, in_c=0, out_coff=0, cout=0, kh=0,
                  kw=0, stride=0, pad=0, relu=0, stem=0, head_mode=0, logits_out=-1, w_off=-1,
                  w_lo_off=-1, b_off=-1, box_w=0, w_shift=0, aux_classes=0, aux_w_off=-1,
-                 aux_b_off=-1, up_prev1=0, tail_w_off=-1, tail_b_off=-1, tail_w_shift=0, reserved0=0)
+                 aux_b_off=-1, up_prev1=0, tail_w_off=-1, tail_b_off=-1, tail_w_shift=0, side=0)
         d.update(kw)
         self.ops.append(d)
 

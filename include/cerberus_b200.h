@@ -110,7 +110,8 @@ typedef struct cerb_op {
   int64_t tail_w_off;
   int64_t tail_b_off;
   int32_t tail_w_shift;
-  int32_t reserved0;
+  int32_t side;        /* 1: nothing later in the plan reads this op's output; when the plan is replayed as a
+                          CUDA graph the op runs on a parallel branch joined at the end (Patch-Class) */
 } cerb_op;
 
 /* ---- context ------------------------------------------------------------------- */
