@@ -1,0 +1,449 @@
+"""WSI mode: mirror of infer/wsi.py (InferManager.process_wsi_list / process_single_file) on the
+B200-native engine (BASELINE config 4).
+
+Same run_args, same skip-if-done rule, same outputs (`<out>/dat/<name>.dat` joblib dict with the
+Nuclei / Gland / Lumen instance tables, `<out>/tissue/<name>.mat` Patch-Class map), different
+plumbing:
+
+  reference                                             here
+  ----------------------------------------------------  --------------------------------------------
+  tiatoolbox WSIReader + 12 loader processes            ArraySlide (wsi_reader.py); the slide lives in
+  (infer/wsi.py:888-942)                                HBM, patches are cut by cerb_extract_patches
+                                                        (zero padded) straight into the network input
+  6 float32 memmaps + 6 count memmaps on disk           ONE device canvas [H, W, 9] float32
+  (merge_prediction, :550-556, :603-621)                (cerb_scatter_patches)
+  nn.DataParallel over the visible GPUs                 one process per GPU: batches are strided over
+                                                        ranks, canvases summed with one NCCL
+                                                        all-reduce (every pixel has one writer)
+  nuclei post-proc in 6 worker processes (:643-683)     cerb_postproc_nuclei on canvas crops
+  gland / lumen: cv2 resize + post_process (:720-800)   cerb_region_half + cerb_postproc_gland_lumen
+
+tiatoolbox / shapely are not available offline; their placement and de-duplication rules are
+restated in wsi_geometry.py (parity unpinned, see there). Per-instance contours / moments stay on
+the host with OpenCV exactly as in the reference (SURVEY.md 8f-2 is the device version).
+
+Known limits of this round: array-backed slides only; no resampling between scan and
+processing resolution; the nuclei watershed of a 4032^2 post-processing tile runs on the
+whole-image emulation kernel (one warp) and is slow; post-processing runs on rank 0.
+"""
+import logging
+import os
+import pathlib
+import time
+import uuid
+from datetime import datetime
+
+import cv2
+import numpy as np
+import torch
+
+from .. import _lib
+from ..instinfo import get_inst_info_dict
+from . import base
+from .wsi_geometry import (boxes_intersect, filter_coordinates, get_coordinates, get_tile_info,
+                           select_tile_instances)
+from .wsi_reader import ArraySlide
+
+# target key gen code : post proc class (infer/wsi.py:49-54); only the contour variants are built
+_SUPPORTED_POSTPROC = ("IP-ERODED-CONTOUR-3", "IP-ERODED-CONTOUR-11")
+
+HEAD_NAMES = ["Nuclei-INST", "Nuclei-TYPE", "Gland-INST", "Gland-TYPE", "Lumen-INST", "Patch-Class"]
+
+
+def _cv_round(v):
+    """cv::saturate_cast<int>(double): round half to even (cv2.resize's dsize from fx / fy)."""
+    return int(np.rint(v))
+
+
+def tiatoolbox_bounding_box(img):
+    """tiatoolbox.utils.misc.get_bounding_box: [start_x, start_y, end_x, end_y], end exclusive."""
+    rows = np.any(img, axis=1)
+    cols = np.any(img, axis=0)
+    rmin, rmax = np.where(rows)[0][[0, -1]]
+    cmin, cmax = np.where(cols)[0][[0, -1]]
+    return np.array([cmin, rmin, cmax + 1, rmax + 1])
+
+
+def get_instance_info(pred_inst, pred_type=None):
+    """tiatoolbox HoVerNet.get_instance_info (infer/wsi.py:150): box is flat [x0, y0, x1, y1]."""
+    info = {}
+    ids = np.unique(pred_inst)[1:]
+    if len(ids) == 0:
+        return info
+    # one pass over the label map for all boxes (same values as the per-instance masks)
+    for inst_id in ids:
+        inst_map = pred_inst == inst_id
+        box = tiatoolbox_bounding_box(inst_map)
+        crop = inst_map[box[1]:box[3], box[0]:box[2]].astype(np.uint8)
+        moment = cv2.moments(crop)
+        contour = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        contour = np.squeeze(contour[0][0].astype(np.int32))
+        if contour.shape[0] < 3 or len(contour.shape) != 2:
+            continue
+        centroid = np.array([moment["m10"] / moment["m00"], moment["m01"] / moment["m00"]])
+        contour = contour + box[:2][None]
+        centroid = centroid + box[:2]
+        info[inst_id] = {"box": box, "centroid": centroid, "contour": contour, "prob": None,
+                         "type": None}
+    if pred_type is not None:
+        for inst_id in list(info.keys()):
+            c0, r0, c1, r1 = info[inst_id]["box"]
+            m = pred_inst[r0:r1, c0:c1] == inst_id
+            t = pred_type[r0:r1, c0:c1][m]
+            tl, tp = np.unique(t, return_counts=True)
+            pairs = sorted(zip(tl, tp), key=lambda x: x[1], reverse=True)
+            inst_type = pairs[0][0]
+            if inst_type == 0 and len(pairs) > 1:
+                inst_type = pairs[1][0]
+            d = {v[0]: v[1] for v in pairs}
+            info[inst_id]["type"] = int(inst_type)
+            info[inst_id]["prob"] = float(d[inst_type] / (np.sum(m) + 1.0e-6))
+    return info
+
+
+def _ptr(t):
+    return _lib.ctypes.c_void_p(t.data_ptr())
+
+
+class InferManager(base.InferManager):
+    # ------------------------------------------------------------------ helpers
+    def _parse_args(self, run_args):
+        """infer/wsi.py:444-452."""
+        for variable, value in run_args.items():
+            self.__setattr__(variable, value)
+        self.chunk_shape = [self.chunk_shape, self.chunk_shape]
+        self.tile_shape = [self.tile_shape, self.tile_shape]
+        self.patch_input_shape = [self.patch_input_shape, self.patch_input_shape]
+        self.patch_output_shape = [self.patch_output_shape, self.patch_output_shape]
+
+    def _dist(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+        return None, 0, 1
+
+    # ------------------------------------------------------------------ inference
+    def _infer_slide(self, slide, patch_inputs, patch_outputs):
+        """Raw prediction of every selected patch, merged into one device canvas [H, W, C]
+        (infer/wsi.py:585-621). Rank r of P handles batches r, r+P, ...; the canvases are then
+        summed (each pixel has exactly one writer)."""
+        eng, ctx, lib = self.engine, self.engine.ctx, self.engine.ctx.lib
+        dist, rank, world = self._dist()
+        H, W = slide.img.shape[:2]
+        C = eng.model.canvas_c
+        pin, pout = self.patch_input_shape[0], self.patch_output_shape[0]
+        B = int(self.batch_size)
+        dev = torch.device("cuda", ctx.device)
+        plan = eng.plan_for(B, pin, pin, pout, pout)
+        slide_dev = torch.from_numpy(np.array(slide.img, dtype=np.uint8, order="C")).to(dev)
+        canvas = torch.zeros((H, W, C), dtype=torch.float32, device=dev)
+        patch_buf = torch.empty((B, pin, pin, 3), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        n = len(patch_inputs)
+        far = -4 * pin  # padding entries of the last batch read only zeros
+        for bi, start in enumerate(range(0, n, B)):
+            if bi % world != rank:
+                continue
+            k = min(B, n - start)
+            tl_in = np.full((B, 2), far, dtype=np.int32)
+            tl_in[:k, 0] = patch_inputs[start:start + k, 1]
+            tl_in[:k, 1] = patch_inputs[start:start + k, 0]
+            _lib.check(lib.cerb_extract_patches(ctx.handle, _ptr(slide_dev), H, W, 0, 0,
+                                                tl_in.ctypes.data_as(_lib.ctypes.c_void_p), B, pin,
+                                                pin, _ptr(patch_buf), 1 | 2 | 4),
+                       "cerb_extract_patches")
+            plan.run(device_ptr=patch_buf.data_ptr())
+            tl_out = np.ascontiguousarray(patch_outputs[start:start + k][:, [1, 0]], dtype=np.int32)
+            _lib.check(lib.cerb_scatter_patches(
+                ctx.handle, _lib.ctypes.c_void_p(plan.tensor_ptr(plan.spec.canvas)), k, pout, pout,
+                C, tl_out.ctypes.data_as(_lib.ctypes.c_void_p), _ptr(canvas), H, W),
+                "cerb_scatter_patches")
+            self.nr_patches_done += k
+        if world > 1:
+            flat = canvas.view(-1)
+            step = 1 << 28  # 1 GiB of float32 per collective
+            for s in range(0, flat.numel(), step):
+                dist.all_reduce(flat[s:s + step])
+            torch.cuda.synchronize(dev)
+        del slide_dev, patch_buf
+        return canvas
+
+    # ------------------------------------------------------------------ nuclei
+    def _process_tile_predictions(self, canvas, tile_bounds, tile_flag, tile_mode, ref_inst_dict,
+                                  margin):
+        """infer/wsi.py:64-268 for one post-processing tile, on the device canvas."""
+        eng, ctx, lib = self.engine, self.engine.ctx, self.engine.ctx.lib
+        idx = eng.model.idx_dict
+        H, W, C = canvas.shape
+        tile_bounds = np.asarray(tile_bounds, dtype=np.int64)
+        tile_tl = tile_bounds[:2]
+        x0, y0 = int(tile_bounds[0]), int(tile_bounds[1])
+        x1, y1 = min(int(tile_bounds[2]), W), min(int(tile_bounds[3]), H)  # numpy slicing clips
+        if x1 <= x0 or y1 <= y0:
+            return {}, []
+        crop = canvas[y0:y1, x0:x1].contiguous()
+        h, w = crop.shape[:2]
+        type_map = crop[..., idx["Nuclei-TYPE"][0]].cpu().numpy() if "Nuclei-TYPE" in idx else None
+        torch.cuda.synchronize(canvas.device)
+        labels = np.empty((h, w), dtype=np.int32)
+        any_fg = np.zeros(1, dtype=np.int32)
+        _lib.check(lib.cerb_postproc_nuclei(ctx.handle, _ptr(crop), 1, h, w, C,
+                                            idx["Nuclei-INST"][0],
+                                            labels.ctypes.data_as(_lib.ctypes.c_void_p),
+                                            any_fg.ctypes.data_as(_lib.ctypes.c_void_p), 1),
+                   "cerb_postproc_nuclei")
+        del crop
+        if not any_fg[0]:
+            return {}, []
+        inst_dict = get_instance_info(labels, type_map)
+        if len(inst_dict) == 0:
+            return {}, []
+        inst_boxes = np.array([v["box"] for v in inst_dict.values()])
+        ref_uids = list(ref_inst_dict.keys())
+        ref_boxes = np.array([ref_inst_dict[u]["box"] for u in ref_uids]) if (
+            tile_mode == 3 and ref_uids) else None
+        sel, sel_ref = select_tile_instances(inst_boxes, tile_bounds, tile_flag, tile_mode, margin,
+                                             ref_boxes)
+        inst_uids = list(inst_dict.keys())
+        remove_in_tile = set(inst_uids[i] for i in sel)
+        remove_in_orig = [ref_uids[i] for i in sel_ref]
+        new_inst_dict = {}
+        for inst_uid, inst_info in inst_dict.items():
+            if inst_uid not in remove_in_tile:
+                inst_info["box"] = inst_info["box"] + np.concatenate([tile_tl] * 2)
+                inst_info["centroid"] = inst_info["centroid"] + tile_tl
+                inst_info["contour"] = inst_info["contour"] + tile_tl
+                new_inst_dict[uuid.uuid4().hex] = inst_info
+        return new_inst_dict, remove_in_orig
+
+    def _postproc_nuclei(self, canvas, patch_outputs, pp_tile_shape, margin):
+        """infer/wsi.py:640-686."""
+        H, W, _ = canvas.shape
+        tile_sets = get_tile_info((W, H), pp_tile_shape, self.patch_output_shape, margin)
+        nuclei = {}
+        for set_idx, (set_bounds, set_flags) in enumerate(tile_sets):
+            results = []
+            for tile_idx, tile_bounds in enumerate(set_bounds):
+                if len(boxes_intersect(patch_outputs, tile_bounds)) == 0:
+                    continue
+                results.append(self._process_tile_predictions(
+                    canvas, tile_bounds, set_flags[tile_idx], set_idx, nuclei, margin))
+            for new_inst_dict, remove_uuid_list in results:
+                nuclei.update(new_inst_dict)
+                for u in remove_uuid_list:
+                    nuclei.pop(u, None)
+        return nuclei
+
+    # ------------------------------------------------------------------ gland / lumen
+    def _postproc_gland_lumen(self, canvas, wsi_mask, mask_downsample_ratio):
+        """infer/wsi.py:720-840. Returns {"Gland": {...}, "Lumen": {...}} (keys present only when
+        an instance was found, as in the reference)."""
+        from scipy import ndimage
+        eng, ctx, lib = self.engine, self.engine.ctx, self.engine.ctx.lib
+        idx = eng.model.idx_dict
+        H, W, C = canvas.shape
+        dev = canvas.device
+        mask_lab = ndimage.label(wsi_mask)[0]
+        ids = np.unique(mask_lab).tolist()
+        tissue_info_list = []
+        if len(ids) > 1:
+            for region_id in ids[1:]:
+                reg = mask_lab == region_id
+                rows, cols = np.any(reg, axis=1), np.any(reg, axis=0)
+                rmin, rmax = np.where(rows)[0][[0, -1]]
+                cmin, cmax = np.where(cols)[0][[0, -1]]
+                tissue_info_list.append([rmin, rmax + 1, cmin, cmax + 1])  # misc/utils.py:82-91
+        else:
+            tissue_info_list.append([0, mask_lab.shape[0], 0, mask_lab.shape[1]])
+        out = {}
+        ds_factor = 0.5
+        for ridx, ti in enumerate(tissue_info_list):
+            rmin = int(round(ti[0] / mask_downsample_ratio))
+            rmax = int(round(ti[1] / mask_downsample_ratio))
+            cmin = int(round(ti[2] / mask_downsample_ratio))
+            cmax = int(round(ti[3] / mask_downsample_ratio))
+            rmax, cmax = min(rmax, H), min(cmax, W)  # numpy slicing of the memmap clips
+            h, w = rmax - rmin, cmax - cmin
+            if h <= 0 or w <= 0:
+                continue
+            tissue_topleft = [cmin, rmin]
+            mask_idx = (mask_lab[ti[0]:ti[1], ti[2]:ti[3]] == ridx + 1)
+            if h != mask_idx.shape[0] and w != mask_idx.shape[1]:  # `and`: as the reference (:768)
+                mask_idx = cv2.resize(mask_idx.astype("uint8"), (w, h), interpolation=cv2.INTER_NEAREST)
+            mask_u8 = np.ascontiguousarray(mask_idx, dtype=np.uint8)
+            if mask_u8.shape != (h, w):
+                raise ValueError("tissue mask segment %r does not match the prediction window %r "
+                                 "(the reference fails here too)" % (mask_u8.shape, (h, w)))
+            oh, ow = _cv_round(h * ds_factor), _cv_round(w * ds_factor)
+            if oh <= 0 or ow <= 0:
+                continue
+            inst_maps, type_maps = {}, {}
+            for tissue in ("Gland", "Lumen"):
+                code = self.decoder_dict[tissue + "-INST"]
+                if code not in _SUPPORTED_POSTPROC:
+                    raise NotImplementedError("post-processing %r (PostProcInstErodedMap) is outside "
+                                              "the hot path (SURVEY.md 8f-4)" % code)
+                chans = list(range(*idx[tissue + "-INST"]))
+                has_type = (tissue + "-TYPE") in HEAD_NAMES and (tissue + "-TYPE") in idx
+                if has_type:
+                    chans += list(range(*idx[tissue + "-TYPE"]))
+                k = len(chans)
+                half = torch.empty((oh, ow, k), dtype=torch.float32, device=dev)
+                ch_arr = np.asarray(chans, dtype=np.int32)
+                torch.cuda.synchronize(dev)
+                _lib.check(lib.cerb_region_half(
+                    ctx.handle, _ptr(canvas), H, W, C, rmin, cmin, h, w,
+                    mask_u8.ctypes.data_as(_lib.ctypes.c_void_p),
+                    ch_arr.ctypes.data_as(_lib.ctypes.c_void_p), k, _ptr(half), oh, ow),
+                    "cerb_region_half")
+                labels = np.empty((oh, ow), dtype=np.int32)
+                _lib.check(lib.cerb_postproc_gland_lumen(
+                    ctx.handle, _ptr(half), 1, oh, ow, k, 0, 0 if tissue == "Gland" else 1,
+                    float(ds_factor), labels.ctypes.data_as(_lib.ctypes.c_void_p), 1),
+                    "cerb_postproc_gland_lumen")
+                inst_maps[tissue] = labels.astype(np.float64)  # loader/postproc.py:290,331
+                type_maps[tissue] = half[..., 2].cpu().numpy() if has_type else None
+                del half
+            # remove lumen predictions not inside glands (:802-807)
+            binary_gland = inst_maps["Gland"].copy()
+            binary_gland[binary_gland > 0] = 1
+            inst_maps["Lumen"] = binary_gland * inst_maps["Lumen"]
+            for tissue in ("Gland", "Lumen"):
+                pred_inst_info = get_inst_info_dict(inst_maps[tissue], type_maps[tissue], ds_factor)
+                for inst_id, inst_info in pred_inst_info.items():
+                    # Reference quirk kept for drop-in parity (:815-829): `box` is [[r0,c0],[r1,c1]]
+                    # but the (x, y) top-left is added to it, i.e. x to the rows and y to the columns.
+                    inst_info["box"] = inst_info["box"] + tissue_topleft
+                    inst_info["contour"] = inst_info["contour"] + tissue_topleft
+                    inst_info["centroid"] = inst_info["centroid"] + tissue_topleft
+                    b = inst_info["box"]
+                    inst_info["box"] = np.array([b[0][1], b[0][0], b[1][1], b[1][0]])
+                    out.setdefault(tissue, {})[uuid.uuid4().hex] = inst_info
+        return out
+
+    # ------------------------------------------------------------------ one slide
+    def process_single_file(self, wsi_idx, wsi_basename, output_dir):
+        """infer/wsi.py:502-857."""
+        eng = self.engine
+        wsi_path = self.imgs[wsi_idx]
+        mask_path = self.masks[wsi_idx]
+        dist, rank, world = self._dist()
+        start = time.perf_counter()
+        slide = ArraySlide.open(wsi_path, self.wsi_proc_mag)
+        self.wsi_proc_shape = slide.slide_dimensions(self.wsi_proc_mag)[::-1]  # YX
+        self.wsi_base_mag = slide.mpp
+        self.wsi_base_shape = np.array(slide.img.shape[:2])
+        H, W = int(self.wsi_proc_shape[0]), int(self.wsi_proc_shape[1])
+        if mask_path is not None and os.path.isfile(mask_path):
+            wsi_mask = cv2.imread(mask_path)
+            wsi_mask = cv2.cvtColor(wsi_mask, cv2.COLOR_BGR2GRAY)
+            wsi_mask[wsi_mask > 0] = 1
+        else:
+            wsi_mask = np.ones((H, W), dtype=np.uint8)
+        mask_downsample_ratio = wsi_mask.shape[0] / H
+        if rank == 0 and self.save_mask:  # the reference crashes here (undefined self.wsi_mask)
+            cv2.imwrite("%s/mask/%s.png" % (self.output_dir, wsi_basename), wsi_mask * 255)
+        if rank == 0 and self.save_thumb:
+            cv2.imwrite("%s/thumb/%s.png" % (self.output_dir, wsi_basename),
+                        cv2.cvtColor(slide.thumbnail(1.25), cv2.COLOR_RGB2BGR))
+
+        pin, pout = self.patch_input_shape, self.patch_output_shape
+        patch_inputs, patch_outputs = get_coordinates((W, H), pin, pout, pout)
+        sel = filter_coordinates(wsi_mask, patch_outputs, (H, W))
+        patch_inputs, patch_outputs = patch_inputs[sel], patch_outputs[sel]
+        self.logger.info("Preparing Input Output Placement: %s" % (time.perf_counter() - start))
+
+        start = time.perf_counter()
+        self.nr_patches_done = 0
+        canvas = self._infer_slide(slide, patch_inputs, patch_outputs)
+        self.logger.info("Inference Time: %s (%d patches on this rank, %d selected)" % (
+            time.perf_counter() - start, self.nr_patches_done, len(patch_inputs)))
+        self.last_canvas = canvas if getattr(self, "keep_canvas", False) else None
+        if rank != 0:
+            del canvas
+            return None
+
+        wsi_inst_info = {}
+        start = time.perf_counter()
+        margin = int(getattr(self, "ambiguous_size", 64))
+        wsi_inst_info["Nuclei"] = self._postproc_nuclei(canvas, patch_outputs,
+                                                        self.postproc_tile_shape, margin)
+        self.logger.info("Nuclei Post Proc Time: %s" % (time.perf_counter() - start))
+
+        start = time.perf_counter()
+        idx = eng.model.idx_dict
+        if "Patch-Class" in self.model_args["decoder_kwargs"].keys() and "Patch-Class" in idx:
+            import scipy.io as sio
+            ds = 0.25
+            ph, pw = _cv_round(H * ds), _cv_round(W * ds)
+            pclass_map = np.empty((ph, pw), dtype=np.float32)
+            ctx = eng.ctx
+            _lib.check(ctx.lib.cerb_nearest_channel(
+                ctx.handle, _ptr(canvas), H, W, canvas.shape[2], idx["Patch-Class"][0], ds,
+                pclass_map.ctypes.data_as(_lib.ctypes.c_void_p), ph, pw), "cerb_nearest_channel")
+            lores = cv2.resize(wsi_mask, (pw, ph), interpolation=cv2.INTER_NEAREST)
+            pclass_map *= lores
+            sio.savemat("%s/tissue/%s.mat" % (output_dir, wsi_basename), {"pclass": pclass_map})
+        self.logger.info("Tissue Region Post Proc Time: %s" % (time.perf_counter() - start))
+
+        start = time.perf_counter()
+        wsi_inst_info.update(self._postproc_gland_lumen(canvas, wsi_mask, mask_downsample_ratio))
+        wsi_inst_info["proc_resolution"] = {"resolution": self.wsi_proc_mag, "units": "mpp"}
+        wsi_inst_info["base_resolution"] = {"resolution": self.wsi_base_mag, "units": "mpp"}
+        wsi_inst_info["proc_dimensions"] = self.wsi_proc_shape
+        wsi_inst_info["base_dimensions"] = self.wsi_base_shape
+        import joblib
+        joblib.dump(wsi_inst_info, "%s/dat/%s.dat" % (output_dir, wsi_basename))
+        self.logger.info("Gland & Lumen Post Proc Time: %s" % (time.perf_counter() - start))
+        del canvas
+        return wsi_inst_info
+
+    # ------------------------------------------------------------------ driver
+    def process_wsi_list(self, run_args):
+        """infer/wsi.py:860-986. The reference parses --tile_shape / --chunk_shape / the patch
+        shapes and then hard-codes 15000 / 4096 / 448 / 144; the same
+        constants are used here unless run_args carries `infer_tile_shape` /
+        `postproc_tile_shape` (test hooks)."""
+        self._parse_args(run_args)
+        for k, code in self.decoder_dict.items():
+            if k.endswith("-INST") and code not in _SUPPORTED_POSTPROC + ("IP-ERODED-3", "IP-ERODED-11"):
+                raise KeyError(code)
+        dist, rank, world = self._dist()
+        for sub in ("/dat/", "/tissue/") + (("/thumb/",) if self.save_thumb else ()) + (
+                ("/mask/",) if self.save_mask else ()):
+            os.makedirs(self.output_dir + sub, exist_ok=True)
+        os.makedirs(self.logging_dir, exist_ok=True)
+        # hard-coded in the reference (infer/wsi.py:885-915)
+        self.patch_input_shape = [448, 448] if not getattr(self, "honour_patch_shapes", False) \
+            else self.patch_input_shape
+        self.patch_output_shape = [144, 144] if not getattr(self, "honour_patch_shapes", False) \
+            else self.patch_output_shape
+        self.postproc_tile_shape = [int(getattr(self, "postproc_tile_shape", 4096))] * 2
+        self.imgs = self.input_list
+        self.masks = self.mask_list
+        from ..postproc import PostProcInstErodedContourMap
+        PostProcInstErodedContourMap.bind(self.engine.ctx)
+        results = {}
+        for wsi_idx, wsi_path in enumerate(self.imgs):
+            wsi_basename = pathlib.Path(wsi_path).stem
+            start = time.perf_counter()
+            dt_string = datetime.now().strftime("%d-%m-%Y_%H:%M:%S")
+            self.logger = logging.getLogger("cerberus_b200.wsi.%d" % rank)
+            fh = logging.FileHandler("%s/%s_%s_std%s.log" % (
+                self.logging_dir, wsi_basename, dt_string, "" if rank == 0 else ".rank%d" % rank), mode="w")
+            fh.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
+            self.logger.addHandler(fh)
+            self.logger.setLevel(logging.DEBUG)
+            if not os.path.exists(self.output_dir + "/dat/%s.dat" % wsi_basename):
+                self.logger.info("Processing %s ..." % wsi_basename)
+                results[wsi_basename] = self.process_single_file(wsi_idx, wsi_basename,
+                                                                 self.output_dir)
+                self.logger.info("Overall Time: %s" % (time.perf_counter() - start))
+                self.logger.info("Finish")
+            else:
+                self.logger.warning("Skip %s- already processed!" % wsi_basename)
+            self.logger.handlers.clear()
+            fh.close()
+            if dist is not None:
+                dist.barrier()
+        return results

@@ -167,6 +167,32 @@ int cerb_plan_write_tensor(cerb_plan* plan, int tensor_id, int plane, const void
  * [n,ph,pw,3]. */
 int cerb_extract_patches(cerb_ctx* ctx, const uint8_t* img, int H, int W, int pad_t, int pad_l,
                          const int32_t* tl_yx, int n, int ph, int pw, uint8_t* out, int flags);
+/* flags bit 2 (value 4): out-of-image pixels are ZERO instead of reflected - the WSI loader's
+ * read_bounds(..., pad_constant_values=0) (infer/wsi.py:936-942, tiatoolbox WSIStreamDataset). */
+
+/* ---- WSI plumbing (infer/wsi.py) -------------------------------------------
+ * The reference merges patch predictions into per-head float32 memmaps on disk
+ * (tiatoolbox merge_prediction, infer/wsi.py:463,615); here ONE device-resident canvas
+ * [H,W,C] (same channel layout as the per-patch canvas) receives them. With the reference's
+ * stride == patch_output_shape each pixel is written once, so the running average is a clipped
+ * write. patches_dev: f32 [n,oh,ow,C] (device); tl_yx: HOST int32 [n][2] output top-left. */
+int cerb_scatter_patches(cerb_ctx* ctx, const float* patches_dev, int n, int oh, int ow, int C,
+                         const int32_t* tl_yx, float* canvas_dev, int H, int W);
+/* Copies the [h,w] window at (y0,x0) of a device image with px_bytes bytes per pixel into a
+ * contiguous buffer (flags bit 1: dst is device memory, else host and the call synchronises). */
+int cerb_crop2d(cerb_ctx* ctx, const void* src_dev, int H, int W, int px_bytes, int y0, int x0,
+                int h, int w, void* dst, int flags);
+/* infer/wsi.py:763-788 for one tissue region: out = cv2.resize(crop[..., chans] * mask, (0,0),
+ * fx=0.5, fy=0.5) (float32; the arithmetic OpenCV 4.x + IPP performs for k = 1, 3, 4 channels and
+ * OpenCV's own area path for k = 2: see csrc/tiles.cu). mask_host: u8 [h,w] 0/1 or NULL;
+ * out_dev: f32 [oh,ow,k] with oh = cvRound(h/2), ow = cvRound(w/2). */
+int cerb_region_half(cerb_ctx* ctx, const float* canvas_dev, int H, int W, int C, int y0, int x0,
+                     int h, int w, const uint8_t* mask_host, const int32_t* chans, int k,
+                     float* out_dev, int oh, int ow);
+/* cv2.resize(canvas[..., ch], (0,0), fx=scale, fy=scale, INTER_NEAREST) into host memory
+ * (infer/wsi.py:694-702, the Patch-Class map at 0.25). */
+int cerb_nearest_channel(cerb_ctx* ctx, const float* canvas_dev, int H, int W, int C, int ch,
+                         double scale, float* out_host, int oh, int ow);
 
 /* infer/tile.py:136-163: canvas[tl : tl + (oh,ow)] += patch (in list order), count likewise,
  * canvas / (count + 1e-8), crop [src_y : src_y + out_h, src_x : src_x + out_w].
