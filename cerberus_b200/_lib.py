@@ -47,6 +47,7 @@ _SIGNATURES = {
     "cerb_ctx_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]),
     "cerb_ctx_read_prof": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
                                           ctypes.c_int]),
+    "cerb_ctx_stat": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p]),
     "cerb_ctx_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "cerb_ctx_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "cerb_plan_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(TensorDesc), ctypes.c_int,

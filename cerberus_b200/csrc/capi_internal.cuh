@@ -24,6 +24,7 @@ struct cerb_ctx {
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved at run time (no libcuda link)
   int64_t launches = 0;
   bool use_graphs = true;  // replay the forward op list as a CUDA graph
+  int64_t stat_ws_large = 0, stat_ws_fallback = 0;  // large-image watershed calls / exact fallbacks
   int conv64_debug = 0;
   long long* prof_dev = nullptr;  // [kProfSlots] in-kernel attribution counters (option "kernel_prof")
   int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only

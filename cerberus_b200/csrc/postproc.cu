@@ -328,11 +328,12 @@ __device__ __forceinline__ void heap_pop(const HeapRef& h, int& n, float& tv, in
 __global__ void __launch_bounds__(32, 1)
 k_watershed(const float* __restrict__ val, const uint8_t* __restrict__ msk, int* __restrict__ out,
             float* __restrict__ heap_v, int* __restrict__ heap_a, int* __restrict__ heap_i, int H,
-            int W) {
+            int W, const int* __restrict__ run_flag) {
   __shared__ float sv[kHeapTop];
   __shared__ int sa[kHeapTop];
   __shared__ int si[kHeapTop];
   if (threadIdx.x != 0) return;
+  if (run_flag != nullptr && run_flag[blockIdx.x] == 0) return;  // the component-parallel path succeeded
   const int hw = H * W;
   const size_t base = static_cast<size_t>(blockIdx.x) * hw;
   const float* v = val + base;
@@ -839,6 +840,162 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
   }
 }
 
+// ---- component-parallel path for LARGE images (WSI post-processing tiles, infer/wsi.py:137-150:
+// up to 4032 x 4032 pixels). Same independence argument as k_watershed_comp, but nothing fits in
+// shared memory: the label map stays int32 in global memory and every mask component floods with
+// a private binary heap carved out of one global pool (a component of s pixels pushes at most s
+// entries, so the pool needs at most hw entries). One thread per component: tens of thousands of
+// nuclei per tile keep the GPU busy where the whole-image emulation runs on a single lane.
+// A tie between two marker entries of one component (bit-equal values, age 0) is decided by the
+// GLOBAL heap layout in the reference; it is detected (consecutive marker pops with equal values)
+// and the tile is then redone, from the saved markers, by the exact whole-image kernel.
+__device__ __forceinline__ uint64_t wsg_key(float v, uint32_t age) {
+  uint32_t u = __float_as_uint(v);
+  if ((u << 1) == 0) u = 0;  // -0.0 == +0.0
+  u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+  return (static_cast<uint64_t>(u) << 32) | age;
+}
+
+// ctl[0] = pool top, ctl[1] = number of components, ctl[2] = tie flag (per image: 4 ints)
+__global__ void k_wsg_alloc(const uint8_t* __restrict__ msk, const int* __restrict__ L,
+                            const int* __restrict__ size, int* __restrict__ off, int* __restrict__ cnt,
+                            int* __restrict__ roots, int* __restrict__ ctl, int hw) {
+  const size_t base = static_cast<size_t>(blockIdx.y) * hw;
+  int* c = ctl + 4 * blockIdx.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    if (!msk[base + p] || L[base + p] != p) continue;
+    off[base + p] = atomicAdd(&c[0], size[base + p]);
+    cnt[base + p] = 0;
+    roots[base + atomicAdd(&c[1], 1)] = p;
+  }
+}
+
+__global__ void k_wsg_seed(const float* __restrict__ val, const uint8_t* __restrict__ msk,
+                           const int* __restrict__ L, const int* __restrict__ lab,
+                           const int* __restrict__ off, int* __restrict__ cnt,
+                           unsigned long long* __restrict__ hk, int* __restrict__ hi, int H, int W) {
+  const int hw = H * W;
+  const size_t base = static_cast<size_t>(blockIdx.y) * hw;
+  const uint8_t* m = msk + base;
+  const int* l = lab + base;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    if (!m[p] || l[p] == 0) continue;
+    const int x = p % W;
+    const bool b = (p >= W && m[p - W] && l[p - W] == 0) || (x > 0 && m[p - 1] && l[p - 1] == 0) ||
+                   (x < W - 1 && m[p + 1] && l[p + 1] == 0) || (p + W < hw && m[p + W] && l[p + W] == 0);
+    if (!b) continue;  // a marker pixel without an unlabeled in-mask neighbour pushes nothing
+    const int root = L[base + p];
+    const int slot = off[base + root] + atomicAdd(&cnt[base + root], 1);
+    hk[base + slot] = wsg_key(val[base + p], 0u);
+    hi[base + slot] = p;
+  }
+}
+
+__global__ void k_wsg_flood(const float* __restrict__ val, const uint8_t* __restrict__ msk,
+                            int* __restrict__ lab, const int* __restrict__ off,
+                            const int* __restrict__ cnt, const int* __restrict__ roots,
+                            unsigned long long* __restrict__ hk, int* __restrict__ hi,
+                            int* __restrict__ ctl, int H, int W) {
+  const int hw = H * W;
+  const size_t base = static_cast<size_t>(blockIdx.y) * hw;
+  const float* v = val + base;
+  const uint8_t* m = msk + base;
+  int* o = lab + base;
+  int* c = ctl + 4 * blockIdx.y;
+  const int n_roots = c[1];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_roots; t += gridDim.x * blockDim.x) {
+    const int root = roots[base + t];
+    int n = cnt[base + root];
+    if (n == 0) continue;
+    unsigned long long* k = hk + base + off[base + root];
+    int* ix = hi + base + off[base + root];
+    for (int j = 1; j < n; ++j) {  // in-place heap build by successive pushes
+      const unsigned long long ek = k[j];
+      const int ei = ix[j];
+      int cidx = j;
+      while (cidx > 0) {
+        const int parent = (cidx - 1) >> 1;
+        if (!(ek < k[parent])) break;
+        k[cidx] = k[parent];
+        ix[cidx] = ix[parent];
+        cidx = parent;
+      }
+      k[cidx] = ek;
+      ix[cidx] = ei;
+    }
+    uint32_t age = 1;
+    unsigned long long last_marker = ~0ull;
+    while (n > 0) {
+      const unsigned long long top = k[0];
+      const int ei = ix[0];
+      if ((top & 0xFFFFFFFFull) == 0) {  // a marker entry
+        if ((top >> 32) == last_marker) { atomicExch(&c[2], 1); break; }
+        last_marker = top >> 32;
+      }
+      --n;
+      if (n > 0) {  // move the last entry to the root and sift down (left child preferred)
+        const unsigned long long xk = k[n];
+        const int xi = ix[n];
+        int i = 0;
+        for (;;) {
+          const int l = 2 * i + 1;
+          if (l >= n) break;
+          int sidx = i;
+          unsigned long long sk = xk;
+          if (k[l] < sk) { sidx = l; sk = k[l]; }
+          if (l + 1 < n && k[l + 1] < sk) { sidx = l + 1; sk = k[l + 1]; }
+          if (sidx == i) break;
+          k[i] = sk;
+          ix[i] = ix[sidx];
+          i = sidx;
+        }
+        k[i] = xk;
+        ix[i] = xi;
+      }
+      const int lb = o[ei];
+      const int x = ei % W;
+#define CERB_WSG_PUSH(cond, qq)                                          \
+      if (cond) {                                                        \
+        const int q = (qq);                                              \
+        if (m[q] && o[q] == 0) {                                         \
+          ++age;                                                         \
+          o[q] = lb;                                                     \
+          const unsigned long long ek = wsg_key(v[q], age);              \
+          int cidx = n++;                                                \
+          while (cidx > 0) {                                             \
+            const int parent = (cidx - 1) >> 1;                          \
+            if (!(ek < k[parent])) break;                                \
+            k[cidx] = k[parent];                                         \
+            ix[cidx] = ix[parent];                                       \
+            cidx = parent;                                               \
+          }                                                              \
+          k[cidx] = ek;                                                  \
+          ix[cidx] = q;                                                  \
+        }                                                                \
+      }
+      CERB_WSG_PUSH(ei >= W, ei - W)
+      CERB_WSG_PUSH(x > 0, ei - 1)
+      CERB_WSG_PUSH(x < W - 1, ei + 1)
+      CERB_WSG_PUSH(ei + W < hw, ei + W)
+#undef CERB_WSG_PUSH
+    }
+  }
+}
+
+// tie seen: put the saved markers back so that the exact whole-image kernel starts from them
+__global__ void k_wsg_restore(int* __restrict__ lab, const int* __restrict__ saved,
+                              const int* __restrict__ ctl, int hw) {
+  if (ctl[4 * blockIdx.y + 2] == 0) return;
+  const size_t base = static_cast<size_t>(blockIdx.y) * hw;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x)
+    lab[base + p] = saved[base + p];
+}
+
+__global__ void k_wsg_flag(const int* __restrict__ ctl, int* __restrict__ run_flag, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) run_flag[i] = ctl[4 * i + 2];
+}
+
 // ------------------------------------------------------------------ gland / lumen
 // loader/postproc.py:277-286 / :319-327
 __global__ void k_gl_threshold(const float* __restrict__ canvas, int C, int ch0, float thr,
@@ -1018,6 +1175,7 @@ struct Workspace {
   int *heap_a = nullptr, *heap_i = nullptr;
   unsigned long long* heap_k = nullptr;
   int *count = nullptr, *any_fg = nullptr;
+  int* ctl = nullptr;  // [n][4] large-image watershed: pool top, component count, tie flag
   float* canvas = nullptr;
   size_t canvas_elems = 0;
   int* bb = nullptr;
@@ -1079,6 +1237,8 @@ int ensure_ws(cerb_ctx* ctx, Workspace*& ws, int n, int hw) {
     CERB_CUDA(grow<int>(ctx, ws->count, c, static_cast<size_t>(n)));
     c = 0;
     CERB_CUDA(grow<int>(ctx, ws->any_fg, c, static_cast<size_t>(n)));
+    c = 0;
+    CERB_CUDA(grow<int>(ctx, ws->ctl, c, static_cast<size_t>(n) * 4));
     ws->count_cap = n;
   }
   return CERB_OK;
@@ -1238,15 +1398,55 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
                                                  reinterpret_cast<uint64_t*>(ws->heap_k), ws->m0,
                                                  ws->rank, ws->heap_v, fast ? ws->count : nullptr, H,
                                                  W);
+  } else if (ctx->ws_mode == 1) {
+    k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W,
+                                 nullptr);
   } else {
-    k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W);
+    // large images: one thread per mask component, heaps in a global pool (see k_wsg_flood).
+    // ws->rank = slice offsets, ws->heap_a = per-root counters / root list is ws->heap_i's upper
+    // neighbour ws->m1-free int array: roots go to ws->rank2 (= heap_v reinterpreted as int).
+    int* off = ws->rank;
+    int* cnt = ws->heap_a;
+    int* roots = reinterpret_cast<int*>(ws->heap_v);
+    CERB_CUDA(cudaMemsetAsync(ws->ctl, 0, sizeof(int) * 4 * n, s));
+    k_wsg_alloc<<<g, kThreads, 0, s>>>(msk, ws->L, ws->size, off, cnt, roots, ws->ctl, hw);
+    // ws->size is dead now: it keeps the markers for the tie fallback
+    CERB_CUDA(cudaMemcpyAsync(ws->size, ws->lab, sizeof(int) * static_cast<size_t>(n) * hw,
+                              cudaMemcpyDeviceToDevice, s));
+    k_wsg_seed<<<g, kThreads, 0, s>>>(ws->val, msk, ws->L, ws->lab, off, cnt, ws->heap_k, ws->heap_i,
+                                      H, W);
+    k_wsg_flood<<<dim3(148 * 8, n), 64, 0, s>>>(ws->val, msk, ws->lab, off, cnt, roots, ws->heap_k,
+                                                ws->heap_i, ws->ctl, H, W);
+    k_wsg_restore<<<g, kThreads, 0, s>>>(ws->lab, ws->size, ws->ctl, hw);
+    k_wsg_flag<<<(n + 255) / 256, 256, 0, s>>>(ws->ctl, ws->count, n);
+    k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W,
+                                 ws->count);
+    ctx->launches += 6;
   }
   ctx->launches += 4;
   if (any_fg_out) {
     CERB_CUDA(cudaMemcpyAsync(any_fg_out, ws->any_fg, sizeof(int) * n,
                               (flags & 2) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   }
-  return finish(ctx, ws->lab, labels_out, static_cast<size_t>(n) * hw, flags & 2);
+  const bool large = hw > 65536 && ctx->ws_mode != 1;
+  rc = finish(ctx, ws->lab, labels_out, static_cast<size_t>(n) * hw, flags & 2);
+  if (rc == CERB_OK && large && !(flags & 2)) {
+    // host-visible call: account for tiles that needed the exact whole-image fallback
+    std::vector<int> ctl(static_cast<size_t>(4) * n);
+    CERB_CUDA(cudaMemcpy(ctl.data(), ws->ctl, sizeof(int) * 4 * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+      ctx->stat_ws_large += 1;
+      ctx->stat_ws_fallback += ctl[4 * i + 2] != 0;
+    }
+  }
+  return rc;
+}
+
+extern "C" int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name) {
+  if (!ctx || !name) return -1;
+  if (strcmp(name, "ws_large_images") == 0) return ctx->stat_ws_large;
+  if (strcmp(name, "ws_large_fallbacks") == 0) return ctx->stat_ws_fallback;
+  return -1;
 }
 
 extern "C" int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int n, int H, int W,

@@ -70,11 +70,18 @@ def get_instance_info(pred_inst, pred_type=None):
     ids = np.unique(pred_inst)[1:]
     if len(ids) == 0:
         return info
-    # one pass over the label map for all boxes (same values as the per-instance masks)
+    # The original builds `pred_inst == inst_id` over the WHOLE tile for every instance
+    # (O(instances x pixels): minutes for a 4032^2 tile); one find_objects pass gives the same
+    # boxes, and the per-instance mask is then cut from the box only.
+    from scipy import ndimage
+    lab = pred_inst if pred_inst.dtype.kind in "iu" else pred_inst.astype(np.int64)
+    if lab.min() < 0:
+        raise ValueError("negative instance ids")
+    slices = ndimage.find_objects(lab)
     for inst_id in ids:
-        inst_map = pred_inst == inst_id
-        box = tiatoolbox_bounding_box(inst_map)
-        crop = inst_map[box[1]:box[3], box[0]:box[2]].astype(np.uint8)
+        sl = slices[int(inst_id) - 1]
+        box = np.array([sl[1].start, sl[0].start, sl[1].stop, sl[0].stop])
+        crop = (lab[sl] == inst_id).astype(np.uint8)
         moment = cv2.moments(crop)
         contour = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
         contour = np.squeeze(contour[0][0].astype(np.int32))
@@ -187,15 +194,19 @@ class InferManager(base.InferManager):
         torch.cuda.synchronize(canvas.device)
         labels = np.empty((h, w), dtype=np.int32)
         any_fg = np.zeros(1, dtype=np.int32)
+        t0 = time.perf_counter()
         _lib.check(lib.cerb_postproc_nuclei(ctx.handle, _ptr(crop), 1, h, w, C,
                                             idx["Nuclei-INST"][0],
                                             labels.ctypes.data_as(_lib.ctypes.c_void_p),
                                             any_fg.ctypes.data_as(_lib.ctypes.c_void_p), 1),
                    "cerb_postproc_nuclei")
+        self.t_dev += time.perf_counter() - t0
         del crop
         if not any_fg[0]:
             return {}, []
+        t0 = time.perf_counter()
         inst_dict = get_instance_info(labels, type_map)
+        self.t_host += time.perf_counter() - t0
         if len(inst_dict) == 0:
             return {}, []
         inst_boxes = np.array([v["box"] for v in inst_dict.values()])
@@ -221,6 +232,7 @@ class InferManager(base.InferManager):
         H, W, _ = canvas.shape
         tile_sets = get_tile_info((W, H), pp_tile_shape, self.patch_output_shape, margin)
         nuclei = {}
+        self.t_dev = self.t_host = 0.0
         for set_idx, (set_bounds, set_flags) in enumerate(tile_sets):
             results = []
             for tile_idx, tile_bounds in enumerate(set_bounds):
@@ -369,6 +381,11 @@ class InferManager(base.InferManager):
         wsi_inst_info["Nuclei"] = self._postproc_nuclei(canvas, patch_outputs,
                                                         self.postproc_tile_shape, margin)
         self.logger.info("Nuclei Post Proc Time: %s" % (time.perf_counter() - start))
+        lib_, h_ = eng.ctx.lib, eng.ctx.handle
+        self.logger.info("Nuclei watershed: %d large tiles, %d redone by the exact whole-tile emulation "
+                         "(marker ties); device %.2f s, host instance info %.2f s" % (
+                             lib_.cerb_ctx_stat(h_, b"ws_large_images"),
+                             lib_.cerb_ctx_stat(h_, b"ws_large_fallbacks"), self.t_dev, self.t_host))
 
         start = time.perf_counter()
         idx = eng.model.idx_dict

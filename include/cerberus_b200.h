@@ -210,6 +210,10 @@ int cerb_stitch(cerb_ctx* ctx, const float* patches, int n, int oh, int ow, int 
  * pre-erosion mask is empty: the reference returns a float64 zero map for those. */
 int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, int H, int W, int C, int ch0,
                          int32_t* labels_out, int32_t* any_fg_out, int flags);
+/* Counters: "ws_large_images" = images > 65536 px labelled by the component-parallel watershed,
+ * "ws_large_fallbacks" = how many of them hit a marker tie and were redone by the exact
+ * whole-image emulation (host-output calls only). -1 for an unknown name. */
+int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name);
 
 enum cerb_tissue { CERB_TISSUE_GLAND = 0, CERB_TISSUE_LUMEN = 1 };
 /* __proc_gland (:270-309) / __proc_lumen (:312-350); ds_factor as in the reference

@@ -1,0 +1,88 @@
+"""WSI-mode measurement (BASELINE config 4 shape, scaled): synthetic array-backed slide + random
+tissue mask through cerberus_b200.infer.wsi.InferManager, stage times from its log.
+  python tools/wsi_bench.py [SIZE] [BATCH] [PP_TILE]        (torchrun for N GPUs)"""
+import json
+import os
+import re
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import cv2  # noqa: E402
+import numpy as np  # noqa: E402
+import yaml  # noqa: E402
+
+
+def main():
+    size = int(sys.argv[1]) if len(sys.argv) > 1 else 4608
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+    pp_tile = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from cerberus_b200 import synth
+    from cerberus_b200.infer.wsi import InferManager
+    tmp = os.environ.get("WSI_BENCH_DIR") or tempfile.mkdtemp(prefix="wsi_bench_")
+    if world > 1:
+        obj = [tmp]
+        dist.broadcast_object_list(obj, src=0)
+        tmp = obj[0]
+    if rank == 0:
+        os.makedirs(tmp + "/wsi", exist_ok=True)
+        os.makedirs(tmp + "/msk", exist_ok=True)
+        n = -(-size // 256)
+        tiles = synth.synthetic_tiles(n * n, 256, 256, seed=5)
+        slide = tiles.reshape(n, n, 256, 256, 3).transpose(0, 2, 1, 3, 4).reshape(n * 256, n * 256, 3)
+        np.save(tmp + "/wsi/slide.npy", np.ascontiguousarray(slide[:size, :size]))
+        # seeded blobs, ~40 % coverage, at 1/10 resolution
+        rng = np.random.RandomState(0)
+        m = cv2.GaussianBlur(rng.rand(size // 10, size // 10).astype(np.float32), (0, 0), size / 160.0)
+        mask = (m > np.quantile(m, 0.6)).astype(np.uint8) * 255
+        cv2.imwrite(tmp + "/msk/slide.png", mask)
+        synth.write_model_dir(tmp + "/model", seed=0)
+    if world > 1:
+        dist.barrier()
+    st = yaml.full_load(open(tmp + "/model/settings.yml"))
+    m = InferManager(checkpoint_path=tmp + "/model/weights.tar",
+                     decoder_dict=st["dataset_kwargs"]["req_target_code"], model_args=st["model_kwargs"],
+                     device=local_rank)
+    run_args = {
+        "nr_inference_workers": 0, "nr_post_proc_workers": 0, "batch_size": batch,
+        "input_list": [tmp + "/wsi/slide.npy"], "mask_list": [tmp + "/msk/slide.png"],
+        "output_dir": tmp + "/out", "patch_input_shape": 448, "patch_output_shape": 144,
+        "save_thumb": False, "save_mask": False, "mask_dir": tmp + "/msk/", "postproc_list": [],
+        "msk_dir": tmp + "/msk/", "tile_shape": 2048, "chunk_shape": 15000, "ambiguous_size": 64,
+        "cache_path": tmp + "/cache", "logging_dir": tmp + "/log", "wsi_proc_mag": 0.5,
+        "postproc_tile_shape": pp_tile,
+    }
+    t0 = time.perf_counter()
+    res = m.process_wsi_list(run_args)
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        logs = sorted(f for f in os.listdir(tmp + "/log") if "rank" not in f)
+        text = open(os.path.join(tmp, "log", logs[-1])).read()
+        stages = {k: float(v) for k, v in re.findall(r"INFO - ([A-Za-z& ]+ Time): ([0-9.]+)", text)}
+        npatch = int(re.search(r"(\d+) selected", text).group(1))
+        ws = re.search(r"Nuclei watershed: (.*)", text)
+        r = res["slide"]
+        line = {"slide": [size, size], "n_gpus": world, "batch": batch, "postproc_tile": pp_tile,
+                "patches_448_to_144": npatch, "wall_s": dt, "stages_s": stages,
+                "nuclei_detail": ws.group(1) if ws else None,
+                "patches_per_s_inference": npatch / stages["Inference Time"],
+                "tiles256_equivalent_per_s": npatch / stages["Inference Time"] * (448 * 448) / (256 * 256),
+                "instances": {k: len(v) for k, v in r.items() if isinstance(v, dict) and k in ("Nuclei", "Gland", "Lumen")}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
