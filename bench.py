@@ -246,6 +246,8 @@ def run_ours(args):
     if post is not None:
         from cerberus_b200.pipeline import TilePipeline
         pipe = TilePipeline(eng, B, TILE, TILE)
+        if os.environ.get("CERB_WS_MODE"):  # robustness experiment: force the exact fallback
+            pipe.pctx.set_option("ws_mode", int(os.environ["CERB_WS_MODE"]))
         post = pipe  # post-processing runs on the pipeline's second context
 
     def step_resident(i):
@@ -273,11 +275,13 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step_resident(i)
     if pipe is not None:
         pipe.join_streams()  # the end event on the compute stream then covers the post stream
     e1.record(stream)
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps
     ctx.sync()
     barrier()
     clocks = sampler.stop()
@@ -303,8 +307,7 @@ def run_ours(args):
         for i in range(args.steps):
             if pipe.submit(host_np[i % n_in]) is not None:
                 got += 1
-        if pipe.flush() is not None:
-            got += 1
+        got += len(pipe.flush())
         barrier()
         dt = time.perf_counter() - t0
         assert got == args.steps, (got, args.steps)
@@ -377,6 +380,15 @@ def run_ours(args):
         roof = {"bound": "tensor", "achieved": None, "peak": peaks["tensor_sustained"],
                 "unit": "TFLOP/s", "frac": None, "traffic": None, "error": str(e)}
 
+    ws_stats = None
+    if pipe is not None:
+        pl = pipe.pctx
+        imgs = int(pl.lib.cerb_ctx_stat(pl.handle, b"ws_images"))
+        ws_stats = {"images": imgs,
+                    "exact_fallback_tie": int(pl.lib.cerb_ctx_stat(pl.handle, b"ws_tie_fallbacks")),
+                    "exact_fallback_capacity": int(pl.lib.cerb_ctx_stat(pl.handle, b"ws_capacity_fallbacks")),
+                    "note": "nuclei watershed, all steps incl. warm-up and e2e: images handled by the "
+                            "component-parallel path vs redone by the exact whole-tile emulation"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference_rate(args, args.cpu_seconds, args.ref_batch)
@@ -393,6 +405,8 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": host_enqueue_ms,
+            "watershed": ws_stats,
             "roofline": roof,
             "cpu_baseline": cpu,
             "tflops_forward": value * GFLOP_PER_TILE_6HEAD / 1e3,

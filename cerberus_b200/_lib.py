@@ -99,6 +99,8 @@ _SIGNATURES = {
                                        ctypes.c_size_t, ctypes.c_int]),
     "cerb_stream_order": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cerb_ctx_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "cerb_ctx_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "cerb_ctx_wait_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "cerb_copy_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cerb_copy_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "cerb_copy_sync": (ctypes.c_int, [ctypes.c_void_p]),

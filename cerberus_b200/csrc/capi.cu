@@ -638,19 +638,24 @@ extern "C" int cerb_ctx_create(int device, int precision, cerb_ctx** out) {
   ctx->device = device;
   ctx->precision = precision;
   ctx->num_sms = prop.multiProcessorCount;
+  ctx->conv_sms = ctx->num_sms;
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
   CERB_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   CERB_CUDA(cudaEventCreateWithFlags(&ctx->side_event, cudaEventDisableTiming));
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i) {
     CERB_CUDA(cudaEventCreateWithFlags(&ctx->slot_event[i], cudaEventDisableTiming));
+    CERB_CUDA(cudaEventCreateWithFlags(&ctx->mark_event[i], cudaEventDisableTiming));
+  }
   CERB_CUDA(cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming));
   CERB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->err_flag_host), sizeof(int) * 4,
                           cudaHostAllocMapped));
   memset(ctx->err_flag_host, 0, sizeof(int) * 4);
   CERB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->err_flag_dev),
                                      ctx->err_flag_host, 0));
+  CERB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->stat_dev), 4 * sizeof(unsigned long long)));
+  CERB_CUDA(cudaMemset(ctx->stat_dev, 0, 4 * sizeof(unsigned long long)));
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   CERB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -669,11 +674,14 @@ extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->side_event) cudaEventDestroy(ctx->side_event);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i) {
     if (ctx->slot_event[i]) cudaEventDestroy(ctx->slot_event[i]);
+    if (ctx->mark_event[i]) cudaEventDestroy(ctx->mark_event[i]);
+  }
   if (ctx->order_event) cudaEventDestroy(ctx->order_event);
   if (ctx->err_flag_host) cudaFreeHost(ctx->err_flag_host);
   if (ctx->prof_dev) cudaFree(ctx->prof_dev);
+  if (ctx->stat_dev) cudaFree(ctx->stat_dev);
   for (void* p : ctx->scratch) cudaFree(p);
   if (ctx->postproc_ws && ctx->postproc_ws_free) ctx->postproc_ws_free(ctx->postproc_ws);
   delete ctx;
@@ -718,6 +726,14 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     ctx->conv3_mode = value;
     return CERB_OK;
   }
+  if (strcmp(name, "conv_sms") == 0) {
+    // persistent convolution kernels launch at most this many CTAs (one per SM); the rest of the
+    // SMs stay free for kernels of other contexts (post-processing blocks that need a whole SM).
+    // Applies to launches / graph captures made afterwards.
+    if (value < 1) return fail(CERB_ERR_ARG, "conv_sms must be >= 1");
+    ctx->conv_sms = value < ctx->num_sms ? value : ctx->num_sms;
+    return CERB_OK;
+  }
   if (strcmp(name, "k_rotate") == 0) {
     ctx->k_rotate = value != 0;
     return CERB_OK;
@@ -760,14 +776,14 @@ extern "C" int cerb_copy_async(cerb_ctx* ctx, void* dst, const void* src, size_t
 }
 
 extern "C" int cerb_copy_mark(cerb_ctx* ctx, int slot) {
-  if (!ctx || slot < 0 || slot > 3) return fail(CERB_ERR_ARG, "cerb_copy_mark: bad arguments");
+  if (!ctx || slot < 0 || slot > 7) return fail(CERB_ERR_ARG, "cerb_copy_mark: bad arguments");
   CERB_CUDA(cudaSetDevice(ctx->device));
   CERB_CUDA(cudaEventRecord(ctx->slot_event[slot], ctx->copy_stream));
   return CERB_OK;
 }
 
 extern "C" int cerb_copy_wait(cerb_ctx* ctx, int slot) {
-  if (!ctx || slot < 0 || slot > 3) return fail(CERB_ERR_ARG, "cerb_copy_wait: bad arguments");
+  if (!ctx || slot < 0 || slot > 7) return fail(CERB_ERR_ARG, "cerb_copy_wait: bad arguments");
   CERB_CUDA(cudaSetDevice(ctx->device));
   CERB_CUDA(cudaEventSynchronize(ctx->slot_event[slot]));
   const int flag = ctx->err_flag_host ? ctx->err_flag_host[0] : 0;
@@ -791,6 +807,21 @@ extern "C" int cerb_ctx_wait(cerb_ctx* waiter, cerb_ctx* signal) {
   CERB_CUDA(cudaSetDevice(waiter->device));
   CERB_CUDA(cudaEventRecord(signal->order_event, signal->stream));
   CERB_CUDA(cudaStreamWaitEvent(waiter->stream, signal->order_event, 0));
+  return CERB_OK;
+}
+
+extern "C" int cerb_ctx_mark(cerb_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 7) return fail(CERB_ERR_ARG, "cerb_ctx_mark: bad arguments");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  CERB_CUDA(cudaEventRecord(ctx->mark_event[slot], ctx->stream));
+  return CERB_OK;
+}
+
+extern "C" int cerb_ctx_wait_mark(cerb_ctx* waiter, cerb_ctx* signal, int slot) {
+  if (!waiter || !signal || waiter->device != signal->device || slot < 0 || slot > 7)
+    return fail(CERB_ERR_ARG, "cerb_ctx_wait_mark: bad arguments");
+  CERB_CUDA(cudaSetDevice(waiter->device));
+  CERB_CUDA(cudaStreamWaitEvent(waiter->stream, signal->mark_event[slot], 0));
   return CERB_OK;
 }
 
@@ -1010,9 +1041,9 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
       }
       break;
     case CERB_OP_CONV:
-      e = st.use64  ? conv64_launch(st.c64, ctx->num_sms, s)
-          : st.use3 ? conv3x3_launch(st.c3, ctx->num_sms, s)
-                    : conv_tc_launch(st.conv, st.split, ctx->num_sms, s);
+      e = st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s)
+          : st.use3 ? conv3x3_launch(st.c3, ctx->conv_sms, s)
+                    : conv_tc_launch(st.conv, st.split, ctx->conv_sms, s);
       break;
     case CERB_OP_MAXPOOL:
       e = launch_maxpool(st.a, st.b, s);

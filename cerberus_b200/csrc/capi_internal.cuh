@@ -12,22 +12,26 @@ struct cerb_ctx {
   int device = 0;
   int precision = 0;
   int num_sms = 148;
+  int conv_sms = 148;  // CTAs of the persistent convolution kernels (option "conv_sms")
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H copies overlapped with compute
   cudaStream_t up_stream = nullptr;    // H2D copies overlapped with compute
   cudaStream_t side_stream = nullptr;  // graph branch for ops flagged `side` (Patch-Class)
   cudaEvent_t side_event = nullptr;
   cudaEvent_t order_event = nullptr;
-  cudaEvent_t slot_event[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t slot_event[8] = {};  // download-stream marks (cerb_copy_mark / cerb_copy_wait)
+  cudaEvent_t mark_event[8] = {};  // compute-stream marks (cerb_ctx_mark / cerb_ctx_wait_mark)
   int* err_flag_host = nullptr;  // mapped pinned memory: readable even after a trapped kernel
   int* err_flag_dev = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved at run time (no libcuda link)
   int64_t launches = 0;
   bool use_graphs = true;  // replay the forward op list as a CUDA graph
+  unsigned long long* stat_dev = nullptr;  // [4] device counters of the small-tile watershed (cerb_ctx_stat)
   int64_t stat_ws_large = 0, stat_ws_fallback = 0;  // large-image watershed calls / exact fallbacks
   int conv64_debug = 0;
   long long* prof_dev = nullptr;  // [kProfSlots] in-kernel attribution counters (option "kernel_prof")
-  int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only
+  int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only;
+                    // 2 (test hook): image 0 of every batch is redone by the exact emulation
   int k_rotate = 1;     // per-CTA rotated K walk in conv3x3.cu (de-synchronises weight-slab reads)
   int conv3_mode = 1;   // 0: generic kernel for the wide 3x3 layers; 1: conv3x3.cu (cout <= 512); 2: always
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout

@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(kWcThreads, 1)
 k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
                  const int* __restrict__ Lroot, const int* __restrict__ csize,
                  int* __restrict__ out, int* __restrict__ aux_map, int* __restrict__ slow_flag, int H,
-                 int W) {
+                 int W, unsigned long long* __restrict__ stat, int force_slow_first) {
   extern __shared__ __align__(16) uint8_t ws_smem[];
   __shared__ int s_warp_cnt[kWcThreads / 32], s_warp_sz[kWcThreads / 32];
   __shared__ int s_ncomp, s_total, s_unsafe;
@@ -672,6 +672,10 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
   uint16_t* lab16 = reinterpret_cast<uint16_t*>(ws_smem + sizeof(uint64_t) * kWcPool);
   int* c_off = reinterpret_cast<int*>(ws_smem + sizeof(uint64_t) * kWcPool + 2u * ((hw + 7) & ~7));
   int* c_cnt = c_off + kWcMaxComp;
+  // marker label of the component's boundary markers, or -1 once two different labels were seen.
+  // A component whose boundary markers all carry ONE label is flooded with that label whatever the
+  // pop order, so a tie between its markers cannot change the result and needs no fallback.
+  int* c_lab = c_cnt + kWcMaxComp;
   const size_t base = static_cast<size_t>(blockIdx.x) * hw;
   const float* v = val + base;
   const uint8_t* m = msk + base;
@@ -712,7 +716,7 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
     for (int w2 = 0; w2 < warp; ++w2) { bc += s_warp_cnt[w2]; ba += s_warp_sz[w2]; }
     if (flag) {
       const int k = bc + c - 1;
-      if (k < kWcMaxComp) { c_off[k] = ba + a - size; c_cnt[k] = 0; }
+      if (k < kWcMaxComp) { c_off[k] = ba + a - size; c_cnt[k] = 0; c_lab[k] = 0; }
       amap[p] = k;
     }
     __syncthreads();
@@ -738,6 +742,8 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
       const int k = amap[L[p]];
       const int slot = c_off[k] + atomicAdd(&c_cnt[k], 1);
       pool[slot] = ws_entry(v[p], 0u, p);
+      const int prev = atomicCAS(&c_lab[k], 0, static_cast<int>(l));
+      if (prev != 0 && prev != static_cast<int>(l)) c_lab[k] = -1;
     }
     __syncthreads();
     // D: one thread per component
@@ -764,7 +770,7 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
         const uint64_t top = hp[0];
         const int ei = static_cast<int>(top & 0xFFFFu);
         if (((top >> 16) & 0xFFFFu) == 0) {  // a marker entry (age 0)
-          if ((top >> 32) == last_marker) { tie = true; break; }
+          if ((top >> 32) == last_marker && c_lab[k] == -1) { tie = true; break; }
           last_marker = top >> 32;
         }
         const int x = ei % W;
@@ -829,11 +835,17 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
     }
   }
   __syncthreads();
-  if (!fits || s_unsafe) {
-    if (tid == 0) slow_flag[blockIdx.x] = 1;  // `out` still holds markers * mask
+  if (!fits || s_unsafe || (force_slow_first && blockIdx.x == 0)) {
+    if (tid == 0) {
+      slow_flag[blockIdx.x] = 1;  // `out` still holds markers * mask
+      if (stat != nullptr) { atomicAdd(stat + 0, 1ull); atomicAdd(stat + (fits ? 2 : 3), 1ull); }
+    }
     return;
   }
-  if (tid == 0) slow_flag[blockIdx.x] = 0;
+  if (tid == 0) {
+    slow_flag[blockIdx.x] = 0;
+    if (stat != nullptr) atomicAdd(stat + 0, 1ull);
+  }
   for (int p = tid; p < hw; p += kWcThreads) {
     const uint16_t l = lab16[p];
     o[p] = l == kWsOutside ? 0 : static_cast<int>(l);
@@ -859,20 +871,22 @@ __device__ __forceinline__ uint64_t wsg_key(float v, uint32_t age) {
 // ctl[0] = pool top, ctl[1] = number of components, ctl[2] = tie flag (per image: 4 ints)
 __global__ void k_wsg_alloc(const uint8_t* __restrict__ msk, const int* __restrict__ L,
                             const int* __restrict__ size, int* __restrict__ off, int* __restrict__ cnt,
-                            int* __restrict__ roots, int* __restrict__ ctl, int hw) {
+                            int* __restrict__ clab, int* __restrict__ roots, int* __restrict__ ctl,
+                            int hw) {
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
   int* c = ctl + 4 * blockIdx.y;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
     if (!msk[base + p] || L[base + p] != p) continue;
     off[base + p] = atomicAdd(&c[0], size[base + p]);
     cnt[base + p] = 0;
+    clab[base + p] = 0;
     roots[base + atomicAdd(&c[1], 1)] = p;
   }
 }
 
 __global__ void k_wsg_seed(const float* __restrict__ val, const uint8_t* __restrict__ msk,
                            const int* __restrict__ L, const int* __restrict__ lab,
-                           const int* __restrict__ off, int* __restrict__ cnt,
+                           const int* __restrict__ off, int* __restrict__ cnt, int* __restrict__ clab,
                            unsigned long long* __restrict__ hk, int* __restrict__ hi, int H, int W) {
   const int hw = H * W;
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
@@ -888,14 +902,17 @@ __global__ void k_wsg_seed(const float* __restrict__ val, const uint8_t* __restr
     const int slot = off[base + root] + atomicAdd(&cnt[base + root], 1);
     hk[base + slot] = wsg_key(val[base + p], 0u);
     hi[base + slot] = p;
+    // one label per component -> ties are harmless (see k_watershed_comp)
+    const int prev = atomicCAS(&clab[base + root], 0, l[p]);
+    if (prev != 0 && prev != l[p]) clab[base + root] = -1;
   }
 }
 
 __global__ void k_wsg_flood(const float* __restrict__ val, const uint8_t* __restrict__ msk,
                             int* __restrict__ lab, const int* __restrict__ off,
-                            const int* __restrict__ cnt, const int* __restrict__ roots,
-                            unsigned long long* __restrict__ hk, int* __restrict__ hi,
-                            int* __restrict__ ctl, int H, int W) {
+                            const int* __restrict__ cnt, const int* __restrict__ clab,
+                            const int* __restrict__ roots, unsigned long long* __restrict__ hk,
+                            int* __restrict__ hi, int* __restrict__ ctl, int H, int W) {
   const int hw = H * W;
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
   const float* v = val + base;
@@ -907,6 +924,7 @@ __global__ void k_wsg_flood(const float* __restrict__ val, const uint8_t* __rest
     const int root = roots[base + t];
     int n = cnt[base + root];
     if (n == 0) continue;
+    const bool multi = clab[base + root] == -1;
     unsigned long long* k = hk + base + off[base + root];
     int* ix = hi + base + off[base + root];
     for (int j = 1; j < n; ++j) {  // in-place heap build by successive pushes
@@ -929,7 +947,7 @@ __global__ void k_wsg_flood(const float* __restrict__ val, const uint8_t* __rest
       const unsigned long long top = k[0];
       const int ei = ix[0];
       if ((top & 0xFFFFFFFFull) == 0) {  // a marker entry
-        if ((top >> 32) == last_marker) { atomicExch(&c[2], 1); break; }
+        if ((top >> 32) == last_marker && multi) { atomicExch(&c[2], 1); break; }
         last_marker = top >> 32;
       }
       --n;
@@ -1170,7 +1188,7 @@ __global__ void k_mask_by(int* __restrict__ lumen, const int* __restrict__ gland
 struct Workspace {
   size_t pixels = 0;  // n * hw capacity
   uint8_t *m0 = nullptr, *m1 = nullptr, *m2 = nullptr;
-  int *L = nullptr, *size = nullptr, *rank = nullptr, *lab = nullptr;
+  int *L = nullptr, *size = nullptr, *rank = nullptr, *lab = nullptr, *aux = nullptr;
   float *val = nullptr, *heap_v = nullptr;
   int *heap_a = nullptr, *heap_i = nullptr;
   unsigned long long* heap_k = nullptr;
@@ -1226,7 +1244,7 @@ int ensure_ws(cerb_ctx* ctx, Workspace*& ws, int n, int hw) {
   c = 0;                                                                               \
   CERB_CUDA(grow<type>(ctx, ws->field, c, need));
     GROW(m0, uint8_t) GROW(m1, uint8_t) GROW(m2, uint8_t)
-    GROW(L, int) GROW(size, int) GROW(rank, int) GROW(lab, int)
+    GROW(L, int) GROW(size, int) GROW(rank, int) GROW(lab, int) GROW(aux, int)
     GROW(val, float) GROW(heap_v, float) GROW(heap_a, int) GROW(heap_i, int)
     GROW(heap_k, unsigned long long)
 #undef GROW
@@ -1381,7 +1399,7 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
                                      226 * 1024));
       attr_set = true;
     }
-    const size_t smem_c = sizeof(uint64_t) * kWcPool + 2u * ((hw + 7) & ~7) + 8u * kWcMaxComp + 16;
+    const size_t smem_c = sizeof(uint64_t) * kWcPool + 2u * ((hw + 7) & ~7) + 12u * kWcMaxComp + 16;
     static bool attr_c = false;
     if (!attr_c) {
       CERB_CUDA(cudaFuncSetAttribute(k_watershed_comp, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1391,7 +1409,8 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
     const bool fast = (ctx->ws_mode != 1);
     if (fast) {
       k_watershed_comp<<<n, kWcThreads, smem_c, s>>>(ws->val, msk, ws->L, ws->size, ws->lab,
-                                                     ws->heap_a, ws->count, H, W);
+                                                     ws->heap_a, ws->count, H, W, ctx->stat_dev,
+                                                     ctx->ws_mode == 2 ? 1 : 0);
       ctx->launches += 1;
     }
     k_watershed_smem<<<n, kWsThreads, smem, s>>>(ws->val, msk, ws->lab,
@@ -1409,14 +1428,14 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
     int* cnt = ws->heap_a;
     int* roots = reinterpret_cast<int*>(ws->heap_v);
     CERB_CUDA(cudaMemsetAsync(ws->ctl, 0, sizeof(int) * 4 * n, s));
-    k_wsg_alloc<<<g, kThreads, 0, s>>>(msk, ws->L, ws->size, off, cnt, roots, ws->ctl, hw);
+    k_wsg_alloc<<<g, kThreads, 0, s>>>(msk, ws->L, ws->size, off, cnt, ws->aux, roots, ws->ctl, hw);
     // ws->size is dead now: it keeps the markers for the tie fallback
     CERB_CUDA(cudaMemcpyAsync(ws->size, ws->lab, sizeof(int) * static_cast<size_t>(n) * hw,
                               cudaMemcpyDeviceToDevice, s));
-    k_wsg_seed<<<g, kThreads, 0, s>>>(ws->val, msk, ws->L, ws->lab, off, cnt, ws->heap_k, ws->heap_i,
-                                      H, W);
-    k_wsg_flood<<<dim3(148 * 8, n), 64, 0, s>>>(ws->val, msk, ws->lab, off, cnt, roots, ws->heap_k,
-                                                ws->heap_i, ws->ctl, H, W);
+    k_wsg_seed<<<g, kThreads, 0, s>>>(ws->val, msk, ws->L, ws->lab, off, cnt, ws->aux, ws->heap_k,
+                                      ws->heap_i, H, W);
+    k_wsg_flood<<<dim3(148 * 8, n), 64, 0, s>>>(ws->val, msk, ws->lab, off, cnt, ws->aux, roots,
+                                                ws->heap_k, ws->heap_i, ws->ctl, H, W);
     k_wsg_restore<<<g, kThreads, 0, s>>>(ws->lab, ws->size, ws->ctl, hw);
     k_wsg_flag<<<(n + 255) / 256, 256, 0, s>>>(ws->ctl, ws->count, n);
     k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W,
@@ -1444,6 +1463,17 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
 
 extern "C" int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name) {
   if (!ctx || !name) return -1;
+  if (strcmp(name, "ws_images") == 0 || strcmp(name, "ws_tie_fallbacks") == 0 ||
+      strcmp(name, "ws_capacity_fallbacks") == 0) {
+    // tiles <= 65536 px: images seen by the component-parallel watershed / redone by the exact
+    // whole-tile emulation because of a marker tie / because the tile exceeded the heap pool
+    if (ctx->stat_dev == nullptr) return 0;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (cudaMemcpy(h, ctx->stat_dev, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return static_cast<int64_t>(name[3] == 'i' ? h[0] : name[3] == 't' ? h[2] : h[3]);
+  }
   if (strcmp(name, "ws_large_images") == 0) return ctx->stat_ws_large;
   if (strcmp(name, "ws_large_fallbacks") == 0) return ctx->stat_ws_fallback;
   return -1;

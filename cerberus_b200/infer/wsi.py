@@ -125,7 +125,7 @@ class InferManager(base.InferManager):
 
     def _dist(self):
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
+        if dist.is_available() and dist.is_initialized() and not getattr(self, "force_single", False):
             return dist, dist.get_rank(), dist.get_world_size()
         return None, 0, 1
 

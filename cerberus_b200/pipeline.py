@@ -91,33 +91,50 @@ class TilePipeline:
     are kept busy at once:
         upload   : H2D of batch k+1                         (engine ctx, cerb_copy_async kind 1)
         compute  : forward of batch k, canvas -> slot copy  (engine ctx)
-        post     : post-processing of batch k-1             (a second ctx on the same device)
-        download : D2H of the label maps of batch k-1       (second ctx, cerb_copy_async kind 2)
+        post     : post-processing of batches k-1, k-2      (a second ctx on the same device)
+        download : D2H of their label maps                  (second ctx, cerb_copy_async kind 2)
     The post-processing kernels are latency-bound (one block per image / instance), so running
-    them next to the next batch's convolutions hides most of their time.
+    them next to the next batches' convolutions hides most of their time. There are `depth`
+    result slots (default 4) and results are handed back LAG = depth - 2 submits late: a batch
+    whose nuclei watershed needs the exact whole-tile emulation (two markers of one touching-
+    nuclei component with bit-equal values: ~13 ms for one image next to a running forward) then
+    delays nothing as long as the average post-processing time stays below the forward time.
 
         pipe = TilePipeline(engine, n, h, w)
         for batch in batches:            # uint8 [n,h,w,3]
-            done = pipe.submit(batch)    # -> labels of the PREVIOUS batch (None for the first)
-        last = pipe.flush()
+            done = pipe.submit(batch)    # -> labels of batch k - LAG (None for the first LAG)
+        rest = pipe.flush()              # -> list of the remaining results, oldest first
 
     Returned dicts {tissue: int32 [n,h,w]} are views of pinned buffers that stay valid until the
     second-next submit()."""
 
-    def __init__(self, engine, n, h, w, ds_factor=1.0):
+    def __init__(self, engine, n, h, w, ds_factor=1.0, depth=4):
+        import os
+        from collections import deque
         from .engine import Context
         self.ctx, self.model = engine.ctx, engine.model
         self.lib = self.ctx.lib
         self.pctx = Context(self.ctx.device, self.ctx.precision)  # post-processing + download
+        # The convolutions are persistent kernels with one CTA per SM and a static tile split; the
+        # watershed blocks of the post-processing need a whole SM each (>200 KB shared memory). If
+        # they have to steal SMs from a running forward, every convolution launched meanwhile
+        # finds fewer SMs than CTAs and runs a second wave. A few SMs are therefore left to the
+        # post-processing (CERB_POST_SMS, default 4; 0 = none).
+        self.post_sms = int(os.environ.get("CERB_POST_SMS", "4"))
+        if self.post_sms > 0:
+            self.ctx.set_option("conv_sms", 148 - self.post_sms)
+        self.depth = max(2, min(8, int(depth)))
+        self.lag = self.depth - 2 if self.depth > 2 else 1
         self.plan = engine.plan_for(n, h, w, h, w)
         self.n, self.h, self.w = n, h, w
         self.in_bytes = n * h * w * 3
         self.canvas_bytes = n * h * w * self.model.canvas_c * 4
-        # two result slots (canvas copy + label maps): batch k-1 is post-processed / downloaded
+        # result slots (canvas copy + label maps): batch k-1.. are post-processed / downloaded
         # while batch k is computed
-        self.post = [DevicePostProc(self.pctx, self.model, n, h, w, ds_factor) for _ in range(2)]
+        self.post = [DevicePostProc(self.pctx, self.model, n, h, w, ds_factor)
+                     for _ in range(self.depth)]
         self.canvas_copy = []
-        for _ in range(2):
+        for _ in range(self.depth):
             cp = self.lib.cerb_dev_alloc(self.ctx.handle, self.canvas_bytes)
             if not cp:
                 _lib.check(-1, "TilePipeline canvas allocation")
@@ -134,7 +151,7 @@ class TilePipeline:
             buf = (ctypes.c_uint8 * self.in_bytes).from_address(hp)
             self._views.append(np.frombuffer(buf, dtype=np.uint8).reshape(n, h, w, 3))
         self.k = 0
-        self.pending = None  # result slot whose D2H is in flight
+        self.pending = deque()  # result slots whose D2H is in flight, oldest first
         self.h2d_bytes = self.in_bytes
         self.d2h_bytes = self.post[0].d2h_bytes
 
@@ -143,7 +160,7 @@ class TilePipeline:
         already resident in HBM (no upload). download=False leaves the label maps on the device
         (self.post[slot].dev) and returns None."""
         lib, ctx, pctx = self.lib, self.ctx, self.pctx
-        s_in, s_out = self.k % 3, self.k & 1
+        s_in, s_out = self.k % 3, self.k % self.depth
         if device_ptr is None:
             np.copyto(self._views[s_in], batch_u8)  # pageable -> pinned (host memcpy)
             _lib.check(lib.cerb_copy_async(ctx.handle, ctypes.c_void_p(self.stage_dev[s_in]),
@@ -152,16 +169,16 @@ class TilePipeline:
             _lib.check(lib.cerb_stream_order(ctx.handle, 0), "cerb_stream_order")  # compute waits H2D
             device_ptr = self.stage_dev[s_in]
         self.plan.run(device_ptr=device_ptr)
-        # canvas -> slot copy on the compute stream, after the post-processing that last read the
-        # slot (batch k-2; waiting for the post stream's tail also covers batch k-1, which is far
-        # shorter than the forward that has just been queued)
-        _lib.check(lib.cerb_ctx_wait(ctx.handle, pctx.handle), "cerb_ctx_wait")
+        # canvas -> slot copy on the compute stream, after the post-processing that last read THIS
+        # slot (batch k - depth), not after everything queued on the post stream
+        _lib.check(lib.cerb_ctx_wait_mark(ctx.handle, pctx.handle, s_out), "cerb_ctx_wait_mark")
         _lib.check(lib.cerb_memcpy(ctx.handle, ctypes.c_void_p(self.canvas_copy[s_out]),
                                    ctypes.c_void_p(self.plan.tensor_ptr(self.plan.spec.canvas)),
                                    self.canvas_bytes, 3), "cerb_memcpy")
         _lib.check(lib.cerb_ctx_wait(pctx.handle, ctx.handle), "cerb_ctx_wait")  # post waits compute
         post = self.post[s_out]
         post.run(self.plan, canvas_ptr=self.canvas_copy[s_out])
+        _lib.check(lib.cerb_ctx_mark(pctx.handle, s_out), "cerb_ctx_mark")
         if not download:
             self.k += 1
             return None
@@ -171,12 +188,13 @@ class TilePipeline:
                                            ctypes.c_void_p(post.dev[t]), post.nbytes, 2),
                        "cerb_copy_async")
         _lib.check(lib.cerb_copy_mark(pctx.handle, s_out), "cerb_copy_mark")
-        done = None
-        if self.pending is not None:  # results of the previous batch (its D2H was queued earlier)
-            _lib.check(lib.cerb_copy_wait(pctx.handle, self.pending), "cerb_copy_wait")
-            done = self.post[self.pending].host
-        self.pending = s_out
+        self.pending.append(s_out)
         self.k += 1
+        done = None
+        if len(self.pending) > self.lag:  # oldest batch: its D2H was queued `lag` submits ago
+            slot = self.pending.popleft()
+            _lib.check(lib.cerb_copy_wait(pctx.handle, slot), "cerb_copy_wait")
+            done = self.post[slot].host
         return done
 
     def join_streams(self):
@@ -184,15 +202,14 @@ class TilePipeline:
         _lib.check(self.lib.cerb_ctx_wait(self.ctx.handle, self.pctx.handle), "cerb_ctx_wait")
 
     def flush(self):
-        if self.pending is None:
-            self.ctx.sync()
-            self.pctx.sync()
-            return None
-        _lib.check(self.lib.cerb_copy_wait(self.pctx.handle, self.pending), "cerb_copy_wait")
+        """Waits for everything queued; returns the results not handed out yet, oldest first."""
+        out = []
+        while self.pending:
+            slot = self.pending.popleft()
+            _lib.check(self.lib.cerb_copy_wait(self.pctx.handle, slot), "cerb_copy_wait")
+            out.append(self.post[slot].host)
         self.ctx.sync()
         self.pctx.sync()
-        out = self.post[self.pending].host
-        self.pending = None
         return out
 
     @property

@@ -210,7 +210,10 @@ int cerb_stitch(cerb_ctx* ctx, const float* patches, int n, int oh, int ow, int 
  * pre-erosion mask is empty: the reference returns a float64 zero map for those. */
 int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, int H, int W, int C, int ch0,
                          int32_t* labels_out, int32_t* any_fg_out, int flags);
-/* Counters: "ws_large_images" = images > 65536 px labelled by the component-parallel watershed,
+/* Counters: "ws_images" / "ws_tie_fallbacks" / "ws_capacity_fallbacks" = tiles of <= 65536 px seen
+ * by the component-parallel nuclei watershed / redone by the exact whole-tile emulation because two
+ * markers of one component tie / because the tile exceeds the shared-memory pool (synchronises);
+ * "ws_large_images" = images > 65536 px labelled by the component-parallel watershed,
  * "ws_large_fallbacks" = how many of them hit a marker tie and were redone by the exact
  * whole-image emulation (host-output calls only). -1 for an unknown name. */
 int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name);
@@ -236,7 +239,7 @@ int cerb_ellipse_rows(int k, int32_t* j1, int32_t* j2);
  *   cerb_stream_order(ctx, 0): later work on the COMPUTE stream waits for everything queued so far
  *                     on the upload stream; (ctx, 1): later work on the DOWNLOAD stream waits for
  *                     the compute stream.
- *   cerb_copy_mark / cerb_copy_wait : record an event (slot 0..3) on the download stream / block
+ *   cerb_copy_mark / cerb_copy_wait : record an event (slot 0..7) on the download stream / block
  *                     the host until it has fired.
  *   cerb_copy_sync  : blocks the host until both copy streams are idle. */
 int cerb_copy_async(cerb_ctx* ctx, void* dst, const void* src, size_t bytes, int kind);
@@ -249,6 +252,12 @@ int cerb_copy_sync(cerb_ctx* ctx);
  * everything queued so far on `signal`'s compute stream (lets a second ctx run the
  * post-processing of batch k while the first runs the forward of batch k+1). */
 int cerb_ctx_wait(cerb_ctx* waiter, cerb_ctx* signal);
+/* Finer grained: cerb_ctx_mark records event `slot` (0..7) on ctx's compute stream;
+ * cerb_ctx_wait_mark makes work queued later on `waiter`'s compute stream wait for that event of
+ * `signal` (no-op if it was never recorded). Lets a pipeline with several result slots wait for
+ * the last reader of ONE slot instead of the whole stream. */
+int cerb_ctx_mark(cerb_ctx* ctx, int slot);
+int cerb_ctx_wait_mark(cerb_ctx* waiter, cerb_ctx* signal, int slot);
 
 /* Pinned (page-locked) host memory for fast asynchronous H2D / D2H copies. */
 void* cerb_host_alloc(size_t bytes);

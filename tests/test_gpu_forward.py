@@ -150,7 +150,8 @@ def test_tile_pipeline_streams_batches_in_order(built_lib, six_head_sd):
         r = pipe.submit(b)
         if r is not None:
             got.append({t: v.copy() for t, v in r.items()})
-    got.append({t: v.copy() for t, v in pipe.flush().items()})
+    for r in pipe.flush():
+        got.append({t: v.copy() for t, v in r.items()})
     assert len(got) == len(want)
     for g, w_ in zip(got, want):
         for t in w_:

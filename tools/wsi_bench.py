@@ -63,9 +63,24 @@ def main():
         "cache_path": tmp + "/cache", "logging_dir": tmp + "/log", "wsi_proc_mag": 0.5,
         "postproc_tile_shape": pp_tile,
     }
+    m.keep_canvas = os.environ.get("WSI_BENCH_VERIFY", "0") == "1"
     t0 = time.perf_counter()
     res = m.process_wsi_list(run_args)
     dt = time.perf_counter() - t0
+    verify = None
+    if m.keep_canvas and world > 1 and rank == 0:
+        # the all-reduced canvas of N ranks must equal the canvas one rank computes alone
+        from cerberus_b200.infer.wsi_geometry import filter_coordinates, get_coordinates
+        from cerberus_b200.infer.wsi_reader import ArraySlide
+        sl = ArraySlide.open(tmp + "/wsi/slide.npy", 0.5)
+        msk = (cv2.cvtColor(cv2.imread(tmp + "/msk/slide.png"), cv2.COLOR_BGR2GRAY) > 0).astype(np.uint8)
+        pi, po = get_coordinates((size, size), [448, 448], [144, 144], [144, 144])
+        sel = filter_coordinates(msk, po, (size, size))
+        m.force_single = True
+        alone = m._infer_slide(sl, pi[sel], po[sel])
+        m.force_single = False
+        d = (alone - m.last_canvas).abs()
+        verify = {"max_abs_diff": float(d.max()), "pixels_differing": int((d.amax(-1) > 0).sum())}
     if rank == 0:
         logs = sorted(f for f in os.listdir(tmp + "/log") if "rank" not in f)
         text = open(os.path.join(tmp, "log", logs[-1])).read()
@@ -75,7 +90,7 @@ def main():
         r = res["slide"]
         line = {"slide": [size, size], "n_gpus": world, "batch": batch, "postproc_tile": pp_tile,
                 "patches_448_to_144": npatch, "wall_s": dt, "stages_s": stages,
-                "nuclei_detail": ws.group(1) if ws else None,
+                "nuclei_detail": ws.group(1) if ws else None, "multi_rank_canvas_check": verify,
                 "patches_per_s_inference": npatch / stages["Inference Time"],
                 "tiles256_equivalent_per_s": npatch / stages["Inference Time"] * (448 * 448) / (256 * 256),
                 "instances": {k: len(v) for k, v in r.items() if isinstance(v, dict) and k in ("Nuclei", "Gland", "Lumen")}}
