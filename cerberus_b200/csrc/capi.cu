@@ -734,6 +734,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     ctx->conv_sms = value < ctx->num_sms ? value : ctx->num_sms;
     return CERB_OK;
   }
+  if (strcmp(name, "use_pdl") == 0) {
+    ctx->use_pdl = value != 0;  // programmatic dependent launch of the convolution kernels
+    return CERB_OK;
+  }
   if (strcmp(name, "k_rotate") == 0) {
     ctx->k_rotate = value != 0;
     return CERB_OK;
@@ -1041,9 +1045,9 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
       }
       break;
     case CERB_OP_CONV:
-      e = st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s)
-          : st.use3 ? conv3x3_launch(st.c3, ctx->conv_sms, s)
-                    : conv_tc_launch(st.conv, st.split, ctx->conv_sms, s);
+      e = st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s, ctx->use_pdl)
+          : st.use3 ? conv3x3_launch(st.c3, ctx->conv_sms, s, ctx->use_pdl)
+                    : conv_tc_launch(st.conv, st.split, ctx->conv_sms, s, ctx->use_pdl);
       break;
     case CERB_OP_MAXPOOL:
       e = launch_maxpool(st.a, st.b, s);

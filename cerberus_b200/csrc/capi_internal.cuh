@@ -25,6 +25,7 @@ struct cerb_ctx {
   int* err_flag_dev = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved at run time (no libcuda link)
   int64_t launches = 0;
+  bool use_pdl = true;     // convolution kernels: programmatic dependent launch (prologue overlap)
   bool use_graphs = true;  // replay the forward op list as a CUDA graph
   unsigned long long* stat_dev = nullptr;  // [4] device counters of the small-tile watershed (cerb_ctx_stat)
   int64_t stat_ws_large = 0, stat_ws_fallback = 0;  // large-image watershed calls / exact fallbacks

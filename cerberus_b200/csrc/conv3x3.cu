@@ -101,6 +101,9 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();  // every global access below depends on the previous kernel (weights
+                         // are streamed together with the activations here)
   const int n_chunks = p.n_chunks;
   // Every CTA needs the SAME weight slabs; walking K in the same order makes all 148 SMs hit the
   // same L2 lines in the same window (measured: the MMA warp waits ~17 % of the time for weight
@@ -362,7 +365,7 @@ size_t conv3x3_smem_bytes(const Conv3Params& p) {
          static_cast<size_t>(p.n_bstages) * p.BN * 128 + 512 + 1024;
 }
 
-cudaError_t conv3x3_launch(const Conv3Params& p, int num_sms, cudaStream_t stream) {
+cudaError_t conv3x3_launch(const Conv3Params& p, int num_sms, cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -371,8 +374,17 @@ cudaError_t conv3x3_launch(const Conv3Params& p, int num_sms, cudaStream_t strea
     attr_set = true;
   }
   const int grid = p.n_items < num_sms ? p.n_items : num_sms;
-  conv3x3_kernel<<<grid, kConv3Threads, conv3x3_smem_bytes(p), stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kConv3Threads);
+  cfg.dynamicSmemBytes = conv3x3_smem_bytes(p);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv3x3_kernel, p);
 }
 
 }  // namespace cerb

@@ -34,6 +34,6 @@ struct Conv3Params {
 
 void conv3x3_plan(Conv3Params& p);
 size_t conv3x3_smem_bytes(const Conv3Params& p);
-cudaError_t conv3x3_launch(const Conv3Params& p, int num_sms, cudaStream_t stream);
+cudaError_t conv3x3_launch(const Conv3Params& p, int num_sms, cudaStream_t stream, bool pdl = false);
 
 }  // namespace cerb

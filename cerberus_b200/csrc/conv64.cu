@@ -112,6 +112,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  ptx::grid_dep_launch();  // the next kernel of the stream may start its own prologue
 
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
@@ -127,6 +128,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * 8192, &p.w_map, w_bar, t * 64, 0);
       if (p.has_tail) ptx::tma_load_2d(sW1, &p.w1_map, w_bar, 0, 0);
     }
+    ptx::grid_dep_wait();  // weights do not depend on the previous kernel, activations do
     int stage = 0;
     uint32_t phase = 0;
     long long prof_a = 0;
@@ -214,6 +216,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     // (models/net_desc.py:185-188). Two groups of four warps build alternate tiles' halos
     // directly in the swizzled shared-memory layout the MMA descriptors expect, so the summed
     // tensor never exists in HBM. Arithmetic and fp16 rounding are those of upadd_kernel.
+    ptx::grid_dep_wait();
     const int grp = (warp - 6) >> 2;
     const int gtid = threadIdx.x - (6 + 4 * grp) * 32;
     const int PH = p.H >> 1, PW = p.W >> 1;
@@ -298,6 +301,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     // rows go to a swizzled shared-memory tile instead and ONE TMA store per tile writes whole
     // lines (and clips partial tiles at the image border). The residual tile arrives in the same
     // staging buffer by TMA while the MMAs of the tile are still running.
+    ptx::grid_dep_wait();  // residual reads / output writes must follow the previous kernel
     const int egrp = (warp - 2) >> 2;
     const bool two_groups = p.up_prev == nullptr;
     const int q = warp & 3;
@@ -555,7 +559,7 @@ size_t conv64_smem_bytes(const Conv64Params& p) {
          (p.up_prev != nullptr ? 2 * kUpStageBytes : 0);
 }
 
-cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t stream) {
+cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -565,8 +569,17 @@ cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t strea
   }
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
   const int threads = p.up_prev != nullptr ? kConv64ThreadsUp : kConv64Threads;
-  conv64_kernel<<<grid, threads, conv64_smem_bytes(p), stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = conv64_smem_bytes(p);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv64_kernel, p);
 }
 
 }  // namespace cerb

@@ -52,6 +52,8 @@ int conv64_box_w(int mode);
 int conv64_tile_w();
 int conv64_tile_h();
 size_t conv64_smem_bytes(const Conv64Params& p);
-cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t stream);
+// pdl: launch with programmatic stream serialisation (the kernel's prologue overlaps the tail of
+// the previous kernel in the stream; see ptx::grid_dep_wait)
+cudaError_t conv64_launch(const Conv64Params& p, int num_sms, cudaStream_t stream, bool pdl = false);
 
 }  // namespace cerb

@@ -108,6 +108,8 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();  // prologue above overlaps the previous kernel's tail (PDL)
 
   const int kAccStages = SPLIT ? 1 : p.n_acc;
   const int kAccStride = SPLIT ? 512 : 512 / p.n_acc;
@@ -499,7 +501,7 @@ size_t conv_tc_smem_bytes(const ConvKParams& p) {
   return b;
 }
 
-cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream) {
+cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream, bool pdl) {
   static bool attr_set[3] = {false, false, false};
   const int variant = split ? 2 : (p.n_acc == 4 ? 1 : 0);
   void (*kern)(ConvKParams) = variant == 2   ? conv_tc_kernel<true, 192>
@@ -513,8 +515,17 @@ cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaSt
   }
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
   const int threads = 64 + 128 * (split ? 1 : p.n_acc);
-  kern<<<grid, threads, conv_tc_smem_bytes(p), stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = conv_tc_smem_bytes(p);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 }  // namespace cerb

@@ -69,7 +69,8 @@ struct ConvKParams {
 };
 
 // Host side: encodes nothing, just launches. `split` selects the 3-MMA hi/lo mode.
-cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream);
+cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream,
+                           bool pdl = false);
 size_t conv_tc_smem_bytes(const ConvKParams& p);
 // Fills n_stages / stage_bytes for a given BN and mode.
 void conv_tc_plan_pipeline(ConvKParams& p, bool split);

@@ -33,6 +33,8 @@ class Context:
         # through shifted descriptors (validated on B200, tools/conv64_modes.py); -1 = generic kernel
         self.conv64_mode = int(os.environ.get("CERB_CONV64_MODE", "1"))
         self.set_option("conv64_mode", self.conv64_mode)
+        if os.environ.get("CERB_USE_PDL") is not None:  # A/B switch for the PDL launches
+            self.set_option("use_pdl", int(os.environ["CERB_USE_PDL"]))
 
     def set_option(self, name, value):
         _lib.check(self.lib.cerb_ctx_set_option(self.handle, name.encode(), int(value)),

@@ -123,6 +123,12 @@ class TilePipeline:
         self.post_sms = int(os.environ.get("CERB_POST_SMS", "4"))
         if self.post_sms > 0:
             self.ctx.set_option("conv_sms", 148 - self.post_sms)
+            # Programmatic dependent launch would let the NEXT convolution's CTAs park on the
+            # spare SMs while they wait for their predecessor, which starves the post-processing
+            # blocks again (measured with a slow exact-watershed image in every 4th batch:
+            # 8.3 ms/step with PDL, 7.5 without; 6.9 with neither when no image is slow).
+            if os.environ.get("CERB_USE_PDL") is None:
+                self.ctx.set_option("use_pdl", 0)
         self.depth = max(2, min(8, int(depth)))
         self.lag = self.depth - 2 if self.depth > 2 else 1
         self.plan = engine.plan_for(n, h, w, h, w)
