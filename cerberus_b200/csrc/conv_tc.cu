@@ -70,6 +70,10 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     if (!mma_tail) {
       for (int i = threadIdx.x; i < p.head_classes * 96; i += blockDim.x) s_head_w[i] = p.head_w[i];
     } else {
+      // hidden-layer bias and head bias in shared memory (broadcast reads in the epilogue)
+      for (int i = threadIdx.x; i < 96; i += blockDim.x) s_head_w[i] = p.bias != nullptr ? p.bias[i] : 0.0f;
+      for (int i = threadIdx.x; i < kHeadMaxC; i += blockDim.x)
+        s_head_w[96 + i] = i < p.head_classes ? p.head_b[i] : 0.0f;
       // B2[n][k] = fp16(head_w[n][k]) for n < C, zero rows up to N = 16
       for (int i = threadIdx.x; i < 16 * 96; i += blockDim.x) {
         const int n = i / 96, k = i - n * 96;
@@ -261,15 +265,15 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
           ptx::tmem_ld32(taddr + j, r);
           ptx::tmem_ld_wait();
           float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(s_head_w + j);
+          const float sc = p.acc_scale;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.acc_scale;
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + j);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-            }
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = b4[i];
+            v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), sc, b.x);
+            v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), sc, b.y);
+            v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z);
+            v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w);
           }
           if (p.relu) {
 #pragma unroll
@@ -322,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
           float hacc[kHeadMaxC];
 #pragma unroll
           for (int c = 0; c < kHeadMaxC; ++c)
-            hacc[c] = c < p.head_classes ? __uint_as_float(r8[c]) + __ldg(p.head_b + c) : 0.0f;
+            hacc[c] = c < p.head_classes ? __uint_as_float(r8[c]) + s_head_w[96 + c] : 0.0f;
           const int y_off = static_cast<int>((p.H - p.oh) * 0.5), x_off = static_cast<int>((p.W - p.ow) * 0.5);
           const int cy = oy - y_off, cx = ox - x_off;
           float* dst = nullptr;

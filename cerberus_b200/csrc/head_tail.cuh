@@ -24,22 +24,21 @@ __device__ __forceinline__ void head_tail(const float (&acc)[kHeadMaxC], int cla
   float e[kHeadMaxC], sum = 0.0f;
 #pragma unroll
   for (int c = 0; c < kHeadMaxC; ++c) {
-    e[c] = (c < classes) ? expf(acc[c] - m) : 0.0f;
+    e[c] = (c < classes) ? __expf(acc[c] - m) : 0.0f;  // 2 ulp: far inside the 1e-3 gate
     sum += e[c];
   }
+  const float inv = __frcp_rn(sum);
   if (mode == 0) {
 #pragma unroll
     for (int c = 1; c < kHeadMaxC; ++c)
-      if (c < classes) dst[c - 1] = e[c] / sum;
+      if (c < classes) dst[c - 1] = e[c] * inv;
   } else {
+    // argmax of the probabilities = argmax of e[] (first maximum wins, as torch.argmax)
     int best = 0;
-    float bp = e[0] / sum;
+    float bp = e[0];
 #pragma unroll
     for (int c = 1; c < kHeadMaxC; ++c) {
-      if (c < classes) {
-        const float pc = e[c] / sum;
-        if (pc > bp) { bp = pc; best = c; }
-      }
+      if (c < classes && e[c] > bp) { bp = e[c]; best = c; }
     }
     dst[0] = static_cast<float>(best);
   }

@@ -23,6 +23,7 @@ SLOTS = ["producer wait empty", "mma wait tempty", "mma wait full", "mma issue",
 def main():
     cin, cout, k, h, w, n = [int(x) for x in sys.argv[1:7]]
     res = len(sys.argv) > 7 and sys.argv[7] == "res"
+    head = len(sys.argv) > 7 and sys.argv[7].startswith("head")  # headC: fused classification head with C classes
     reps = int(sys.argv[8]) if len(sys.argv) > 8 else 20
     rng = np.random.RandomState(0)
     blob = BlobBuilder()
@@ -32,7 +33,16 @@ def main():
     ti = spec._tensor("in", n, h, w, cin)
     to = spec._tensor("out", n, h, w, cout)
     tr = spec._tensor("res", n, h, w, cout) if res else -1
-    spec._conv(layer, ti, to, relu=1, residual=tr)
+    if head:
+        ncls = int(sys.argv[7][4:] or 3)
+        from cerberus_b200 import _lib as L_
+        w2 = (rng.standard_normal((ncls, 96)) / 10.0).astype(np.float32)
+        b2 = rng.uniform(-0.5, 0.5, ncls).astype(np.float32)
+        tc = spec._tensor("canvas", n, h, w, 9, L_.CERB_F32)
+        spec._conv(layer, ti, tc, relu=1, out_coff=0, aux_classes=ncls, aux_w_off=blob.add(w2),
+                   aux_b_off=blob.add(b2), head_mode=L_.HEAD_INST)
+    else:
+        spec._conv(layer, ti, to, relu=1, residual=tr)
     ctx = Context(0, "f16")
     ctx.set_option("kernel_prof", 1)
     ctx.set_option("use_graphs", 0)
