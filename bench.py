@@ -364,7 +364,8 @@ def run_ours(args):
         agg = flops / (all_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_sustained"],
                 "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": traffic,
-                "kernel": "conv64_kernel, 256x256 64->64 3x3, batch %d: %d launches/step, %.4f ms avg, "
+                "kernel": ("conv64x_kernel (even/odd N=128 formulation)" if ctx.conv64_mode == 3
+                           else "conv64_kernel") + ", 256x256 64->64 3x3, batch %d: %d launches/step, %.4f ms avg, "
                           "%.1f GFLOP (algorithmic) per launch" % (B, dom_n, dom_ms / max(dom_n, 1),
                                                                    dom_fl / max(dom_n, 1) / 1e9),
                 "peak_source": peaks["source"] + " bf16 cuBLAS sustained (kernel timed inside a long step)",

@@ -19,6 +19,7 @@
 #include "capi_internal.cuh"
 #include "conv3x3.cuh"
 #include "conv64.cuh"
+#include "conv64x.cuh"
 #include "conv_tc.cuh"
 #include "ops.cuh"
 
@@ -58,6 +59,8 @@ struct Step {
   ConvKParams conv;
   Conv64Params c64;
   Conv3Params c3;
+  Conv64xParams c64x;
+  bool use64x = false;
   bool use64 = false;
   bool use3 = false;
   bool side = false;  // may overlap the ops that follow (nothing later in the plan reads its output)
@@ -108,8 +111,8 @@ ActRef act_ref(const Tensor& t) {
 }
 
 int encode_map(cerb_ctx* ctx, CUtensorMap* m, void* base, int rank, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, int x_stride = 1) {
+  cuuint32_t estr[5] = {1, static_cast<cuuint32_t>(x_stride), 1, 1, 1};
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), base, dims,
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -303,6 +306,81 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
   return CERB_OK;
 }
 
+int build_conv64x(cerb_plan* pl, const cerb_op& op, Step& st) {
+  cerb_ctx* ctx = pl->ctx;
+  const Tensor& in = pl->tensors[op.in0];
+  const Tensor& out = pl->tensors[op.out];
+  Conv64xParams& p = st.c64x;
+  memset(&p, 0, sizeof(p));
+  st.use64x = true;
+  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  const size_t es = 2;
+  p.n_img = N;
+  p.H = H;
+  p.W = W;
+  if (op.in_coff % 8 != 0 || op.in_coff + 64 > in.d.c || in.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv64x: bad input channels");
+  if (op.out_coff % 8 != 0 || op.out_coff + 64 > out.d.c || out.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv64x: bad output channels");
+  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(N)};
+  {
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * in.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * in.d.c * es};
+    const cuuint32_t box[4] = {64, 18, 18, 1};  // element stride 2 in x: 9 columns of one parity
+    int rc = encode_map(ctx, &p.in_map, static_cast<__half*>(in.plane[0]) + op.in_coff, 4, dims,
+                        strides, box, 2);
+    if (rc) return rc;
+  }
+  if (op.w_off < 0 || op.w_off % 16 != 0 ||
+      static_cast<size_t>(op.w_off) + 64u * 576u * es > pl->blob_bytes)
+    return fail(CERB_ERR_ARG, "conv64x: weight offset out of range");
+  {
+    const cuuint64_t wd[2] = {576, 64};
+    const cuuint64_t ws[1] = {576 * es};
+    const cuuint32_t wb[2] = {64, 64};
+    int rc = encode_map(ctx, &p.w_map, pl->blob + op.w_off, 2, wd, ws, wb);
+    if (rc) return rc;
+  }
+  if (op.b_off >= 0) {
+    if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + 64 * 4u > pl->blob_bytes)
+      return fail(CERB_ERR_ARG, "conv64x: bias offset out of range");
+    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+  }
+  {
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(out.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * out.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * out.d.c * es};
+    const cuuint32_t box[4] = {64, 16, 16, 1};  // element stride 2 in x: the 8 pixels of one parity
+    int rc = encode_map(ctx, &p.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, dims,
+                        strides, box, 2);
+    if (rc) return rc;
+  }
+  if (op.in1 >= 0) {
+    if (op.in1 >= static_cast<int>(pl->tensors.size()))
+      return fail(CERB_ERR_ARG, "conv64x: residual id out of range");
+    const Tensor& res = pl->tensors[op.in1];
+    if (res.d.n != N || res.d.h != H || res.d.w != W || res.d.c < 64 || res.d.c % 8 != 0 ||
+        res.d.dtype != CERB_F16)
+      return fail(CERB_ERR_ARG, "conv64x: residual shape mismatch");
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(res.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * res.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * res.d.c * es};
+    const cuuint32_t box[4] = {64, 16, 16, 1};
+    int rc = encode_map(ctx, &p.res_map, res.plane[0], 4, dims, strides, box, 2);
+    if (rc) return rc;
+    p.has_res = 1;
+  }
+  p.relu = op.relu;
+  if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64x: w_shift out of range");
+  p.acc_scale = ldexpf(1.0f, -op.w_shift);
+  p.err_flag = ctx->err_flag_dev;
+  p.prof = ctx->prof_dev;
+  conv64x_plan(p);
+  return CERB_OK;
+}
+
 int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
   cerb_ctx* ctx = pl->ctx;
   const Tensor& in = pl->tensors[op.in0];
@@ -433,6 +511,7 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   if (op.up_prev1 > 0 && !(conv64_ok && ctx->conv64_mode == 1))
     return fail(CERB_ERR_ARG, "conv: fused upsample+add needs the 64->64 3x3 kernel (conv64_mode 1, "
                 "CERB_PREC_F16)");
+  if (conv64_ok && ctx->conv64_mode == 3 && op.up_prev1 <= 0) return build_conv64x(pl, op, st);
   if (conv64_ok) return build_conv64(pl, op, st);
   // wide 3x3 stride-1 layers: halo reuse + two M tiles per weight slab (csrc/conv3x3.cu)
   const bool conv3_ok = !split && !op.stem && !fused_head && ctx->conv3_mode > 0 && op.kh == 3 &&
@@ -717,7 +796,7 @@ extern "C" int cerb_ctx_sync(cerb_ctx* ctx) {
 extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return fail(CERB_ERR_ARG, "cerb_ctx_set_option: bad arguments");
   if (strcmp(name, "conv64_mode") == 0) {
-    if (value < -1 || value > 2) return fail(CERB_ERR_ARG, "conv64_mode must be -1, 0, 1 or 2");
+    if (value < -1 || value > 3) return fail(CERB_ERR_ARG, "conv64_mode must be -1, 0, 1, 2 or 3");
     ctx->conv64_mode = value;
     return CERB_OK;
   }
@@ -1045,7 +1124,8 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
       }
       break;
     case CERB_OP_CONV:
-      e = st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s, ctx->use_pdl)
+      e = st.use64x ? conv64x_launch(st.c64x, ctx->conv_sms, s, ctx->use_pdl)
+          : st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s, ctx->use_pdl)
           : st.use3 ? conv3x3_launch(st.c3, ctx->conv_sms, s, ctx->use_pdl)
                     : conv_tc_launch(st.conv, st.split, ctx->conv_sms, s, ctx->use_pdl);
       break;

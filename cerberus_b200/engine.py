@@ -29,9 +29,11 @@ class Context:
         h = ctypes.c_void_p()
         _lib.check(self.lib.cerb_ctx_create(device, prec, ctypes.byref(h)), "cerb_ctx_create")
         self.handle = h
-        # halo layout of the 64->64 3x3 kernel (csrc/conv64.cu): 1 = single halo slab addressed
-        # through shifted descriptors (validated on B200, tools/conv64_modes.py); -1 = generic kernel
-        self.conv64_mode = int(os.environ.get("CERB_CONV64_MODE", "1"))
+        # 64->64 3x3 kernel: 3 = even/odd N = 128 formulation (csrc/conv64x.cu, fastest); 1 = single
+        # halo slab addressed through shifted descriptors (csrc/conv64.cu; also what the opt-in
+        # fused variants CERB_FUSE_UPADD / CERB_FUSE_TAIL need); 0 / 2 = other halo layouts of
+        # conv64.cu (tools/conv64_modes.py); -1 = generic kernel
+        self.conv64_mode = int(os.environ.get("CERB_CONV64_MODE", "3"))
         self.set_option("conv64_mode", self.conv64_mode)
         if os.environ.get("CERB_USE_PDL") is not None:  # A/B switch for the PDL launches
             self.set_option("use_pdl", int(os.environ["CERB_USE_PDL"]))

@@ -76,6 +76,20 @@ def _run_case(precision, n, h, w, cin, cout, k, stride, residual, relu, seed=0):
     return got, ref
 
 
+@pytest.mark.parametrize("mode", [-1, 0, 1, 2, 3])
+@pytest.mark.parametrize("case", [c for c in CASES if c[3] == 64 and c[4] == 64 and c[5] == 3 and c[6] == 1] +
+                         [(2, 50, 36, 64, 64, 3, 1, True, True), (1, 16, 8, 64, 64, 3, 1, False, False)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv64_every_kernel_variant(case, mode, built_lib, monkeypatch):
+    """64->64 3x3: generic kernel (-1), the three halo layouts of conv64.cu and the even/odd
+    N = 128 formulation of conv64x.cu (3, the default), incl. partial regions and a residual."""
+    monkeypatch.setenv("CERB_CONV64_MODE", str(mode))
+    got, ref = _run_case("f16", *case)
+    err = np.abs(got - ref)
+    tol = 2e-3 * np.abs(ref) + 2e-3
+    assert np.all(err <= tol), "mode %d: max err %g" % (mode, err.max())
+
+
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
 def test_conv_f16(case, built_lib):
     got, ref = _run_case("f16", *case)
@@ -150,6 +164,7 @@ def test_conv64_fused_upsample_add(shape, built_lib):
             spec._op(_lib.OP_UPADD, in0=t_skip, in1=t_prev, out=t_sum)
             spec._conv(layer, t_sum, t_out, relu=1)
         ctx = Context(0, "f16")
+        ctx.set_option("conv64_mode", 1)  # the fused producer lives in conv64.cu (halo layout 1)
         plan = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
         plan.write(t_skip, skip.astype(np.float16))
         plan.write(t_prev, prev.astype(np.float16))
