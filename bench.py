@@ -358,7 +358,8 @@ def run_ours(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tpath) and B == 32:
-            tj = json.load(open(tpath)).get("conv64_kernel 256x256 64->64 3x3 batch 32")
+            tj = json.load(open(tpath)).get("%s 256x256 64->64 3x3 batch 32" % (
+                "conv64x_kernel" if ctx.conv64_mode == 3 else "conv64_kernel"))
             if tj:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         agg = flops / (all_ms * 1e-3) / 1e12
