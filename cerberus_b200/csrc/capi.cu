@@ -175,7 +175,10 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
   st.use64 = true;
   const bool tail = op.aux_classes > 0;  // fused classification head: `out` is the fp32 canvas
   const int H = tail ? in.d.h : out.d.h, W = tail ? in.d.w : out.d.w, N = out.d.n;
-  p.mode = ctx->conv64_mode;
+  p.mode = ctx->conv64_mode == 3 ? 1 : ctx->conv64_mode;  // mode 3 routes plain convs to conv64x.cu
+  p.n_taps = 9;
+  p.halo_x = 1;
+  p.halo_y = 1;
   p.debug = ctx->conv64_debug;
   p.n_img = N;
   p.H = H;
@@ -300,6 +303,78 @@ int build_conv64(cerb_plan* pl, const cerb_op& op, Step& st) {
   conv64_plan(p);  // after up_prev is known: the fused producer needs staging shared memory
   p.relu = op.relu;
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64: w_shift out of range");
+  p.acc_scale = ldexpf(1.0f, -op.w_shift);
+  p.err_flag = ctx->err_flag_dev;
+  p.prof = ctx->prof_dev;
+  return CERB_OK;
+}
+
+// 7x7 stem on the resident-weight halo kernel (conv64.cu mode 4)
+int build_stem64(cerb_plan* pl, const cerb_op& op, Step& st) {
+  cerb_ctx* ctx = pl->ctx;
+  const Tensor& in = pl->tensors[op.in0];
+  const Tensor& out = pl->tensors[op.out];
+  Conv64Params& p = st.c64;
+  memset(&p, 0, sizeof(p));
+  st.use64 = true;
+  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  const size_t es = 2;
+  if (in.d.c != 8 || in.d.h != H || in.d.w != W + 8 || op.kh != 7 || op.kw != 7 || op.stride != 1 ||
+      op.pad != 3 || op.cout != 64 || op.in1 >= 0)
+    return fail(CERB_ERR_ARG, "conv: stem expects a 7x7 s1 p3 3->64 conv over a PREP tensor");
+  p.mode = 4;
+  p.n_taps = 7;
+  p.halo_x = 0;
+  p.halo_y = 3;
+  p.n_img = N;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + conv64_tile_w() - 1) / conv64_tile_w();
+  p.tiles_y = (H + conv64_tile_h() - 1) / conv64_tile_h();
+  p.n_tiles = N * p.tiles_x * p.tiles_y;
+  {
+    // overlapping windows: "pixel" x of the view = padded columns x .. x+7 (8 px x 8 ch = 64 K)
+    const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {8 * es, static_cast<cuuint64_t>(W + 8) * 8 * es,
+                                   static_cast<cuuint64_t>(H) * (W + 8) * 8 * es};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(conv64_tile_w()),
+                               static_cast<cuuint32_t>(conv64_tile_h() + 6), 1};
+    int rc = encode_map(ctx, &p.in_map, in.plane[0], 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (op.w_off < 0 || op.w_off % 16 != 0 ||
+      static_cast<size_t>(op.w_off) + 64u * 448u * es > pl->blob_bytes)
+    return fail(CERB_ERR_ARG, "conv: stem weight offset out of range");
+  {
+    const cuuint64_t dims[2] = {448, 64};
+    const cuuint64_t strides[1] = {448 * es};
+    const cuuint32_t box[2] = {64, 64};
+    int rc = encode_map(ctx, &p.w_map, pl->blob + op.w_off, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (op.b_off >= 0) {
+    if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + 64 * 4u > pl->blob_bytes)
+      return fail(CERB_ERR_ARG, "conv: stem bias offset out of range");
+    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+  }
+  if (op.out_coff % 8 != 0 || op.out_coff + 64 > out.d.c || out.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv: stem output channels");
+  {
+    const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(out.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * out.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * out.d.c * es};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(conv64_tile_w()),
+                               static_cast<cuuint32_t>(conv64_tile_h()), 1};
+    int rc = encode_map(ctx, &p.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, dims,
+                        strides, box);
+    if (rc) return rc;
+  }
+  conv64_plan(p);
+  p.relu = op.relu;
+  if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv: w_shift out of range");
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
   p.prof = ctx->prof_dev;
@@ -511,6 +586,9 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   if (op.up_prev1 > 0 && !(conv64_ok && ctx->conv64_mode == 1))
     return fail(CERB_ERR_ARG, "conv: fused upsample+add needs the 64->64 3x3 kernel (conv64_mode 1, "
                 "CERB_PREC_F16)");
+  if (op.stem && !split && !fused_head && ctx->conv64_mode >= 1 && ctx->stem_mode == 1 &&
+      in.d.dtype == CERB_F16 && out.d.dtype == CERB_F16)
+    return build_stem64(pl, op, st);
   if (conv64_ok && ctx->conv64_mode == 3 && op.up_prev1 <= 0) return build_conv64x(pl, op, st);
   if (conv64_ok) return build_conv64(pl, op, st);
   // wide 3x3 stride-1 layers: halo reuse + two M tiles per weight slab (csrc/conv3x3.cu)
@@ -811,6 +889,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     // Applies to launches / graph captures made afterwards.
     if (value < 1) return fail(CERB_ERR_ARG, "conv_sms must be >= 1");
     ctx->conv_sms = value < ctx->num_sms ? value : ctx->num_sms;
+    return CERB_OK;
+  }
+  if (strcmp(name, "stem_mode") == 0) {
+    ctx->stem_mode = value;  // 1: stem on the resident-weight halo kernel, 0: generic kernel
     return CERB_OK;
   }
   if (strcmp(name, "use_pdl") == 0) {

@@ -123,9 +123,10 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     const bool leader = ptx::elect_one() != 0;
     if (leader) {
       // resident weights: one 2-D box per tap
-      ptx::mbar_arrive_expect_tx(w_bar, kWBytes + (p.has_tail ? kTailW1Bytes : 0));
+      ptx::mbar_arrive_expect_tx(w_bar, p.n_taps * 8192 + (p.has_tail ? kTailW1Bytes : 0));
 #pragma unroll
-      for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * 8192, &p.w_map, w_bar, t * 64, 0);
+      for (int t = 0; t < 9; ++t)
+        if (t < p.n_taps) ptx::tma_load_2d(sW + t * 8192, &p.w_map, w_bar, t * 64, 0);
       if (p.has_tail) ptx::tma_load_2d(sW1, &p.w1_map, w_bar, 0, 0);
     }
     ptx::grid_dep_wait();  // weights do not depend on the previous kernel, activations do
@@ -136,7 +137,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
       const int img = tile / tiles_per_img;
       const int rem = tile - img * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int x0 = tx * kTileW - 1, y0 = ty * kTileH - 1;
+      const int x0 = tx * kTileW - p.halo_x, y0 = ty * kTileH - p.halo_y;
       CERB_PROF_T0(t_pe);
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 21);
       CERB_PROF_ADD(prof_a, t_pe);
@@ -168,7 +169,9 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
     for (int t = 0; t < 9; ++t) {
       const int r = t / 3, s = t - 3 * r;
       tap_off[t] = static_cast<uint32_t>(
-          (p.mode == 0 ? s * p.copy_bytes + r * (kTileW * 128) : (r * p.pitch_px + s) * 128) >> 4);
+          (p.mode == 4   ? t * (kTileW * 128)  // stem: seven vertical taps, no horizontal shift
+           : p.mode == 0 ? s * p.copy_bytes + r * (kTileW * 128)
+                         : (r * p.pitch_px + s) * 128) >> 4);
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -191,6 +194,7 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
         const uint32_t a_lo = a_lo0 + static_cast<uint32_t>((stage * stage_bytes) >> 4);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
+          if (t >= p.n_taps) break;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + tap_off[t] + 2 * k);
@@ -529,6 +533,16 @@ void conv64_plan(Conv64Params& p) {
     p.stage_bytes = 3 * p.copy_bytes;
     p.tx_bytes = 3 * p.copy_bytes;
     p.sbo_bytes = 1024;
+  } else if (p.mode == 4) {
+    // 7x7 stem (models/backbone/resnet.py:195-200) through the overlapping-window view of the
+    // PREP tensor: a "pixel" of the halo is an 8-pixel x 8-channel window (one filter row = one
+    // K chunk), so only the seven vertical taps shift the view: 22 rows x 8 windows, all
+    // descriptors 1024-byte aligned
+    p.pitch_px = kTileW;
+    p.copy_bytes = (kTileH + 6) * kTileW * 128;  // 22528
+    p.stage_bytes = p.copy_bytes;
+    p.tx_bytes = p.copy_bytes;
+    p.sbo_bytes = 1024;
   } else if (p.mode == 1) {
     p.pitch_px = kTileW + 2;
     p.copy_bytes = 18 * p.pitch_px * 128;  // 23040
@@ -549,7 +563,7 @@ void conv64_plan(Conv64Params& p) {
   p.n_stages = n;
 }
 
-int conv64_box_w(int mode) { return mode == 0 ? kTileW : (mode == 1 ? kTileW + 2 : 16); }
+int conv64_box_w(int mode) { return (mode == 0 || mode == 4) ? kTileW : (mode == 1 ? kTileW + 2 : 16); }
 int conv64_tile_w() { return kTileW; }
 int conv64_tile_h() { return kTileH; }
 

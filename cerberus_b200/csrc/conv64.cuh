@@ -30,7 +30,9 @@ struct Conv64Params {
   float* canvas;         // [N, oh, ow, canvas_c]
   float* logits;         // optional [N, H, W, C]
   int oh, ow, canvas_c, canvas_coff;
-  int mode;            // halo layout, see conv64.cu
+  int mode;            // halo layout, see conv64.cu (4 = 7x7 stem over the PREP tensor)
+  int n_taps;          // 9, or 7 for the stem
+  int halo_x, halo_y;  // halo origin = tile origin - (halo_x, halo_y): (1, 1), stem (0, 3)
   int n_img, H, W;
   int tiles_x, tiles_y, n_tiles;
   const float* bias;
