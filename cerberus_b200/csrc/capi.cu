@@ -95,6 +95,8 @@ struct cerb_plan {
   // graph on the second run (the first run doubles as warm-up / attribute setup) and replayed
   cudaGraphExec_t graph_exec = nullptr;
   int runs = 0;
+  int* cur_counter = nullptr;    // counter of the op being built
+  int* tile_counters = nullptr;  // one per op (dynamic tile scheduling), zeroed at the start of a run
 };
 
 namespace {
@@ -452,6 +454,7 @@ int build_conv64x(cerb_plan* pl, const cerb_op& op, Step& st) {
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
   p.prof = ctx->prof_dev;
+  p.tile_counter = ctx->dyn_sched ? pl->cur_counter : nullptr;
   conv64x_plan(p);
   return CERB_OK;
 }
@@ -891,6 +894,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     ctx->conv_sms = value < ctx->num_sms ? value : ctx->num_sms;
     return CERB_OK;
   }
+  if (strcmp(name, "dyn_sched") == 0) {
+    ctx->dyn_sched = value != 0;  // persistent conv kernels take tiles from a global counter
+    return CERB_OK;
+  }
   if (strcmp(name, "stem_mode") == 0) {
     ctx->stem_mode = value;  // 1: stem on the resident-weight halo kernel, 0: generic kernel
     return CERB_OK;
@@ -1020,6 +1027,7 @@ extern "C" void cerb_plan_destroy(cerb_plan* pl) {
     if (t.plane[1]) cudaFree(t.plane[1]);
   }
   if (pl->blob) cudaFree(pl->blob);
+  if (pl->tile_counters) cudaFree(pl->tile_counters);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   delete pl;
 }
@@ -1063,10 +1071,13 @@ extern "C" int cerb_plan_create(cerb_ctx* ctx, const cerb_tensor_desc* tensors, 
       cudaMemsetAsync(t.plane[pnum], 0, t.bytes, ctx->stream);
     }
   }
+  if (cudaMalloc(reinterpret_cast<void**>(&pl->tile_counters), sizeof(int) * n_ops) != cudaSuccess)
+    return bail(fail(CERB_ERR_CUDA, "cudaMalloc for the tile counters failed"));
   pl->steps.resize(n_ops);
   for (int i = 0; i < n_ops; ++i) {
     const cerb_op& op = ops[i];
     Step& st = pl->steps[i];
+    pl->cur_counter = pl->tile_counters + i;
     st.kind = op.kind;
     st.side = op.side != 0;
     switch (op.kind) {
@@ -1247,6 +1258,7 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
   }
   const bool capture = ctx->use_graphs && pl->runs >= 1;
   if (capture) CERB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  CERB_CUDA(cudaMemsetAsync(pl->tile_counters, 0, sizeof(int) * pl->steps.size(), s));
   bool forked = false;
   for (Step& st : pl->steps) {
     cudaStream_t ls = s;
@@ -1301,6 +1313,7 @@ extern "C" int cerb_plan_profile(cerb_plan* pl, int reps, float* ms_per_op, int3
   for (cudaEvent_t& e : ev) CERB_CUDA(cudaEventCreate(&e));
   for (int r = 0; r < reps; ++r) {
     cudaEvent_t* e = ev.data() + static_cast<size_t>(r) * (n + 1);
+    CERB_CUDA(cudaMemsetAsync(pl->tile_counters, 0, sizeof(int) * n, s));
     CERB_CUDA(cudaEventRecord(e[0], s));
     for (size_t i = 0; i < n; ++i) {
       cudaError_t le = launch_step(ctx, pl->steps[i], s);

@@ -33,6 +33,7 @@ struct cerb_ctx {
   long long* prof_dev = nullptr;  // [kProfSlots] in-kernel attribution counters (option "kernel_prof")
   int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only;
                     // 2 (test hook): image 0 of every batch is redone by the exact emulation
+  bool dyn_sched = true;  // dynamic tile scheduling in the persistent conv kernels
   int stem_mode = 1;    // 1: 7x7 stem on conv64.cu (mode 4); 0: generic kernel
   int k_rotate = 1;     // per-CTA rotated K walk in conv3x3.cu (de-synchronises weight-slab reads)
   int conv3_mode = 1;   // 0: generic kernel for the wide 3x3 layers; 1: conv3x3.cu (cout <= 512); 2: always

@@ -63,6 +63,8 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
   uint64_t* w_bar = tempty_bar + kAccStages;
   uint64_t* res_bar = w_bar + 1;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 1);
+  // region ids handed from the producer to the MMA / epilogue warps (dynamic scheduling)
+  volatile int* s_ring = reinterpret_cast<volatile int*>(tmem_holder + 2);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.in_map);
@@ -112,7 +114,20 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
     long long prof_a = 0;
     int stage = 0;
     uint32_t phase = 0;
-    for (int rg = blockIdx.x; rg < p.n_regions; rg += gridDim.x) {
+    const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
+    // Region ids come from a global counter (dynamic scheduling): a CTA that starts late - its SM
+    // was busy with a block of another stream - simply finds less work, instead of forcing a
+    // second wave as a static blockIdx-strided split would. The id travels to the other warps
+    // through s_ring (slot i & 7), published before the arrive on full_bar; -1 ends the kernel.
+    for (int i = 0;; ++i) {
+      int rg = 0;
+      if (p.tile_counter != nullptr) {
+        if (leader) rg = atomicAdd(p.tile_counter, 1);
+        rg = __shfl_sync(0xffffffffu, rg, leader_lane);
+      } else {
+        rg = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      }
+      const bool done = rg >= p.n_regions;
       const int img = rg / regions_per_img;
       const int rem = rg - img * regions_per_img;
       const int ry = rem / p.regions_x, rx = rem - ry * p.regions_x;
@@ -121,12 +136,18 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 41);
       CERB_PROF_ADD(prof_a, t_p);
       if (leader) {
-        uint8_t* dst = sA + stage * kStageBytes;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kPlaneTx);
-        ptx::tma_load_4d(dst, &p.in_map, &full_bar[stage], 0, x0 - 1, y0, img);            // odd columns
-        ptx::tma_load_4d(dst + kPlaneBytes, &p.in_map, &full_bar[stage], 0, x0, y0, img);  // even columns
+        s_ring[i & 7] = done ? -1 : rg;
+        if (done) {
+          ptx::mbar_arrive(&full_bar[stage]);
+        } else {
+          uint8_t* dst = sA + stage * kStageBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kPlaneTx);
+          ptx::tma_load_4d(dst, &p.in_map, &full_bar[stage], 0, x0 - 1, y0, img);            // odd columns
+          ptx::tma_load_4d(dst + kPlaneBytes, &p.in_map, &full_bar[stage], 0, x0, y0, img);  // even columns
+        }
       }
       __syncwarp();
+      if (done) break;
       if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
     if (p.prof != nullptr && lane == 0) p.prof[blockIdx.x * 16 + 0] = prof_a;
@@ -146,13 +167,18 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int rg = blockIdx.x; rg < p.n_regions; rg += gridDim.x) {
+    for (int i = 0;; ++i) {
       CERB_PROF_T0(t_m0);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 43);
       CERB_PROF_ADD(prof_a, t_m0);
       CERB_PROF_T0(t_m1);
       ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 44);
       CERB_PROF_ADD(prof_b, t_m1);
+      if (s_ring[i & 7] < 0) {  // no more regions: pass the end marker on to the epilogue
+        if (leader) ptx::mbar_arrive(&tfull_bar[acc]);
+        __syncwarp();
+        break;
+      }
       ptx::tc_fence_after();
       CERB_PROF_T0(t_m2);
       if (leader) {
@@ -218,9 +244,14 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
     uint32_t res_phase = 0;
     int it = 0;
-    for (int rg = blockIdx.x; rg < p.n_regions; rg += gridDim.x, ++it) {
+    for (;; ++it) {
       const int acc = it % kAccStages;
       const uint32_t acc_phase = (it / kAccStages) & 1;
+      CERB_PROF_T0(t_e0);
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 45);
+      CERB_PROF_ADD(prof_a, t_e0);
+      const int rg = s_ring[it & 7];
+      if (rg < 0) break;
       const int img = rg / regions_per_img;
       const int rem = rg - img * regions_per_img;
       const int ry = rem / p.regions_x, rx = rem - ry * p.regions_x;
@@ -233,9 +264,6 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
           ptx::tma_load_4d(sOut + kOutBytes / 2, &p.res_map, res_bar, 0, x0 + 1, y0, img);
         }
       }
-      CERB_PROF_T0(t_e0);
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 45);
-      CERB_PROF_ADD(prof_a, t_e0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + half * 64;
       uint32_t r0[32], r1[32];

@@ -26,6 +26,7 @@ struct Conv64xParams {
   float acc_scale;
   int relu;
   int n_stages;
+  int* tile_counter;  // zeroed before the launch: dynamic region scheduling; null = static split
   int* err_flag;
   long long* prof;
 };
