@@ -538,7 +538,10 @@ int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
   p.prof = ctx->prof_dev;
-  p.rotate = ctx->k_rotate;
+  p.tile_counter = ctx->dyn_sched ? pl->cur_counter : nullptr;
+  // a K walk rotated per CTA would make the fp32 accumulation order of a work item depend on
+  // which CTA drew it: only with the static split (it made no measurable difference anyway)
+  p.rotate = ctx->k_rotate && p.tile_counter == nullptr;
   conv3x3_plan(p);
   return CERB_OK;
 }
@@ -761,6 +764,7 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
   p.prof = ctx->prof_dev;
+  p.tile_counter = ctx->dyn_sched ? pl->cur_counter : nullptr;
   conv_tc_plan_pipeline(p, split);
   return CERB_OK;
 }

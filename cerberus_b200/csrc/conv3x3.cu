@@ -74,6 +74,9 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;  // [group * 2 + buffer]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 4);
+  // work-item ids handed from the producer to the MMA / epilogue warps (dynamic scheduling,
+  // see conv64x.cu); -1 ends the kernel
+  volatile int* s_ring = reinterpret_cast<volatile int*>(tmem_holder + 2);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.in_map);
@@ -134,14 +137,29 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
       __syncwarp();
       ++a_issued;
     };
-    int cur_item = blockIdx.x, cur_c = 0;
-    if (cur_item < p.n_items) issue_a(cur_item, 0);
+    const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
+    int n_fetched = 0;
+    auto fetch = [&]() -> int {
+      int item = 0;
+      if (p.tile_counter != nullptr) {
+        if (leader) item = atomicAdd(p.tile_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, leader_lane);
+      } else {
+        item = static_cast<int>(blockIdx.x) + n_fetched * static_cast<int>(gridDim.x);
+      }
+      if (item >= p.n_items) item = -1;
+      if (leader) s_ring[n_fetched & 7] = item;  // before the arrive that announces its first halo
+      ++n_fetched;
+      return item;
+    };
+    int cur_item = fetch(), cur_c = 0;
+    if (cur_item >= 0) issue_a(cur_item, 0);
     int nxt_item = cur_item, nxt_c = 1;
-    if (nxt_c == n_chunks) { nxt_c = 0; nxt_item += gridDim.x; }
-    while (cur_item < p.n_items) {
+    if (cur_item >= 0 && nxt_c == n_chunks) { nxt_c = 0; nxt_item = fetch(); }
+    while (cur_item >= 0) {
       const int nt = cur_item % p.n_ntiles;
       for (int t = 0; t < 9; ++t) {
-        if (t == 4 && nxt_item < p.n_items) issue_a(nxt_item, nxt_c);
+        if (t == 4 && nxt_item >= 0) issue_a(nxt_item, nxt_c);
         const int bs = b_cnt % n_bstages;
         const uint32_t bph = (b_cnt / n_bstages) & 1;
         CERB_PROF_T0(t_p);
@@ -158,7 +176,13 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
       }
       cur_item = nxt_item;
       cur_c = nxt_c;
-      if (++nxt_c == n_chunks) { nxt_c = 0; nxt_item += gridDim.x; }
+      if (nxt_item >= 0 && ++nxt_c == n_chunks) { nxt_c = 0; nxt_item = fetch(); }
+    }
+    {  // end marker: wake the MMA warp on the halo barrier it will wait on next
+      const int st = a_issued & 1;
+      ptx::mbar_wait(&a_empty[st], ((a_issued >> 1) & 1) ^ 1, p.err_flag, 31);
+      if (leader) ptx::mbar_arrive(&a_full[st]);
+      __syncwarp();
     }
     if (p.prof != nullptr && lane == 0) p.prof[blockIdx.x * 16 + 0] = prof_a;
   } else if (warp == 1) {
@@ -179,7 +203,8 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
     CERB_PROF_T0(t_all);
     int a_idx = 0, b_cnt = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    bool done = false;
+    for (;; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       CERB_PROF_T0(t_m0);
@@ -192,6 +217,12 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
         CERB_PROF_T0(t_m1);
         ptx::mbar_wait(&a_full[ast], (a_idx >> 1) & 1, p.err_flag, 34);
         CERB_PROF_ADD(prof_b, t_m1);
+        if (c == 0 && s_ring[it & 7] < 0) {  // end marker: pass it on to the epilogue
+          if (leader) ptx::mbar_arrive(&tfull_bar[acc]);
+          __syncwarp();
+          done = true;
+          break;
+        }
         const uint64_t a_st = a_d0 + static_cast<uint32_t>((ast * kAStageBytes) >> 4);
 #pragma unroll
         for (int t = 0; t < 9; ++t, ++b_cnt) {
@@ -218,6 +249,7 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
           CERB_PROF_ADD(prof_d, t_m3);
         }
       }
+      if (done) break;
       if (leader) ptx::umma_commit(&tfull_bar[acc]);
       __syncwarp();
     }
@@ -239,9 +271,15 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
     const int n_slabs = p.BN >> 6;
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
     int sidx = 0, it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    for (;; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      CERB_PROF_T0(t_e0);
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 36);
+      CERB_PROF_ADD(prof_a, t_e0);
+      const int item = s_ring[it & 7];
+      if (item < 0) break;
+      ptx::tc_fence_after();
       const Item im = decode(p, item);
       const int x0 = im.rx * kRegion + 8 * g, y0 = im.ry * kRegion;
       const int n0 = im.nt * p.BN;
@@ -256,12 +294,6 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
             ptx::mbar_arrive_expect_tx(rbar, kSlabBytes);
             ptx::tma_load_4d(sO, &p.res_map, rbar, n0 + slab * 64, x0, y0, im.img);
           }
-        }
-        if (slab == 0) {
-          CERB_PROF_T0(t_e0);
-          ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 36);
-          CERB_PROF_ADD(prof_a, t_e0);
-          ptx::tc_fence_after();
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + g * 128 + slab * 64;
         uint32_t r0[32], r1[32];

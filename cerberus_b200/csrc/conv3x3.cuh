@@ -28,6 +28,7 @@ struct Conv3Params {
   const float* bias;  // [Cout] fp32 (BN folded), may be null
   float acc_scale;    // 2^-w_shift
   int relu;
+  int* tile_counter;  // zeroed before the launch: dynamic work-item scheduling; null = static split
   int* err_flag;
   long long* prof;
 };

@@ -51,6 +51,9 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   const int stage_bytes = p.stage_bytes;
   const int b_tile_bytes = p.BN * 128;
 
+  // tile ids handed from the producer to the MMA / epilogue warps (dynamic scheduling, see
+  // conv64x.cu); -1 ends the kernel. Lives behind the head-weight area.
+  volatile int* s_ring = nullptr;
   // MMA tail (fp16 mode, fused classification head): per epilogue group a [128 x 96] fp16 hidden
   // tile (two 128-byte-swizzled 64-channel slabs) and the [16 x 96] fp16 head weights, both
   // K-major UMMA operands, sit between the pipeline stages and the barriers.
@@ -66,6 +69,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   // [C][96] fp32 when the head tail is fused (16-byte aligned for float4 reads)
   float* s_head_w = reinterpret_cast<float*>(
       (reinterpret_cast<uintptr_t>(head_bar + kMaxAcc) + 15) & ~static_cast<uintptr_t>(15));
+  s_ring = reinterpret_cast<volatile int*>(s_head_w + kHeadMaxC * 96);
   if (p.head_classes > 0) {
     if (!mma_tail) {
       for (int i = threadIdx.x; i < p.head_classes * 96; i += blockDim.x) s_head_w[i] = p.head_w[i];
@@ -132,7 +136,26 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     uint32_t phase = 0;
     const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (kATileBytes + b_tile_bytes);
     long long prof_a = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
+    for (int it = 0;; ++it) {
+      int tile = 0;
+      if (p.tile_counter != nullptr) {
+        if (leader) tile = atomicAdd(p.tile_counter, 1);
+        tile = __shfl_sync(0xffffffffu, tile, leader_lane);
+      } else {
+        tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      }
+      if (tile >= p.n_tiles) {
+        // end marker for the MMA warp and for every epilogue group (each waits for its own next tile)
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+        if (leader) {
+          for (int g = 0; g < kMaxAcc; ++g) s_ring[(it + g) & 15] = -1;
+          ptx::mbar_arrive(&full_bar[stage]);
+        }
+        __syncwarp();
+        break;
+      }
+      if (leader) s_ring[it & 15] = tile;  // published by the arrive of the tile's first k-step
       const int nt = tile % p.n_ntiles;
       const int mt = tile / p.n_ntiles;
       const int tx = mt % p.tiles_x;
@@ -182,7 +205,8 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     uint32_t acc_phase = 0;
     long long prof_a = 0, prof_b = 0, prof_c = 0;
     CERB_PROF_T0(t_all);
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    bool done = false;
+    for (int it = 0; !done; ++it) {
       CERB_PROF_T0(t_m0);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
       CERB_PROF_ADD(prof_a, t_m0);
@@ -192,6 +216,20 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
         CERB_PROF_T0(t_m1);
         ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
         CERB_PROF_ADD(prof_b, t_m1);
+        if (ks == 0 && s_ring[it & 15] < 0) {
+          // end marker: wake every epilogue group on the accumulator stage it waits for next.
+          // A stage is signalled only after its last real tile was drained (tempty), so the plain
+          // arrive can never overtake a pending tcgen05.commit on the same barrier.
+          for (int g = 0; g < kAccStages; ++g) {
+            if (g > 0) ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 2);
+            if (leader) ptx::mbar_arrive(&tfull_bar[acc]);
+            __syncwarp();
+            acc = (acc + 1) % kAccStages;
+            if (acc == 0) acc_phase ^= 1;
+          }
+          done = true;
+          break;
+        }
         ptx::tc_fence_after();
         CERB_PROF_T0(t_m2);
         if (leader) {
@@ -214,6 +252,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
         CERB_PROF_ADD(prof_c, t_m2);
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
+      if (done) break;
       if (leader) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
       __syncwarp();
       acc = (acc + 1) % kAccStages;
@@ -234,9 +273,13 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     const int acc = grp;
     uint32_t use = 0;
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
-    for (int tile = blockIdx.x + grp * gridDim.x; grp < kAccStages && tile < p.n_tiles;
-         tile += kAccStages * gridDim.x, ++use) {
+    for (int it = grp; grp < kAccStages; it += kAccStages, ++use) {
       const uint32_t acc_phase = use & 1;
+      CERB_PROF_T0(t_e0);
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
+      CERB_PROF_ADD(prof_a, t_e0);
+      const int tile = s_ring[it & 15];
+      if (tile < 0) break;
       const int nt = tile % p.n_ntiles;
       const int mt = tile / p.n_ntiles;
       const int tx = mt % p.tiles_x;
@@ -247,9 +290,6 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
       const size_t pix = (static_cast<size_t>(img) * p.H + oy) * p.W + ox;
       const int n0 = nt * p.BN;
 
-      CERB_PROF_T0(t_e0);
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err_flag, 4);
-      CERB_PROF_ADD(prof_a, t_e0);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
       CERB_PROF_T0(t_e1);
@@ -499,7 +539,7 @@ size_t conv_tc_smem_bytes(const ConvKParams& p) {
   // tiles + barriers (+ tmem holder) + slack for the manual 1024-byte alignment.
   // Always above half the SM's shared memory so that exactly one CTA (and one 512-column
   // TMEM allocation) lives on an SM at a time.
-  size_t b = static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 + 3200;
+  size_t b = static_cast<size_t>(p.n_stages) * p.stage_bytes + 256 + 1024 + 3328;
   if (p.mma_tail) b += kMaxAcc * kHeadA2Bytes + 4096;
   if (b < 120 * 1024) b = 120 * 1024;
   return b;

@@ -64,6 +64,7 @@ struct ConvKParams {
   int n_stages;
   int stage_bytes;
   int mma_tail;  // fused head: 1x1 96 -> C on the tensor core (fp16 mode), else fp32 FMAs
+  int* tile_counter;  // zeroed before the launch: dynamic tile scheduling; null = static split
   int* err_flag;
   long long* prof;  // optional [grid][16] per-role cycle counters (option "kernel_prof")
 };

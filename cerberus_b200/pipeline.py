@@ -115,20 +115,20 @@ class TilePipeline:
         self.ctx, self.model = engine.ctx, engine.model
         self.lib = self.ctx.lib
         self.pctx = Context(self.ctx.device, self.ctx.precision)  # post-processing + download
-        # The convolutions are persistent kernels with one CTA per SM and a static tile split; the
-        # watershed blocks of the post-processing need a whole SM each (>200 KB shared memory). If
-        # they have to steal SMs from a running forward, every convolution launched meanwhile
-        # finds fewer SMs than CTAs and runs a second wave. A few SMs are therefore left to the
-        # post-processing (CERB_POST_SMS, default 4; 0 = none).
-        self.post_sms = int(os.environ.get("CERB_POST_SMS", "4"))
+        # The post-processing's watershed blocks need a whole SM each (>200 KB shared memory) and
+        # take them from the persistent convolution kernels of the next forward. Those draw their
+        # tiles from a global counter (dynamic scheduling), so a CTA that starts late just finds
+        # less work; with the earlier static split every convolution launched meanwhile ran a
+        # second wave, and a few SMs had to be reserved (CERB_POST_SMS, still available:
+        # 6.39 ms/step with 4 reserved SMs vs 6.32 with none).
+        self.post_sms = int(os.environ.get("CERB_POST_SMS", "0"))
         if self.post_sms > 0:
             self.ctx.set_option("conv_sms", 148 - self.post_sms)
-            # Programmatic dependent launch would let the NEXT convolution's CTAs park on the
-            # spare SMs while they wait for their predecessor, which starves the post-processing
-            # blocks again (measured with a slow exact-watershed image in every 4th batch:
-            # 8.3 ms/step with PDL, 7.5 without; 6.9 with neither when no image is slow).
-            if os.environ.get("CERB_USE_PDL") is None:
-                self.ctx.set_option("use_pdl", 0)
+        # Programmatic dependent launch lets the NEXT convolution's CTAs park on freed SMs while
+        # they wait for their predecessor, which starves the post-processing blocks (measured with
+        # a slow exact-watershed image in every 4th batch: 8.3 ms/step with PDL, 7.5 without).
+        if os.environ.get("CERB_USE_PDL") is None:
+            self.ctx.set_option("use_pdl", 0)
         self.depth = max(2, min(8, int(depth)))
         self.lag = self.depth - 2 if self.depth > 2 else 1
         self.plan = engine.plan_for(n, h, w, h, w)
