@@ -288,8 +288,14 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = launches_now() - l0
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    per_rank_ms = [ms]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:
+        per_rank_ms = [ms / args.steps]
     ms_max = float(t.item())
     value = world * B * args.steps / (ms_max * 1e-3)
 
@@ -391,6 +397,11 @@ def run_ours(args):
                     "exact_fallback_capacity": int(pl.lib.cerb_ctx_stat(pl.handle, b"ws_capacity_fallbacks")),
                     "note": "nuclei watershed, all steps incl. warm-up and e2e: images handled by the "
                             "component-parallel path vs redone by the exact whole-tile emulation"}
+    if world > 1 and pipe is not None:  # which ranks were slowed by exact-watershed images
+        mine = torch.tensor([float(ws_stats["exact_fallback_tie"])], device="cuda", dtype=torch.float64)
+        allw = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allw, mine)
+        ws_stats["exact_fallback_tie_per_rank"] = [int(x.item()) for x in allw]
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample = cpu_reference_rate(args, args.cpu_seconds, args.ref_batch)
@@ -408,6 +419,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": host_enqueue_ms,
+            "ms_per_step_per_rank": per_rank_ms,
             "watershed": ws_stats,
             "roofline": roof,
             "cpu_baseline": cpu,
