@@ -24,7 +24,8 @@ the host with OpenCV exactly as in the reference (SURVEY.md 8f-2 is the device v
 
 Known limits of this round: array-backed slides only; no resampling between scan and
 processing resolution; the nuclei watershed of a 4032^2 post-processing tile runs on the
-whole-image emulation kernel (one warp) and is slow; post-processing runs on rank 0.
+component-parallel watershed but falls back to the whole-tile emulation (one warp, seconds)
+when two markers of one touching-nuclei component tie.
 """
 import logging
 import os
@@ -228,22 +229,33 @@ class InferManager(base.InferManager):
         return new_inst_dict, remove_in_orig
 
     def _postproc_nuclei(self, canvas, patch_outputs, pp_tile_shape, margin):
-        """infer/wsi.py:640-686."""
+        """infer/wsi.py:640-686. With several ranks every rank holds the merged canvas; the tiles
+        of a set are strided over ranks (the reference's ProcessPoolExecutor), the per-tile results
+        are gathered and merged on rank 0 in the reference's tile order."""
+        dist, rank, world = self._dist()
         H, W, _ = canvas.shape
         tile_sets = get_tile_info((W, H), pp_tile_shape, self.patch_output_shape, margin)
         nuclei = {}
         self.t_dev = self.t_host = 0.0
         for set_idx, (set_bounds, set_flags) in enumerate(tile_sets):
-            results = []
-            for tile_idx, tile_bounds in enumerate(set_bounds):
-                if len(boxes_intersect(patch_outputs, tile_bounds)) == 0:
-                    continue
-                results.append(self._process_tile_predictions(
-                    canvas, tile_bounds, set_flags[tile_idx], set_idx, nuclei, margin))
-            for new_inst_dict, remove_uuid_list in results:
-                nuclei.update(new_inst_dict)
-                for u in remove_uuid_list:
-                    nuclei.pop(u, None)
+            todo = [i for i, tb in enumerate(set_bounds) if len(boxes_intersect(patch_outputs, tb)) > 0]
+            ref = nuclei
+            if world > 1 and set_idx == 3:
+                # cross tiles replace accumulated instances: every rank needs their boxes
+                obj = [[(u, v["box"]) for u, v in nuclei.items()] if rank == 0 else None]
+                dist.broadcast_object_list(obj, src=0)
+                ref = {u: {"box": b} for u, b in obj[0]}
+            local = [(i, self._process_tile_predictions(canvas, set_bounds[i], set_flags[i], set_idx,
+                                                        ref, margin)) for i in todo[rank::world]]
+            if world > 1:
+                gathered = [None] * world
+                dist.all_gather_object(gathered, local)
+                local = sorted((x for part in gathered for x in part), key=lambda x: x[0])
+            if rank == 0:
+                for _, (new_inst_dict, remove_uuid_list) in local:
+                    nuclei.update(new_inst_dict)
+                    for u in remove_uuid_list:
+                        nuclei.pop(u, None)
         return nuclei
 
     # ------------------------------------------------------------------ gland / lumen
@@ -267,9 +279,13 @@ class InferManager(base.InferManager):
                 tissue_info_list.append([rmin, rmax + 1, cmin, cmax + 1])  # misc/utils.py:82-91
         else:
             tissue_info_list.append([0, mask_lab.shape[0], 0, mask_lab.shape[1]])
+        dist, rank, world = self._dist()
         out = {}
+        per_region = []  # (region index, tissue, instance info) of the regions this rank handles
         ds_factor = 0.5
         for ridx, ti in enumerate(tissue_info_list):
+            if ridx % world != rank:
+                continue
             rmin = int(round(ti[0] / mask_downsample_ratio))
             rmax = int(round(ti[1] / mask_downsample_ratio))
             cmin = int(round(ti[2] / mask_downsample_ratio))
@@ -330,7 +346,13 @@ class InferManager(base.InferManager):
                     inst_info["centroid"] = inst_info["centroid"] + tissue_topleft
                     b = inst_info["box"]
                     inst_info["box"] = np.array([b[0][1], b[0][0], b[1][1], b[1][0]])
-                    out.setdefault(tissue, {})[uuid.uuid4().hex] = inst_info
+                    per_region.append((ridx, tissue, inst_info))
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, per_region)
+            per_region = sorted((x for part in gathered for x in part), key=lambda x: x[0])
+        for _, tissue, inst_info in per_region:  # region order, Gland before Lumen inside a region
+            out.setdefault(tissue, {})[uuid.uuid4().hex] = inst_info
         return out
 
     # ------------------------------------------------------------------ one slide
@@ -371,10 +393,6 @@ class InferManager(base.InferManager):
         self.logger.info("Inference Time: %s (%d patches on this rank, %d selected)" % (
             time.perf_counter() - start, self.nr_patches_done, len(patch_inputs)))
         self.last_canvas = canvas if getattr(self, "keep_canvas", False) else None
-        if rank != 0:
-            del canvas
-            return None
-
         wsi_inst_info = {}
         start = time.perf_counter()
         margin = int(getattr(self, "ambiguous_size", 64))
@@ -389,7 +407,7 @@ class InferManager(base.InferManager):
 
         start = time.perf_counter()
         idx = eng.model.idx_dict
-        if "Patch-Class" in self.model_args["decoder_kwargs"].keys() and "Patch-Class" in idx:
+        if rank == 0 and "Patch-Class" in self.model_args["decoder_kwargs"].keys() and "Patch-Class" in idx:
             import scipy.io as sio
             ds = 0.25
             ph, pw = _cv_round(H * ds), _cv_round(W * ds)
@@ -405,6 +423,9 @@ class InferManager(base.InferManager):
 
         start = time.perf_counter()
         wsi_inst_info.update(self._postproc_gland_lumen(canvas, wsi_mask, mask_downsample_ratio))
+        if rank != 0:
+            del canvas
+            return None
         wsi_inst_info["proc_resolution"] = {"resolution": self.wsi_proc_mag, "units": "mpp"}
         wsi_inst_info["base_resolution"] = {"resolution": self.wsi_base_mag, "units": "mpp"}
         wsi_inst_info["proc_dimensions"] = self.wsi_proc_shape

@@ -59,3 +59,56 @@ def test_shard_units_edge_cases():
     assert shard_units(9, 1, 4) == [1, 5]
     allu = sorted(u for r in range(8) for u in shard_units(100, r, 8))
     assert allu == list(range(100))
+
+
+class _FakeCanvas:
+    shape = (700, 1000, 9)
+
+
+def _wsi_worker(rank, world, port, out_dir):
+    """WSI mode: the post-processing tiles of a set are strided over ranks and merged on rank 0
+    (cerberus_b200/infer/wsi.py::_postproc_nuclei); the device call is replaced by a deterministic
+    stand-in so that the sharding / gather / merge logic runs on CPU."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cerberus_b200.infer.wsi import InferManager
+    from cerberus_b200.infer.wsi_geometry import get_coordinates, select_tile_instances
+    m = object.__new__(InferManager)
+    m.patch_output_shape = [144, 144]
+    calls = []
+
+    def fake_tile(canvas, tile_bounds, tile_flag, tile_mode, ref_inst_dict, margin):
+        tb = np.asarray(tile_bounds)
+        calls.append(tuple(int(v) for v in tb))
+        rng = np.random.RandomState(int(tb.sum()) % 100000 + 7 * tile_mode)
+        w, h = int(tb[2] - tb[0]), int(tb[3] - tb[1])
+        xy = np.stack([rng.randint(0, max(w - 12, 1), 40), rng.randint(0, max(h - 12, 1), 40)], -1)
+        boxes = np.concatenate([xy, xy + rng.randint(4, 12, (40, 2))], -1)
+        ref_uids = list(ref_inst_dict.keys())
+        ref_boxes = np.array([ref_inst_dict[u]["box"] for u in ref_uids]) if (tile_mode == 3 and ref_uids) else None
+        sel, sel_ref = select_tile_instances(boxes, tb, tile_flag, tile_mode, margin, ref_boxes)
+        new = {"m%d_%d_%d_%d" % (tile_mode, tb[0], tb[1], k): {"box": b + np.concatenate([tb[:2]] * 2)}
+               for k, b in enumerate(boxes) if k not in set(sel)}
+        return new, [ref_uids[i] for i in sel_ref]
+
+    m._process_tile_predictions = fake_tile
+    _, pout = get_coordinates((1000, 700), [448, 448], [144, 144], [144, 144])
+    nuclei = m._postproc_nuclei(_FakeCanvas(), pout, [300, 300], 64)
+    torch.save({"keys": sorted(nuclei.keys()), "n_calls": len(calls)}, os.path.join(out_dir, "w%d_r%d.pt" % (world, rank)))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_wsi_postproc_tiles_shard_over_ranks_and_merge_like_one_rank(tmp_path):
+    _wsi_worker(0, 1, _free_port(), str(tmp_path))
+    mp.spawn(_wsi_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    one = torch.load(os.path.join(str(tmp_path), "w1_r0.pt"))
+    r0 = torch.load(os.path.join(str(tmp_path), "w2_r0.pt"))
+    r1 = torch.load(os.path.join(str(tmp_path), "w2_r1.pt"))
+    assert len(one["keys"]) > 100
+    assert r0["keys"] == one["keys"]            # rank 0 ends up with the single-rank result
+    assert r1["keys"] == []                      # other ranks only contribute
+    assert r0["n_calls"] + r1["n_calls"] == one["n_calls"] and r1["n_calls"] > 0
