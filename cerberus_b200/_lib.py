@@ -93,6 +93,11 @@ _SIGNATURES = {
                                                  ctypes.c_void_p, ctypes.c_int]),
     "cerb_mask_lumen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_size_t]),
+    "cerb_inst_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_int32)]),
+    "cerb_inst_info_read": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 6),
     "cerb_ellipse_rows": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32)]),
     "cerb_copy_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

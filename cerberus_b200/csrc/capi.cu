@@ -848,6 +848,7 @@ extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
   if (ctx->stat_dev) cudaFree(ctx->stat_dev);
   for (void* p : ctx->scratch) cudaFree(p);
   if (ctx->postproc_ws && ctx->postproc_ws_free) ctx->postproc_ws_free(ctx->postproc_ws);
+  if (ctx->instinfo_ws && ctx->instinfo_ws_free) ctx->instinfo_ws_free(ctx->instinfo_ws);
   delete ctx;
 }
 

@@ -41,6 +41,8 @@ struct cerb_ctx {
   std::vector<void*> scratch;  // device allocations owned by the ctx (post-proc workspaces)
   void* postproc_ws = nullptr;             // csrc/postproc.cu Workspace, created on first use
   void (*postproc_ws_free)(void*) = nullptr;
+  void* instinfo_ws = nullptr;             // csrc/instinfo.cu Workspace, created on first use
+  void (*instinfo_ws_free)(void*) = nullptr;
 };
 
 namespace cerb {

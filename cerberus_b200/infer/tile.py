@@ -148,18 +148,19 @@ def _post_process_patches(patch_info_list, image_info, postproc_code=None, postp
         binary_gland[binary_gland > 0] = 1
         pred_inst_map_dict["Lumen"] = binary_gland * pred_inst_map_dict["Lumen"]
 
+    # tile.py:193-203: the reference resizes the instance / type maps x2 (cv2 INTER_NEAREST) and
+    # calls get_inst_info_dict on the copies; the device version addresses the upsampled image
+    # through `up=2` without materialising it.
     pred_type_tmp = None
     for tissue_code in postproc_list:
         tissue_code = tissue_code.capitalize()
         if tissue_code != "Patch-class":
-            pred_inst_tmp = cv2.resize(pred_inst_map_dict[tissue_code], (0, 0), fx=2, fy=2,
-                                       interpolation=cv2.INTER_NEAREST)
             if tissue_code != "Lumen":
                 if pred_type_map_dict[tissue_code] is not None:
-                    pred_type_tmp = cv2.resize(pred_type_map_dict[tissue_code], (0, 0), fx=2, fy=2,
-                                               interpolation=cv2.INTER_NEAREST)
+                    pred_type_tmp = pred_type_map_dict[tissue_code]
             # reference quirk (tile.py:193-203): Lumen inherits the previous tissue's type map
-            pred_inst_info_dict[tissue_code] = get_inst_info_dict(pred_inst_tmp, pred_type_tmp)
+            pred_inst_info_dict[tissue_code] = get_inst_info_dict(
+                pred_inst_map_dict[tissue_code], pred_type_tmp, ctx=ctx, up=2)
 
     return (image_info["name"], image_info["src_image"], pred_inst_map_dict, pred_inst_info_dict,
             pred_type_map_dict, pclass_map)

@@ -39,7 +39,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..instinfo import get_inst_info_dict
+from ..instinfo import get_inst_info_dict, get_instance_info
 from . import base
 from .wsi_geometry import (boxes_intersect, filter_coordinates, get_coordinates, get_tile_info,
                            select_tile_instances)
@@ -63,50 +63,6 @@ def tiatoolbox_bounding_box(img):
     rmin, rmax = np.where(rows)[0][[0, -1]]
     cmin, cmax = np.where(cols)[0][[0, -1]]
     return np.array([cmin, rmin, cmax + 1, rmax + 1])
-
-
-def get_instance_info(pred_inst, pred_type=None):
-    """tiatoolbox HoVerNet.get_instance_info (infer/wsi.py:150): box is flat [x0, y0, x1, y1]."""
-    info = {}
-    ids = np.unique(pred_inst)[1:]
-    if len(ids) == 0:
-        return info
-    # The original builds `pred_inst == inst_id` over the WHOLE tile for every instance
-    # (O(instances x pixels): minutes for a 4032^2 tile); one find_objects pass gives the same
-    # boxes, and the per-instance mask is then cut from the box only.
-    from scipy import ndimage
-    lab = pred_inst if pred_inst.dtype.kind in "iu" else pred_inst.astype(np.int64)
-    if lab.min() < 0:
-        raise ValueError("negative instance ids")
-    slices = ndimage.find_objects(lab)
-    for inst_id in ids:
-        sl = slices[int(inst_id) - 1]
-        box = np.array([sl[1].start, sl[0].start, sl[1].stop, sl[0].stop])
-        crop = (lab[sl] == inst_id).astype(np.uint8)
-        moment = cv2.moments(crop)
-        contour = cv2.findContours(crop, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
-        contour = np.squeeze(contour[0][0].astype(np.int32))
-        if contour.shape[0] < 3 or len(contour.shape) != 2:
-            continue
-        centroid = np.array([moment["m10"] / moment["m00"], moment["m01"] / moment["m00"]])
-        contour = contour + box[:2][None]
-        centroid = centroid + box[:2]
-        info[inst_id] = {"box": box, "centroid": centroid, "contour": contour, "prob": None,
-                         "type": None}
-    if pred_type is not None:
-        for inst_id in list(info.keys()):
-            c0, r0, c1, r1 = info[inst_id]["box"]
-            m = pred_inst[r0:r1, c0:c1] == inst_id
-            t = pred_type[r0:r1, c0:c1][m]
-            tl, tp = np.unique(t, return_counts=True)
-            pairs = sorted(zip(tl, tp), key=lambda x: x[1], reverse=True)
-            inst_type = pairs[0][0]
-            if inst_type == 0 and len(pairs) > 1:
-                inst_type = pairs[1][0]
-            d = {v[0]: v[1] for v in pairs}
-            info[inst_id]["type"] = int(inst_type)
-            info[inst_id]["prob"] = float(d[inst_type] / (np.sum(m) + 1.0e-6))
-    return info
 
 
 def _ptr(t):
@@ -206,7 +162,7 @@ class InferManager(base.InferManager):
         if not any_fg[0]:
             return {}, []
         t0 = time.perf_counter()
-        inst_dict = get_instance_info(labels, type_map)
+        inst_dict = get_instance_info(labels, type_map, ctx=ctx)
         self.t_host += time.perf_counter() - t0
         if len(inst_dict) == 0:
             return {}, []
@@ -337,7 +293,8 @@ class InferManager(base.InferManager):
             binary_gland[binary_gland > 0] = 1
             inst_maps["Lumen"] = binary_gland * inst_maps["Lumen"]
             for tissue in ("Gland", "Lumen"):
-                pred_inst_info = get_inst_info_dict(inst_maps[tissue], type_maps[tissue], ds_factor)
+                pred_inst_info = get_inst_info_dict(inst_maps[tissue], type_maps[tissue], ds_factor,
+                                                    ctx=self.engine.ctx)
                 for inst_id, inst_info in pred_inst_info.items():
                     # Reference quirk kept for drop-in parity (:815-829): `box` is [[r0,c0],[r1,c1]]
                     # but the (x, y) top-left is added to it, i.e. x to the rows and y to the columns.

@@ -1,56 +1,110 @@
-"""Mirror of loader/postproc.py:12-98 (get_inst_info_dict) and misc/utils.py:82-91
-(get_bounding_box): per-instance box / centroid / contour / majority type on the host with
-OpenCV, exactly as the reference does (a device version is row f-2)."""
-import cv2
+"""Mirror of loader/postproc.py:12-98 (get_inst_info_dict) and of tiatoolbox's
+HoVerNet.get_instance_info (infer/wsi.py:150) over the C ABI.
+
+The reference loops over instances in Python and calls cv2.moments / cv2.findContours on each
+bounding-box crop; here `cerb_inst_info` builds the whole table on the device (box, moments,
+majority type, contour [0][0] — csrc/instinfo.cu, csrc/contour_core.h) and this module only
+reshapes it into the reference's dict. Same keys, dtypes, skip rules and ds_factor rounding.
+No CPU fallback: without a bound device context the call raises.
+"""
+import ctypes
+
 import numpy as np
 
+from . import _lib
 
-def get_bounding_box(img):
-    rows = np.any(img, axis=1)
-    cols = np.any(img, axis=0)
-    rmin, rmax = np.where(rows)[0][[0, -1]]
-    cmin, cmax = np.where(cols)[0][[0, -1]]
-    rmax += 1
-    cmax += 1
-    return [rmin, rmax, cmin, cmax]
+_ctx = None
 
 
-def get_inst_info_dict(inst_map, type_map, ds_factor=1.0):
-    inst_id_list = np.unique(inst_map)[1:]  # reference quirk: drops the smallest value
+def bind(ctx):
+    """Device context used when a call does not pass one (set by InferManager)."""
+    global _ctx
+    _ctx = ctx
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class InstTable:
+    """Host copy of the device table, rows in ascending instance id."""
+    __slots__ = ("ids", "box", "moments", "type", "contour_off", "contour_xy", "any_background")
+
+
+def inst_table(ctx, inst_map, type_map=None, up=1, on_device=False, shape=None):
+    """Runs cerb_inst_info. `inst_map` / `type_map` are host arrays ([H,W]; any integer-valued
+    dtype) or, with on_device=True, device pointers (int) of int32 / float32 [H,W] = `shape`."""
+    ctx = ctx or _ctx
+    if ctx is None:
+        raise RuntimeError("instinfo.bind(ctx) has not been called: the instance tables are built "
+                           "on the CUDA device only")
+    lib = ctx.lib
+    if on_device:
+        H, W = shape
+        lab_p = ctypes.c_void_p(inst_map)
+        typ_p = ctypes.c_void_p(type_map) if type_map else None
+        flags = 1
+    else:
+        inst_map = np.asarray(inst_map)
+        lab = np.ascontiguousarray(inst_map, dtype=np.int32)
+        if lab.shape != inst_map.shape or (inst_map.dtype.kind == "f" and (lab != inst_map).any()):
+            raise ValueError("instance map holds non-integer ids")
+        H, W = lab.shape
+        lab_p = _ptr(lab)
+        typ = None
+        if type_map is not None:
+            typ = np.ascontiguousarray(type_map, dtype=np.float32)
+            if typ.shape != lab.shape:
+                raise ValueError("type map shape %r != instance map shape %r" % (typ.shape, lab.shape))
+        typ_p = _ptr(typ) if typ is not None else None
+        flags = 0
+    n = ctypes.c_int32(0)
+    npts = ctypes.c_int64(0)
+    any_bg = ctypes.c_int32(0)
+    _lib.check(lib.cerb_inst_info(ctx.handle, lab_p, H, W, typ_p, int(up), flags, ctypes.byref(n),
+                                  ctypes.byref(npts), ctypes.byref(any_bg)), "cerb_inst_info")
+    t = InstTable()
+    t.ids = np.empty(n.value, dtype=np.int32)
+    t.box = np.empty((n.value, 4), dtype=np.int32)
+    t.moments = np.empty((n.value, 3), dtype=np.int64)
+    t.type = np.empty((n.value, 2), dtype=np.int32)
+    t.contour_off = np.zeros(n.value + 1, dtype=np.int64)
+    t.contour_xy = np.empty((npts.value, 2), dtype=np.int32)
+    t.any_background = bool(any_bg.value)
+    _lib.check(lib.cerb_inst_info_read(ctx.handle, _ptr(t.ids), _ptr(t.box), _ptr(t.moments),
+                                       _ptr(t.type), _ptr(t.contour_off), _ptr(t.contour_xy)),
+               "cerb_inst_info_read")
+    return t
+
+
+def _rows(table):
+    """Instances in the order of `np.unique(inst_map)[1:]` that survive the reference's contour
+    checks (postproc.py:31-37: fewer than 3 points -> skipped)."""
+    first = 0 if table.any_background else 1  # [1:] drops the smallest id when there is no 0
+    counts = np.diff(table.contour_off)
+    return [i for i in range(first, len(table.ids)) if counts[i] >= 3]
+
+
+def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dtype=None):
+    """loader/postproc.py:12-98. `up` folds the cv2.resize(fx=up, fy=up, INTER_NEAREST) of
+    infer/tile.py:196-201 into the call (pass the maps at processing resolution)."""
+    table = inst_table(ctx, inst_map, type_map, up=up)
+    if key_dtype is None:
+        key_dtype = np.asarray(inst_map).dtype.type  # np.unique keeps the map's dtype
     info = {}
-    for inst_id in inst_id_list:
-        single = inst_map == inst_id
-        rmin, rmax, cmin, cmax = get_bounding_box(single)
+    m = table.moments.astype(np.float64)
+    for i in _rows(table):
+        rmin, cmin, rmax, cmax = (int(v) for v in table.box[i])
         bbox = np.array([[rmin, cmin], [rmax, cmax]])
-        single = single[bbox[0][0]:bbox[1][0], bbox[0][1]:bbox[1][1]].astype(np.uint8)
-        moment = cv2.moments(single)
-        contour = cv2.findContours(single, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
-        contour = np.squeeze(contour[0][0].astype("int32"))
-        if contour.shape[0] < 3:
-            continue
-        if len(contour.shape) != 2:
-            continue
-        centroid = np.array([moment["m10"] / moment["m00"], moment["m01"] / moment["m00"]])
-        contour[:, 0] += bbox[0][1]
-        contour[:, 1] += bbox[0][0]
-        centroid[0] += bbox[0][1]
-        centroid[1] += bbox[0][0]
-        info[inst_id] = {"box": bbox, "centroid": centroid, "contour": contour}
-
-    if type_map is not None:
-        for inst_id in list(info.keys()):
-            rmin, cmin, rmax, cmax = (info[inst_id]["box"]).flatten()
-            crop = inst_map[rmin:rmax, cmin:cmax] == inst_id
-            inst_type = type_map[rmin:rmax, cmin:cmax][crop]
-            type_list, type_pixels = np.unique(inst_type, return_counts=True)
-            type_list = sorted(zip(type_list, type_pixels), key=lambda x: x[1], reverse=True)
-            inst_type = type_list[0][0]
-            if inst_type == 0 and len(type_list) > 1:
-                inst_type = type_list[1][0]
-            type_dict = {v[0]: v[1] for v in type_list}
-            info[inst_id]["type"] = int(inst_type)
-            info[inst_id]["type_prob"] = float(type_dict[inst_type] / (np.sum(crop) + 1.0e-6))
-
+        centroid = np.array([m[i, 1] / m[i, 0], m[i, 2] / m[i, 0]])
+        centroid[0] += cmin
+        centroid[1] += rmin
+        contour = table.contour_xy[table.contour_off[i]:table.contour_off[i + 1]].copy()
+        d = {"box": bbox, "centroid": centroid, "contour": contour}
+        if type_map is not None:
+            d["type"] = int(table.type[i, 0] / 4.0)  # int(np.float) truncates (postproc.py:69)
+            d["type_prob"] = float(table.type[i, 1] / (table.moments[i, 0] + 1.0e-6))
+        info[key_dtype(table.ids[i])] = d
     if ds_factor != 1.0:
         for inst_id in list(info.keys()):
             d = info[inst_id]
@@ -60,4 +114,24 @@ def get_inst_info_dict(inst_map, type_map, ds_factor=1.0):
             if "type" in d:
                 new["type"], new["type_prob"] = d["type"], d["type_prob"]
             info[inst_id] = new
+    return info
+
+
+def get_instance_info(pred_inst, pred_type=None, ctx=None):
+    """tiatoolbox HoVerNet.get_instance_info (infer/wsi.py:150): box is flat [x0, y0, x1, y1],
+    keys `type` / `prob` (None without a type map)."""
+    table = inst_table(ctx, pred_inst, pred_type)
+    key_dtype = np.asarray(pred_inst).dtype.type
+    info = {}
+    m = table.moments.astype(np.float64)
+    for i in _rows(table):
+        rmin, cmin, rmax, cmax = (int(v) for v in table.box[i])
+        box = np.array([cmin, rmin, cmax, rmax])
+        centroid = np.array([m[i, 1] / m[i, 0], m[i, 2] / m[i, 0]]) + box[:2]
+        contour = table.contour_xy[table.contour_off[i]:table.contour_off[i + 1]].copy()
+        d = {"box": box, "centroid": centroid, "contour": contour, "prob": None, "type": None}
+        if pred_type is not None:
+            d["type"] = int(table.type[i, 0] / 4.0)
+            d["prob"] = float(table.type[i, 1] / (table.moments[i, 0] + 1.0e-6))
+        info[key_dtype(table.ids[i])] = d
     return info

@@ -13,6 +13,7 @@
  *       -> cerb_postproc_nuclei / cerb_postproc_gland_lumen
  *   a16 infer/tile.py:136-163  canvas stitch           -> cerb_stitch
  *   a19 infer/tile.py:187-191  lumen *= (gland > 0)    -> cerb_mask_lumen
+ *   a20 loader/postproc.py:12-98 get_inst_info_dict    -> cerb_inst_info / cerb_inst_info_read
  *   a1/a2 infer/tile.py:43-106 + loader/infer_loader.py:57-69 (reflect pad + patch
  *       slicing)                                        -> cerb_extract_patches
  *
@@ -228,6 +229,28 @@ int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int n, int H, 
 
 /* infer/tile.py:187-191: lumen *= (gland > 0), both device int32 label maps. */
 int cerb_mask_lumen(cerb_ctx* ctx, int32_t* lumen_dev, const int32_t* gland_dev, size_t elems);
+
+/* ---- instance tables (a20 / SURVEY 8f-2): loader/postproc.py:12-98 get_inst_info_dict and
+ * tiatoolbox HoVerNet.get_instance_info (infer/wsi.py:150) -------------------------------------
+ * labels: int32 [H,W]; type_map: f32 [H,W] of class ids (multiples of 0.25 in [0,16): integers, or
+ * their 2x2 means after the WSI path's cv2.resize(fx=0.5), infer/wsi.py:773-790), or NULL (flags
+ * bit 0: both are device memory). `up` >= 1 is the nearest-neighbour cv2.resize(fx=up, fy=up) the tile
+ * mode applies to both maps before the call (infer/tile.py:196-201): all results are in the
+ * upsampled image, which is never materialised. Synchronous; the table stays in the ctx until
+ * the next call. Returns the number of instances (every id > 0 that occurs), the total number of
+ * contour points, and whether a 0 pixel exists (np.unique(inst_map)[1:] drops the smallest id
+ * when there is none). Fails if type_map holds any other value. */
+int cerb_inst_info(cerb_ctx* ctx, const int32_t* labels, int H, int W, const float* type_map,
+                   int up, int flags, int32_t* n_inst, int64_t* n_points, int32_t* any_background);
+/* Host copies of the table of the last cerb_inst_info call, rows in ascending id order (any
+ * pointer may be NULL):
+ *   ids [n]; box [n][4] = rmin, cmin, rmax, cmax (max exclusive, misc/utils.py:82-91);
+ *   moments [n][3] = cv2.moments m00, m10, m01 of the box crop (exact integers);
+ *   type [n][2] = 4 x the majority type value by the rule of postproc.py:60-68 and its pixel
+ *   count (-1, 0 without a type map); contour_off [n+1], contour_xy [n_points][2] = (x, y) image coordinates
+ *   of cv2.findContours(crop, RETR_TREE, CHAIN_APPROX_SIMPLE)[0][0] + box origin. */
+int cerb_inst_info_read(cerb_ctx* ctx, int32_t* ids, int32_t* box, int64_t* moments, int32_t* type,
+                        int64_t* contour_off, int32_t* contour_xy);
 
 /* cv2.getStructuringElement(MORPH_ELLIPSE, (k,k)) as row runs [j1[i], j2[i]) (1 <= k <= 32). */
 int cerb_ellipse_rows(int k, int32_t* j1, int32_t* j2);

@@ -224,9 +224,105 @@ def gen_stitch():
     print("wrote", path, os.path.getsize(path))
 
 
+def instinfo_cases():
+    """Seeded label / type maps for the instance-table golden: (name, inst_map, type_map | None,
+    ds_factor, up). `up` > 1: the reference sees cv2.resize(fx=up, fy=up, INTER_NEAREST) copies,
+    as in infer/tile.py:196-201. Rebuilt identically by tests/test_gpu_instinfo.py."""
+    from scipy import ndimage
+    from oracle import postproc_oracle as po
+    cases = []
+    rng = np.random.RandomState(11)
+
+    def field(h, w, sigma, seed):
+        f = ndimage.gaussian_filter(np.random.RandomState(seed).randn(h, w), sigma)
+        return (f - f.min()) / (f.max() - f.min())
+
+    # watershed-like nuclei labels with a blocky type map
+    f = field(160, 200, 3, 1)
+    nuc = ndimage.label(f > 0.55)[0].astype(np.int32)
+    typ = (field(160, 200, 12, 2) * 6.99).astype(np.int32).astype(np.float32)
+    cases.append(("nuclei", nuc, typ, 1.0, 1))
+    cases.append(("nuclei_up2", nuc, typ, 1.0, 2))
+    cases.append(("nuclei_notype", nuc, None, 1.0, 1))
+    # gland-like float64 labels: big blobs, sparse ids, holes, pieces split by a higher id
+    g = ndimage.label(field(180, 150, 9, 3) > 0.5)[0].astype(np.float64) * 3
+    g[field(180, 150, 4, 4) > 0.72] = 0          # holes
+    g[60:75, :] = np.where(g[60:75, :] > 0, 50, 0)  # a band repainted with another id splits blobs
+    gt = (field(180, 150, 20, 5) * 2.99).astype(np.int32).astype(np.float32)
+    cases.append(("gland_up2", g, gt, 1.0, 2))
+    # WSI flavour: half-resolution maps, type values are 2x2 means (multiples of 0.25), ds 0.5
+    gq = (rng.randint(0, 9, g.shape) / 4.0).astype(np.float32)
+    gq = ndimage.uniform_filter(gq, 1)
+    cases.append(("gland_ds05_quarter", g, gq, 0.5, 1))
+    # salt-and-pepper ids: nested holes / islands, one-pixel and two-pixel instances, lines
+    noise = rng.randint(0, 4, (48, 61)).astype(np.int32)
+    noise[rng.rand(48, 61) < 0.3] = 0
+    cases.append(("noise", noise, rng.randint(0, 5, noise.shape).astype(np.float32), 1.0, 1))
+    cases.append(("noise_up2", noise, None, 1.0, 2))
+    # many medium components with holes per id (the LAST top-level component's border is wanted)
+    patchy = (field(96, 120, 1.6, 6) > 0.5).astype(np.int32) * (1 + (np.arange(120)[None, :] // 47))
+    cases.append(("patchy", patchy, None, 1.0, 1))
+    cases.append(("patchy_up2", patchy, (patchy * 2 % 5).astype(np.float32), 1.0, 2))
+    thin = np.zeros((20, 30), np.int32)
+    thin[2, 3] = 1            # single pixel -> 1 point -> skipped
+    thin[5, 2:12] = 2         # horizontal line -> 2 points -> skipped
+    thin[8:15, 20] = 3        # vertical line
+    thin[10:13, 5:9] = 4      # rectangle -> 4 points
+    thin[16, 3] = thin[17, 4] = thin[18, 5] = 5  # diagonal (8-connected)
+    thin[15:19, 12:16] = 6
+    thin[16:18, 13:15] = 0    # ring
+    thin[16, 13] = 7          # island in the ring's hole
+    cases.append(("thin", thin, None, 1.0, 1))
+    # no background pixel at all: np.unique(...)[1:] drops the smallest id
+    full = (1 + (np.arange(24)[:, None] // 8) * 3 + np.arange(36)[None, :] // 12).astype(np.int32)
+    cases.append(("no_background", full, (full % 3).astype(np.float32), 1.0, 1))
+    # two instances, 0 is the most frequent type -> runner-up wins; equal counts -> smaller id
+    tie = np.zeros((12, 12), np.int32)
+    tie[1:5, 1:9] = 1
+    tie[6:11, 2:10] = 2
+    tt = np.zeros((12, 12), np.float32)
+    tt[1:5, 1:3] = 3
+    tt[1:5, 3:5] = 2          # instance 1: 16 x type 0, 8 x type 3, 8 x type 2 -> 2
+    tt[6:11, 2:6] = 5
+    tt[6:11, 6:10] = 4        # instance 2: 20 x 5, 20 x 4 -> 4
+    cases.append(("type_rules", tie, tt, 1.0, 1))
+    return cases
+
+
+def gen_instinfo():
+    """loader/postproc.py:12-98 (get_inst_info_dict), UNMODIFIED, on the maps above."""
+    import cv2
+    from oracle import postproc_oracle as po
+    ref_shim.install(po)
+    from loader.postproc import get_inst_info_dict
+    rec = {}
+    for name, inst, typ, ds, up in instinfo_cases():
+        a, t = inst, typ
+        if up != 1:
+            a = cv2.resize(inst, (0, 0), fx=up, fy=up, interpolation=cv2.INTER_NEAREST)
+            t = None if typ is None else cv2.resize(typ, (0, 0), fx=up, fy=up,
+                                                    interpolation=cv2.INTER_NEAREST)
+        info = get_inst_info_dict(a, t, ds)
+        keys = list(info.keys())
+        rec[name + "/inst_sum"] = np.array([float(np.asarray(inst, np.float64).sum()), inst.shape[0], inst.shape[1]])
+        rec[name + "/ids"] = np.array([float(k) for k in keys])
+        rec[name + "/box"] = np.array([info[k]["box"] for k in keys]).reshape(-1, 2, 2)
+        rec[name + "/centroid"] = np.array([info[k]["centroid"] for k in keys], dtype=np.float64).reshape(-1, 2)
+        cnt = [np.asarray(info[k]["contour"]).reshape(-1, 2) for k in keys]
+        rec[name + "/contour_off"] = np.cumsum([0] + [len(c) for c in cnt])
+        rec[name + "/contour"] = (np.concatenate(cnt) if cnt else np.zeros((0, 2))).astype(np.int32)
+        if typ is not None:
+            rec[name + "/type"] = np.array([info[k]["type"] for k in keys])
+            rec[name + "/type_prob"] = np.array([info[k]["type_prob"] for k in keys], dtype=np.float64)
+        print(name, inst.shape, "instances", len(keys), "points", int(rec[name + "/contour_off"][-1]))
+    path = os.path.join(GOLD, "instinfo.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["forward", "patching", "postproc", "stitch"]
+    which = sys.argv[1:] or ["forward", "patching", "postproc", "stitch", "instinfo"]
     for w in which:
         fn = globals().get("gen_" + w)
         if fn is None:

@@ -8,9 +8,8 @@ import cv2
 import numpy as np
 from scipy import ndimage
 
-from cerberus_b200.infer.wsi import get_instance_info
 from cerberus_b200.infer.wsi_geometry import boxes_intersect, get_tile_info, select_tile_instances
-from cerberus_b200.instinfo import get_inst_info_dict
+from oracle.instinfo_oracle import get_inst_info_dict, get_instance_info
 from oracle import postproc_oracle as po
 
 

@@ -16,6 +16,55 @@ import numpy as np  # noqa: E402
 import yaml  # noqa: E402
 
 
+def single_rank_checks(m, tmp, size, pp_tile):
+    """WSI_BENCH_VERIFY=1 on one GPU: (1) a second inference pass reproduces the canvas bit for bit,
+    (2) the nuclei labelling of the first post-processing tile is reproducible, (3) the device
+    instance table of that tile equals the OpenCV loop (oracle/instinfo_oracle.py)."""
+    import torch
+    from cerberus_b200 import _lib, instinfo
+    from cerberus_b200.infer.wsi_geometry import filter_coordinates, get_coordinates
+    from cerberus_b200.infer.wsi_reader import ArraySlide
+    from oracle import instinfo_oracle as oi
+    sl = ArraySlide.open(tmp + "/wsi/slide.npy", 0.5)
+    msk = (cv2.cvtColor(cv2.imread(tmp + "/msk/slide.png"), cv2.COLOR_BGR2GRAY) > 0).astype(np.uint8)
+    pi, po = get_coordinates((size, size), [448, 448], [144, 144], [144, 144])
+    sel = filter_coordinates(msk, po, (size, size))
+    again = m._infer_slide(sl, pi[sel], po[sel])
+    d = (again != m.last_canvas)
+    out = {"canvas_pixels_differing_between_two_passes": int(d.any(-1).sum())}
+    del d, again
+    ctx, lib = m.engine.ctx, m.engine.ctx.lib
+    idx = m.engine.model.idx_dict
+    t = (pp_tile // 144) * 144
+    crop = m.last_canvas[:t, :t].contiguous()
+    h, w, C = crop.shape
+    labs = []
+    for _ in range(2):
+        labels = np.empty((h, w), dtype=np.int32)
+        any_fg = np.zeros(1, dtype=np.int32)
+        torch.cuda.synchronize()
+        _lib.check(lib.cerb_postproc_nuclei(ctx.handle, _lib.ctypes.c_void_p(crop.data_ptr()), 1, h, w, C,
+                                            idx["Nuclei-INST"][0],
+                                            labels.ctypes.data_as(_lib.ctypes.c_void_p),
+                                            any_fg.ctypes.data_as(_lib.ctypes.c_void_p), 1), "nuclei")
+        labs.append(labels)
+    out["tile0_label_pixels_differing_between_two_runs"] = int((labs[0] != labs[1]).sum())
+    typ = crop[..., idx["Nuclei-TYPE"][0]].cpu().numpy()
+    t0 = time.perf_counter()
+    a = instinfo.get_instance_info(labs[0], typ, ctx=ctx)
+    t1 = time.perf_counter()
+    b = oi.get_instance_info(labs[0], typ)
+    t2 = time.perf_counter()
+    bad = [k for k in b if k not in a or not (np.array_equal(a[k]["box"], b[k]["box"]) and
+                                             np.array_equal(a[k]["contour"], b[k]["contour"]) and
+                                             np.array_equal(a[k]["centroid"], b[k]["centroid"]) and
+                                             a[k]["type"] == b[k]["type"] and a[k]["prob"] == b[k]["prob"])]
+    out["tile0_instances"] = {"device": len(a), "opencv_loop": len(b), "mismatching": len(bad),
+                              "first_bad": [int(k) for k in bad[:5]],
+                              "device_s": round(t1 - t0, 3), "opencv_loop_s": round(t2 - t1, 3)}
+    return out
+
+
 def main():
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 4608
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 30
@@ -81,6 +130,8 @@ def main():
         m.force_single = False
         d = (alone - m.last_canvas).abs()
         verify = {"max_abs_diff": float(d.max()), "pixels_differing": int((d.amax(-1) > 0).sum())}
+    if m.keep_canvas and world == 1:
+        verify = single_rank_checks(m, tmp, size, pp_tile)
     if rank == 0:
         logs = sorted(f for f in os.listdir(tmp + "/log") if "rank" not in f)
         text = open(os.path.join(tmp, "log", logs[-1])).read()
