@@ -29,6 +29,7 @@ struct cerb_ctx {
   bool use_graphs = true;  // replay the forward op list as a CUDA graph
   unsigned long long* stat_dev = nullptr;  // [4] device counters of the small-tile watershed (cerb_ctx_stat)
   int64_t stat_ws_large = 0, stat_ws_fallback = 0;  // large-image watershed calls / exact fallbacks
+  int64_t stat_ws_tied = 0;  // components of large images whose marker ties were settled by enumeration
   int conv64_debug = 0;
   long long* prof_dev = nullptr;  // [kProfSlots] in-kernel attribution counters (option "kernel_prof")
   int ws_mode = 0;  // 0: component-parallel watershed with exact fallback; 1: whole-tile emulation only;

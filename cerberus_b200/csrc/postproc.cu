@@ -889,7 +889,9 @@ __device__ __forceinline__ uint64_t wsg_key(float v, uint32_t age) {
   return (static_cast<uint64_t>(u) << 32) | age;
 }
 
-// ctl[0] = pool top, ctl[1] = number of components, ctl[2] = tie flag (per image: 4 ints)
+// ctl[0] = pool top, ctl[1] = number of components, ctl[2] = "redo the image with the exact
+// whole-image kernel", ctl[3] = components that saw a marker tie (per image: 4 ints)
+constexpr int kWsgTied = -2;  // clab value of a component waiting for k_wsg_certify
 __global__ void k_wsg_alloc(const uint8_t* __restrict__ msk, const int* __restrict__ L,
                             const int* __restrict__ size, int* __restrict__ off, int* __restrict__ cnt,
                             int* __restrict__ clab, int* __restrict__ roots, int* __restrict__ ctl,
@@ -908,13 +910,16 @@ __global__ void k_wsg_alloc(const uint8_t* __restrict__ msk, const int* __restri
 __global__ void k_wsg_seed(const float* __restrict__ val, const uint8_t* __restrict__ msk,
                            const int* __restrict__ L, const int* __restrict__ lab,
                            const int* __restrict__ off, int* __restrict__ cnt, int* __restrict__ clab,
-                           unsigned long long* __restrict__ hk, int* __restrict__ hi, int H, int W) {
+                           unsigned long long* __restrict__ hk, int* __restrict__ hi, int H, int W,
+                           const int* __restrict__ ctl, int tied_only) {
   const int hw = H * W;
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
   const uint8_t* m = msk + base;
   const int* l = lab + base;
+  if (tied_only && ctl[4 * blockIdx.y + 3] == 0) return;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
     if (!m[p] || l[p] == 0) continue;
+    if (tied_only && clab[base + L[base + p]] != kWsgTied) continue;
     const int x = p % W;
     const bool b = (p >= W && m[p - W] && l[p - W] == 0) || (x > 0 && m[p - 1] && l[p - 1] == 0) ||
                    (x < W - 1 && m[p + 1] && l[p + 1] == 0) || (p + W < hw && m[p + W] && l[p + W] == 0);
@@ -923,101 +928,241 @@ __global__ void k_wsg_seed(const float* __restrict__ val, const uint8_t* __restr
     const int slot = off[base + root] + atomicAdd(&cnt[base + root], 1);
     hk[base + slot] = wsg_key(val[base + p], 0u);
     hi[base + slot] = p;
+    if (tied_only) continue;
     // one label per component -> ties are harmless (see k_watershed_comp)
     const int prev = atomicCAS(&clab[base + root], 0, l[p]);
     if (prev != 0 && prev != l[p]) clab[base + root] = -1;
   }
 }
 
+// Floods one mask component from the n entries in its heap slice (k, ix). CERT = false: the
+// regular pass - marker entries carry age 0 and the function returns false as soon as two marker
+// entries with bit-equal values surface in a component whose markers carry different labels.
+// CERT = true (k_wsg_certify): the age field of the marker entries holds an explicit rank, pushed
+// entries get ages above every rank, every labelled pixel is appended to `log`.
+template <bool CERT>
+__device__ __forceinline__ bool wsg_flood_component(const float* __restrict__ v,
+                                                    const uint8_t* __restrict__ m, int* __restrict__ o,
+                                                    int W, int hw, unsigned long long* __restrict__ k,
+                                                    int* __restrict__ ix, int n, bool multi,
+                                                    uint32_t age, int* __restrict__ log, int& nlog) {
+  for (int j = 1; j < n; ++j) {  // in-place heap build by successive pushes
+    const unsigned long long ek = k[j];
+    const int ei = ix[j];
+    int cidx = j;
+    while (cidx > 0) {
+      const int parent = (cidx - 1) >> 1;
+      if (!(ek < k[parent])) break;
+      k[cidx] = k[parent];
+      ix[cidx] = ix[parent];
+      cidx = parent;
+    }
+    k[cidx] = ek;
+    ix[cidx] = ei;
+  }
+  unsigned long long last_marker = ~0ull;
+  while (n > 0) {
+    const unsigned long long top = k[0];
+    const int ei = ix[0];
+    if (!CERT && (top & 0xFFFFFFFFull) == 0) {  // a marker entry
+      if ((top >> 32) == last_marker && multi) return false;
+      last_marker = top >> 32;
+    }
+    --n;
+    if (n > 0) {  // move the last entry to the root and sift down (left child preferred)
+      const unsigned long long xk = k[n];
+      const int xi = ix[n];
+      int i = 0;
+      for (;;) {
+        const int l = 2 * i + 1;
+        if (l >= n) break;
+        int sidx = i;
+        unsigned long long sk = xk;
+        if (k[l] < sk) { sidx = l; sk = k[l]; }
+        if (l + 1 < n && k[l + 1] < sk) { sidx = l + 1; sk = k[l + 1]; }
+        if (sidx == i) break;
+        k[i] = sk;
+        ix[i] = ix[sidx];
+        i = sidx;
+      }
+      k[i] = xk;
+      ix[i] = xi;
+    }
+    const int lb = o[ei];
+    const int x = ei % W;
+#define CERB_WSG_PUSH(cond, qq)                                          \
+    if (cond) {                                                          \
+      const int q = (qq);                                                \
+      if (m[q] && o[q] == 0) {                                           \
+        ++age;                                                           \
+        o[q] = lb;                                                       \
+        if (CERT) log[nlog++] = q;                                       \
+        const unsigned long long ek = wsg_key(v[q], age);                \
+        int cidx = n++;                                                  \
+        while (cidx > 0) {                                               \
+          const int parent = (cidx - 1) >> 1;                            \
+          if (!(ek < k[parent])) break;                                  \
+          k[cidx] = k[parent];                                           \
+          ix[cidx] = ix[parent];                                         \
+          cidx = parent;                                                 \
+        }                                                                \
+        k[cidx] = ek;                                                    \
+        ix[cidx] = q;                                                    \
+      }                                                                  \
+    }
+    CERB_WSG_PUSH(ei >= W, ei - W)
+    CERB_WSG_PUSH(x > 0, ei - 1)
+    CERB_WSG_PUSH(x < W - 1, ei + 1)
+    CERB_WSG_PUSH(ei + W < hw, ei + W)
+#undef CERB_WSG_PUSH
+  }
+  return true;
+}
+
 __global__ void k_wsg_flood(const float* __restrict__ val, const uint8_t* __restrict__ msk,
                             int* __restrict__ lab, const int* __restrict__ off,
-                            const int* __restrict__ cnt, const int* __restrict__ clab,
+                            const int* __restrict__ cnt, int* __restrict__ clab,
                             const int* __restrict__ roots, unsigned long long* __restrict__ hk,
                             int* __restrict__ hi, int* __restrict__ ctl, int H, int W) {
   const int hw = H * W;
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
-  const float* v = val + base;
-  const uint8_t* m = msk + base;
-  int* o = lab + base;
   int* c = ctl + 4 * blockIdx.y;
   const int n_roots = c[1];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_roots; t += gridDim.x * blockDim.x) {
     const int root = roots[base + t];
-    int n = cnt[base + root];
+    const int n = cnt[base + root];
     if (n == 0) continue;
-    const bool multi = clab[base + root] == -1;
+    int nlog = 0;
+    if (!wsg_flood_component<false>(val + base, msk + base, lab + base, W, hw,
+                                    hk + base + off[base + root], hi + base + off[base + root], n,
+                                    clab[base + root] == -1, 1u, nullptr, nlog)) {
+      clab[base + root] = kWsgTied;  // abandoned half-flooded: k_wsg_certify redoes it
+      atomicAdd(&c[3], 1);
+    }
+  }
+}
+
+// ---- marker ties without the whole-image emulation ---------------------------------------------
+// Entries with bit-equal (value, age 0) keys leave the reference's heap in an order fixed by its
+// global array layout; everything else in a component follows the keys alone. So the true run of
+// a tied component is "key order, with SOME order inside each group of tied marker entries". If
+// every such order yields the same labels, that labelling is the reference's, whatever its heap
+// did. k_wsg_certify floods a tied component once per combination of permutations of its tie
+// groups (marker ranks in the age field) and compares the label sets; only when two orders
+// disagree - or there are more than kTieMaxVariants of them (plateaus) - is the image handed to the
+// exact whole-image kernel.
+constexpr int kTieMaxVariants = 24;
+constexpr int kTieMaxGroups = 4;
+constexpr int kTieMaxSeeds = 8192;
+
+// markers back, flood undone, seed counters cleared for the tied components
+__global__ void k_wsg_tied_reset(const uint8_t* __restrict__ msk, const int* __restrict__ L,
+                                 const int* __restrict__ clab, const int* __restrict__ saved,
+                                 int* __restrict__ lab, int* __restrict__ cnt,
+                                 const int* __restrict__ ctl, int hw) {
+  if (ctl[4 * blockIdx.y + 3] == 0) return;
+  const size_t base = static_cast<size_t>(blockIdx.y) * hw;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    if (!msk[base + p]) continue;
+    const int root = L[base + p];
+    if (clab[base + root] != kWsgTied) continue;
+    lab[base + p] = saved[base + p];
+    if (p == root) cnt[base + root] = 0;
+  }
+}
+
+__global__ void k_wsg_certify(const float* __restrict__ val, const uint8_t* __restrict__ msk,
+                              int* __restrict__ lab, const int* __restrict__ off,
+                              const int* __restrict__ cnt, const int* __restrict__ clab,
+                              const int* __restrict__ roots, unsigned long long* __restrict__ hk,
+                              int* __restrict__ hi, int* __restrict__ ctl, int* __restrict__ saved,
+                              int* __restrict__ logbuf, int* __restrict__ seedbuf, int H, int W) {
+  const int hw = H * W;
+  const size_t base = static_cast<size_t>(blockIdx.y) * hw;
+  int* c = ctl + 4 * blockIdx.y;
+  if (c[3] == 0) return;
+  const float* v = val + base;
+  int* o = lab + base;
+  int* sv = saved + base;
+  const int n_roots = c[1];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_roots; t += gridDim.x * blockDim.x) {
+    const int root = roots[base + t];
+    if (clab[base + root] != kWsgTied) continue;
+    const int n = cnt[base + root];
     unsigned long long* k = hk + base + off[base + root];
     int* ix = hi + base + off[base + root];
-    for (int j = 1; j < n; ++j) {  // in-place heap build by successive pushes
-      const unsigned long long ek = k[j];
-      const int ei = ix[j];
-      int cidx = j;
-      while (cidx > 0) {
-        const int parent = (cidx - 1) >> 1;
-        if (!(ek < k[parent])) break;
-        k[cidx] = k[parent];
-        ix[cidx] = ix[parent];
-        cidx = parent;
+    int* lg = logbuf + base + off[base + root];
+    int* sd = seedbuf + base + off[base + root];
+    if (n > kTieMaxSeeds) { atomicExch(&c[2], 1); continue; }
+    // seeds sorted by (value, pixel): tie groups become runs
+    for (int j = 0; j < n; ++j) {
+      const int p = ix[j];
+      const unsigned long long key = wsg_key(v[p], 0u) | static_cast<unsigned>(p);
+      int i = j;
+      while (i > 0) {
+        const int q = sd[i - 1];
+        if ((wsg_key(v[q], 0u) | static_cast<unsigned>(q)) <= key) break;
+        sd[i] = q;
+        --i;
       }
-      k[cidx] = ek;
-      ix[cidx] = ei;
+      sd[i] = p;
     }
-    uint32_t age = 1;
-    unsigned long long last_marker = ~0ull;
-    while (n > 0) {
-      const unsigned long long top = k[0];
-      const int ei = ix[0];
-      if ((top & 0xFFFFFFFFull) == 0) {  // a marker entry
-        if ((top >> 32) == last_marker && multi) { atomicExch(&c[2], 1); break; }
-        last_marker = top >> 32;
-      }
-      --n;
-      if (n > 0) {  // move the last entry to the root and sift down (left child preferred)
-        const unsigned long long xk = k[n];
-        const int xi = ix[n];
-        int i = 0;
-        for (;;) {
-          const int l = 2 * i + 1;
-          if (l >= n) break;
-          int sidx = i;
-          unsigned long long sk = xk;
-          if (k[l] < sk) { sidx = l; sk = k[l]; }
-          if (l + 1 < n && k[l + 1] < sk) { sidx = l + 1; sk = k[l + 1]; }
-          if (sidx == i) break;
-          k[i] = sk;
-          ix[i] = ix[sidx];
-          i = sidx;
+    int g_start[kTieMaxGroups], g_len[kTieMaxGroups], n_groups = 0;
+    long long variants = 1;
+    for (int j = 0; j < n && variants > 0;) {
+      int e = j + 1;
+      while (e < n && wsg_key(v[sd[e]], 0u) == wsg_key(v[sd[j]], 0u)) ++e;
+      if (e - j > 1) {
+        if (n_groups == kTieMaxGroups) { variants = -1; break; }
+        g_start[n_groups] = j;
+        g_len[n_groups] = e - j;
+        ++n_groups;
+        for (int f = 2; f <= e - j && variants > 0; ++f) {
+          variants *= f;
+          if (variants > kTieMaxVariants) variants = -1;
         }
-        k[i] = xk;
-        ix[i] = xi;
       }
-      const int lb = o[ei];
-      const int x = ei % W;
-#define CERB_WSG_PUSH(cond, qq)                                          \
-      if (cond) {                                                        \
-        const int q = (qq);                                              \
-        if (m[q] && o[q] == 0) {                                         \
-          ++age;                                                         \
-          o[q] = lb;                                                     \
-          const unsigned long long ek = wsg_key(v[q], age);              \
-          int cidx = n++;                                                \
-          while (cidx > 0) {                                             \
-            const int parent = (cidx - 1) >> 1;                          \
-            if (!(ek < k[parent])) break;                                \
-            k[cidx] = k[parent];                                         \
-            ix[cidx] = ix[parent];                                       \
-            cidx = parent;                                               \
-          }                                                              \
-          k[cidx] = ek;                                                  \
-          ix[cidx] = q;                                                  \
-        }                                                                \
-      }
-      CERB_WSG_PUSH(ei >= W, ei - W)
-      CERB_WSG_PUSH(x > 0, ei - 1)
-      CERB_WSG_PUSH(x < W - 1, ei + 1)
-      CERB_WSG_PUSH(ei + W < hw, ei + W)
-#undef CERB_WSG_PUSH
+      j = e;
     }
+    if (variants < 0) { atomicExch(&c[2], 1); continue; }
+    bool same = true;
+    for (int var = 0; var < static_cast<int>(variants) && same; ++var) {
+      for (int j = 0; j < n; ++j) {
+        k[j] = wsg_key(v[sd[j]], static_cast<uint32_t>(j));
+        ix[j] = sd[j];
+      }
+      int code = var;
+      for (int g = 0; g < n_groups; ++g) {  // var -> one permutation per group (Lehmer code)
+        int fact = 1;
+        for (int f = 2; f <= g_len[g]; ++f) fact *= f;
+        int idx = code % fact;
+        code /= fact;
+        unsigned used = 0;
+        for (int i = 0; i < g_len[g]; ++i) {
+          fact /= (g_len[g] - i);
+          int sel = idx / fact;
+          idx %= fact;
+          int r = 0;
+          for (;; ++r) {
+            if (used & (1u << r)) continue;
+            if (sel-- == 0) break;
+          }
+          used |= 1u << r;
+          k[g_start[g] + i] = wsg_key(v[sd[g_start[g] + i]], static_cast<uint32_t>(g_start[g] + r));
+        }
+      }
+      int nlog = 0;
+      wsg_flood_component<true>(v, msk + base, o, W, hw, k, ix, n, true, static_cast<uint32_t>(n), lg,
+                                nlog);
+      if (var == 0) {
+        for (int j = 0; j < nlog; ++j) sv[lg[j]] = -o[lg[j]];  // non-marker pixels: saved == 0 so far
+      } else {
+        for (int j = 0; j < nlog && same; ++j) same = (o[lg[j]] == -sv[lg[j]]);
+      }
+      if (same && var + 1 < static_cast<int>(variants))
+        for (int j = 0; j < nlog; ++j) o[lg[j]] = 0;
+    }
+    if (!same) atomicExch(&c[2], 1);
   }
 }
 
@@ -1027,7 +1172,7 @@ __global__ void k_wsg_restore(int* __restrict__ lab, const int* __restrict__ sav
   if (ctl[4 * blockIdx.y + 2] == 0) return;
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x)
-    lab[base + p] = saved[base + p];
+    lab[base + p] = max(saved[base + p], 0);  // k_wsg_certify parks its labels there as negatives
 }
 
 __global__ void k_wsg_flag(const int* __restrict__ ctl, int* __restrict__ run_flag, int n) {
@@ -1214,7 +1359,9 @@ struct Workspace {
   int *heap_a = nullptr, *heap_i = nullptr;
   unsigned long long* heap_k = nullptr;
   int *count = nullptr, *any_fg = nullptr;
-  int* ctl = nullptr;  // [n][4] large-image watershed: pool top, component count, tie flag
+  int* ctl = nullptr;  // [n][4] large-image watershed: pool top, component count, redo flag, tied components
+  int *tie_log = nullptr, *tie_seeds = nullptr;  // large images only: k_wsg_certify scratch planes
+  size_t tie_cap = 0;
   float* canvas = nullptr;
   size_t canvas_elems = 0;
   int* bb = nullptr;
@@ -1445,6 +1592,13 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
     // large images: one thread per mask component, heaps in a global pool (see k_wsg_flood).
     // ws->rank = slice offsets, ws->heap_a = per-root counters / root list is ws->heap_i's upper
     // neighbour ws->m1-free int array: roots go to ws->rank2 (= heap_v reinterpreted as int).
+    if (static_cast<size_t>(n) * hw > ws->tie_cap) {
+      size_t c = 0;
+      CERB_CUDA(grow<int>(ctx, ws->tie_log, c, static_cast<size_t>(n) * hw));
+      c = 0;
+      CERB_CUDA(grow<int>(ctx, ws->tie_seeds, c, static_cast<size_t>(n) * hw));
+      ws->tie_cap = static_cast<size_t>(n) * hw;
+    }
     int* off = ws->rank;
     int* cnt = ws->heap_a;
     int* roots = reinterpret_cast<int*>(ws->heap_v);
@@ -1454,9 +1608,18 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
     CERB_CUDA(cudaMemcpyAsync(ws->size, ws->lab, sizeof(int) * static_cast<size_t>(n) * hw,
                               cudaMemcpyDeviceToDevice, s));
     k_wsg_seed<<<g, kThreads, 0, s>>>(ws->val, msk, ws->L, ws->lab, off, cnt, ws->aux, ws->heap_k,
-                                      ws->heap_i, H, W);
+                                      ws->heap_i, H, W, ws->ctl, 0);
     k_wsg_flood<<<dim3(148 * 8, n), 64, 0, s>>>(ws->val, msk, ws->lab, off, cnt, ws->aux, roots,
                                                 ws->heap_k, ws->heap_i, ws->ctl, H, W);
+    // components that saw a marker tie: all orders of the tied entries (each kernel returns at
+    // once when the image has none)
+    k_wsg_tied_reset<<<g, kThreads, 0, s>>>(msk, ws->L, ws->aux, ws->size, ws->lab, cnt, ws->ctl, hw);
+    k_wsg_seed<<<g, kThreads, 0, s>>>(ws->val, msk, ws->L, ws->lab, off, cnt, ws->aux, ws->heap_k,
+                                      ws->heap_i, H, W, ws->ctl, 1);
+    k_wsg_certify<<<dim3(148 * 8, n), 64, 0, s>>>(ws->val, msk, ws->lab, off, cnt, ws->aux, roots,
+                                                  ws->heap_k, ws->heap_i, ws->ctl, ws->size,
+                                                  ws->tie_log, ws->tie_seeds, H, W);
+    ctx->launches += 3;
     k_wsg_restore<<<g, kThreads, 0, s>>>(ws->lab, ws->size, ws->ctl, hw);
     k_wsg_flag<<<(n + 255) / 256, 256, 0, s>>>(ws->ctl, ws->count, n);
     k_watershed<<<n, 32, 0, s>>>(ws->val, msk, ws->lab, ws->heap_v, ws->heap_a, ws->heap_i, H, W,
@@ -1477,6 +1640,7 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
     for (int i = 0; i < n; ++i) {
       ctx->stat_ws_large += 1;
       ctx->stat_ws_fallback += ctl[4 * i + 2] != 0;
+      ctx->stat_ws_tied += ctl[4 * i + 3];
     }
   }
   return rc;
@@ -1497,6 +1661,7 @@ extern "C" int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name) {
   }
   if (strcmp(name, "ws_large_images") == 0) return ctx->stat_ws_large;
   if (strcmp(name, "ws_large_fallbacks") == 0) return ctx->stat_ws_fallback;
+  if (strcmp(name, "ws_large_tied_components") == 0) return ctx->stat_ws_tied;
   return -1;
 }
 

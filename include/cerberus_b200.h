@@ -215,7 +215,9 @@ int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, int H, int W
  * by the component-parallel nuclei watershed / redone by the exact whole-tile emulation because two
  * markers of one component tie / because the tile exceeds the shared-memory pool (synchronises);
  * "ws_large_images" = images > 65536 px labelled by the component-parallel watershed,
- * "ws_large_fallbacks" = how many of them hit a marker tie and were redone by the exact
+ * "ws_large_tied_components" = mask components of those images in which two marker entries tied
+ * (settled by flooding every order of the tied entries), "ws_large_fallbacks" = images in which
+ * two such orders disagreed (or there were too many) and which were redone by the exact
  * whole-image emulation (host-output calls only). -1 for an unknown name. */
 int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name);
 

@@ -80,3 +80,70 @@ def test_idempotence_property(ctx):
     # labels are exactly 1..K
     ids = np.unique(a[0])
     assert np.array_equal(ids, np.arange(ids.size))
+
+
+def _tie_field(order_matters, seed):
+    """320 x 320 (> 65536 px: the large-image watershed) fields whose every value is unique except
+    for engineered marker ties. Clusters = two 10 x 10 marker squares A, B in one mask rectangle.
+    order_matters=False: the tied marker pixels sit on the far sides of A and B (and a three-way
+    tie A, A, B) - every pop order of the tied entries gives the same labels.
+    order_matters=True: A and B are one pixel apart and the tied pixels face each other with the
+    globally smallest key: whichever pops first labels the gap pixel."""
+    rng = np.random.RandomState(seed)
+    H = W = 320
+    inner = np.zeros((H, W), np.float32)
+    cnt = np.zeros((H, W), np.float32)
+    hi_vals = (0.6 + rng.permutation(70000) * 2.0 ** -18).astype(np.float32)   # markers, unique
+    lo_vals = (0.05 + rng.permutation(100000) * 2.0 ** -18).astype(np.float32)  # gaps, unique
+    hi_i = lo_i = 0
+    ties = []
+    for ci, (y0, x0) in enumerate([(20, 30), (20, 180), (120, 60), (200, 30), (220, 200)]):
+        gap = 1 if order_matters else 6
+        h, w = 24, 10 + gap + 10 + 8
+        cnt[y0:y0 + h, x0:x0 + w] = 0.6
+        reg = inner[y0:y0 + h, x0:x0 + w]
+        reg[...] = lo_vals[lo_i:lo_i + h * w].reshape(h, w)
+        lo_i += h * w
+        ay, ax = y0 + 7, x0 + 4
+        by, bx = y0 + 7, x0 + 4 + 10 + gap
+        for (sy, sx) in ((ay, ax), (by, bx)):
+            inner[sy:sy + 10, sx:sx + 10] = hi_vals[hi_i:hi_i + 100].reshape(10, 10)
+            hi_i += 100
+        if ci >= 3:
+            continue  # clusters without a tie
+        if order_matters:
+            pix = [(ay + 5, ax + 9), (by + 5, bx)]          # facing each other across the gap pixel
+            v = np.float32(0.97 + ci * 0.001)               # larger than every other inner value
+        else:
+            pix = [(ay + 5, ax), (by + 5, bx + 9)]          # far sides
+            if ci == 1:
+                pix.append((ay, ax + 5))                    # three-way tie: 6 orders
+            v = np.float32(0.93 + ci * 0.001)
+        for (y, x) in pix:
+            inner[y, x] = v
+        ties.append(pix)
+    return np.stack([inner, cnt], axis=-1), ties
+
+
+def test_marker_ties_are_settled_by_enumerating_pop_orders(ctx):
+    lib, h = ctx.lib, ctx.handle
+    stat = lambda name: lib.cerb_ctx_stat(h, name)  # noqa: E731
+    for order_matters in (False, True):
+        f, ties = _tie_field(order_matters, seed=3 + order_matters)
+        canvas = np.zeros((1, 320, 320, 2), np.float32)
+        canvas[0] = f
+        before = (stat(b"ws_large_images"), stat(b"ws_large_tied_components"), stat(b"ws_large_fallbacks"))
+        got, any_fg = post_process_batch(ctx, canvas, 0, "Nuclei", 1.0)
+        after = (stat(b"ws_large_images"), stat(b"ws_large_tied_components"), stat(b"ws_large_fallbacks"))
+        ref = po.proc_nuclei(f)
+        assert ref.max() == 10 and np.array_equal(got[0], ref), order_matters
+        assert after[0] - before[0] == 1
+        assert after[1] - before[1] == len(ties) == 3, (before, after)
+        # harmless ties never reach the whole-image emulation; facing ties must
+        assert after[2] - before[2] == (1 if order_matters else 0), (before, after)
+    # the facing-tie field really is order dependent: swapping which marker owns the gap pixel
+    # changes the oracle's answer, so the fallback above was needed
+    f, ties = _tie_field(True, seed=4)
+    ref = po.proc_nuclei(f)
+    (ya, xa), (yb, xb) = ties[0]
+    assert xb - xa == 2 and ref[ya, xa + 1] in (ref[ya, xa], ref[yb, xb]) and ref[ya, xa] != ref[yb, xb]
