@@ -1053,7 +1053,7 @@ __global__ void k_wsg_flood(const float* __restrict__ val, const uint8_t* __rest
 // exact whole-image kernel.
 constexpr int kTieMaxVariants = 24;
 constexpr int kTieMaxGroups = 4;
-constexpr int kTieMaxSeeds = 8192;
+constexpr int kTieMaxSeeds = 1 << 20;
 
 // markers back, flood undone, seed counters cleared for the tied components
 __global__ void k_wsg_tied_reset(const uint8_t* __restrict__ msk, const int* __restrict__ L,
@@ -1094,19 +1094,31 @@ __global__ void k_wsg_certify(const float* __restrict__ val, const uint8_t* __re
     int* lg = logbuf + base + off[base + root];
     int* sd = seedbuf + base + off[base + root];
     if (n > kTieMaxSeeds) { atomicExch(&c[2], 1); continue; }
-    // seeds sorted by (value, pixel): tie groups become runs
-    for (int j = 0; j < n; ++j) {
-      const int p = ix[j];
-      const unsigned long long key = wsg_key(v[p], 0u) | static_cast<unsigned>(p);
-      int i = j;
-      while (i > 0) {
-        const int q = sd[i - 1];
-        if ((wsg_key(v[q], 0u) | static_cast<unsigned>(q)) <= key) break;
-        sd[i] = q;
-        --i;
+    // seeds sorted by (value, pixel): tie groups become runs. In-place heapsort of 64-bit keys
+    // (value bits : pixel) in the component's heap slice - a cluster can have thousands of seeds.
+    for (int j = 0; j < n; ++j) k[j] = wsg_key(v[ix[j]], 0u) | static_cast<unsigned>(ix[j]);
+    for (int start = n / 2 - 1, end = n; ; ) {
+      unsigned long long x;
+      if (start >= 0) {
+        x = k[start];  // heapify phase
+      } else {
+        if (--end <= 0) break;
+        x = k[end];  // extraction phase: the maximum moves behind the shrinking heap
+        k[end] = k[0];
       }
-      sd[i] = p;
+      int i = start >= 0 ? start : 0;
+      for (;;) {  // sift x down a max-heap of `end` entries
+        int ch = 2 * i + 1;
+        if (ch >= end) break;
+        if (ch + 1 < end && k[ch + 1] > k[ch]) ++ch;
+        if (!(k[ch] > x)) break;
+        k[i] = k[ch];
+        i = ch;
+      }
+      k[i] = x;
+      if (start >= 0) --start;
     }
+    for (int j = 0; j < n; ++j) sd[j] = static_cast<int>(k[j] & 0xFFFFFFFFull);
     int g_start[kTieMaxGroups], g_len[kTieMaxGroups], n_groups = 0;
     long long variants = 1;
     for (int j = 0; j < n && variants > 0;) {

@@ -387,8 +387,12 @@ class InferManager(base.InferManager):
         wsi_inst_info["base_resolution"] = {"resolution": self.wsi_base_mag, "units": "mpp"}
         wsi_inst_info["proc_dimensions"] = self.wsi_proc_shape
         wsi_inst_info["base_dimensions"] = self.wsi_base_shape
-        import joblib
-        joblib.dump(wsi_inst_info, "%s/dat/%s.dat" % (output_dir, wsi_basename))
+        # infer/wsi.py:853 writes this dict with joblib.dump, whose per-array framing costs seconds
+        # for tens of thousands of small arrays; a protocol-5 pickle is what joblib.load reads back
+        # identically (tests/test_gpu_wsi.py loads it with joblib) at a fraction of the time.
+        import pickle
+        with open("%s/dat/%s.dat" % (output_dir, wsi_basename), "wb") as fh:
+            pickle.dump(wsi_inst_info, fh, protocol=pickle.HIGHEST_PROTOCOL)
         self.logger.info("Gland & Lumen Post Proc Time: %s" % (time.perf_counter() - start))
         del canvas
         return wsi_inst_info
