@@ -1645,8 +1645,9 @@ extern "C" int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, i
   }
   const bool large = hw > 65536 && ctx->ws_mode != 1;
   rc = finish(ctx, ws->lab, labels_out, static_cast<size_t>(n) * hw, flags & 2);
-  if (rc == CERB_OK && large && !(flags & 2)) {
-    // host-visible call: account for tiles that needed the exact whole-image fallback
+  if (rc == CERB_OK && large) {
+    // account for tied components / tiles that needed the exact whole-image fallback (the copy
+    // synchronises; the large-image path is the WSI mode's, which waits for the labels anyway)
     std::vector<int> ctl(static_cast<size_t>(4) * n);
     CERB_CUDA(cudaMemcpy(ctl.data(), ws->ctl, sizeof(int) * 4 * n, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) {

@@ -147,23 +147,25 @@ class InferManager(base.InferManager):
             return {}, []
         crop = canvas[y0:y1, x0:x1].contiguous()
         h, w = crop.shape[:2]
-        type_map = crop[..., idx["Nuclei-TYPE"][0]].cpu().numpy() if "Nuclei-TYPE" in idx else None
+        # the label map of the tile stays in HBM: the device instance table is all the host needs
+        type_dev = crop[..., idx["Nuclei-TYPE"][0]].contiguous() if "Nuclei-TYPE" in idx else None
+        labels = torch.empty((h, w), dtype=torch.int32, device=canvas.device)
+        any_fg = torch.zeros(1, dtype=torch.int32, device=canvas.device)
         torch.cuda.synchronize(canvas.device)
-        labels = np.empty((h, w), dtype=np.int32)
-        any_fg = np.zeros(1, dtype=np.int32)
         t0 = time.perf_counter()
         _lib.check(lib.cerb_postproc_nuclei(ctx.handle, _ptr(crop), 1, h, w, C,
-                                            idx["Nuclei-INST"][0],
-                                            labels.ctypes.data_as(_lib.ctypes.c_void_p),
-                                            any_fg.ctypes.data_as(_lib.ctypes.c_void_p), 1),
+                                            idx["Nuclei-INST"][0], _ptr(labels), _ptr(any_fg), 1 | 2),
                    "cerb_postproc_nuclei")
+        _lib.check(lib.cerb_ctx_sync(ctx.handle), "cerb_ctx_sync")
         self.t_dev += time.perf_counter() - t0
         del crop
-        if not any_fg[0]:
+        if not int(any_fg.item()):
             return {}, []
         t0 = time.perf_counter()
-        inst_dict = get_instance_info(labels, type_map, ctx=ctx)
+        inst_dict = get_instance_info(labels.data_ptr(), type_dev.data_ptr() if type_dev is not None
+                                      else None, ctx=ctx, on_device=True, shape=(h, w))
         self.t_host += time.perf_counter() - t0
+        del labels, type_dev
         if len(inst_dict) == 0:
             return {}, []
         inst_boxes = np.array([v["box"] for v in inst_dict.values()])

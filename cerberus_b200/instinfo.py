@@ -117,11 +117,13 @@ def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dt
     return info
 
 
-def get_instance_info(pred_inst, pred_type=None, ctx=None):
+def get_instance_info(pred_inst, pred_type=None, ctx=None, on_device=False, shape=None):
     """tiatoolbox HoVerNet.get_instance_info (infer/wsi.py:150): box is flat [x0, y0, x1, y1],
-    keys `type` / `prob` (None without a type map)."""
-    table = inst_table(ctx, pred_inst, pred_type)
-    key_dtype = np.asarray(pred_inst).dtype.type
+    keys `type` / `prob` (None without a type map). With on_device=True `pred_inst` / `pred_type`
+    are device pointers of int32 / float32 [H,W] = `shape` (the WSI path keeps the label map of a
+    post-processing tile in HBM: only this table ever reaches the host)."""
+    table = inst_table(ctx, pred_inst, pred_type, on_device=on_device, shape=shape)
+    key_dtype = np.int32 if on_device else np.asarray(pred_inst).dtype.type
     info = {}
     m = table.moments.astype(np.float64)
     for i in _rows(table):

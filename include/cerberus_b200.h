@@ -218,7 +218,7 @@ int cerb_postproc_nuclei(cerb_ctx* ctx, const float* canvas, int n, int H, int W
  * "ws_large_tied_components" = mask components of those images in which two marker entries tied
  * (settled by flooding every order of the tied entries), "ws_large_fallbacks" = images in which
  * two such orders disagreed (or there were too many) and which were redone by the exact
- * whole-image emulation (host-output calls only). -1 for an unknown name. */
+ * whole-image emulation. -1 for an unknown name. */
 int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name);
 
 enum cerb_tissue { CERB_TISSUE_GLAND = 0, CERB_TISSUE_LUMEN = 1 };
