@@ -1194,11 +1194,16 @@ __global__ void k_wsg_flag(const int* __restrict__ ctl, int* __restrict__ run_fl
 
 // ------------------------------------------------------------------ gland / lumen
 // loader/postproc.py:277-286 / :319-327
+// single != 0: PostProcInstErodedMap (loader/postproc.py:154-155 etc.), one channel > thr
 __global__ void k_gl_threshold(const float* __restrict__ canvas, int C, int ch0, float thr,
-                               uint8_t* __restrict__ fg, int hw) {
+                               uint8_t* __restrict__ fg, int hw, int single) {
   const size_t base = static_cast<size_t>(blockIdx.y) * hw;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
     const float inner = canvas[(base + p) * C + ch0];
+    if (single) {
+      fg[base + p] = inner > thr;
+      continue;
+    }
     const float cnt = canvas[(base + p) * C + ch0 + 1];
     const float c01 = cnt > 0.5f ? 1.0f : 0.0f;
     fg[base + p] = __fsub_rn(inner, c01) > thr;
@@ -1678,22 +1683,16 @@ extern "C" int64_t cerb_ctx_stat(cerb_ctx* ctx, const char* name) {
   return -1;
 }
 
-extern "C" int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int n, int H, int W,
-                                         int C, int ch0, int tissue, double ds_factor,
-                                         int32_t* labels_out, int flags) {
-  if (!ctx || !canvas || !labels_out || n <= 0 || H <= 0 || W <= 0 || C < 2 || ch0 < 0 ||
-      ch0 + 2 > C || (tissue != 0 && tissue != 1) || !(ds_factor > 0.0))
-    return fail(CERB_ERR_ARG, "cerb_postproc_gland_lumen: bad arguments");
+// Shared tail of the per-instance "dilate inside a padded crop, fill holes, paint" post-processing
+// (loader/postproc.py:147-265 and :270-350): threshold -> remove_small_objects -> label -> one
+// block per instance. `single`: the foreground is one channel > thr, else inner - (contour > 0.5).
+static int gl_pipeline(cerb_ctx* ctx, const char* what, const float* canvas, int n, int H, int W,
+                       int C, int ch0, int single, float thr, int k, int min_size,
+                       int32_t* labels_out, int flags) {
   if (static_cast<size_t>(H) * W > static_cast<size_t>(INT_MAX) / 4)
-    return fail(CERB_ERR_ARG, "cerb_postproc_gland_lumen: image too large");
-  // loader/postproc.py:272-275,287 (gland) / :314-317,328 (lumen)
-  const int ksize_ = tissue == 0 ? 11 : 3;
-  const int k = static_cast<int>((ksize_ - 1) * ds_factor);
-  const int min_size = static_cast<int>((tissue == 0 ? 1000 : 150) * (ds_factor * ds_factor));
-  const float thr = tissue == 0 ? 0.55f : 0.5f;
+    return fail(CERB_ERR_ARG, "%s: image too large", what);
   if (k < 1 || k > 32)
-    return fail(CERB_ERR_ARG, "cerb_postproc_gland_lumen: structuring element size %d unsupported "
-                "(ds_factor %g)", k, ds_factor);
+    return fail(CERB_ERR_ARG, "%s: structuring element size %d unsupported", what, k);
   CERB_CUDA(cudaSetDevice(ctx->device));
   const int hw = H * W;
   Workspace* ws = nullptr;
@@ -1705,7 +1704,7 @@ extern "C" int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int
   cudaStream_t s = ctx->stream;
   const dim3 g = grid2(hw, n);
   uint8_t* fg = ws->m0;
-  k_gl_threshold<<<g, kThreads, 0, s>>>(dcanvas, C, ch0, thr, fg, hw);
+  k_gl_threshold<<<g, kThreads, 0, s>>>(dcanvas, C, ch0, thr, fg, hw, single);
   ctx->launches += 1;
   cc_label(ctx, ws, fg, n, H, W, min_size > 0 ? min_size : 0);
   // ws->any_fg doubles as the per-image "has a background pixel" flag here
@@ -1736,6 +1735,35 @@ extern "C" int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int
       ctx->err_flag_dev + 1);
   ctx->launches += 3;
   return finish(ctx, out, labels_out, static_cast<size_t>(n) * hw, flags & 2);
+}
+
+extern "C" int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int n, int H, int W,
+                                         int C, int ch0, int tissue, double ds_factor,
+                                         int32_t* labels_out, int flags) {
+  if (!ctx || !canvas || !labels_out || n <= 0 || H <= 0 || W <= 0 || C < 2 || ch0 < 0 ||
+      ch0 + 2 > C || (tissue != 0 && tissue != 1) || !(ds_factor > 0.0))
+    return fail(CERB_ERR_ARG, "cerb_postproc_gland_lumen: bad arguments");
+  // loader/postproc.py:272-275,287 (gland) / :314-317,328 (lumen)
+  const int ksize_ = tissue == 0 ? 11 : 3;
+  const int k = static_cast<int>((ksize_ - 1) * ds_factor);
+  const int min_size = static_cast<int>((tissue == 0 ? 1000 : 150) * (ds_factor * ds_factor));
+  const float thr = tissue == 0 ? 0.55f : 0.5f;
+  return gl_pipeline(ctx, "cerb_postproc_gland_lumen", canvas, n, H, W, C, ch0, 0, thr, k, min_size,
+                     labels_out, flags);
+}
+
+// PostProcInstErodedMap (loader/postproc.py:147-265): tissue 0 gland (ellipse 11,
+// min size 1500), 1 lumen (3, 150), 2 nuclei (3, 8); foreground = channel ch0 > 0.5.
+extern "C" int cerb_postproc_eroded_map(cerb_ctx* ctx, const float* canvas, int n, int H, int W,
+                                        int C, int ch0, int tissue, int32_t* labels_out,
+                                        int flags) {
+  if (!ctx || !canvas || !labels_out || n <= 0 || H <= 0 || W <= 0 || C < 1 || ch0 < 0 ||
+      ch0 + 1 > C || tissue < 0 || tissue > 2)
+    return fail(CERB_ERR_ARG, "cerb_postproc_eroded_map: bad arguments");
+  const int k = tissue == 0 ? 11 : 3;
+  const int min_size = tissue == 0 ? 1500 : tissue == 1 ? 150 : 8;
+  return gl_pipeline(ctx, "cerb_postproc_eroded_map", canvas, n, H, W, C, ch0, 1, 0.5f, k, min_size,
+                     labels_out, flags);
 }
 
 // infer/tile.py:187-191: lumen *= (gland > 0)

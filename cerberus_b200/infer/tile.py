@@ -22,12 +22,13 @@ import scipy.io as sio
 
 from .. import _lib
 from ..instinfo import get_inst_info_dict
-from ..postproc import PostProcInstErodedContourMap
+from ..postproc import PostProcInstErodedContourMap, PostProcInstErodedMap
 from . import base
 
-# infer/tile.py:35-40 — the IP-ERODED-* (PostProcInstErodedMap) codes are not used by any
-# shipped settings.
+# infer/tile.py:35-40 (the IP-ERODED-3/11 codes are not used by any shipped settings: SURVEY.md 8f-4)
 _postproc_func_dict = {
+    "IP-ERODED-3": PostProcInstErodedMap,
+    "IP-ERODED-11": PostProcInstErodedMap,
     "IP-ERODED-CONTOUR-3": PostProcInstErodedContourMap,
     "IP-ERODED-CONTOUR-11": PostProcInstErodedContourMap,
 }

@@ -1,4 +1,5 @@
-"""Host mirror of loader/postproc.py:268-407 (PostProcInstErodedContourMap) over the C ABI.
+"""Host mirror of loader/postproc.py:147-407 (PostProcInstErodedContourMap, and the
+PostProcInstErodedMap variant of the IP-ERODED-* codes) over the C ABI.
 
 Same call signature and return dtypes as the reference; the arithmetic runs in
 csrc/postproc.cu on the device. No CPU fallback.
@@ -71,6 +72,43 @@ class PostProcInstErodedContourMap:
         if type_ch in list(idx_dict.keys()):
             type_map = raw_map[..., idx_dict[type_ch][0]:idx_dict[type_ch][1]]
             type_map = np.squeeze(type_map)
+        else:
+            type_map = None
+        return inst_map, type_map
+
+
+class PostProcInstErodedMap:
+    """Drop-in for loader/postproc.py:147-265 (target codes IP-ERODED-3 / IP-ERODED-11,
+    infer/tile.py:35-37): `post_process(raw_map, idx_dict, tissue_mode, scale) ->
+    (float64 inst_map, type_map)`; the type map is the raw channel slice (not squeezed), as in
+    the reference. Shares the device context bound to PostProcInstErodedContourMap."""
+
+    _TISSUE = {"GLAND": 0, "LUMEN": 1, "NUCLEI": 2}
+
+    @classmethod
+    def post_process(cls, raw_map, idx_dict, tissue_mode, scale=1.0):
+        ctx = PostProcInstErodedContourMap._ctx
+        if ctx is None:
+            raise RuntimeError("PostProcInstErodedContourMap.bind(ctx) has not been called: the "
+                               "post-processing runs on the CUDA device only")
+        assert tissue_mode.upper() in cls._TISSUE
+        tissue_ch = "%s-INST" % tissue_mode
+        assert tissue_ch in list(idx_dict.keys())
+        raw_map = np.asarray(raw_map)
+        lo, hi = idx_dict[tissue_ch]
+        if hi - lo != 1:
+            raise ValueError("%s must be a single channel for the eroded-map post-processing "
+                             "(the reference's np.squeeze + 2-D label map breaks otherwise)" % tissue_ch)
+        canvas = np.ascontiguousarray(raw_map[None], dtype=np.float32)
+        n, H, W, C = canvas.shape
+        out = np.empty((n, H, W), dtype=np.int32)
+        _lib.check(ctx.lib.cerb_postproc_eroded_map(ctx.handle, _as_ptr(canvas), n, H, W, C, lo,
+                                                    cls._TISSUE[tissue_mode.upper()], _as_ptr(out), 0),
+                   "cerb_postproc_eroded_map")
+        inst_map = out[0].astype(np.float64)  # loader/postproc.py:157,187,217
+        type_ch = tissue_mode + "-" + "TYPE"
+        if type_ch in list(idx_dict.keys()):
+            type_map = raw_map[..., idx_dict[type_ch][0]:idx_dict[type_ch][1]]
         else:
             type_map = None
         return inst_map, type_map

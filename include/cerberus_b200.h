@@ -229,6 +229,14 @@ int cerb_postproc_gland_lumen(cerb_ctx* ctx, const float* canvas, int n, int H, 
                               int ch0, int tissue, double ds_factor, int32_t* labels_out,
                               int flags);
 
+/* PostProcInstErodedMap.post_process (loader/postproc.py:147-265, the "IP-ERODED-3/11" target
+ * codes of infer/tile.py:35-37): foreground = channel ch0 > 0.5,
+ * remove_small_objects (1500 gland / 150 lumen / 8 nuclei), label, per instance dilate with
+ * ELLIPSE 11 / 3 / 3 inside the box padded by 2k (pad skipped at the border), fill holes, paint.
+ * tissue: 0 gland, 1 lumen, 2 nuclei. The reference returns a float64 map. */
+int cerb_postproc_eroded_map(cerb_ctx* ctx, const float* canvas, int n, int H, int W, int C,
+                             int ch0, int tissue, int32_t* labels_out, int flags);
+
 /* infer/tile.py:187-191: lumen *= (gland > 0), both device int32 label maps. */
 int cerb_mask_lumen(cerb_ctx* ctx, int32_t* lumen_dev, const int32_t* gland_dev, size_t elems);
 

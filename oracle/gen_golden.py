@@ -137,6 +137,34 @@ def gen_postproc():
     print("wrote", path, os.path.getsize(path))
 
 
+def gen_postproc_eroded():
+    """PostProcInstErodedMap.post_process (loader/postproc.py:147-265), UNMODIFIED,
+    on the inner channel of every ds = 1 field of postproc.npz, for all three tissues."""
+    from oracle import postproc_oracle as po
+    ref_shim.install(po)
+    from loader.postproc import PostProcInstErodedMap as PP
+    rec = {}
+    names = []
+    for name, tissue0, ds, field in postproc_cases():
+        if ds != 1.0:
+            continue
+        for tissue in ("Gland", "Lumen", "Nuclei"):
+            if tissue != tissue0 and not name.startswith("adv"):
+                continue
+            raw = np.ascontiguousarray(field[..., :1])
+            inst, type_map = PP.post_process(raw, {tissue + "-INST": [0, 1]}, tissue)
+            assert type_map is None and inst.max() < 65536
+            key = "%s/%s/%s" % (name, tissue0, tissue)
+            rec[key + "/inst"] = inst.astype(np.uint16)
+            rec[key + "/dtype"] = np.array(str(inst.dtype))
+            names.append(key)
+            print(key, field.shape, "instances", int(inst.max()), inst.dtype)
+    rec["names"] = np.array(names)
+    path = os.path.join(GOLD, "postproc_eroded.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path))
+
+
 PATCHING_CASES = [(256, 256, 448, 144), (256, 256, 256, 256), (300, 517, 448, 144), (40, 60, 448, 144),
                   (500, 333, 256, 256)]
 
@@ -322,7 +350,7 @@ def gen_instinfo():
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["forward", "patching", "postproc", "stitch", "instinfo"]
+    which = sys.argv[1:] or ["forward", "patching", "postproc", "postproc_eroded", "stitch", "instinfo"]
     for w in which:
         fn = globals().get("gen_" + w)
         if fn is None:

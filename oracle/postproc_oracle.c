@@ -256,24 +256,13 @@ int orc_proc_nuclei(const float* fg, int cs, int H, int W, int32_t* out) {
   return 1;
 }
 
-/* loader/postproc.py:270-309 (tissue 0, gland) / :312-350 (tissue 1, lumen). out: int32
- * (the reference holds the same integers in a float64 map). */
-void orc_proc_gland_lumen(const float* fg, int cs, int H, int W, int tissue, double ds, int32_t* out) {
+/* Shared tail of loader/postproc.py:147-265 (PostProcInstErodedMap) and :270-350
+ * (PostProcInstErodedContourMap gland / lumen): `b` is the thresholded foreground. */
+static void orc_instances_dilate_fill(uint8_t* b, int H, int W, int k, int min_size, int32_t* out) {
   const int hw = H * W;
-  const int ksize_ = tissue == 0 ? 11 : 3;
-  const int k = (int)((ksize_ - 1) * ds);
-  const int min_size = (int)((tissue == 0 ? 1000 : 150) * (ds * ds));
-  const float thr = tissue == 0 ? 0.55f : 0.5f;
   uint8_t* elem = (uint8_t*)malloc((size_t)(k > 0 ? k * k : 1));
   orc_ellipse(k, elem);
-  uint8_t* b = (uint8_t*)malloc((size_t)hw);
   int32_t* lab = (int32_t*)malloc(sizeof(int32_t) * (size_t)hw);
-  for (int p = 0; p < hw; ++p) {
-    const float inner = fg[(size_t)p * cs];
-    const float cnt = fg[(size_t)p * cs + 1] > 0.5f ? 1.0f : 0.0f;
-    const float d = inner - cnt;
-    b[p] = d > thr;
-  }
   orc_label4(b, H, W, lab);           /* remove_small_objects on a bool array labels it first */
   orc_remove_small(lab, hw, min_size);
   for (int p = 0; p < hw; ++p) b[p] = lab[p] != 0;
@@ -312,5 +301,36 @@ void orc_proc_gland_lumen(const float* fg, int cs, int H, int W, int tissue, dou
       for (int x = 0; x < cw; ++x)
         if (fil[y * cw + x]) out[(y1 + y) * W + x1 + x] = id;
   }
-  free(crop); free(dil); free(fil); free(b); free(lab); free(elem);
+  free(crop); free(dil); free(fil); free(lab); free(elem);
+}
+
+/* loader/postproc.py:270-309 (tissue 0, gland) / :312-350 (tissue 1, lumen). out: int32
+ * (the reference holds the same integers in a float64 map). */
+void orc_proc_gland_lumen(const float* fg, int cs, int H, int W, int tissue, double ds, int32_t* out) {
+  const int hw = H * W;
+  const int ksize_ = tissue == 0 ? 11 : 3;
+  const int k = (int)((ksize_ - 1) * ds);
+  const int min_size = (int)((tissue == 0 ? 1000 : 150) * (ds * ds));
+  const float thr = tissue == 0 ? 0.55f : 0.5f;
+  uint8_t* b = (uint8_t*)malloc((size_t)hw);
+  for (int p = 0; p < hw; ++p) {
+    const float inner = fg[(size_t)p * cs];
+    const float cnt = fg[(size_t)p * cs + 1] > 0.5f ? 1.0f : 0.0f;
+    const float d = inner - cnt;
+    b[p] = d > thr;
+  }
+  orc_instances_dilate_fill(b, H, W, k, min_size, out);
+  free(b);
+}
+
+/* loader/postproc.py:147-265 PostProcInstErodedMap: tissue 0 gland (:149-176: ksize 11, min 1500),
+ * 1 lumen (:179-206: 3, 150), 2 nuclei (:209-236: 3, 8); foreground = the single channel > 0.5. */
+void orc_proc_eroded_map(const float* fg, int cs, int H, int W, int tissue, int32_t* out) {
+  const int hw = H * W;
+  const int k = tissue == 0 ? 11 : 3;
+  const int min_size = tissue == 0 ? 1500 : tissue == 1 ? 150 : 8;
+  uint8_t* b = (uint8_t*)malloc((size_t)hw);
+  for (int p = 0; p < hw; ++p) b[p] = fg[(size_t)p * cs] > 0.5f;
+  orc_instances_dilate_fill(b, H, W, k, min_size, out);
+  free(b);
 }

@@ -184,6 +184,28 @@ def proc_gland_lumen(inst_fg, tissue, ds_factor=1.0):
     return out.astype(np.float64)  # loader/postproc.py:290,331
 
 
+def proc_eroded_map(inst_fg, tissue):
+    """PostProcInstErodedMap.__proc_gland / __proc_lumen / __proc_nuclei (loader/postproc.py:149-236)."""
+    fg = np.ascontiguousarray(inst_fg, dtype=np.float32)
+    if fg.ndim == 2:
+        fg = fg[..., None]
+    H, W, c = fg.shape
+    out = np.empty((H, W), dtype=np.int32)
+    lib().orc_proc_eroded_map(_p(fg), c, H, W, {"GLAND": 0, "LUMEN": 1, "NUCLEI": 2}[tissue.upper()],
+                              _p(out))
+    return out.astype(np.float64)  # loader/postproc.py:157,187,217
+
+
+def post_process_eroded(raw_map, idx_dict, tissue_mode, scale=1.0):
+    """PostProcInstErodedMap.post_process (loader/postproc.py:238-265): the type map is the raw
+    channel slice, NOT squeezed."""
+    lo, hi = idx_dict[tissue_mode + "-INST"]
+    inst_map = proc_eroded_map(raw_map[..., lo:hi], tissue_mode)
+    type_ch = tissue_mode + "-TYPE"
+    type_map = raw_map[..., idx_dict[type_ch][0]:idx_dict[type_ch][1]] if type_ch in idx_dict else None
+    return inst_map, type_map
+
+
 def post_process(raw_map, idx_dict, tissue_mode, ds_factor=1.0):
     """loader/postproc.py:383-407."""
     tissue_ch = tissue_mode + "-INST"

@@ -147,3 +147,30 @@ def test_marker_ties_are_settled_by_enumerating_pop_orders(ctx):
     ref = po.proc_nuclei(f)
     (ya, xa), (yb, xb) = ties[0]
     assert xb - xa == 2 and ref[ya, xa + 1] in (ref[ya, xa], ref[yb, xb]) and ref[ya, xa] != ref[yb, xb]
+
+
+def test_eroded_map_postproc_matches_reference_golden(ctx):
+    """PostProcInstErodedMap (IP-ERODED-3/11 codes) through cerb_postproc_eroded_map."""
+    from cerberus_b200.postproc import PostProcInstErodedMap
+    from tests.test_oracle_postproc import eroded_golden_cases
+    bad = []
+    n = 0
+    for key, tissue, field, inst, dtype in eroded_golden_cases():
+        raw = np.zeros(field.shape[:2] + (3,), np.float32)
+        raw[..., 1:2] = field           # channel offset != 0
+        raw[..., 2] = 1.0               # a type channel: returned as a [H,W,1] slice
+        got, typ = PostProcInstErodedMap.post_process(raw, {tissue + "-INST": [1, 2], tissue + "-TYPE": [2, 3]},
+                                                      tissue)
+        assert typ.shape == field.shape[:2] + (1,)
+        if str(got.dtype) != dtype or not np.array_equal(got.astype(np.int64), inst):
+            bad.append((key, int((got.astype(np.int64) != inst).sum())))
+        n += 1
+    assert n >= 70 and not bad, bad
+    # a larger field against the oracle, all three tissues
+    f = synth.postproc_field(600, 700, "Gland", seed=11)[..., :1]
+    for tissue in ("Gland", "Lumen", "Nuclei"):
+        got, _ = PostProcInstErodedMap.post_process(f, {tissue + "-INST": [0, 1]}, tissue)
+        ref, _ = po.post_process_eroded(f, {tissue + "-INST": [0, 1]}, tissue)
+        assert ref.max() > 0 and np.array_equal(got, ref), tissue
+    with pytest.raises(ValueError):
+        PostProcInstErodedMap.post_process(np.zeros((8, 8, 2), np.float32), {"Gland-INST": [0, 2]}, "Gland")

@@ -85,3 +85,30 @@ def test_watershed_c_matches_python_transcription():
         assert np.array_equal(po.watershed_spec(img, mk, mask), po.watershed(img, mk, mask=mask))
 
     run()
+
+
+GOLD_ERODED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "postproc_eroded.npz")
+
+
+def eroded_golden_cases():
+    """(key, tissue, single-channel field [H,W,1], reference label map, dtype): outputs of the
+    UNMODIFIED PostProcInstErodedMap.post_process (oracle/gen_golden.py postproc_eroded) on the
+    inner channel of the ds = 1 fields of postproc.npz."""
+    base = np.load(GOLD)
+    g = np.load(GOLD_ERODED)
+    for key in g["names"]:
+        key = str(key)
+        name, tissue0, tissue = key.split("/")
+        field = (base["%s/%s/field_q12" % (name, tissue0)].astype(np.float32) / 4096.0).astype(np.float32)
+        yield key, tissue, np.ascontiguousarray(field[..., :1]), g[key + "/inst"].astype(np.int64), str(g[key + "/dtype"])
+
+
+def test_eroded_map_oracle_matches_reference_golden():
+    n = with_instances = 0
+    for key, tissue, field, inst, dtype in eroded_golden_cases():
+        got, type_map = po.post_process_eroded(field, {tissue + "-INST": [0, 1]}, tissue)
+        assert str(got.dtype) == dtype and type_map is None, key
+        assert np.array_equal(got.astype(np.int64), inst), key
+        n += 1
+        with_instances += inst.max() > 0
+    assert n >= 70 and with_instances >= 40
