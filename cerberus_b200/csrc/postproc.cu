@@ -270,6 +270,48 @@ __global__ void k_mask_markers(int* __restrict__ lab, const uint8_t* __restrict_
     if (!msk[base + p]) lab[base + p] = 0;
 }
 
+// ---- marker ties that provably cannot matter -----------------------------------------------------
+// Two marker entries a, e of one component with bit-equal values leave the reference's queue in an
+// order fixed by its global heap layout. ws_tie_harmless proves, from the flood itself, that the
+// order is irrelevant. Setting: a and e surfaced back to back - no other entry left the queue in
+// between ("clean"), so every pixel a pushed has a value >= the tie value. a_mask / e_mask: which
+// of the neighbours -W, -1, +1, +W (bits 0..3) each of them labelled and pushed when it surfaced.
+// Harmless iff (1) no pixel pushed by a is 4-adjacent to e (a pixel next to both would get the
+// label of whichever surfaces first), (2) no pixel pushed by e has a value below the tie value (in
+// the other order it would surface - and flood - before a), (3) no pixel pushed by a shares its
+// value with a pixel pushed by e (their ages swap between the two orders; ages only break ties
+// between equal values). Then both orders push the same pixels with the same labels, the age
+// counter ends at the same value, and only the ages of those <= 8 entries are exchanged between
+// entries of different value: every later event is identical. The argument is pairwise, so a
+// group of k tied entries that are pairwise harmless is harmless in all k! orders.
+__device__ __forceinline__ uint32_t ws_valkey(float v) {
+  uint32_t u = __float_as_uint(v);
+  if ((u << 1) == 0) u = 0;  // -0.0 == +0.0
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ int ws_nb(int p, int i, int W) {
+  return i == 0 ? p - W : i == 1 ? p - 1 : i == 2 ? p + 1 : p + W;
+}
+__device__ __noinline__ bool ws_tie_harmless(const float* __restrict__ v, int W, int a,
+                                             unsigned a_mask, int e, unsigned e_mask) {
+  const int ey = e / W, ex = e % W;
+  const uint32_t tie = ws_valkey(v[e]);
+  for (int i = 0; i < 4; ++i) {
+    if (!(a_mask & (1u << i))) continue;
+    const int q = ws_nb(a, i, W);
+    const int dy = q / W - ey, dx = q % W - ex;
+    if (dy * dy + dx * dx == 1) return false;  // (1)
+  }
+  for (int j = 0; j < 4; ++j) {
+    if (!(e_mask & (1u << j))) continue;
+    const uint32_t kr = ws_valkey(v[ws_nb(e, j, W)]);
+    if (kr < tie) return false;  // (2)
+    for (int i = 0; i < 4; ++i)
+      if ((a_mask & (1u << i)) && ws_valkey(v[ws_nb(a, i, W)]) == kr) return false;  // (3)
+  }
+  return true;
+}
+
 // ---- exact emulation of skimage 0.19 watershed_raveled (connectivity 1, no compactness,
 // no watershed line). Ordering is (value, age) with a global push counter, ties between
 // equal keys are decided by the array-heap layout, so the heap itself is reproduced:
@@ -674,8 +716,9 @@ k_watershed_smem(const float* __restrict__ val, const uint8_t* __restrict__ msk,
 // by the global heap layout). Marker pixels without an unlabeled in-mask neighbour push nothing
 // and are inert. So: one thread per mask component floods it with a private heap holding only
 // its boundary markers; markers leave the queue in non-decreasing value order, so a tie shows
-// up as two consecutive marker pops with equal values - the tile is then handed, untouched, to
-// the exact whole-tile emulation above (k_watershed_smem). Results are identical either way.
+// up as two consecutive marker pops with equal values. Most ties provably cannot matter
+// (ws_tie_harmless) and the flood goes on; otherwise the tile is handed, untouched, to the exact
+// whole-tile emulation above (k_watershed_smem). Results are identical either way.
 constexpr int kWcThreads = 256;
 constexpr int kWcPool = 9000;     // heap entries (8 bytes) in shared memory
 constexpr int kWcMaxComp = 1024;
@@ -787,12 +830,26 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
       uint32_t age = 1;
       uint64_t last_marker = ~0ull;
       bool tie = false;
+      // current group of tied marker entries, see ws_tie_harmless
+      int g_pix0 = -1, g_pix1 = -1, g_n = 0;
+      unsigned g_mask0 = 0, g_mask1 = 0;
+      bool g_clean = false;
       while (n > 0) {
         const uint64_t top = hp[0];
         const int ei = static_cast<int>(top & 0xFFFFu);
-        if (((top >> 16) & 0xFFFFu) == 0) {  // a marker entry (age 0)
-          if ((top >> 32) == last_marker && c_lab[k] == -1) { tie = true; break; }
+        const bool is_marker = ((top >> 16) & 0xFFFFu) == 0;  // age 0
+        bool tie_now = false;
+        if (is_marker) {
+          if ((top >> 32) == last_marker && c_lab[k] == -1) {
+            if (!g_clean || g_n >= 3) { tie = true; break; }
+            tie_now = true;
+          } else {
+            g_n = 0;
+            g_clean = true;
+          }
           last_marker = top >> 32;
+        } else {
+          g_clean = false;
         }
         const int x = ei % W;
         const uint16_t lab = lab16[ei];
@@ -801,6 +858,17 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
         const bool c1 = x > 0 && lab16[q1] == 0;
         const bool c2 = x < W - 1 && lab16[q2] == 0;
         const bool c3 = q3 < hw && lab16[q3] == 0;
+        if (is_marker) {
+          const unsigned e_mask = (c0 ? 1u : 0u) | (c1 ? 2u : 0u) | (c2 ? 4u : 0u) | (c3 ? 8u : 0u);
+          if (tie_now && (!ws_tie_harmless(v, W, g_pix0, g_mask0, ei, e_mask) ||
+                          (g_n == 2 && !ws_tie_harmless(v, W, g_pix1, g_mask1, ei, e_mask)))) {
+            tie = true;
+            break;
+          }
+          if (g_n == 0) { g_pix0 = ei; g_mask0 = e_mask; }
+          else if (g_n == 1) { g_pix1 = ei; g_mask1 = e_mask; }
+          ++g_n;
+        }
         float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
         if (c0) v0 = __ldg(v + q0);
         if (c1) v1 = __ldg(v + q1);
@@ -961,13 +1029,30 @@ __device__ __forceinline__ bool wsg_flood_component(const float* __restrict__ v,
     ix[cidx] = ei;
   }
   unsigned long long last_marker = ~0ull;
+  // current group of tied marker entries (first two members) and whether only its members left
+  // the queue since it started: see ws_tie_harmless
+  int g_pix0 = -1, g_pix1 = -1, g_n = 0;
+  unsigned g_mask0 = 0, g_mask1 = 0;
+  bool g_clean = false, tie_now = false;
   while (n > 0) {
     const unsigned long long top = k[0];
     const int ei = ix[0];
-    if (!CERT && (top & 0xFFFFFFFFull) == 0) {  // a marker entry
-      if ((top >> 32) == last_marker && multi) return false;
-      last_marker = top >> 32;
+    if (!CERT) {
+      tie_now = false;
+      if ((top & 0xFFFFFFFFull) == 0) {  // a marker entry
+        if ((top >> 32) == last_marker && multi) {
+          if (!g_clean || g_n >= 3) return false;
+          tie_now = true;
+        } else {
+          g_n = 0;
+          g_clean = true;
+        }
+        last_marker = top >> 32;
+      } else {
+        g_clean = false;
+      }
     }
+    unsigned e_mask = 0;
     --n;
     if (n > 0) {  // move the last entry to the root and sift down (left child preferred)
       const unsigned long long xk = k[n];
@@ -990,12 +1075,13 @@ __device__ __forceinline__ bool wsg_flood_component(const float* __restrict__ v,
     }
     const int lb = o[ei];
     const int x = ei % W;
-#define CERB_WSG_PUSH(cond, qq)                                          \
+#define CERB_WSG_PUSH(cond, qq, bit)                                     \
     if (cond) {                                                          \
       const int q = (qq);                                                \
       if (m[q] && o[q] == 0) {                                           \
         ++age;                                                           \
         o[q] = lb;                                                       \
+        e_mask |= (bit);                                                 \
         if (CERT) log[nlog++] = q;                                       \
         const unsigned long long ek = wsg_key(v[q], age);                \
         int cidx = n++;                                                  \
@@ -1010,11 +1096,20 @@ __device__ __forceinline__ bool wsg_flood_component(const float* __restrict__ v,
         ix[cidx] = q;                                                    \
       }                                                                  \
     }
-    CERB_WSG_PUSH(ei >= W, ei - W)
-    CERB_WSG_PUSH(x > 0, ei - 1)
-    CERB_WSG_PUSH(x < W - 1, ei + 1)
-    CERB_WSG_PUSH(ei + W < hw, ei + W)
+    CERB_WSG_PUSH(ei >= W, ei - W, 1u)
+    CERB_WSG_PUSH(x > 0, ei - 1, 2u)
+    CERB_WSG_PUSH(x < W - 1, ei + 1, 4u)
+    CERB_WSG_PUSH(ei + W < hw, ei + W, 8u)
 #undef CERB_WSG_PUSH
+    if (!CERT && (top & 0xFFFFFFFFull) == 0) {
+      if (tie_now) {  // pairwise against the earlier members of the group
+        if (!ws_tie_harmless(v, W, g_pix0, g_mask0, ei, e_mask)) return false;
+        if (g_n == 2 && !ws_tie_harmless(v, W, g_pix1, g_mask1, ei, e_mask)) return false;
+      }
+      if (g_n == 0) { g_pix0 = ei; g_mask0 = e_mask; }
+      else if (g_n == 1) { g_pix1 = ei; g_mask1 = e_mask; }
+      ++g_n;
+    }
   }
   return true;
 }

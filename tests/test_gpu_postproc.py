@@ -82,22 +82,25 @@ def test_idempotence_property(ctx):
     assert np.array_equal(ids, np.arange(ids.size))
 
 
-def _tie_field(order_matters, seed):
+def _tie_field(order_matters, seed, size=320, equal_pushes=True):
     """320 x 320 (> 65536 px: the large-image watershed) fields whose every value is unique except
     for engineered marker ties. Clusters = two 10 x 10 marker squares A, B in one mask rectangle.
     order_matters=False: the tied marker pixels sit on the far sides of A and B (and a three-way
-    tie A, A, B) - every pop order of the tied entries gives the same labels.
+    tie A, A, B) - every pop order of the tied entries gives the same labels. Two clusters are
+    provably harmless inside the flood (ws_tie_harmless), the third needs the enumeration.
     order_matters=True: A and B are one pixel apart and the tied pixels face each other with the
     globally smallest key: whichever pops first labels the gap pixel."""
     rng = np.random.RandomState(seed)
-    H = W = 320
+    H = W = size
     inner = np.zeros((H, W), np.float32)
     cnt = np.zeros((H, W), np.float32)
     hi_vals = (0.6 + rng.permutation(70000) * 2.0 ** -18).astype(np.float32)   # markers, unique
     lo_vals = (0.05 + rng.permutation(100000) * 2.0 ** -18).astype(np.float32)  # gaps, unique
     hi_i = lo_i = 0
     ties = []
-    for ci, (y0, x0) in enumerate([(20, 30), (20, 180), (120, 60), (200, 30), (220, 200)]):
+    origins = [(20, 30), (20, 180), (120, 60), (200, 30), (220, 200)] if size >= 320 else \
+        [(10, 10), (10, 120), (60, 40), (110, 10), (130, 120)]
+    for ci, (y0, x0) in enumerate(origins):
         gap = 1 if order_matters else 6
         h, w = 24, 10 + gap + 10 + 8
         cnt[y0:y0 + h, x0:x0 + w] = 0.6
@@ -118,6 +121,10 @@ def _tie_field(order_matters, seed):
             pix = [(ay + 5, ax), (by + 5, bx + 9)]          # far sides
             if ci == 1:
                 pix.append((ay, ax + 5))                    # three-way tie: 6 orders
+            if ci == 2 and equal_pushes:
+                # the pixels the two tied markers push first share a value: not provably harmless
+                # (their ages swap with the pop order), so this cluster goes through k_wsg_certify
+                inner[ay + 5, ax - 1] = inner[by + 5, bx + 10] = np.float32(0.3)
             v = np.float32(0.93 + ci * 0.001)
         for (y, x) in pix:
             inner[y, x] = v
@@ -138,7 +145,9 @@ def test_marker_ties_are_settled_by_enumerating_pop_orders(ctx):
         ref = po.proc_nuclei(f)
         assert ref.max() == 10 and np.array_equal(got[0], ref), order_matters
         assert after[0] - before[0] == 1
-        assert after[1] - before[1] == len(ties) == 3, (before, after)
+        # components handed to k_wsg_certify: all three facing ties / only the cluster whose tie the
+        # flood cannot prove harmless on its own
+        assert len(ties) == 3 and after[1] - before[1] == (3 if order_matters else 1), (before, after)
         # harmless ties never reach the whole-image emulation; facing ties must
         assert after[2] - before[2] == (1 if order_matters else 0), (before, after)
     # the facing-tie field really is order dependent: swapping which marker owns the gap pixel
@@ -174,3 +183,20 @@ def test_eroded_map_postproc_matches_reference_golden(ctx):
         assert ref.max() > 0 and np.array_equal(got, ref), tissue
     with pytest.raises(ValueError):
         PostProcInstErodedMap.post_process(np.zeros((8, 8, 2), np.float32), {"Gland-INST": [0, 2]}, "Gland")
+
+
+def test_small_tile_marker_ties_fall_back_only_when_the_order_can_matter(ctx):
+    """<= 65536 px: k_watershed_comp proves most ties harmless inside the flood; facing ties (and
+    ties it cannot prove harmless) go to the exact whole-tile emulation. Bit-exact either way."""
+    lib, h = ctx.lib, ctx.handle
+    stat = lambda name: lib.cerb_ctx_stat(h, name)  # noqa: E731
+    for order_matters, equal_pushes, expect in ((False, False, 0), (False, True, 1), (True, False, 1)):
+        f, ties = _tie_field(order_matters, seed=7 + order_matters, size=240, equal_pushes=equal_pushes)
+        canvas = np.zeros((1, 240, 240, 2), np.float32)
+        canvas[0] = f
+        before = (stat(b"ws_images"), stat(b"ws_tie_fallbacks"))
+        got, _ = post_process_batch(ctx, canvas, 0, "Nuclei", 1.0)
+        after = (stat(b"ws_images"), stat(b"ws_tie_fallbacks"))
+        ref = po.proc_nuclei(f)
+        assert ref.max() == 10 and np.array_equal(got[0], ref), (order_matters, equal_pushes)
+        assert after[0] - before[0] == 1 and after[1] - before[1] == expect, (order_matters, equal_pushes, before, after)
