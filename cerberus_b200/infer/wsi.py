@@ -39,7 +39,8 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..instinfo import get_inst_info_dict, get_instance_info
+from ..instinfo import _rows as instinfo_rows
+from ..instinfo import get_inst_info_dict, inst_table, tiatoolbox_dicts
 from . import base
 from .wsi_geometry import (boxes_intersect, filter_coordinates, get_coordinates, get_tile_info,
                            select_tile_instances)
@@ -67,6 +68,13 @@ def tiatoolbox_bounding_box(img):
 
 def _ptr(t):
     return _lib.ctypes.c_void_p(t.data_ptr())
+
+
+def _unique_ids(n):
+    """n random 128-bit hex keys (the reference draws uuid.uuid4().hex per instance, infer/wsi.py:265;
+    one os.urandom call instead of half a million uuid objects)."""
+    raw = os.urandom(16 * n).hex()
+    return [raw[32 * i:32 * i + 32] for i in range(n)]
 
 
 class InferManager(base.InferManager):
@@ -133,9 +141,10 @@ class InferManager(base.InferManager):
         return canvas
 
     # ------------------------------------------------------------------ nuclei
-    def _process_tile_predictions(self, canvas, tile_bounds, tile_flag, tile_mode, ref_inst_dict,
-                                  margin):
-        """infer/wsi.py:64-268 for one post-processing tile, on the device canvas."""
+    def _process_tile_predictions(self, canvas, tile_bounds, tile_flag, tile_mode, ref_boxes, margin):
+        """infer/wsi.py:64-268 for one post-processing tile, on the device canvas. ref_boxes: [n,4]
+        boxes of the instances accumulated so far (cross tiles replace some of them). Returns the
+        tile's instances keyed by fresh ids and the INDICES into ref_boxes it replaces."""
         eng, ctx, lib = self.engine, self.engine.ctx, self.engine.ctx.lib
         idx = eng.model.idx_dict
         H, W, C = canvas.shape
@@ -148,7 +157,8 @@ class InferManager(base.InferManager):
         crop = canvas[y0:y1, x0:x1].contiguous()
         h, w = crop.shape[:2]
         # the label map of the tile stays in HBM: the device instance table is all the host needs
-        type_dev = crop[..., idx["Nuclei-TYPE"][0]].contiguous() if "Nuclei-TYPE" in idx else None
+        type_map_present = "Nuclei-TYPE" in idx
+        type_dev = crop[..., idx["Nuclei-TYPE"][0]].contiguous() if type_map_present else None
         labels = torch.empty((h, w), dtype=torch.int32, device=canvas.device)
         any_fg = torch.zeros(1, dtype=torch.int32, device=canvas.device)
         torch.cuda.synchronize(canvas.device)
@@ -162,29 +172,22 @@ class InferManager(base.InferManager):
         if not int(any_fg.item()):
             return {}, []
         t0 = time.perf_counter()
-        inst_dict = get_instance_info(labels.data_ptr(), type_dev.data_ptr() if type_dev is not None
-                                      else None, ctx=ctx, on_device=True, shape=(h, w))
-        self.t_host += time.perf_counter() - t0
+        table = inst_table(ctx, labels.data_ptr(), type_dev.data_ptr() if type_dev is not None else None,
+                           on_device=True, shape=(h, w))
         del labels, type_dev
-        if len(inst_dict) == 0:
+        rows = np.asarray(instinfo_rows(table), dtype=np.int64)
+        if len(rows) == 0:
+            self.t_host += time.perf_counter() - t0
             return {}, []
-        inst_boxes = np.array([v["box"] for v in inst_dict.values()])
-        ref_uids = list(ref_inst_dict.keys())
-        ref_boxes = np.array([ref_inst_dict[u]["box"] for u in ref_uids]) if (
-            tile_mode == 3 and ref_uids) else None
+        inst_boxes = table.box[rows][:, [1, 0, 3, 2]]  # tile coordinates, [x0, y0, x1, y1]
         sel, sel_ref = select_tile_instances(inst_boxes, tile_bounds, tile_flag, tile_mode, margin,
-                                             ref_boxes)
-        inst_uids = list(inst_dict.keys())
-        remove_in_tile = set(inst_uids[i] for i in sel)
-        remove_in_orig = [ref_uids[i] for i in sel_ref]
-        new_inst_dict = {}
-        for inst_uid, inst_info in inst_dict.items():
-            if inst_uid not in remove_in_tile:
-                inst_info["box"] = inst_info["box"] + np.concatenate([tile_tl] * 2)
-                inst_info["centroid"] = inst_info["centroid"] + tile_tl
-                inst_info["contour"] = inst_info["contour"] + tile_tl
-                new_inst_dict[uuid.uuid4().hex] = inst_info
-        return new_inst_dict, remove_in_orig
+                                             ref_boxes if tile_mode == 3 else None)
+        keep = np.ones(len(rows), dtype=bool)
+        keep[np.asarray(sel, dtype=np.int64)] = False
+        dicts = tiatoolbox_dicts(table, rows[keep], offset_xy=tile_tl, has_type=type_map_present)
+        new_inst_dict = dict(zip(_unique_ids(len(dicts)), dicts))
+        self.t_host += time.perf_counter() - t0
+        return new_inst_dict, sel_ref
 
     def _postproc_nuclei(self, canvas, patch_outputs, pp_tile_shape, margin):
         """infer/wsi.py:640-686. With several ranks every rank holds the merged canvas; the tiles
@@ -197,23 +200,28 @@ class InferManager(base.InferManager):
         self.t_dev = self.t_host = 0.0
         for set_idx, (set_bounds, set_flags) in enumerate(tile_sets):
             todo = [i for i, tb in enumerate(set_bounds) if len(boxes_intersect(patch_outputs, tb)) > 0]
-            ref = nuclei
-            if world > 1 and set_idx == 3:
-                # cross tiles replace accumulated instances: every rank needs their boxes
-                obj = [[(u, v["box"]) for u, v in nuclei.items()] if rank == 0 else None]
-                dist.broadcast_object_list(obj, src=0)
-                ref = {u: {"box": b} for u, b in obj[0]}
+            # cross tiles (set 3) replace accumulated instances: every tile of the set sees the boxes
+            # accumulated before the set started (the reference submits the whole set at once)
+            ref_uids, ref_boxes = None, None
+            if set_idx == 3:
+                if rank == 0:
+                    ref_uids = list(nuclei.keys())
+                    ref_boxes = np.array([nuclei[u]["box"] for u in ref_uids], dtype=np.int64).reshape(-1, 4)
+                if world > 1:
+                    obj = [ref_boxes]
+                    dist.broadcast_object_list(obj, src=0)
+                    ref_boxes = obj[0]
             local = [(i, self._process_tile_predictions(canvas, set_bounds[i], set_flags[i], set_idx,
-                                                        ref, margin)) for i in todo[rank::world]]
+                                                        ref_boxes, margin)) for i in todo[rank::world]]
             if world > 1:
                 gathered = [None] * world
                 dist.all_gather_object(gathered, local)
                 local = sorted((x for part in gathered for x in part), key=lambda x: x[0])
             if rank == 0:
-                for _, (new_inst_dict, remove_uuid_list) in local:
+                for _, (new_inst_dict, remove_idx_list) in local:
                     nuclei.update(new_inst_dict)
-                    for u in remove_uuid_list:
-                        nuclei.pop(u, None)
+                    for j in remove_idx_list:
+                        nuclei.pop(ref_uids[j], None)
         return nuclei
 
     # ------------------------------------------------------------------ gland / lumen
@@ -282,21 +290,26 @@ class InferManager(base.InferManager):
                     mask_u8.ctypes.data_as(_lib.ctypes.c_void_p),
                     ch_arr.ctypes.data_as(_lib.ctypes.c_void_p), k, _ptr(half), oh, ow),
                     "cerb_region_half")
-                labels = np.empty((oh, ow), dtype=np.int32)
+                labels = torch.empty((oh, ow), dtype=torch.int32, device=dev)
                 _lib.check(lib.cerb_postproc_gland_lumen(
                     ctx.handle, _ptr(half), 1, oh, ow, k, 0, 0 if tissue == "Gland" else 1,
-                    float(ds_factor), labels.ctypes.data_as(_lib.ctypes.c_void_p), 1),
-                    "cerb_postproc_gland_lumen")
-                inst_maps[tissue] = labels.astype(np.float64)  # loader/postproc.py:290,331
-                type_maps[tissue] = half[..., 2].cpu().numpy() if has_type else None
+                    float(ds_factor), _ptr(labels), 1 | 2), "cerb_postproc_gland_lumen")
+                # the label maps stay in HBM; only the instance tables reach the host (the
+                # reference keeps float64 maps, loader/postproc.py:290,331, hence float64 keys)
+                inst_maps[tissue] = labels
+                torch.cuda.synchronize(dev)  # the ctx stream is done with `half` before torch reads it
+                type_maps[tissue] = half[..., 2].contiguous() if has_type else None
                 del half
+            torch.cuda.synchronize(dev)
             # remove lumen predictions not inside glands (:802-807)
-            binary_gland = inst_maps["Gland"].copy()
-            binary_gland[binary_gland > 0] = 1
-            inst_maps["Lumen"] = binary_gland * inst_maps["Lumen"]
+            _lib.check(lib.cerb_mask_lumen(ctx.handle, _ptr(inst_maps["Lumen"]), _ptr(inst_maps["Gland"]),
+                                           oh * ow), "cerb_mask_lumen")
             for tissue in ("Gland", "Lumen"):
-                pred_inst_info = get_inst_info_dict(inst_maps[tissue], type_maps[tissue], ds_factor,
-                                                    ctx=self.engine.ctx)
+                tm = type_maps[tissue]
+                pred_inst_info = get_inst_info_dict(inst_maps[tissue].data_ptr(),
+                                                    tm.data_ptr() if tm is not None else None, ds_factor,
+                                                    ctx=ctx, on_device=True, shape=(oh, ow),
+                                                    key_dtype=np.float64)
                 for inst_id, inst_info in pred_inst_info.items():
                     # Reference quirk kept for drop-in parity (:815-829): `box` is [[r0,c0],[r1,c1]]
                     # but the (x, y) top-left is added to it, i.e. x to the rows and y to the columns.
@@ -393,8 +406,11 @@ class InferManager(base.InferManager):
         # for tens of thousands of small arrays; a protocol-5 pickle is what joblib.load reads back
         # identically (tests/test_gpu_wsi.py loads it with joblib) at a fraction of the time.
         import pickle
+        t_out = time.perf_counter()
         with open("%s/dat/%s.dat" % (output_dir, wsi_basename), "wb") as fh:
             pickle.dump(wsi_inst_info, fh, protocol=pickle.HIGHEST_PROTOCOL)
+        # part of the reference's "Gland & Lumen Post Proc Time" (:853-856); logged on its own too
+        self.logger.info("Output File Time: %s" % (time.perf_counter() - t_out))
         self.logger.info("Gland & Lumen Post Proc Time: %s" % (time.perf_counter() - start))
         del canvas
         return wsi_inst_info

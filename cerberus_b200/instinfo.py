@@ -82,15 +82,45 @@ def _rows(table):
     checks (postproc.py:31-37: fewer than 3 points -> skipped)."""
     first = 0 if table.any_background else 1  # [1:] drops the smallest id when there is no 0
     counts = np.diff(table.contour_off)
-    return [i for i in range(first, len(table.ids)) if counts[i] >= 3]
+    return (np.nonzero(counts[first:] >= 3)[0] + first).tolist()
 
 
-def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dtype=None):
+def tiatoolbox_dicts(table, rows, offset_xy=(0, 0), has_type=True):
+    """Rows of a device table as tiatoolbox-style instance dicts (box flat [x0, y0, x1, y1], int64
+    contours), shifted by `offset_xy` (the tile's top-left in infer/wsi.py:225-227). Every field is
+    computed for all rows at once - half a million nuclei per slide go through here - with the
+    reference's operation order ((m10 / m00 + box origin) + offset in float64)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    off = np.asarray(offset_xy, dtype=np.int64)
+    box = table.box[rows][:, [1, 0, 3, 2]].astype(np.int64)          # x0, y0, x1, y1
+    m = table.moments[rows].astype(np.float64)
+    cen = np.stack([m[:, 1] / m[:, 0], m[:, 2] / m[:, 0]], axis=1)
+    cen = cen + box[:, :2]
+    if off.any():
+        cen = cen + off
+        box = box + np.concatenate([off, off])
+    xy = table.contour_xy.astype(np.int64) + off
+    starts = table.contour_off[rows].tolist()
+    stops = table.contour_off[rows + 1].tolist()
+    if has_type:
+        types = (table.type[rows, 0] / 4.0).astype(np.int64).tolist()  # int(np.float) truncates
+        probs = (table.type[rows, 1] / (table.moments[rows, 0] + 1.0e-6)).tolist()
+    else:
+        types = probs = [None] * len(rows)
+    return [{"box": box[j], "centroid": cen[j], "contour": xy[starts[j]:stops[j]], "prob": probs[j],
+             "type": types[j]} for j in range(len(rows))]
+
+
+def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dtype=None,
+                       on_device=False, shape=None):
     """loader/postproc.py:12-98. `up` folds the cv2.resize(fx=up, fy=up, INTER_NEAREST) of
-    infer/tile.py:196-201 into the call (pass the maps at processing resolution)."""
-    table = inst_table(ctx, inst_map, type_map, up=up)
+    infer/tile.py:196-201 into the call (pass the maps at processing resolution). With
+    on_device=True the maps are device pointers of int32 / float32 [H,W] = `shape` (pass
+    key_dtype: the reference's keys carry the dtype of its label map, e.g. float64 for glands)."""
+    table = inst_table(ctx, inst_map, type_map, up=up, on_device=on_device, shape=shape)
     if key_dtype is None:
-        key_dtype = np.asarray(inst_map).dtype.type  # np.unique keeps the map's dtype
+        key_dtype = np.int32 if on_device else np.asarray(inst_map).dtype.type  # np.unique keeps the dtype
+    has_type = bool(type_map) if on_device else type_map is not None
     info = {}
     m = table.moments.astype(np.float64)
     for i in _rows(table):
@@ -101,7 +131,7 @@ def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dt
         centroid[1] += rmin
         contour = table.contour_xy[table.contour_off[i]:table.contour_off[i + 1]].copy()
         d = {"box": bbox, "centroid": centroid, "contour": contour}
-        if type_map is not None:
+        if has_type:
             d["type"] = int(table.type[i, 0] / 4.0)  # int(np.float) truncates (postproc.py:69)
             d["type_prob"] = float(table.type[i, 1] / (table.moments[i, 0] + 1.0e-6))
         info[key_dtype(table.ids[i])] = d
@@ -120,20 +150,9 @@ def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dt
 def get_instance_info(pred_inst, pred_type=None, ctx=None, on_device=False, shape=None):
     """tiatoolbox HoVerNet.get_instance_info (infer/wsi.py:150): box is flat [x0, y0, x1, y1],
     keys `type` / `prob` (None without a type map). With on_device=True `pred_inst` / `pred_type`
-    are device pointers of int32 / float32 [H,W] = `shape` (the WSI path keeps the label map of a
-    post-processing tile in HBM: only this table ever reaches the host)."""
+    are device pointers of int32 / float32 [H,W] = `shape`."""
     table = inst_table(ctx, pred_inst, pred_type, on_device=on_device, shape=shape)
     key_dtype = np.int32 if on_device else np.asarray(pred_inst).dtype.type
-    info = {}
-    m = table.moments.astype(np.float64)
-    for i in _rows(table):
-        rmin, cmin, rmax, cmax = (int(v) for v in table.box[i])
-        box = np.array([cmin, rmin, cmax, rmax])
-        centroid = np.array([m[i, 1] / m[i, 0], m[i, 2] / m[i, 0]]) + box[:2]
-        contour = table.contour_xy[table.contour_off[i]:table.contour_off[i + 1]].copy()
-        d = {"box": box, "centroid": centroid, "contour": contour, "prob": None, "type": None}
-        if pred_type is not None:
-            d["type"] = int(table.type[i, 0] / 4.0)
-            d["prob"] = float(table.type[i, 1] / (table.moments[i, 0] + 1.0e-6))
-        info[key_dtype(table.ids[i])] = d
-    return info
+    rows = _rows(table)
+    dicts = tiatoolbox_dicts(table, rows, has_type=pred_type is not None)
+    return {key_dtype(table.ids[i]): d for i, d in zip(rows, dicts)}

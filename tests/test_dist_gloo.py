@@ -79,19 +79,18 @@ def _wsi_worker(rank, world, port, out_dir):
     m.patch_output_shape = [144, 144]
     calls = []
 
-    def fake_tile(canvas, tile_bounds, tile_flag, tile_mode, ref_inst_dict, margin):
+    def fake_tile(canvas, tile_bounds, tile_flag, tile_mode, ref_boxes, margin):
         tb = np.asarray(tile_bounds)
         calls.append(tuple(int(v) for v in tb))
         rng = np.random.RandomState(int(tb.sum()) % 100000 + 7 * tile_mode)
         w, h = int(tb[2] - tb[0]), int(tb[3] - tb[1])
         xy = np.stack([rng.randint(0, max(w - 12, 1), 40), rng.randint(0, max(h - 12, 1), 40)], -1)
         boxes = np.concatenate([xy, xy + rng.randint(4, 12, (40, 2))], -1)
-        ref_uids = list(ref_inst_dict.keys())
-        ref_boxes = np.array([ref_inst_dict[u]["box"] for u in ref_uids]) if (tile_mode == 3 and ref_uids) else None
-        sel, sel_ref = select_tile_instances(boxes, tb, tile_flag, tile_mode, margin, ref_boxes)
+        sel, sel_ref = select_tile_instances(boxes, tb, tile_flag, tile_mode, margin,
+                                             ref_boxes if tile_mode == 3 else None)
         new = {"m%d_%d_%d_%d" % (tile_mode, tb[0], tb[1], k): {"box": b + np.concatenate([tb[:2]] * 2)}
                for k, b in enumerate(boxes) if k not in set(sel)}
-        return new, [ref_uids[i] for i in sel_ref]
+        return new, sel_ref  # indices into ref_boxes, resolved to keys on rank 0
 
     m._process_tile_predictions = fake_tile
     _, pout = get_coordinates((1000, 700), [448, 448], [144, 144], [144, 144])

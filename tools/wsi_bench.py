@@ -87,10 +87,16 @@ def main():
     if rank == 0:
         os.makedirs(tmp + "/wsi", exist_ok=True)
         os.makedirs(tmp + "/msk", exist_ok=True)
-        n = -(-size // 256)
+        # H&E-like tiles; above 5120 px a 2560 x 2560 block is repeated (the generator is CPU-bound:
+        # 100 s for the 6241 tiles of a 20000^2 slide; the work per patch does not depend on content)
+        n = min(-(-size // 256), 10)
         tiles = synth.synthetic_tiles(n * n, 256, 256, seed=5)
         slide = tiles.reshape(n, n, 256, 256, 3).transpose(0, 2, 1, 3, 4).reshape(n * 256, n * 256, 3)
+        reps = -(-size // (n * 256))
+        if reps > 1:
+            slide = np.tile(slide, (reps, reps, 1))
         np.save(tmp + "/wsi/slide.npy", np.ascontiguousarray(slide[:size, :size]))
+        del slide
         # seeded blobs, ~40 % coverage, at 1/10 resolution
         rng = np.random.RandomState(0)
         m = cv2.GaussianBlur(rng.rand(size // 10, size // 10).astype(np.float32), (0, 0), size / 160.0)
