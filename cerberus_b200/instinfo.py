@@ -120,6 +120,8 @@ def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dt
     table = inst_table(ctx, inst_map, type_map, up=up, on_device=on_device, shape=shape)
     if key_dtype is None:
         key_dtype = np.int32 if on_device else np.asarray(inst_map).dtype.type  # np.unique keeps the dtype
+        if up != 1 and key_dtype is np.int64:
+            key_dtype = np.int32  # the cv2.resize this call folds in hands int64 maps back as int32
     has_type = bool(type_map) if on_device else type_map is not None
     info = {}
     m = table.moments.astype(np.float64)
