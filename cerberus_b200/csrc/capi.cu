@@ -849,6 +849,10 @@ extern "C" void cerb_ctx_destroy(cerb_ctx* ctx) {
   for (void* p : ctx->scratch) cudaFree(p);
   if (ctx->postproc_ws && ctx->postproc_ws_free) ctx->postproc_ws_free(ctx->postproc_ws);
   if (ctx->instinfo_ws && ctx->instinfo_ws_free) ctx->instinfo_ws_free(ctx->instinfo_ws);
+  for (int i = 0; i < cerb_ctx::kParamSlots; ++i)
+    if (ctx->param_event[i]) cudaEventDestroy(ctx->param_event[i]);
+  if (ctx->param_host) cudaFreeHost(ctx->param_host);
+  if (ctx->param_dev) cudaFree(ctx->param_dev);
   delete ctx;
 }
 

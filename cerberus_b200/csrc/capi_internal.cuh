@@ -42,6 +42,14 @@ struct cerb_ctx {
   std::vector<void*> scratch;  // device allocations owned by the ctx (post-proc workspaces)
   void* postproc_ws = nullptr;             // csrc/postproc.cu Workspace, created on first use
   void (*postproc_ws_free)(void*) = nullptr;
+  // ring of small parameter blocks (patch top-left tables): pinned host slot -> device slot by an
+  // asynchronous copy, so that device-resident tile plumbing calls return without synchronising
+  static constexpr int kParamSlots = 64;
+  static constexpr size_t kParamBytes = 8192;
+  char* param_host = nullptr;
+  char* param_dev = nullptr;
+  cudaEvent_t param_event[kParamSlots] = {};
+  int param_next = 0;
   void* instinfo_ws = nullptr;             // csrc/instinfo.cu Workspace, created on first use
   void (*instinfo_ws_free)(void*) = nullptr;
 };

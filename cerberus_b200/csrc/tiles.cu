@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "capi_internal.cuh"
@@ -222,6 +223,34 @@ struct DevBuf {
 };
 }  // namespace
 
+namespace {
+// Copies a small host array into the next slot of the ctx's parameter ring and returns its device
+// address; the copy is queued on the ctx stream and the slot is reused 64 calls later (its event
+// is waited for then). *dev = nullptr when the array does not fit a slot.
+int stage_params(cerb_ctx* ctx, const void* host, size_t bytes, const void** dev) {
+  *dev = nullptr;
+  if (bytes > cerb_ctx::kParamBytes) return CERB_OK;
+  if (!ctx->param_host) {
+    CERB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->param_host),
+                             cerb_ctx::kParamSlots * cerb_ctx::kParamBytes));
+    CERB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->param_dev),
+                         cerb_ctx::kParamSlots * cerb_ctx::kParamBytes));
+    for (int i = 0; i < cerb_ctx::kParamSlots; ++i)
+      CERB_CUDA(cudaEventCreateWithFlags(&ctx->param_event[i], cudaEventDisableTiming));
+  }
+  const int slot = ctx->param_next;
+  ctx->param_next = (slot + 1) % cerb_ctx::kParamSlots;
+  CERB_CUDA(cudaEventSynchronize(ctx->param_event[slot]));  // never recorded: returns at once
+  char* h = ctx->param_host + slot * cerb_ctx::kParamBytes;
+  char* d = ctx->param_dev + slot * cerb_ctx::kParamBytes;
+  memcpy(h, host, bytes);
+  CERB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CERB_CUDA(cudaEventRecord(ctx->param_event[slot], ctx->stream));
+  *dev = d;
+  return CERB_OK;
+}
+}  // namespace
+
 extern "C" int cerb_extract_patches(cerb_ctx* ctx, const uint8_t* img, int H, int W, int pad_t,
                                     int pad_l, const int32_t* tl_yx, int n, int ph, int pw,
                                     uint8_t* out, int flags) {
@@ -238,8 +267,19 @@ extern "C" int cerb_extract_patches(cerb_ctx* ctx, const uint8_t* img, int H, in
     CERB_CUDA(cudaMemcpyAsync(dimg.p, img, img_bytes, cudaMemcpyHostToDevice, s));
     src = static_cast<const uint8_t*>(dimg.p);
   }
-  CERB_CUDA(cudaMalloc(&dtl.p, sizeof(int) * 2 * n));
-  CERB_CUDA(cudaMemcpyAsync(dtl.p, tl_yx, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, s));
+  // image and patches both resident: nothing of the caller's is read after the call returns
+  // (the top-left table goes through the parameter ring), so the call stays asynchronous
+  const bool resident = (flags & 1) && (flags & 2);
+  const void* tl_dev = nullptr;
+  if (resident) {
+    const int rc = stage_params(ctx, tl_yx, sizeof(int) * 2 * n, &tl_dev);
+    if (rc) return rc;
+  }
+  if (!tl_dev) {
+    CERB_CUDA(cudaMalloc(&dtl.p, sizeof(int) * 2 * n));
+    CERB_CUDA(cudaMemcpyAsync(dtl.p, tl_yx, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, s));
+    tl_dev = dtl.p;
+  }
   uint8_t* dst = out;
   if (!(flags & 2)) {
     CERB_CUDA(cudaMalloc(&dout.p, out_bytes));
@@ -247,13 +287,14 @@ extern "C" int cerb_extract_patches(cerb_ctx* ctx, const uint8_t* img, int H, in
   }
   int gx = (ph * pw + 255) / 256;
   if (gx > 64) gx = 64;
-  k_extract<<<dim3(gx, n), 256, 0, s>>>(src, H, W, pad_t, pad_l, static_cast<const int*>(dtl.p), ph,
+  k_extract<<<dim3(gx, n), 256, 0, s>>>(src, H, W, pad_t, pad_l, static_cast<const int*>(tl_dev), ph,
                                         pw, dst, (flags & 4) ? 1 : 0);
   CERB_CUDA(cudaGetLastError());
   ctx->launches += 1;
   if (!(flags & 2)) {
     CERB_CUDA(cudaMemcpyAsync(out, dst, out_bytes, cudaMemcpyDeviceToHost, s));
   }
+  if (resident && tl_dev != dtl.p) return CERB_OK;
   return cerb_ctx_sync(ctx);  // tl_yx / temporaries are released on return
 }
 
@@ -298,14 +339,21 @@ extern "C" int cerb_scatter_patches(cerb_ctx* ctx, const float* patches_dev, int
   CERB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   DevBuf dtl(ctx);
-  CERB_CUDA(cudaMalloc(&dtl.p, sizeof(int) * 2 * n));
-  CERB_CUDA(cudaMemcpyAsync(dtl.p, tl_yx, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, s));
+  const void* tl_dev = nullptr;
+  const int rc = stage_params(ctx, tl_yx, sizeof(int) * 2 * n, &tl_dev);
+  if (rc) return rc;
+  if (!tl_dev) {
+    CERB_CUDA(cudaMalloc(&dtl.p, sizeof(int) * 2 * n));
+    CERB_CUDA(cudaMemcpyAsync(dtl.p, tl_yx, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, s));
+    tl_dev = dtl.p;
+  }
   int gx = (oh * ow * C + 255) / 256;
   if (gx > 64) gx = 64;
-  k_scatter<<<dim3(gx, n), 256, 0, s>>>(patches_dev, oh, ow, C, static_cast<const int*>(dtl.p),
+  k_scatter<<<dim3(gx, n), 256, 0, s>>>(patches_dev, oh, ow, C, static_cast<const int*>(tl_dev),
                                         canvas_dev, H, W);
   CERB_CUDA(cudaGetLastError());
   ctx->launches += 1;
+  if (tl_dev != dtl.p) return CERB_OK;  // asynchronous: everything involved is device memory
   return cerb_ctx_sync(ctx);
 }
 

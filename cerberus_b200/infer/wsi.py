@@ -131,6 +131,9 @@ class InferManager(base.InferManager):
                 C, tl_out.ctypes.data_as(_lib.ctypes.c_void_p), _ptr(canvas), H, W),
                 "cerb_scatter_patches")
             self.nr_patches_done += k
+        # extract / forward / scatter are queued asynchronously on the ctx stream (the loop above
+        # never waits for the GPU); torch must not touch or free these buffers before it is idle
+        _lib.check(lib.cerb_ctx_sync(ctx.handle), "cerb_ctx_sync")
         if world > 1:
             flat = canvas.view(-1)
             step = 1 << 28  # 1 GiB of float32 per collective

@@ -159,7 +159,10 @@ int cerb_plan_write_tensor(cerb_plan* plan, int tensor_id, int plane, const void
 
 /* ---- tile plumbing (a1/a2/a16) --------------------------------------------------------
  * `flags` bit 0: the input buffer is device memory; bit 1: the output buffer is device
- * memory. Host outputs make the call synchronous. */
+ * memory. A call with a host buffer is synchronous. cerb_extract_patches with both buffers
+ * on the device and cerb_scatter_patches only QUEUE their work on the ctx stream (the host
+ * tl_yx table is copied before they return): order later use with cerb_ctx_sync or by staying
+ * on the ctx stream. */
 
 /* infer/tile.py:64-69 (np.pad "reflect", multi-bounce when the pad exceeds the image) fused
  * with loader/infer_loader.py:57-69 (patch slicing): out[i] = padded[tl[i] : tl[i] + (ph,pw)]

@@ -64,6 +64,7 @@ def test_scatter_writes_each_patch_once_and_clips(ctx):
     tl = np.ascontiguousarray(pout[:, [1, 0]], dtype=np.int32)
     _lib.check(ctx.lib.cerb_scatter_patches(ctx.handle, _dp(pd), len(pout), o, o, C, _vp(tl), _dp(canvas),
                                             H, W), "scatter")
+    _lib.check(ctx.lib.cerb_ctx_sync(ctx.handle), "sync")  # device-resident plumbing calls are asynchronous
     assert np.array_equal(canvas.cpu().numpy(), ref)
 
 
