@@ -409,7 +409,8 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": "tiles/sec (256x256x3) end-to-end incl. post-proc",
+            "metric": "tiles/sec (256x256x3) end-to-end incl. post-proc" if not args.no_postproc
+            else "tiles/sec (256x256x3) forward only (BASELINE config 2; --no-postproc)",
             "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
