@@ -246,13 +246,54 @@ class InferManager(base.InferManager):
                 file_path_list.append(file_path)
         file_path_list.sort()
         assert len(file_path_list) > 0, "Not Detected Any Files From Path"
-        for file_path in file_path_list:
-            img = cv2.imread(file_path)
-            img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
-            results = self.process_image(img, pathlib.Path(file_path).stem)
-            self._save(results, self.output_dir)
-            print("Done Assembling %s" % file_path)
+        # The reference decodes images in DataLoader worker processes (--nr_inference_workers) and
+        # post-processes / saves in a ProcessPoolExecutor (--nr_post_proc_workers). Here every GPU
+        # call stays on this thread (a cerb_ctx is single-threaded); the same two flags size a
+        # loader thread pool (PNG decode of the next images) and a writer thread pool (overlay,
+        # .mat files of the previous images), both of which spend their time inside OpenCV /
+        # scipy.io with the GIL released. 0 workers = everything inline, as in the reference.
+        from concurrent.futures import ThreadPoolExecutor
+        n_load = int(getattr(self, "nr_inference_workers", 0) or 0)
+        n_save = int(getattr(self, "nr_post_proc_workers", 0) or 0)
+        loaders = ThreadPoolExecutor(n_load) if n_load > 0 else None
+        savers = ThreadPoolExecutor(n_save) if n_save > 0 else None
+        ahead = max(2 * n_load, 1)
+        pending_saves = []
+        try:
+            loads = {}
+            for i, file_path in enumerate(file_path_list):
+                if loaders is not None:
+                    for j in range(i, min(i + ahead, len(file_path_list))):
+                        if j not in loads:
+                            loads[j] = loaders.submit(self._load_rgb, file_path_list[j])
+                    img = loads.pop(i).result()
+                else:
+                    img = self._load_rgb(file_path)
+                results = self.process_image(img, pathlib.Path(file_path).stem)
+                if savers is not None:
+                    pending_saves.append((file_path, savers.submit(self._save, results, self.output_dir)))
+                    while len(pending_saves) > 4 * n_save:  # bound the results held in memory
+                        done_path, fut = pending_saves.pop(0)
+                        fut.result()
+                        print("Done Assembling %s" % done_path)
+                else:
+                    self._save(results, self.output_dir)
+                    print("Done Assembling %s" % file_path)
+            for done_path, fut in pending_saves:  # a failed write raises here: no silent crash
+                fut.result()
+                print("Done Assembling %s" % done_path)
+        finally:
+            for pool in (loaders, savers):
+                if pool is not None:
+                    pool.shutdown(wait=True)
         return
+
+    @staticmethod
+    def _load_rgb(file_path):
+        img = cv2.imread(file_path)
+        if img is None:
+            raise IOError("cannot read image %s" % file_path)
+        return cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
 
     @staticmethod
     def _save(results, save_root_dir):

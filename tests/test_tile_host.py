@@ -104,3 +104,47 @@ def test_library_loads_and_exports_every_header_symbol(built_lib):
         h = ctypes.c_void_p()
         rc = built_lib.cerb_ctx_create(0, 0, ctypes.byref(h))
         assert rc == -4 and b"no CPU path" in built_lib.cerb_last_error()
+
+
+def test_process_file_list_overlaps_loading_and_saving_with_threads(tmp_path, monkeypatch):
+    """--nr_inference_workers / --nr_post_proc_workers size loader / writer thread pools; every
+    file is processed once, in order, on the calling thread; a failed write is not swallowed."""
+    import threading
+
+    import cv2
+    from cerberus_b200.infer import tile as tile_mod
+
+    in_dir, out_dir = tmp_path / "in", tmp_path / "out"
+    in_dir.mkdir()
+    for i in range(7):
+        cv2.imwrite(str(in_dir / ("img%d.png" % i)), np.full((8, 9, 3), 10 * i, np.uint8))
+    m = object.__new__(tile_mod.InferManager)
+    main = threading.get_ident()
+    seen, saved = [], []
+
+    def fake_process(img, name="image"):
+        assert threading.get_ident() == main      # device work never leaves the calling thread
+        assert img.shape == (8, 9, 3)
+        seen.append((name, int(img[0, 0, 0])))
+        return (name, img, {}, {}, {}, None)
+
+    def fake_save(results, root):
+        if results[0] == "img5" and fail["on"]:
+            raise RuntimeError("disk full")
+        saved.append((results[0], threading.get_ident() != main))
+
+    fail = {"on": False}
+    monkeypatch.setattr(m, "process_image", fake_process, raising=False)
+    monkeypatch.setattr(tile_mod.InferManager, "_save", staticmethod(fake_save))
+    for workers in (0, 2):
+        seen.clear()
+        saved.clear()
+        m.process_file_list({"input_dir": str(in_dir), "output_dir": str(out_dir), "postproc_list": ["gland"],
+                             "nr_inference_workers": workers, "nr_post_proc_workers": workers})
+        assert seen == [("img%d" % i, 10 * i) for i in range(7)]
+        assert sorted(s[0] for s in saved) == ["img%d" % i for i in range(7)]
+        assert all(s[1] == (workers > 0) for s in saved)
+    fail["on"] = True
+    with pytest.raises(RuntimeError):
+        m.process_file_list({"input_dir": str(in_dir), "output_dir": str(out_dir), "postproc_list": ["gland"],
+                             "nr_inference_workers": 2, "nr_post_proc_workers": 2})
