@@ -120,3 +120,44 @@ def test_rank_strided_batches_cover_every_patch_once():
                 if bi % world == rank:
                     seen[start:start + B] += 1
         assert (seen == 1).all()
+
+
+def test_dat_writer_round_trips_like_a_plain_pickle(tmp_path):
+    """dump_dat (fast ndarray reducer) -> joblib.load / pickle.load give the arrays a plain
+    pickle.dump would: same values, dtypes, shapes, writable and owning their data."""
+    import pickle
+
+    import joblib
+    from cerberus_b200.infer.wsi import dump_dat
+    rng = np.random.RandomState(0)
+    big = rng.randint(0, 1000, (50, 2)).astype(np.int64)
+    obj = {"Nuclei": {"k%d" % i: {"box": np.arange(4) + i, "centroid": rng.rand(2),
+                                  "contour": big[i:i + 7], "prob": 0.25 * i, "type": i}
+                      for i in range(20)},
+           "odd": {"strided": big[::3, 1], "fortran": np.asfortranarray(rng.rand(3, 4)),
+                   "zero_d": np.array(3.5), "empty": np.zeros((0, 2), np.int32),
+                   "bool": rng.rand(5) > 0.5, "f32": rng.rand(2, 3).astype(np.float32),
+                   "obj": np.array([None, "a"], dtype=object),
+                   "struct": np.zeros(2, dtype=[("a", "<i4"), ("b", "<f8")])},
+           "proc_dimensions": np.array([700, 900]), "proc_resolution": {"resolution": 0.5, "units": "mpp"}}
+    path = str(tmp_path / "x.dat")
+    dump_dat(obj, path)
+
+    def same(a, b):
+        if isinstance(a, dict):
+            assert list(a.keys()) == list(b.keys())
+            for k in a:
+                same(a[k], b[k])
+        elif isinstance(a, np.ndarray):
+            assert a.dtype == b.dtype and a.shape == b.shape
+            assert (a == b).all() if a.dtype != object else list(a) == list(b)
+            assert b.flags.writeable
+        else:
+            assert a == b and type(a) is type(b)
+
+    ref = pickle.loads(pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL))
+    for loaded in (joblib.load(path), pickle.load(open(path, "rb"))):
+        same(obj, loaded)
+        same(ref, loaded)
+        loaded["Nuclei"]["k3"]["contour"] += 1  # writable, not a view of anything shared
+        assert loaded["Nuclei"]["k3"]["contour"].flags.owndata
