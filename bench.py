@@ -36,6 +36,10 @@ def parse():
     ap.add_argument("--precision", default="f16", choices=["f16", "f16x2"])
     ap.add_argument("--no-postproc", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-second-precision", action="store_true",
+                    help="skip timing the other precision mode (f16x2 when --precision f16)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (CPU oracle, ~10 s)")
+    ap.add_argument("--parity-tiles", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-batch", type=int, default=4)
     return ap.parse_args()
@@ -110,31 +114,42 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_rate(args, seconds, batch):
-    """The reference's CPU path (oracle restatement: models/run_desc.py:439-502 +
-    loader/postproc.py post_process) on this host's cores. Returns (tiles/s, cores, sample)."""
+def cpu_step_fn(args, batch):
+    """One CPU step of the bench workload on `batch` tiles. Prefers the UNMODIFIED reference
+    modules (oracle/_ref, staged by oracle/make_ref.py; kind "reference"), falls back to the
+    oracle restatement (kind "port"). Returns (callable, kind, description)."""
     import torch
     from cerberus_b200 import synth
-    from oracle import net_oracle
     margs = synth.model_args()
     sd = synth.make_state_dict(seed=0)
     tiles = synth.synthetic_tiles(batch, TILE, TILE, seed=123)
     torch.set_num_threads(host_cores())  # torchrun exports OMP_NUM_THREADS=1
-    cores = torch.get_num_threads()
-    post = None
-    if not args.no_postproc:
-        try:
-            from oracle import pipeline_oracle
-            post = pipeline_oracle.postprocess_step
-        except Exception:
-            post = None
+    from oracle import ref_runner
+    if ref_runner.available() and not os.environ.get("CERB_BENCH_PORT"):
+        ref = ref_runner.ReferenceTilePath(sd, margs)
+        if args.no_postproc:
+            return (lambda: ref.infer_step(tiles, TILE)), "reference", \
+                "unmodified reference create_model + infer_step (models/run_desc.py:439-502)"
+        return (lambda: ref.step_with_labels(tiles)), "reference", \
+            "unmodified reference create_model + infer_step + PostProcInstErodedContourMap.post_process " \
+            "(skimage watershed / remove_small_objects restated in C)"
+    from oracle import net_oracle, pipeline_oracle
 
     def one():
         step, _ = net_oracle.infer_step(sd, tiles, TILE, margs["decoder_kwargs"],
                                         margs["considered_tasks"])
-        if post is not None:
-            post(step, margs)
+        if not args.no_postproc:
+            pipeline_oracle.postprocess_step(step, margs)
 
+    return one, "port", "oracle restatement of infer_step%s" % ("" if args.no_postproc else " + post_process")
+
+
+def cpu_reference_rate(args, seconds, batch):
+    """The reference's CPU path on this host's cores, bounded to `seconds` of work.
+    Returns (tiles/s, cores, sample, kind)."""
+    import torch
+    one, kind, what = cpu_step_fn(args, batch)
+    cores = torch.get_num_threads()
     one()  # warm-up
     t0 = time.perf_counter()
     n = 0
@@ -144,9 +159,8 @@ def cpu_reference_rate(args, seconds, batch):
         if time.perf_counter() - t0 >= seconds:
             break
     dt = time.perf_counter() - t0
-    sample = "%d tiles (batches of %d) of the bench workload, oracle infer_step%s, torch %d threads" % (
-        n, batch, " + post_process" if post is not None else "", cores)
-    return n / dt, cores, sample
+    sample = "%d tiles (batches of %d) of the bench workload: %s, torch %d threads" % (n, batch, what, cores)
+    return n / dt, cores, sample, kind
 
 
 def run_reference(args):
@@ -154,27 +168,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cerberus_b200 import synth
-    from oracle import net_oracle
-    margs = synth.model_args()
-    sd = synth.make_state_dict(seed=0)
     b = args.ref_batch
-    tiles = synth.synthetic_tiles(b, TILE, TILE, seed=123)
-    torch.set_num_threads(host_cores())  # torchrun exports OMP_NUM_THREADS=1
-    post = None
-    if not args.no_postproc:
-        try:
-            from oracle import pipeline_oracle
-            post = pipeline_oracle.postprocess_step
-        except Exception:
-            post = None
-
-    def one():
-        step, _ = net_oracle.infer_step(sd, tiles, TILE, margs["decoder_kwargs"],
-                                        margs["considered_tasks"])
-        if post is not None:
-            post(step, margs)
-
+    one, kind, what = cpu_step_fn(args, b)
     for _ in range(args.warmup):
         one()
     t0 = time.perf_counter()
@@ -183,14 +178,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = b * args.steps / dt
     cores = torch.get_num_threads()
-    sample = "each step = %d tiles of the bench workload on the host CPU (oracle port of the reference path)" % b
+    sample = "each step = %d tiles of the bench workload on the host CPU: %s" % (b, what)
     line = {
         "impl": "reference", "metric": "tiles/sec (256x256x3) end-to-end incl. post-proc",
         "value": val, "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, b, post is not None),
-        "cpu_baseline": {"value": val, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, b, not args.no_postproc),
+        "cpu_baseline": {"value": val, "unit": "tiles/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -208,12 +203,232 @@ def workload_config(args, batch, postproc):
     }
 
 
+class Arm:
+    """One precision mode of the CUDA path on this rank: engine + plan + streaming pipeline."""
+
+    def __init__(self, model, local_rank, precision, batch, postproc):
+        import torch
+        from cerberus_b200.engine import Engine
+        self.eng = Engine(None, None, device=local_rank, precision=precision, packed=model)
+        self.ctx = self.eng.ctx
+        self.precision = precision
+        self.B = batch
+        self.plan = self.eng.plan_for(batch, TILE, TILE, TILE, TILE)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=local_rank)
+        self.pipe = None
+        if postproc:
+            from cerberus_b200.pipeline import TilePipeline
+            self.pipe = TilePipeline(self.eng, batch, TILE, TILE)
+            if os.environ.get("CERB_WS_MODE"):  # robustness experiment: force the exact fallback
+                self.pipe.pctx.set_option("ws_mode", int(os.environ["CERB_WS_MODE"]))
+
+    def launches(self):
+        return self.pipe.launch_count if self.pipe is not None else self.ctx.launch_count
+
+    def step_resident(self, dev_ptr):
+        if self.pipe is not None:  # forward of batch i overlaps the post-processing of batch i-1
+            self.pipe.submit(device_ptr=dev_ptr, download=False)
+        else:
+            self.plan.run(device_ptr=dev_ptr)
+
+    def settle(self):
+        self.ctx.sync()
+        if self.pipe is not None:
+            self.pipe.flush()
+
+    def close(self):
+        if self.pipe is not None:
+            self.pipe.close()
+        self.eng.close()
+
+
+def time_resident(arm, dev_batches, steps, warmup, barrier, forward_only=False):
+    """K steps with the uint8 batches already in HBM; CUDA events on the ctx stream.
+    Returns (ms_total, launches, host_enqueue_ms_per_step)."""
+    import torch
+    n_in = len(dev_batches)
+    run = (lambda i: arm.plan.run(device_ptr=dev_batches[i % n_in].data_ptr())) if forward_only \
+        else (lambda i: arm.step_resident(dev_batches[i % n_in].data_ptr()))
+    for i in range(warmup):
+        run(i)
+    arm.settle()
+    l0 = arm.launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(arm.stream)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        run(i)
+    if arm.pipe is not None and not forward_only:
+        arm.pipe.join_streams()  # the end event on the compute stream then covers the post stream
+    e1.record(arm.stream)
+    enq = 1e3 * (time.perf_counter() - t0) / steps
+    arm.settle()
+    barrier()
+    return e0.elapsed_time(e1), arm.launches() - l0, enq
+
+
+def time_e2e(arm, host_np, steps, warmup, barrier):
+    """K steps through the public API with HOST buffers: every step uploads its uint8 batch and
+    downloads its result (label maps; the fp32 canvas when there is no post-processing). The
+    copies of neighbouring steps overlap the compute (cerberus_b200.pipeline.TilePipeline).
+    Returns (seconds, h2d_bytes_per_step, d2h_bytes_per_step)."""
+    n_in = len(host_np)
+    pipe, plan = arm.pipe, arm.plan
+    if pipe is not None:
+        for i in range(max(2, warmup)):
+            pipe.submit(host_np[i % n_in])
+        pipe.flush()
+        barrier()
+        t0 = time.perf_counter()
+        got = 0
+        for i in range(steps):
+            if pipe.submit(host_np[i % n_in]) is not None:
+                got += 1
+        got += len(pipe.flush())
+        barrier()
+        dt = time.perf_counter() - t0
+        assert got == steps, (got, steps)
+        return dt, int(pipe.h2d_bytes), int(pipe.d2h_bytes)
+    for i in range(max(1, warmup // 2)):
+        plan.run(host_np[i % n_in])
+        plan.read_canvas()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        plan.run(host_np[i % n_in])
+        plan.read_canvas()
+    barrier()
+    dt = time.perf_counter() - t0
+    return dt, int(host_np[0].size), int(arm.B * TILE * TILE * arm.eng.model.canvas_c * 4)
+
+
+def conv_roofline(arm, dev_ptr, peaks):
+    """Roofline of the dominant kernel: per-op CUDA events on the ctx stream (cerb_plan_profile).
+    Dominant = the 64->64 3x3 kernel on the full-resolution layers (largest single share of the
+    step); the aggregate over every conv launch and the per-kind breakdown are reported with it."""
+    from cerberus_b200.engine import profile_ops
+    plan, ctx, B = arm.plan, arm.ctx, arm.B
+    prof = profile_ops(plan, dev_ptr, reps=3)
+    spec = plan.spec
+    dom_ms, dom_fl, dom_n = 0.0, 0.0, 0
+    all_ms, n_conv = 0.0, 0
+    enc_ms, enc_fl = 0.0, 0.0
+    in_encoder = True
+    for (kind, ms_), op in zip(prof, spec.ops):
+        if kind == "pclass":
+            in_encoder = False
+        if kind != "conv":
+            if in_encoder:
+                enc_ms += ms_
+            continue
+        all_ms += ms_
+        n_conv += 1
+        tid = op["in0"] if op["aux_classes"] else op["out"]
+        _, n_, h_, w_, _, _ = spec.tensors[tid]
+        cin = 3 if op["stem"] else op["in_c"]
+        fl = 2.0 * n_ * h_ * w_ * op["cout"] * op["kh"] * op["kw"] * cin
+        if in_encoder:
+            enc_ms += ms_
+            enc_fl += fl
+        if (op["in_c"] == 64 and op["cout"] == 64 and op["kh"] == 3 and op["stride"] == 1
+                and h_ == TILE and w_ == TILE and not op["stem"] and not op["aux_classes"]):
+            dom_ms += ms_
+            dom_n += 1
+            dom_fl += fl
+    flops = spec.conv_flops()
+    achieved = dom_fl / (dom_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    kname = "conv64x_kernel" if ctx.conv64_mode == 3 else "conv64_kernel"
+    if os.path.exists(tpath) and B == 32 and arm.precision == "f16":
+        tj = json.load(open(tpath)).get("%s 256x256 64->64 3x3 batch 32" % kname)
+        if tj:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    agg = flops / (all_ms * 1e-3) / 1e12
+    enc = enc_fl / (enc_ms * 1e-3) / 1e12 if enc_ms > 0 else None
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_burst"],
+            "unit": "TFLOP/s", "frac": achieved / peaks["tensor_burst"], "traffic": traffic,
+            "kernel": ("%s (even/odd N=128 formulation)" % kname if ctx.conv64_mode == 3 else kname)
+            + ", 256x256 64->64 3x3, batch %d: %d launches/step, %.4f ms avg, %.1f GFLOP "
+              "(algorithmic) per launch" % (B, dom_n, dom_ms / max(dom_n, 1), dom_fl / max(dom_n, 1) / 1e9),
+            "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json bf16_tflops): "
+                                             "the kernel is timed alone by per-op events",
+            "frac_of_sustained": achieved / peaks["tensor_sustained"],
+            "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_traffic.json); "
+                            "algorithmic bytes 536.9 MB (fp16 in + out)",
+            "all_convs": {"achieved": agg, "frac": agg / peaks["tensor_burst"],
+                          "launches_per_step": n_conv, "ms_per_step": all_ms,
+                          "gflop_per_step": flops / 1e9},
+            "encoder_stack": {"achieved": enc, "frac": enc / peaks["tensor_burst"] if enc else None,
+                              "ms": enc_ms, "gflop": enc_fl / 1e9,
+                              "note": "prep + stem + maxpool + layer1-4 (SURVEY 8a a3-a9), per-op events"},
+            "step_breakdown_ms": {k: sum(m for kk, m in prof if kk == k)
+                                  for k in sorted(set(k for k, _ in prof))}}, prof
+
+
+def hbm_rooflines(arm, prof, peaks, barrier, reps=10):
+    """HBM-bound stages: extract (uint8 tile -> fp16 NHWC stem input, prep_kernel) and
+    the post-processing chain, against the measured copy bandwidth. Algorithmic bytes per tile:
+    196,608 + 393,216 (extract); 2,359,296 + 786,432 (post-proc)."""
+    import torch
+    B = arm.B
+    out = {}
+    prep_ms = sum(m for k, m in prof if k == "prep")
+    if prep_ms > 0:
+        by = B * (196608 + 393216)
+        a = by / (prep_ms * 1e-3) / 1e9
+        out["extract"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm"], "unit": "GB/s",
+                          "frac": a / peaks["hbm"], "traffic": None, "ms": prep_ms,
+                          "kernel": "prep_kernel, %d tiles per launch (%.1f MB algorithmic)" % (B, by / 1e6)}
+    if arm.pipe is not None:
+        pipe = arm.pipe
+        pstream = torch.cuda.ExternalStream(pipe.pctx.stream, device=arm.ctx.device)
+        post = pipe.post[0]
+        canvas = pipe.canvas_copy[(pipe.k - 1) % pipe.depth]  # canvas of the last submitted batch
+        post.run(arm.plan, canvas_ptr=canvas)
+        pipe.pctx.sync()
+        l0 = pipe.pctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(pstream)
+        for _ in range(reps):
+            post.run(arm.plan, canvas_ptr=canvas)
+        e1.record(pstream)
+        pipe.pctx.sync()
+        ms = e0.elapsed_time(e1) / reps
+        by = B * (2359296 + 786432)
+        a = by / (ms * 1e-3) / 1e9
+        out["postproc"] = {"bound": "hbm", "achieved": a, "peak": peaks["hbm"], "unit": "GB/s",
+                           "frac": a / peaks["hbm"], "traffic": None, "ms": ms,
+                           "launches": (pipe.pctx.launch_count - l0) // reps,
+                           "kernel": "nuclei + gland + lumen post-processing chain of one batch of %d "
+                                     "images, run alone on the post stream (%.1f MB algorithmic)"
+                                     % (B, by / 1e6)}
+    return out
+
+
+def parity_report(arms, sd, margs, n_tiles=4):
+    """BASELINE.md section 5 in the same run: logit error of every timed precision vs the fp32
+    reference forward and vs the net.half() restatement, and the end-to-end label agreement
+    when each side uses its own forward. CPU side: oracle/ (checker only)."""
+    from cerberus_b200 import synth
+    from oracle import parity_report as pr
+    tiles = synth.synthetic_tiles(n_tiles, TILE, TILE, seed=4242)
+    ora = pr.oracle_side(sd, margs, tiles)
+    rep = {"tiles": n_tiles, "tolerance_north_star": 1e-3,
+           "reference": "oracle/net_oracle.py (fp32, pinned to the unmodified reference by "
+                        "tests/golden/forward_*.npz) + oracle post-processing"}
+    for arm in arms:
+        lg, lab = pr.device_side(arm.eng, tiles)
+        rep[arm.precision] = pr.compare(lg, lab, ora)
+    return rep
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from cerberus_b200 import synth
-    from cerberus_b200.engine import Context, ForwardPlan, canvas_to_step_outputs
-    from cerberus_b200.plan import PackedModel, PlanSpec
+    from cerberus_b200.plan import PackedModel
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -225,196 +440,121 @@ def run_ours(args):
     margs = synth.model_args()
     # rank 0 folds + packs the checkpoint; the packed blob is NCCL-broadcast once
     from cerberus_b200.dist import broadcast_packed_model
-    model = PackedModel(synth.make_state_dict(seed=0), margs) if rank == 0 else None
+    sd = synth.make_state_dict(seed=0) if rank == 0 else None
+    model = PackedModel(sd, margs) if rank == 0 else None
     model = broadcast_packed_model(model, margs, rank, world, torch.device("cuda", local_rank))
 
     B = args.batch
-    from cerberus_b200.engine import Engine
-    eng = Engine(None, None, device=local_rank, precision=args.precision, packed=model)
-    ctx = eng.ctx
-    plan = eng.plan_for(B, TILE, TILE, TILE, TILE)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    post = None if args.no_postproc else True
+    postproc = not args.no_postproc
+    arm = Arm(model, local_rank, args.precision, B, postproc)
 
     n_in = 4
     host_batches = [synth.synthetic_tiles(B, TILE, TILE, seed=1000 * rank + i) for i in range(n_in)]
     pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
     dev_batches = [p.cuda() for p in pinned]
+    host_np = [p.numpy() for p in pinned]
     torch.cuda.synchronize()
-
-    pipe = None
-    if post is not None:
-        from cerberus_b200.pipeline import TilePipeline
-        pipe = TilePipeline(eng, B, TILE, TILE)
-        if os.environ.get("CERB_WS_MODE"):  # robustness experiment: force the exact fallback
-            pipe.pctx.set_option("ws_mode", int(os.environ["CERB_WS_MODE"]))
-        post = pipe  # post-processing runs on the pipeline's second context
-
-    def step_resident(i):
-        if pipe is not None:  # forward of batch i overlaps the post-processing of batch i-1
-            pipe.submit(device_ptr=dev_batches[i % n_in].data_ptr(), download=False)
-        else:
-            plan.run(device_ptr=dev_batches[i % n_in].data_ptr())
-
-    def launches_now():
-        return pipe.launch_count if pipe is not None else ctx.launch_count
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step_resident(i)
-    ctx.sync()
-    if pipe is not None:
-        pipe.flush()
-    l0 = launches_now()
+    def over_ranks_max(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    t_host0 = time.perf_counter()
-    for i in range(args.steps):
-        step_resident(i)
-    if pipe is not None:
-        pipe.join_streams()  # the end event on the compute stream then covers the post stream
-    e1.record(stream)
-    host_enqueue_ms = 1e3 * (time.perf_counter() - t_host0) / args.steps
-    ctx.sync()
-    barrier()
+    ms, launches, host_enqueue_ms = time_resident(arm, dev_batches, args.steps, args.warmup, barrier)
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = launches_now() - l0
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    per_rank_ms = [ms]
+    per_rank_ms = [ms / args.steps]
     if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         per_rank_ms = [float(x.item()) / args.steps for x in allt]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    else:
-        per_rank_ms = [ms / args.steps]
-    ms_max = float(t.item())
+    ms_max = over_ranks_max(ms)
     value = world * B * args.steps / (ms_max * 1e-3)
 
-    # ---- e2e: host buffers in, host results out, through the public API. Every step uploads its
-    # uint8 batch from host memory and downloads its result (the label maps); the copies of
-    # neighbouring steps overlap the compute (cerberus_b200.pipeline.TilePipeline).
-    host_np = [p.numpy() for p in pinned]
-    if pipe is not None:
-        for i in range(max(2, args.warmup)):
-            pipe.submit(host_np[i % n_in])
-        pipe.flush()
-        barrier()
-        t0 = time.perf_counter()
-        got = 0
-        for i in range(args.steps):
-            if pipe.submit(host_np[i % n_in]) is not None:
-                got += 1
-        got += len(pipe.flush())
-        barrier()
-        dt = time.perf_counter() - t0
-        assert got == args.steps, (got, args.steps)
-        h2d, d2h = int(pipe.h2d_bytes), int(pipe.d2h_bytes)
-    else:
-        for i in range(max(1, args.warmup // 2)):
-            plan.run(host_np[i % n_in])
-            plan.read_canvas()
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            plan.run(host_np[i % n_in])
-            plan.read_canvas()
-        barrier()
-        dt = time.perf_counter() - t0
-        h2d, d2h = int(pinned[0].numel()), int(B * TILE * TILE * model.canvas_c * 4)
-    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * args.steps / float(t.item())
+    dt, h2d, d2h = time_e2e(arm, host_np, args.steps, args.warmup, barrier)
+    e2e_val = world * B * args.steps / over_ranks_max(dt)
 
-    # ---- roofline of the dominant kernel: per-op CUDA events on the ctx stream (cerb_plan_profile)
-    # Dominant = conv64_kernel on the full-resolution 64->64 3x3 layers (largest single share of
-    # the step); the aggregate over every conv launch is reported next to it.
+    # forward only (BASELINE config 2) in the same run
+    fwd = None
+    if postproc:
+        fms, _, _ = time_resident(arm, dev_batches, args.steps, args.warmup, barrier, forward_only=True)
+        fms = over_ranks_max(fms)
+        fv = world * B * args.steps / (fms * 1e-3)
+        fwd = {"value": fv, "unit": "tiles/s", "ms_per_step": fms / args.steps,
+               "tflops": fv * GFLOP_PER_TILE_6HEAD / 1e3, "note": "BASELINE config 2: forward only, "
+               "batch resident in HBM, CUDA events"}
+
     peaks = load_peaks()
-    roof = None
+    roof, hbm = None, None
     try:
-        from cerberus_b200 import _lib as L_
-        from cerberus_b200.engine import profile_ops
-        prof = profile_ops(plan, dev_batches[0].data_ptr(), reps=3)
-        spec = plan.spec
-        dom_ms, dom_fl, dom_n = 0.0, 0.0, 0
-        all_ms, n_conv = 0.0, 0
-        for (kind, ms_), op in zip(prof, spec.ops):
-            if kind != "conv":
-                continue
-            all_ms += ms_
-            n_conv += 1
-            tid = op["in0"] if op["aux_classes"] else op["out"]
-            _, n_, h_, w_, _, _ = spec.tensors[tid]
-            if (op["in_c"] == 64 and op["cout"] == 64 and op["kh"] == 3 and op["stride"] == 1
-                    and h_ == TILE and w_ == TILE and not op["stem"] and not op["aux_classes"]):
-                dom_ms += ms_
-                dom_n += 1
-                dom_fl += 2.0 * n_ * h_ * w_ * 64 * 576
-        flops = spec.conv_flops()
-        achieved = dom_fl / (dom_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath) and B == 32:
-            tj = json.load(open(tpath)).get("%s 256x256 64->64 3x3 batch 32" % (
-                "conv64x_kernel" if ctx.conv64_mode == 3 else "conv64_kernel"))
-            if tj:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        agg = flops / (all_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"], "traffic": traffic,
-                "kernel": ("conv64x_kernel (even/odd N=128 formulation)" if ctx.conv64_mode == 3
-                           else "conv64_kernel") + ", 256x256 64->64 3x3, batch %d: %d launches/step, %.4f ms avg, "
-                          "%.1f GFLOP (algorithmic) per launch" % (B, dom_n, dom_ms / max(dom_n, 1),
-                                                                   dom_fl / max(dom_n, 1) / 1e9),
-                "peak_source": peaks["source"] + " bf16 cuBLAS sustained (kernel timed inside a long step)",
-                "frac_of_burst": achieved / peaks["tensor_burst"],
-                "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_traffic.json); "
-                                "algorithmic bytes 536.9 MB (fp16 in + out)",
-                "all_convs": {"achieved": agg, "frac": agg / peaks["tensor_sustained"],
-                              "launches_per_step": n_conv, "ms_per_step": all_ms,
-                              "gflop_per_step": flops / 1e9},
-                "step_breakdown_ms": {k: sum(m for kk, m in prof if kk == k)
-                                      for k in sorted(set(k for k, _ in prof))}}
+        roof, prof = conv_roofline(arm, dev_batches[0].data_ptr(), peaks)
+        if fwd is not None:
+            fwd["frac_of_burst"] = fwd["tflops"] / world / peaks["tensor_burst"]
+        hbm = hbm_rooflines(arm, prof, peaks, barrier)
     except Exception as e:  # profiling is evidence, never a reason to lose the line
-        roof = {"bound": "tensor", "achieved": None, "peak": peaks["tensor_sustained"],
+        roof = {"bound": "tensor", "achieved": None, "peak": peaks["tensor_burst"],
                 "unit": "TFLOP/s", "frac": None, "traffic": None, "error": str(e)}
 
     ws_stats = None
-    if pipe is not None:
-        pl = pipe.pctx
+    if arm.pipe is not None:
+        pl = arm.pipe.pctx
         imgs = int(pl.lib.cerb_ctx_stat(pl.handle, b"ws_images"))
         ws_stats = {"images": imgs,
                     "exact_fallback_tie": int(pl.lib.cerb_ctx_stat(pl.handle, b"ws_tie_fallbacks")),
                     "exact_fallback_capacity": int(pl.lib.cerb_ctx_stat(pl.handle, b"ws_capacity_fallbacks")),
                     "note": "nuclei watershed, all steps incl. warm-up and e2e: images handled by the "
                             "component-parallel path vs redone by the exact whole-tile emulation"}
-    if world > 1 and pipe is not None:  # which ranks were slowed by exact-watershed images
-        mine = torch.tensor([float(ws_stats["exact_fallback_tie"])], device="cuda", dtype=torch.float64)
-        allw = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allw, mine)
-        ws_stats["exact_fallback_tie_per_rank"] = [int(x.item()) for x in allw]
+        if world > 1:  # which ranks were slowed by exact-watershed images
+            mine = torch.tensor([float(ws_stats["exact_fallback_tie"])], device="cuda", dtype=torch.float64)
+            allw = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allw, mine)
+            ws_stats["exact_fallback_tie_per_rank"] = [int(x.item()) for x in allw]
+
+    # ---- the other precision mode, timed in the same invocation (fewer steps)
+    other = None
+    arms = [arm]
+    other_prec = "f16x2" if args.precision == "f16" else "f16"
+    if not args.no_second_precision:
+        arm2 = Arm(model, local_rank, other_prec, B, postproc)
+        arms.append(arm2)
+        k2, w2 = max(3, args.steps // 2), max(3, args.warmup)
+        ms2, l2, _ = time_resident(arm2, dev_batches, k2, w2, barrier)
+        ms2 = over_ranks_max(ms2)
+        dt2, _, _ = time_e2e(arm2, host_np, k2, w2, barrier)
+        dt2 = over_ranks_max(dt2)
+        other = {"value": world * B * k2 / (ms2 * 1e-3), "unit": "tiles/s", "ms_per_step": ms2 / k2,
+                 "steps": k2, "warmup": w2, "gpu_launches": int(l2),
+                 "e2e": {"value": world * B * k2 / dt2, "unit": "tiles/s"},
+                 "dtype": other_prec}
+
+    parity = None
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_reference_rate(args, args.cpu_seconds, args.ref_batch)
-        cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0 and world == 1:
+        if not args.no_parity:
+            try:
+                parity = parity_report(arms, sd, margs, args.parity_tiles)
+            except Exception as e:
+                parity = {"error": "%s: %s" % (type(e).__name__, e)}
+        if not args.no_cpu_baseline:
+            v, cores, sample, kind = cpu_reference_rate(args, args.cpu_seconds, args.ref_batch)
+            cpu = {"value": v, "unit": "tiles/s", "cores": cores, "kind": kind, "sample": sample}
 
     if rank == 0:
         line = {
-            "metric": "tiles/sec (256x256x3) end-to-end incl. post-proc" if not args.no_postproc
+            "metric": "tiles/sec (256x256x3) end-to-end incl. post-proc" if postproc
             else "tiles/sec (256x256x3) forward only (BASELINE config 2; --no-postproc)",
             "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": workload_config(args, B, post is not None),
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(args, B, postproc),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
@@ -423,10 +563,16 @@ def run_ours(args):
             "ms_per_step_per_rank": per_rank_ms,
             "watershed": ws_stats,
             "roofline": roof,
+            "roofline_hbm": hbm,
+            "forward_only": fwd,
+            other_prec: other,
+            "parity": parity,
             "cpu_baseline": cpu,
             "tflops_forward": value * GFLOP_PER_TILE_6HEAD / 1e3,
         }
         print(json.dumps(line))
+    for a in arms:
+        a.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -358,10 +358,14 @@ __global__ void pclass_kernel(PClassParams p) {
   const int h4 = p.x4.h, w4 = p.x4.w;
   int y0 = 0, x0 = 0, ch = h4, cw = w4;
   if (h4 != 9 && w4 != 9) {  // models/net_desc.py:173 (note the `and`)
-    y0 = static_cast<int>((h4 - 9) * 0.5);
-    x0 = static_cast<int>((w4 - 9) * 0.5);
-    ch = 9;
-    cw = 9;
+    // cropping_center (models/utils/misc_utils.py:6-25) is the Python slice
+    // x[h0 : h0 + 9] with h0 = int((H - 9) * 0.5): for maps smaller than 9 the stop is clamped
+    // to H and a NEGATIVE start counts from the end (H = 8 -> rows 0..7, H = 6 -> row 5 only)
+    const int hy = static_cast<int>((h4 - 9) * 0.5), hx = static_cast<int>((w4 - 9) * 0.5);
+    y0 = hy < 0 ? max(h4 + hy, 0) : hy;
+    x0 = hx < 0 ? max(w4 + hx, 0) : hx;
+    ch = max(min(hy + 9, h4) - y0, 0);
+    cw = max(min(hx + 9, w4) - x0, 0);
   }
   const float* bn_s = p.params;
   const float* bn_b = bn_s + 512;

@@ -392,7 +392,9 @@ class InferManager(base.InferManager):
         self.last_canvas = canvas if getattr(self, "keep_canvas", False) else None
         wsi_inst_info = {}
         start = time.perf_counter()
-        margin = int(getattr(self, "ambiguous_size", 64))
+        # hard-coded in both IOSegmentorConfigs of the reference (infer/wsi.py:898,909), which
+        # ignores --ambiguous_size; `_test_margin` is a test hook only
+        margin = int(getattr(self, "_test_margin", 64))
         wsi_inst_info["Nuclei"] = self._postproc_nuclei(canvas, patch_outputs,
                                                         self.postproc_tile_shape, margin)
         self.logger.info("Nuclei Post Proc Time: %s" % (time.perf_counter() - start))
@@ -458,7 +460,10 @@ class InferManager(base.InferManager):
             else self.patch_input_shape
         self.patch_output_shape = [144, 144] if not getattr(self, "honour_patch_shapes", False) \
             else self.patch_output_shape
-        self.postproc_tile_shape = [int(getattr(self, "postproc_tile_shape", 4096))] * 2
+        # run_args may carry a scalar `postproc_tile_shape` (test hook; the reference hard-codes
+        # 4096): keep the scalar, derive the list, so that a second call on this manager works
+        self._pp_tile = int(run_args.get("postproc_tile_shape", getattr(self, "_pp_tile", 4096)))
+        self.postproc_tile_shape = [self._pp_tile] * 2
         self.imgs = self.input_list
         self.masks = self.mask_list
         from ..postproc import PostProcInstErodedContourMap

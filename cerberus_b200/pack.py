@@ -61,6 +61,39 @@ def split_f16(x):
     return hi, lo
 
 
+def round_f16_diffused(w):
+    """fp16 rounding of a weight tensor [O, I, kh, kw] with error diffusion along K.
+
+    Round-to-nearest leaves every weight with an independent error of up to half an ulp; a
+    post-ReLU input channel has a large positive mean (and is smooth over the 3x3 window), so
+    those errors add up COHERENTLY: sum_k dw[o,k] * mean_k is a constant offset per output
+    channel that the next 50 layers amplify. Measured on the six-head model
+    (tools/precision_study.py): weight rounding alone costs 0.23 max-abs on the logits, the
+    fp16 activations only 0.04. Here the rounding error of each weight is carried into the
+    next one of the same output channel, walking K as (input channel, tap), so the sum of the
+    errors over the nine taps of one input channel - and over the whole row - stays below one
+    ulp: 0.23 -> 0.04 at zero run-time cost. The residual w - hi still fits the lo plane."""
+    w = np.asarray(w, dtype=np.float64)
+    o = w.shape[0]
+    flat = w.reshape(o, -1)
+    hi = np.empty(flat.shape, dtype=np.float16)
+    carry = np.zeros(o, dtype=np.float64)
+    for k in range(flat.shape[1]):
+        want = flat[:, k] + carry
+        r = want.astype(np.float16)
+        carry = want - r.astype(np.float64)
+        hi[:, k] = r
+    return hi.reshape(w.shape)
+
+
+def split_f16_diffused(w):
+    """[O, I, kh, kw] -> (hi, lo): hi by error diffusion along K, lo = fp16(w - hi)."""
+    w = np.asarray(w, dtype=np.float64)
+    hi = round_f16_diffused(w)
+    lo = (w - hi.astype(np.float64)).astype(np.float16)
+    return hi, lo
+
+
 def weight_shift(w):
     """Power-of-two pre-scale: max|w * 2^shift| lands in [256, 512], far from fp16 subnormals
     (so the lo plane keeps its precision) and far from overflow."""
@@ -74,9 +107,10 @@ def pack_conv(blob, w, b):
     """w [O,I,kh,kw] float64 (BN folded) -> K-major [O][kh*kw][I] fp16 hi/lo; b -> fp32.
     Returns dict(w_off, w_lo_off, b_off, cout, cin, kh, kw)."""
     o, i, kh, kw = w.shape
-    km = np.transpose(w, (0, 2, 3, 1)).reshape(o, kh * kw * i)
-    sh = weight_shift(km)
-    hi, lo = split_f16(np.ldexp(km, sh))
+    sh = weight_shift(w)
+    hi, lo = split_f16_diffused(np.ldexp(w, sh))
+    km = lambda a: np.ascontiguousarray(np.transpose(a, (0, 2, 3, 1)).reshape(o, kh * kw * i))  # noqa: E731
+    hi, lo = km(hi), km(lo)
     out = {"w_off": blob.add(hi), "w_lo_off": blob.add(lo), "cout": o, "cin": i, "kh": kh, "kw": kw,
            "w_shift": sh}
     out["b_off"] = blob.add(b.astype(np.float32)) if b is not None else -1
@@ -91,10 +125,15 @@ def pack_stem(blob, w, b):
     o, i, kh, kw = w.shape
     assert (i, kh, kw) == (3, 7, 7)
     w = w / 255.0
-    km = np.zeros((o, 7, 8, 8), dtype=np.float64)
-    km[:, :, :7, :3] = np.transpose(w, (0, 2, 3, 1))
-    sh = weight_shift(km)
-    hi, lo = split_f16(np.ldexp(km.reshape(o, 7 * 64), sh))
+    sh = weight_shift(w)
+    whi, wlo = split_f16_diffused(np.ldexp(w, sh))
+
+    def km(a):
+        out = np.zeros((o, 7, 8, 8), dtype=np.float16)
+        out[:, :, :7, :3] = np.transpose(a, (0, 2, 3, 1))
+        return out.reshape(o, 7 * 64)
+
+    hi, lo = km(whi), km(wlo)
     return {"w_off": blob.add(hi), "w_lo_off": blob.add(lo), "b_off": blob.add(b.astype(np.float32)),
             "cout": o, "cin": 3, "kh": 7, "kw": 7, "w_shift": sh}
 

@@ -47,11 +47,43 @@ def cropping_center_nhwc(x, crop_shape):
     return x[:, h0:h0 + crop_shape[0], w0:w0 + crop_shape[1]]
 
 
-def forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, return_feats=False):
+def forward_half(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks):
+    """The same forward as `net.half()` would compute it ("vs net.half()
+    reference"): parameters and the input rounded to fp16, every module output (conv, BN, ReLU,
+    add, interpolate, pool) rounded to fp16, arithmetic inside a module in fp32 - which is
+    what cuDNN / ATen half kernels do (fp32 accumulation, fp16 storage). Returns fp32 logits."""
+    return forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, _half=True)
+
+
+def _half_ops(enabled):
+    """(F-like namespace, rounding function): every call's result goes through fp16."""
+    if not enabled:
+        return F, (lambda t: t), _bn
+
+    def r(t):
+        return t.half().float()
+
+    class H:
+        conv2d = staticmethod(lambda *a, **k: r(F.conv2d(*a, **k)))
+        relu = staticmethod(lambda x: r(F.relu(x)))
+        max_pool2d = staticmethod(lambda *a, **k: F.max_pool2d(*a, **k))
+        interpolate = staticmethod(lambda *a, **k: r(F.interpolate(*a, **k)))
+        adaptive_avg_pool2d = staticmethod(lambda *a, **k: r(F.adaptive_avg_pool2d(*a, **k)))
+
+    return H, r, (lambda x, sd, p, eps=1e-5: r(_bn(x, sd, p, eps)))
+
+
+def forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, return_feats=False, _half=False):
     """imgs: float32 NCHW in 0..255. Returns OrderedDict head -> NCHW logits (net_desc.py:198)."""
     sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    if _half:
+        sd = {k: (v.half().float() if v.is_floating_point() else v) for k, v in sd.items()}
+    return _forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, return_feats, *_half_ops(_half))
+
+
+def _forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, return_feats, F, r, _bn):  # noqa: N803
     with torch.no_grad():
-        x = imgs_nchw_f32 / 255.0  # net_desc.py:147
+        x = r(r(imgs_nchw_f32) / 255.0)  # net_desc.py:147
         x = F.conv2d(x, sd["backbone.conv1.weight"], None, 1, 3)  # resnet.py:195-197 (stride 1!)
         x0 = x = F.relu(_bn(x, sd, "backbone.bn1"))
         x = F.max_pool2d(x, 3, 2, 1)  # resnet.py:201
@@ -69,7 +101,7 @@ def forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, return_feats=Fa
                     idn = _bn(idn, sd, p + ".downsample.1")
                 else:
                     idn = x
-                x = F.relu(out + idn)
+                x = F.relu(r(out + idn))
             feats.append(x)
         bottom = feats[-1]
         feat_list = list(feats)
@@ -94,7 +126,7 @@ def forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, return_feats=Fa
             prev = feat_list[-1]
             for idx in range(1, len(feat_list)):  # net_desc.py:184-189
                 prev = F.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=False)
-                prev = feat_list[-(idx + 1)] + prev
+                prev = r(feat_list[-(idx + 1)] + prev)
                 for cv in range(2):
                     p = "decoder_head.%s.%d.block.%d" % (d, idx - 1, cv)
                     prev = F.conv2d(prev, sd[p + ".conv.weight"], sd[p + ".conv.bias"], 1, 1)

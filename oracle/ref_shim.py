@@ -17,9 +17,12 @@ import types
 REF = "/root/reference"
 
 
-def install(skimage_impl=None):
-    if not os.path.isdir(REF):
-        raise RuntimeError("%s is not present: goldens can only be regenerated in the build container" % REF)
+def install(skimage_impl=None, ref=None):
+    """`ref`: directory holding the reference packages (default /root/reference; the CPU arm of
+    bench.py passes the staged copy oracle/_ref on the GPU box)."""
+    ref = ref or REF
+    if not os.path.isdir(ref):
+        raise RuntimeError("%s is not present: goldens can only be regenerated in the build container" % ref)
     sys.dont_write_bytecode = True
     import numpy as np
     import scipy
@@ -66,5 +69,5 @@ def install(skimage_impl=None):
 
         to._cerb_cpu_shim = True
         torch.Tensor.to = to
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    if ref not in sys.path:
+        sys.path.insert(0, ref)

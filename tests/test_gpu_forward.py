@@ -66,20 +66,48 @@ def test_logits_match_reference_golden_f16x2(name, built_lib):
     eng.close()
 
 
+# fp16 throughput mode (the precision bench.py times). Stated bounds, not the 1e-3 gate:
+#   * max-abs logit error vs the fp32 reference forward <= 0.12 (CPU emulation of the mode,
+#     tools/precision_study.py: 0.055 with error-diffused weight rounding; 0.23 with plain
+#     round-to-nearest weights; `net.half()` itself sits 0.2 from fp32) and no further from fp32
+#     than the net.half() restatement is;
+#   * end-to-end, each side using its own forward: foreground pixel
+#     mismatch of the instance maps <= 1 % per tissue.
+F16_LOGIT_BOUND = 0.12
+F16_FG_MISMATCH_BOUND = 0.01
+
+
 def test_fp16_mode_error_is_bounded(built_lib, six_head_sd):
-    """Throughput mode (plain fp16 operands): report + bound the error, do not claim 1e-3."""
+    from oracle import parity_report as pr
     args = synth.model_args()
-    tiles = synth.synthetic_tiles(2, 256, 256, seed=7)
+    tiles = synth.synthetic_tiles(3, 256, 256, seed=7)
+    ora = pr.oracle_side(six_head_sd, args, tiles)
     eng = Engine(six_head_sd, args, precision="f16")
-    plan = eng.plan_for(2, 256, 256, 256, 256, want_logits=True)
-    plan.run(tiles)
-    got = plan.read_logits()
-    ref = _oracle_logits(six_head_sd, args, tiles)
-    worst = 0.0
-    for k in ref:
-        worst = max(worst, float(np.abs(got[k].reshape(ref[k].shape) - ref[k]).max()))
-    print("fp16 mode max-abs logit error vs fp32 oracle: %.4f" % worst)
-    assert worst < 0.5
+    logits, labels = pr.device_side(eng, tiles)
+    rep = pr.compare(logits, labels, ora)
+    print("fp16 mode parity report:", rep)
+    assert rep["logits_max_abs_vs_fp32"] <= F16_LOGIT_BOUND
+    assert rep["logits_max_abs_vs_fp32"] <= rep["half_reference_max_abs_vs_fp32"]
+    for t, r in rep["labels_own_forward"].items():
+        assert r["foreground_pixel_mismatch"] <= F16_FG_MISMATCH_BOUND, (t, r)
+    eng.close()
+
+
+def test_split_mode_labels_match_reference_end_to_end(built_lib, six_head_sd):
+    """Parity mode, each side on its own forward: logits within 1e-3 and (because the floats
+    differ by < 1e-3 only) label maps equal except where a probability sits within the logit
+    tolerance of a post-processing threshold."""
+    from oracle import parity_report as pr
+    args = synth.model_args()
+    tiles = synth.synthetic_tiles(3, 256, 256, seed=7)
+    ora = pr.oracle_side(six_head_sd, args, tiles, with_half=False)
+    eng = Engine(six_head_sd, args, precision="f16x2")
+    logits, labels = pr.device_side(eng, tiles)
+    rep = pr.compare(logits, labels, ora)
+    print("split mode parity report:", rep)
+    assert rep["logits_max_abs_vs_fp32"] <= LOGIT_TOL
+    for t, r in rep["labels_own_forward"].items():
+        assert r["foreground_pixel_mismatch"] <= 1e-3, (t, r)
     eng.close()
 
 

@@ -25,7 +25,7 @@ def manager(built_lib, tmp_path_factory):
     st = yaml.full_load(open(os.path.join(str(d), "settings.yml")))
     m = InferManager(checkpoint_path=os.path.join(str(d), "weights.tar"),
                      decoder_dict=st["dataset_kwargs"]["req_target_code"],
-                     model_args=st["model_kwargs"])
+                     model_args=st["model_kwargs"], precision="f16")
     PostProcInstErodedContourMap.bind(m.engine.ctx)
     yield m
     m.engine.close()

@@ -136,7 +136,7 @@ def test_process_wsi_list_matches_cpu_restatement(built_lib, tmp_path):
     synth.write_model_dir(model_dir, seed=0)
     st = yaml.full_load(open(os.path.join(model_dir, "settings.yml")))
     m = InferManager(checkpoint_path=os.path.join(model_dir, "weights.tar"),
-                     decoder_dict=st["dataset_kwargs"]["req_target_code"], model_args=st["model_kwargs"])
+                     decoder_dict=st["dataset_kwargs"]["req_target_code"], model_args=st["model_kwargs"], precision="f16")
     m.keep_canvas = True
     run_args = {
         "nr_inference_workers": 0, "nr_post_proc_workers": 0, "batch_size": 6,

@@ -108,7 +108,7 @@ def main():
     st = yaml.full_load(open(tmp + "/model/settings.yml"))
     m = InferManager(checkpoint_path=tmp + "/model/weights.tar",
                      decoder_dict=st["dataset_kwargs"]["req_target_code"], model_args=st["model_kwargs"],
-                     device=local_rank)
+                     device=local_rank, precision=os.environ.get("CERB_PRECISION", "f16"))
     run_args = {
         "nr_inference_workers": 0, "nr_post_proc_workers": 0, "batch_size": batch,
         "input_list": [tmp + "/wsi/slide.npy"], "mask_list": [tmp + "/msk/slide.png"],
