@@ -38,6 +38,26 @@ class Op(ctypes.Structure):
     ]
 
 
+MAX_DECODERS = 8
+(L_STEM, L_BLOCK_CONV1, L_BLOCK_CONV2, L_BLOCK_DOWN, L_CONV_MAP, L_DEC_FIRST, L_DEC_CONV,
+ L_HEAD_HIDDEN, L_HEAD_OUT, L_PCLASS) = range(10)
+
+
+class Layer(ctypes.Structure):
+    _fields_ = [("role", ctypes.c_int32), ("a", ctypes.c_int32), ("b", ctypes.c_int32),
+                ("c", ctypes.c_int32), ("cout", ctypes.c_int32), ("cin", ctypes.c_int32),
+                ("kh", ctypes.c_int32), ("kw", ctypes.c_int32), ("w_shift", ctypes.c_int32),
+                ("classes", ctypes.c_int32), ("w_off", ctypes.c_int64), ("w_lo_off", ctypes.c_int64),
+                ("b_off", ctypes.c_int64)]
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("n_decoders", ctypes.c_int32), ("head_mode", ctypes.c_int32 * MAX_DECODERS),
+                ("classes", ctypes.c_int32 * MAX_DECODERS), ("canvas_coff", ctypes.c_int32 * MAX_DECODERS),
+                ("has_pclass", ctypes.c_int32), ("pclass_classes", ctypes.c_int32),
+                ("pclass_canvas_coff", ctypes.c_int32), ("canvas_c", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/cerberus_b200.h declares.
 _SIGNATURES = {
     "cerb_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
@@ -63,6 +83,27 @@ _SIGNATURES = {
                                              ctypes.c_void_p, ctypes.c_size_t]),
     "cerb_plan_write_tensor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_void_p, ctypes.c_size_t]),
+    "cerb_model_spec": (ctypes.c_int, [ctypes.POINTER(ModelDesc), ctypes.POINTER(Layer), ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.POINTER(TensorDesc), ctypes.POINTER(ctypes.c_int),
+                                       ctypes.POINTER(Op), ctypes.POINTER(ctypes.c_int),
+                                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "cerb_model_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ModelDesc), ctypes.POINTER(Layer),
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                         ctypes.POINTER(ctypes.c_void_p)]),
+    "cerb_model_destroy": (None, [ctypes.c_void_p]),
+    "cerb_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_int]),
+    "cerb_model_plan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32)]),
+    "cerb_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "cerb_nccl_comm_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.POINTER(ctypes.c_void_p)]),
+    "cerb_nccl_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "cerb_bcast_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int]),
     "cerb_extract_patches": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int,

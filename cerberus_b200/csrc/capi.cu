@@ -90,6 +90,7 @@ struct cerb_plan {
   std::vector<Step> steps;
   uint8_t* blob = nullptr;
   size_t blob_bytes = 0;
+  bool owns_blob = true;  // false: the blob belongs to a cerb_model shared by several plans
   int prep_in_tensor = -1;
   // the op list is launch-bound on the host (~100 small launches): it is captured into a CUDA
   // graph on the second run (the first run doubles as warm-up / attribute setup) and replayed
@@ -1035,7 +1036,7 @@ extern "C" void cerb_plan_destroy(cerb_plan* pl) {
     if (t.plane[0]) cudaFree(t.plane[0]);
     if (t.plane[1]) cudaFree(t.plane[1]);
   }
-  if (pl->blob) cudaFree(pl->blob);
+  if (pl->blob && pl->owns_blob) cudaFree(pl->blob);
   if (pl->tile_counters) cudaFree(pl->tile_counters);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   delete pl;
@@ -1044,6 +1045,12 @@ extern "C" void cerb_plan_destroy(cerb_plan* pl) {
 extern "C" int cerb_plan_create(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n_tensors,
                                 const cerb_op* ops, int n_ops, const void* weight_blob,
                                 size_t blob_bytes, cerb_plan** out) {
+  return cerb::plan_create_impl(ctx, tensors, n_tensors, ops, n_ops, weight_blob, blob_bytes, nullptr, out);
+}
+
+int cerb::plan_create_impl(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n_tensors,
+                           const cerb_op* ops, int n_ops, const void* weight_blob, size_t blob_bytes,
+                           uint8_t* shared_dev_blob, cerb_plan** out) {
   if (!ctx || !tensors || !ops || !out || n_tensors <= 0 || n_ops <= 0)
     return fail(CERB_ERR_ARG, "cerb_plan_create: bad arguments");
   *out = nullptr;
@@ -1057,7 +1064,10 @@ extern "C" int cerb_plan_create(cerb_ctx* ctx, const cerb_tensor_desc* tensors, 
   };
   const bool split = ctx->precision == CERB_PREC_F16X2;
   pl->blob_bytes = blob_bytes;
-  if (blob_bytes > 0) {
+  if (shared_dev_blob != nullptr) {
+    pl->blob = shared_dev_blob;
+    pl->owns_blob = false;
+  } else if (blob_bytes > 0) {
     if (cudaMalloc(reinterpret_cast<void**>(&pl->blob), blob_bytes) != cudaSuccess)
       return bail(fail(CERB_ERR_CUDA, "cudaMalloc(%zu) for the weight blob failed", blob_bytes));
     if (cudaMemcpy(pl->blob, weight_blob, blob_bytes, cudaMemcpyHostToDevice) != cudaSuccess)

@@ -60,6 +60,11 @@ constexpr int kProfSlots = 256 * 16;
 
 extern thread_local std::string g_last_error;
 int fail(int code, const char* fmt, ...);
+// cerb_plan_create with an optional device-resident weight blob owned by someone else (a
+// cerb_model shares one upload between the plans of all its batch shapes)
+int plan_create_impl(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n_tensors, const cerb_op* ops,
+                     int n_ops, const void* weight_blob, size_t blob_bytes, uint8_t* shared_dev_blob,
+                     cerb_plan** out);
 
 }  // namespace cerb
 

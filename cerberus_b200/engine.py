@@ -208,6 +208,42 @@ def canvas_to_step_outputs(canvas, model):
     return [OrderedDict((k, v[i]) for k, v in per_head.items()) for i in range(n)]
 
 
+class CModel:
+    """The model-level C ABI (cerb_model_create / cerb_forward): the op graph is built inside the
+    library, Python only hands over the packed blob and its layer table. Same kernels, same
+    results as ForwardPlan over PlanSpec; this is the entry a non-Python host uses."""
+
+    def __init__(self, ctx, packed, handle=None):
+        from .plan import c_model_tables
+        self.ctx, self.packed = ctx, packed
+        if handle is not None:  # received by cerb_bcast_weights
+            self.handle = handle
+            return
+        desc, layers = c_model_tables(packed)
+        self._keep = (desc, layers)
+        h = ctypes.c_void_p()
+        blob = packed.blob
+        _lib.check(ctx.lib.cerb_model_create(ctx.handle, ctypes.byref(desc), layers, len(layers),
+                                             blob.ctypes.data_as(ctypes.c_void_p), blob.nbytes,
+                                             ctypes.byref(h)), "cerb_model_create")
+        self.handle = h
+
+    def forward(self, batch_u8, out_h, out_w, canvas_c):
+        """uint8 [n,h,w,3] host batch -> float32 [n,out_h,out_w,canvas_c] canvas (synchronous)."""
+        a = np.ascontiguousarray(batch_u8, dtype=np.uint8)
+        n, h, w, _ = a.shape
+        out = np.empty((n, out_h, out_w, canvas_c), dtype=np.float32)
+        _lib.check(self.ctx.lib.cerb_forward(self.handle, a.ctypes.data_as(ctypes.c_void_p), 0, n, h, w,
+                                             out_h, out_w, out.ctypes.data_as(ctypes.c_void_p), 0),
+                   "cerb_forward")
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.cerb_model_destroy(self.handle)
+            self.handle = None
+
+
 class Engine:
     """Model directory -> run_step. Plans are cached per (N,H,W,out) shape."""
 

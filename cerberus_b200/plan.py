@@ -129,6 +129,55 @@ class PackedModel:
         self.blob = blob.finish()
 
 
+def c_model_tables(model):
+    """PackedModel -> (cerb_model_desc, cerb_layer array) for cerb_model_create / cerb_model_spec:
+    the layer table of the blob in the role / index vocabulary of include/cerberus_b200.h."""
+    L = model.layers
+    rows = []
+
+    def add(role, layer, a=0, b=0, c=0, classes=0):
+        rows.append(_lib.Layer(role, a, b, c, layer.get("cout", 0), layer.get("cin", 0),
+                               layer.get("kh", 0), layer.get("kw", 0), layer.get("w_shift", 0),
+                               classes, layer["w_off"], layer.get("w_lo_off", -1),
+                               layer.get("b_off", -1)))
+
+    add(_lib.L_STEM, L["stem"])
+    for li, nblocks in enumerate(RESNET34_BLOCKS, start=1):
+        for bi in range(nblocks):
+            p = "backbone.layer%d.%d" % (li, bi)
+            add(_lib.L_BLOCK_CONV1, L[p + ".conv1"], li, bi)
+            add(_lib.L_BLOCK_CONV2, L[p + ".conv2"], li, bi)
+            if (p + ".downsample") in L:
+                add(_lib.L_BLOCK_DOWN, L[p + ".downsample"], li, bi)
+    add(_lib.L_CONV_MAP, L["conv_map"])
+    desc = _lib.ModelDesc()
+    desc.n_decoders = len(model.seg_decoders)
+    if desc.n_decoders > _lib.MAX_DECODERS:
+        raise ValueError("more than %d segmentation decoders" % _lib.MAX_DECODERS)
+    if model.seg_decoders:
+        add(_lib.L_DEC_FIRST, L["dec.first"])
+    for di, d in enumerate(model.seg_decoders):
+        for blk in range(4):
+            for cv in range(2):
+                if blk == 0 and cv == 0:
+                    continue
+                add(_lib.L_DEC_CONV, L["dec.%s.%d.%d" % (d, blk, cv)], di, blk, cv)
+        add(_lib.L_HEAD_HIDDEN, L["head.%s.hidden" % d], di)
+        ho = L["head.%s.out" % d]
+        add(_lib.L_HEAD_OUT, ho, di, classes=ho["classes"])
+        desc.head_mode[di] = _lib.HEAD_INST if ho["clf"] == "INST" else _lib.HEAD_TYPE
+        desc.classes[di] = ho["classes"]
+        desc.canvas_coff[di] = model.idx_dict[HEAD_NAME_MAP[d]][0]
+    desc.has_pclass = int(model.has_pclass)
+    if model.has_pclass:
+        add(_lib.L_PCLASS, L["pclass"], classes=L["pclass"]["classes"])
+        desc.pclass_classes = L["pclass"]["classes"]
+        desc.pclass_canvas_coff = model.idx_dict["Patch-Class"][0]
+    desc.canvas_c = model.canvas_c
+    arr = (_lib.Layer * len(rows))(*rows)
+    return desc, arr
+
+
 class PlanSpec:
     """Tensors + ops for one batch shape. Pure host data (testable without a GPU)."""
 

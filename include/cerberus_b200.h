@@ -35,6 +35,7 @@ extern "C" {
 
 typedef struct cerb_ctx cerb_ctx;
 typedef struct cerb_plan cerb_plan;
+typedef struct cerb_model cerb_model;
 
 enum cerb_status {
   CERB_OK = 0,
@@ -156,6 +157,92 @@ int cerb_plan_read_tensor(cerb_plan* plan, int tensor_id, int plane, void* host_
 /* Synchronous H2D copy into a tensor plane (tests feed intermediate activations). */
 int cerb_plan_write_tensor(cerb_plan* plan, int tensor_id, int plane, const void* host_src,
                            size_t bytes);
+
+/* ---- model: the whole forward driven from this header alone (SURVEY.md 8b "C ABI") ----------
+ * The plan-level API above takes an op graph from its caller. cerb_model_* builds that graph
+ * INSIDE the library from the architecture of models/net_desc.py:23-200 (ResNet34 encoder,
+ * models/backbone/resnet.py:202-211; U-Net decoders, models/utils/net_layers.py:23-46; heads;
+ * Patch-Class branch), so a host in any language runs a model directory with
+ *     cerb_ctx_create -> cerb_model_create -> cerb_forward -> (cerb_postproc_* ...)
+ * Only the folding of BatchNorm into the weights and their packing into one blob stay outside
+ * (cerberus_b200/pack.py; layout = cerb_layer table below). */
+
+#define CERB_MAX_DECODERS 8
+
+enum cerb_layer_role {
+  CERB_L_STEM = 0,        /* backbone.conv1 + bn1 (7x7, /255 folded in)                       */
+  CERB_L_BLOCK_CONV1 = 1, /* backbone.layer<a>.<b>.conv1 + bn1   a = 1..4, b = block index    */
+  CERB_L_BLOCK_CONV2 = 2, /* backbone.layer<a>.<b>.conv2 + bn2                                */
+  CERB_L_BLOCK_DOWN = 3,  /* backbone.layer<a>.0.downsample (1x1 stride 2 + bn), a = 2..4     */
+  CERB_L_CONV_MAP = 4,    /* conv_map 1x1 512->256 (net_desc.py:52)                           */
+  CERB_L_DEC_FIRST = 5,   /* first conv of EVERY decoder's u4 block, output channels concatenated */
+  CERB_L_DEC_CONV = 6,    /* decoder_head.<a>.<b>.block.<c>: a = decoder index, b = level 0..3, c = 0..1 */
+  CERB_L_HEAD_HIDDEN = 7, /* output_head.<a>...x.0 (1x1 64->96 + BN + ReLU)                   */
+  CERB_L_HEAD_OUT = 8,    /* output_head.<a>...x.1 (1x1 96->classes): fp32 [classes][96] at w_off, fp32 bias at b_off */
+  CERB_L_PCLASS = 9       /* Patch-Class branch parameters (fp32, layout of cerberus_b200/plan.py) at w_off */
+};
+
+/* One packed layer of the weight blob. Offsets are byte offsets into the blob. */
+typedef struct cerb_layer {
+  int32_t role;        /* cerb_layer_role */
+  int32_t a, b, c;     /* role-specific indices (see above), 0 when unused */
+  int32_t cout, cin, kh, kw;
+  int32_t w_shift;     /* conv weights are stored multiplied by 2^w_shift */
+  int32_t classes;     /* HEAD_OUT / PCLASS */
+  int64_t w_off;       /* fp16 hi weights [cout][kh*kw][cin] (HEAD_OUT / PCLASS: fp32 parameters) */
+  int64_t w_lo_off;    /* fp16 lo weights, or -1 */
+  int64_t b_off;       /* fp32 bias [cout], or -1 */
+} cerb_layer;
+
+/* What the checkpoint's settings.yml says about the heads (model_kwargs.decoder_kwargs filtered
+ * by considered_tasks, in nn.ModuleDict order = decoder_kwargs order) and where each head's
+ * channels sit in the per-patch canvas (the table of infer/tile.py:116-134). */
+typedef struct cerb_model_desc {
+  int32_t n_decoders;                       /* segmentation decoders (not Patch-Class) */
+  int32_t head_mode[CERB_MAX_DECODERS];     /* cerb_head_mode */
+  int32_t classes[CERB_MAX_DECODERS];
+  int32_t canvas_coff[CERB_MAX_DECODERS];   /* first canvas channel of the head */
+  int32_t has_pclass, pclass_classes, pclass_canvas_coff;
+  int32_t canvas_c;                         /* channels of the canvas */
+} cerb_model_desc;
+
+/* The op graph (tensors + ops) the model runs for one batch shape, without touching a device:
+ * introspection, and the CPU-side check that it equals the graph cerberus_b200/plan.py builds.
+ * On entry *n_tensors / *n_ops are the capacities of the arrays, on exit the counts;
+ * logit_tensors (nullable, int32 [CERB_MAX_DECODERS + 1]) receives the fp32 logit tensor of every
+ * head (Patch-Class last) or -1. h and w must be multiples of 16. */
+int cerb_model_spec(const cerb_model_desc* desc, const cerb_layer* layers, int n_layers, int n, int h,
+                    int w, int out_h, int out_w, int want_logits, cerb_tensor_desc* tensors,
+                    int* n_tensors, cerb_op* ops, int* n_ops, int32_t* canvas_tensor,
+                    int32_t* logit_tensors);
+/* Uploads the blob once (shared by every plan of the model). weight_blob may be NULL when the
+ * weights will arrive by cerb_bcast_weights. */
+int cerb_model_create(cerb_ctx* ctx, const cerb_model_desc* desc, const cerb_layer* layers,
+                      int n_layers, const void* weight_blob, size_t blob_bytes, cerb_model** out);
+void cerb_model_destroy(cerb_model* model);
+/* infer/base.py:51-53 run_step for one batch: tiles u8 [n,h,w,3] (host, or device memory when
+ * tiles_on_device != 0) -> the per-patch canvas f32 [n,out_h,out_w,canvas_c] (softmax / channel
+ * drop / argmax / centre crop of models/run_desc.py:451-491 applied, channel layout of
+ * infer/tile.py:116-134). Plans are built on first use of a shape and cached. canvas_out: host
+ * buffer (the call synchronises), device buffer (canvas_on_device != 0: queued on the ctx stream),
+ * or NULL (leave it in the plan: cerb_model_plan + cerb_plan_tensor_ptr). */
+int cerb_forward(cerb_model* model, const uint8_t* tiles, int tiles_on_device, int n, int h, int w,
+                 int out_h, int out_w, float* canvas_out, int canvas_on_device);
+/* The cached plan of a shape (created if needed) and its canvas tensor id. */
+int cerb_model_plan(cerb_model* model, int n, int h, int w, int out_h, int out_w, int want_logits,
+                    cerb_plan** plan, int32_t* canvas_tensor);
+
+/* ---- multi-GPU: one process per GPU; the only data-path collective of the inference path is
+ * the start-up broadcast of the packed weights (replaces nn.DataParallel's
+ * per-forward replicate of infer/base.py:46). NCCL is resolved at run time (dlopen libnccl.so.2);
+ * communicators are opaque here (ncclComm_t). id128 = the 128 bytes of an ncclUniqueId: rank 0
+ * creates it, the host program hands it to the other ranks (file, socket, MPI ...). */
+int cerb_nccl_unique_id(void* id128);
+int cerb_nccl_comm_create(cerb_ctx* ctx, int nranks, int rank, const void* id128, void** comm);
+int cerb_nccl_comm_destroy(void* comm);
+/* Root: *model is a created model, its description, layer table and device blob are broadcast.
+ * Other ranks: *model == NULL on entry, a ready model on this rank's ctx on exit. */
+int cerb_bcast_weights(cerb_ctx* ctx, cerb_model** model, void* nccl_comm, int root, int rank);
 
 /* ---- tile plumbing (a1/a2/a16) --------------------------------------------------------
  * `flags` bit 0: the input buffer is device memory; bit 1: the output buffer is device

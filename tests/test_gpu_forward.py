@@ -246,3 +246,22 @@ def test_fused_head_crops_and_partial_tiles(built_lib, six_head_sd):
     assert outs[0].shape == outs[1].shape == (1, 144, 144, eng.model.canvas_c)
     # the two runs also use different 64->64 kernels (accumulation order): fp16-mode noise
     assert float(np.abs(outs[0][..., inst] - outs[1][..., inst]).max()) <= 2e-2
+
+
+def test_model_api_forward_equals_plan_api(built_lib, six_head_sd):
+    """cerb_model_create + cerb_forward (op graph built inside the library, csrc/model.cu) vs the
+    plan-level API fed by cerberus_b200/plan.py: same kernels, bit-identical canvas; 448 -> 144
+    crop as well."""
+    from cerberus_b200.engine import CModel
+    args = synth.model_args()
+    eng = Engine(six_head_sd, args, precision="f16")
+    cm = CModel(eng.ctx, eng.model)
+    for (n, size, out, seed) in ((3, 256, 256, 5), (1, 448, 144, 6)):
+        tiles = synth.synthetic_tiles(n, size, size, seed=seed)
+        plan = eng.plan_for(n, size, size, out, out)
+        plan.run(tiles)
+        want = plan.read_canvas().copy()
+        got = cm.forward(tiles, out, out, eng.model.canvas_c)
+        assert got.shape == want.shape and np.array_equal(got, want)
+    cm.close()
+    eng.close()

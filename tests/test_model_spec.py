@@ -1,0 +1,71 @@
+"""CPU: the op graph cerb_model_spec builds inside the library (csrc/model.cu) equals the one
+cerberus_b200/plan.py::PlanSpec builds in Python - tensor for tensor, op field for op field -
+for the six-head model, a single-decoder model and a model without Patch-Class, at several batch
+shapes. (No device call: cerb_model_spec is pure host code.)"""
+import ctypes
+
+import pytest
+
+from cerberus_b200 import _lib, synth
+from cerberus_b200.plan import PackedModel, PlanSpec, c_model_tables
+
+CASES = [
+    (None, 2, 256, 256, 256, 256, False),
+    (None, 1, 448, 448, 144, 144, True),
+    (None, 3, 64, 96, 48, 80, False),
+    (["Nuclei"], 1, 256, 256, 256, 256, True),
+    (["Gland", "Gland#TYPE", "Lumen"], 4, 128, 128, 128, 128, False),
+    (["Patch-Class"], 2, 256, 256, 16, 16, True),
+]
+
+
+@pytest.fixture(scope="module")
+def models():
+    out = {}
+    for tasks in {tuple(c[0]) if c[0] else None for c in CASES}:
+        t = list(tasks) if tasks else None
+        args = synth.model_args(t)
+        out[tasks] = PackedModel(synth.make_state_dict(args["considered_tasks"], seed=0), args)
+    return out
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%dx%dx%d" % ("all" if c[0] is None else "+".join(c[0]), c[1], c[2], c[3]))
+def test_library_graph_equals_python_graph(case, models, built_lib):
+    tasks, n, h, w, oh, ow, logits = case
+    model = models[tuple(tasks) if tasks else None]
+    spec = PlanSpec(model, n, h, w, oh, ow, want_logits=logits)
+    td_py, ops_py = spec.c_arrays()
+    desc, layers = c_model_tables(model)
+    cap_t, cap_o = ctypes.c_int(256), ctypes.c_int(512)
+    td = (_lib.TensorDesc * 256)()
+    ops = (_lib.Op * 512)()
+    canvas = ctypes.c_int32(-1)
+    lg = (ctypes.c_int32 * (_lib.MAX_DECODERS + 1))()
+    _lib.check(built_lib.cerb_model_spec(ctypes.byref(desc), layers, len(layers), n, h, w, oh, ow,
+                                         int(logits), td, ctypes.byref(cap_t), ops, ctypes.byref(cap_o),
+                                         ctypes.byref(canvas), lg), "cerb_model_spec")
+    assert cap_t.value == len(td_py) and cap_o.value == len(ops_py)
+    assert canvas.value == spec.canvas
+    for i in range(len(td_py)):
+        for f, _ in _lib.TensorDesc._fields_:
+            assert getattr(td[i], f) == getattr(td_py[i], f), ("tensor", i, f)
+    for i in range(len(ops_py)):
+        for f, _ in _lib.Op._fields_:
+            assert getattr(ops[i], f) == getattr(ops_py[i], f), ("op", i, f, getattr(ops[i], f), getattr(ops_py[i], f))
+    # logit tensors: decoders in order, Patch-Class last
+    want = [spec.logit_tensors.get(k, -1) for k in
+            [__import__("cerberus_b200.plan", fromlist=["HEAD_NAME_MAP"]).HEAD_NAME_MAP[d] for d in model.seg_decoders]]
+    assert [lg[i] for i in range(len(want))] == want
+    assert lg[_lib.MAX_DECODERS] == spec.logit_tensors.get("Patch-Class", -1)
+
+
+def test_spec_rejects_bad_shapes(models, built_lib):
+    model = models[None]
+    desc, layers = c_model_tables(model)
+    n_t, n_o = ctypes.c_int(0), ctypes.c_int(0)
+    rc = built_lib.cerb_model_spec(ctypes.byref(desc), layers, len(layers), 1, 250, 256, 250, 256, 0,
+                                   None, ctypes.byref(n_t), None, ctypes.byref(n_o), None, None)
+    assert rc == -2 and b"multiple of 16" in built_lib.cerb_last_error()
+    rc = built_lib.cerb_model_spec(ctypes.byref(desc), layers, len(layers) - 1, 1, 256, 256, 256, 256, 0,
+                                   None, ctypes.byref(n_t), None, ctypes.byref(n_o), None, None)
+    assert rc == -2 and b"layer table lacks" in built_lib.cerb_last_error()
