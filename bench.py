@@ -40,6 +40,11 @@ def parse():
                     help="skip timing the other precision mode (f16x2 when --precision f16)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (CPU oracle, ~10 s)")
     ap.add_argument("--parity-tiles", type=int, default=4)
+    ap.add_argument("--config", default="3", choices=["1", "3", "tile448"],
+                    help="BASELINE.json config: 3 (default; 2 with --no-postproc) = batch of 256^2 tiles, six "
+                         "heads; 1 = ONE 256^2 image, encoder + Nuclei head, batch 1, through the "
+                         "run_infer_tile.py plumbing (InferManager), CPU reference beside it; tile448 = a "
+                         "directory of PNGs through process_file_list at the CLI defaults 448/144")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-batch", type=int, default=4)
     return ap.parse_args()
@@ -577,10 +582,232 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _tile_manager(tmp, tasks, precision, batch, in_shape, out_shape, postproc_list):
+    """Model directory on disk -> InferManager, exactly as run_infer_tile.py builds it."""
+    import yaml
+    from cerberus_b200 import synth
+    from cerberus_b200.infer.tile import InferManager
+    mdir = os.path.join(tmp, "model_%s" % "_".join(tasks or ["all"]).replace("#", ""))
+    if not os.path.exists(os.path.join(mdir, "weights.tar")):
+        synth.write_model_dir(mdir, considered_tasks=tasks, seed=0)
+    st = yaml.full_load(open(os.path.join(mdir, "settings.yml")))
+    m = InferManager(checkpoint_path=os.path.join(mdir, "weights.tar"),
+                     decoder_dict=st["dataset_kwargs"]["req_target_code"], model_args=st["model_kwargs"],
+                     precision=precision)
+    m.patch_input_shape, m.patch_output_shape, m.patch_output_overlap = in_shape, out_shape, 0
+    m.batch_size, m.postproc_list = batch, postproc_list
+    return m, st
+
+
+def run_config1(args):
+    """BASELINE config 1: ONE 256x256x3 synthetic image, ResNet34 encoder + Nuclei decoder head,
+    batch 1, patch 256 -> 256, through the run_infer_tile.py plumbing: InferManager(model dir) ->
+    patch grid -> device extract -> forward -> stitch -> __proc_nuclei -> instance tables. A step
+    is one image. `value`: image uploaded per step, results left in HBM; `e2e`: host image in,
+    host label map + type-less instance dict out (what the CLI hands to its .mat writer). The CPU
+    reference (unmodified modules, oracle/_ref) runs the same image through _prepare_patching ->
+    infer_step -> _post_process_patches beside it."""
+    import tempfile
+
+    import torch
+    from cerberus_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.cuda.set_device(0)
+    tmp = tempfile.mkdtemp(prefix="cerb_cfg1_")
+    img = synth.synthetic_tiles(1, TILE, TILE, seed=0)[0]
+    out = {}
+    gflop = 54.891  # SURVEY 8d: encoder + Nuclei decoder / head
+    for prec in ("f16", "f16x2"):
+        m, st = _tile_manager(tmp, ["Nuclei"], prec, 1, TILE, TILE, ["nuclei"])
+        ctx = m.engine.ctx
+        for _ in range(max(3, args.warmup)):
+            res = m.process_image(img, "t")
+        ctx.sync()
+        l0 = ctx.launch_count
+        sampler = ClockSampler(0)
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m.process_images([("t", img)], to_host=False)
+        ctx.sync()
+        dt_res = (time.perf_counter() - t0) / args.steps
+        launches = ctx.launch_count - l0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = m.process_image(img, "t")
+        dt_e2e = (time.perf_counter() - t0) / args.steps
+        clocks = sampler.stop()
+        # forward alone (device events): the part the tensor roofline applies to
+        plan = m.engine.plan_for(1, TILE, TILE, TILE, TILE)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=0)
+        dev = torch.from_numpy(img[None].copy()).cuda()
+        plan.run(device_ptr=dev.data_ptr())
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            plan.run(device_ptr=dev.data_ptr())
+        e1.record(stream)
+        ctx.sync()
+        fwd_ms = e0.elapsed_time(e1) / args.steps
+        out[prec] = {"value": 1.0 / dt_res, "ms_per_step": 1e3 * dt_res, "e2e": 1.0 / dt_e2e,
+                     "e2e_ms": 1e3 * dt_e2e, "launches": int(launches), "forward_ms": fwd_ms,
+                     "forward_tflops": gflop / fwd_ms, "instances": len(res[3]["Nuclei"]), "clocks": clocks}
+        m.release_device_buffers()
+        m.engine.close()
+    # parity of this very image: device label map vs reference on own forwards
+    cpu = None
+    parity = None
+    from oracle import ref_runner
+    if not args.no_cpu_baseline and ref_runner.available():
+        torch.set_num_threads(host_cores())
+        margs = synth.model_args(["Nuclei"])
+        sd = synth.make_state_dict(["Nuclei"], seed=0)
+        ref = ref_runner.ReferenceTilePath(sd, margs)
+        code = dict(synth.DEFAULT_REQ_TARGET_CODE)
+        r = ref.process_image(img, TILE, TILE, code, ["nuclei"])  # warm-up
+        best = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            r = ref.process_image(img, TILE, TILE, code, ["nuclei"])
+            best = min(best, time.perf_counter() - t0)
+        cpu = {"value": 1.0 / best, "unit": "tiles/s", "cores": torch.get_num_threads(), "kind": "reference",
+               "sample": "the same image, best of 5: unmodified _prepare_patching -> infer_step (the "
+                         "reference infers the single patch TWICE, infer/tile.py:90-103) -> "
+                         "_post_process_patches incl. get_inst_info_dict; %.1f ms" % (1e3 * best)}
+        m2, _ = _tile_manager(tmp, ["Nuclei"], "f16x2", 1, TILE, TILE, ["nuclei"])
+        mine = m2.process_image(img, "t")
+        a, b = np.asarray(mine[2]["Nuclei"]).astype(np.int64), np.asarray(r[2]["Nuclei"]).astype(np.int64)
+        parity = {"f16x2_label_map_identical_to_reference": bool(np.array_equal(a, b)),
+                  "pixel_mismatch": float((a != b).mean()), "instances": [int(a.max()), int(b.max())],
+                  "instance_ids_equal": list(mine[3]["Nuclei"].keys()) == list(r[3]["Nuclei"].keys())}
+        m2.release_device_buffers()
+        m2.engine.close()
+    peaks = load_peaks()
+    main = out[args.precision]
+    line = {
+        "metric": "tiles/sec (256x256x3) end-to-end incl. post-proc", "value": main["value"],
+        "unit": "tiles/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "BASELINE config 1: single 256x256x3 synthetic image, ResNet34 encoder + 1 "
+                               "nuclei-seg decoder head, batch=1, run_infer_tile.py plumbing "
+                               "(InferManager.process_image, patch 256 -> 256) incl. nuclei post-processing "
+                               "and instance tables", "tile": [TILE, TILE, 3], "batch_per_gpu": 1, "heads": 1,
+                   "precision": args.precision,
+                   "l2": "latency-bound single-image case: the working set fits L2; nothing to flush"},
+        "clocks": main["clocks"],
+        "e2e": {"value": main["e2e"], "unit": "tiles/s", "h2d_bytes_per_step": int(img.nbytes),
+                "d2h_bytes_per_step": int(TILE * TILE * 4)},
+        "gpu_launches": main["launches"],
+        "roofline": {"bound": "tensor", "achieved": main["forward_tflops"], "peak": peaks["tensor_burst"],
+                     "unit": "TFLOP/s", "frac": main["forward_tflops"] / peaks["tensor_burst"], "traffic": None,
+                     "kernel": "whole forward of ONE tile (54.891 GFLOP, %.3f ms): 64 regions of 16x16 px "
+                               "on 148 SMs - launch / latency bound by construction" % main["forward_ms"]},
+        "per_precision": out, "parity": parity, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def run_tile448(args):
+    """The CLI path at its defaults: a directory of PNGs through InferManager.process_file_list
+    (PNG decode -> 448/144 patches batched ACROSS files -> forward -> stitch -> post-processing ->
+    instance tables -> .mat / overlay files), one rank per GPU, files sharded over ranks."""
+    import shutil
+    import tempfile
+
+    import cv2
+    import torch
+    import torch.distributed as dist
+    from cerberus_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tmp = os.environ.get("CERB_BENCH_TMP") or os.path.join(tempfile.gettempdir(), "cerb_tile448")
+    n_files, size = int(os.environ.get("CERB_TILE448_FILES", "32")) * world, 1000
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True)
+        os.makedirs(tmp + "/in")
+        for i in range(n_files):
+            img = synth.synthetic_tiles(1, 1008, 1008, seed=500 + i)[0][:size, :size]
+            cv2.imwrite("%s/in/img%03d.png" % (tmp, i), cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+        synth.write_model_dir(tmp + "/model_all", seed=0)
+    if world > 1:
+        dist.barrier()
+    import yaml
+    from cerberus_b200.infer.tile import InferManager
+    st = yaml.full_load(open(tmp + "/model_all/settings.yml"))
+    m = InferManager(checkpoint_path=tmp + "/model_all/weights.tar",
+                     decoder_dict=st["dataset_kwargs"]["req_target_code"], model_args=st["model_kwargs"],
+                     precision=args.precision, device=local_rank)
+    run_args = {"nr_inference_workers": 4, "nr_post_proc_workers": 4, "batch_size": args.batch,
+                "input_dir": tmp + "/in", "output_dir": tmp + "/out_warm", "patch_input_shape": 448,
+                "patch_output_shape": 144, "patch_output_overlap": 0,
+                "postproc_list": ["gland", "lumen", "nuclei", "patch-class"]}
+    os.makedirs(run_args["output_dir"], exist_ok=True)
+    import io
+    from contextlib import redirect_stdout
+    with redirect_stdout(io.StringIO()):
+        m.process_file_list(dict(run_args))  # warm-up: plans, buffers
+        if world > 1:
+            dist.barrier()
+        m.nr_patches_inferred = 0
+        run_args["output_dir"] = tmp + "/out"
+        os.makedirs(run_args["output_dir"], exist_ok=True)
+        l0 = m.engine.ctx.launch_count
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.process_file_list(dict(run_args))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+    t = torch.tensor([dt, float(m.nr_patches_inferred)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, patches = float(mx[0].item()), float(t[1].item())
+    else:
+        patches = float(t[1].item())
+    if rank == 0:
+        n_out = len([f for f in os.listdir(tmp + "/out/nuclei_mat") if f.endswith(".mat")])
+        px = n_files * size * size
+        line = {"metric": "tiles/sec (256x256x3) end-to-end incl. post-proc",
+                "value": px / 65536.0 / dt, "unit": "tiles/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "CLI defaults: %d synthetic %dx%d PNGs through "
+                                       "InferManager.process_file_list, patch 448 -> 144 (each output pixel "
+                                       "costs 9.7x the network work of the in == out bench), batch %d filled "
+                                       "across files, six heads + post-processing + instance tables + .mat / "
+                                       "overlay files; value = image pixels / 65536 per second"
+                                       % (n_files, size, size, args.batch),
+                           "files": n_files, "patches_448_inferred": int(patches),
+                           "patches_per_s": patches / dt, "files_per_s": n_files / dt,
+                           "precision": args.precision, "mat_files_written": n_out},
+                "e2e": {"value": px / 65536.0 / dt, "unit": "tiles/s",
+                        "h2d_bytes_per_step": int(px * 3), "d2h_bytes_per_step": int(px * 4 * 6)},
+                "gpu_launches": int(m.engine.ctx.launch_count - l0),
+                "tflops_forward": patches / dt * 370.953 / 1e3}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "1":
+        run_config1(args)
+    elif args.config == "tile448":
+        run_tile448(args)
     else:
         run_ours(args)
 

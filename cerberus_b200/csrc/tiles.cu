@@ -414,3 +414,34 @@ extern "C" int cerb_nearest_channel(cerb_ctx* ctx, const float* canvas_dev, int 
   CERB_CUDA(cudaMemcpyAsync(out_host, d.p, bytes, cudaMemcpyDeviceToHost, s));
   return cerb_ctx_sync(ctx);
 }
+
+// ------------------------------------------------------------------ channel plane of an HWC canvas
+namespace {
+__global__ void k_channel_plane(const float* __restrict__ canvas, size_t hw, int C, int ch,
+                                float* __restrict__ out) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = canvas[i * C + ch];
+}
+}  // namespace
+
+extern "C" int cerb_channel_plane(cerb_ctx* ctx, const float* canvas_dev, int H, int W, int C, int ch,
+                                  float* out, int flags) {
+  if (!ctx || !canvas_dev || !out || H <= 0 || W <= 0 || ch < 0 || ch >= C)
+    return fail(CERB_ERR_ARG, "cerb_channel_plane: bad arguments");
+  CERB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t hw = static_cast<size_t>(H) * W;
+  DevBuf d(ctx);
+  float* dst = out;
+  if (!(flags & 2)) {
+    CERB_CUDA(cudaMalloc(&d.p, hw * sizeof(float)));
+    dst = static_cast<float*>(d.p);
+  }
+  k_channel_plane<<<148 * 8, 256, 0, s>>>(canvas_dev, hw, C, ch, dst);
+  CERB_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  if (flags & 2) return CERB_OK;  // queued on the ctx stream
+  CERB_CUDA(cudaMemcpyAsync(out, dst, hw * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return cerb_ctx_sync(ctx);
+}

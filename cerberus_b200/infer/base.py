@@ -37,8 +37,25 @@ class InferManager(object):
         """infer/base.py:17-54. `checkpoint_path` is a torch.save({"desc": state_dict}) file whose
         keys may carry the DataParallel `module.` prefix; `model_args` is settings.yml's
         model_kwargs (encoder_backbone_name, decoder_kwargs, considered_tasks)."""
-        saved = torch.load(self.checkpoint_path, map_location="cpu")["desc"]
-        self.engine = Engine(saved, self.model_args, device=self.device, precision=self.precision)
+        import torch.distributed as dist
+        self.rank, self.world_size = 0, 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # one process per GPU: rank 0 reads, folds and packs the checkpoint, the other ranks
+            # receive the packed blob by ONE broadcast (SURVEY.md 8e) - the B200-native stand-in
+            # for nn.DataParallel's per-forward replicate (infer/base.py:46)
+            from ..dist import broadcast_packed_model
+            from ..plan import PackedModel
+            self.rank, self.world_size = dist.get_rank(), dist.get_world_size()
+            packed = None
+            if self.rank == 0:
+                saved = torch.load(self.checkpoint_path, map_location="cpu")["desc"]
+                packed = PackedModel(saved, self.model_args)
+            dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            packed = broadcast_packed_model(packed, self.model_args, self.rank, self.world_size, dev)
+            self.engine = Engine(None, None, device=self.device, precision=self.precision, packed=packed)
+        else:
+            saved = torch.load(self.checkpoint_path, map_location="cpu")["desc"]
+            self.engine = Engine(saved, self.model_args, device=self.device, precision=self.precision)
         self.run_step = lambda input_batch, output_shape: self.engine.run_step(
             input_batch, output_shape)
         return

@@ -207,13 +207,194 @@ class InferManager(base.InferManager):
             patch_size, patch_size, out.ctypes.data_as(ctypes.c_void_p), 0), "cerb_extract_patches")
         return out
 
+    # ------------------------------------------------------------------ device-resident path
+    def _dev(self, key, nbytes):
+        """Grow-only device buffer owned by the manager."""
+        bufs = self.__dict__.setdefault("_dev_bufs", {})
+        cur = bufs.get(key)
+        if cur is None or cur[1] < nbytes:
+            ctx = self.engine.ctx
+            if cur is not None:
+                ctx.lib.cerb_dev_free(ctx.handle, ctypes.c_void_p(cur[0]))
+            p = ctx.lib.cerb_dev_alloc(ctx.handle, int(nbytes))
+            if not p:
+                _lib.check(-1, "cerb_dev_alloc(%d)" % nbytes)
+            bufs[key] = cur = (p, int(nbytes))
+        return cur[0]
+
+    def release_device_buffers(self):
+        ctx = self.engine.ctx
+        for p, _ in self.__dict__.get("_dev_bufs", {}).values():
+            ctx.lib.cerb_dev_free(ctx.handle, ctypes.c_void_p(p))
+        self._dev_bufs = {}
+
+    def process_images(self, named_images, to_host=True):
+        """A group of RGB uint8 images -> one result tuple per image (the tuple
+        _post_process_patches returns). This is what `process_file_list` runs per cache group
+        (the reference caches files until > 256 patches and batches across them,
+        infer/tile.py:294-325). Everything between the uploaded image and the label maps stays in
+        HBM:  image H2D -> cerb_extract_patches (reflect pad + slicing) straight into the batch
+        buffer -> forward plan of `batch_size` patches (batches are filled ACROSS images; the tail
+        of the last batch runs on stale patches whose outputs are ignored) -> per-patch canvases
+        collected in a device store -> cerb_stitch -> post-processing -> instance tables.
+        Per image the host receives the label maps, the type / Patch-Class planes and the
+        instance tables, nothing else. Every distinct patch is inferred once: the duplicate grid
+        the reference appends (tile.py:90-103) averages a patch with itself, which is exact."""
+        eng = self.engine
+        ctx, lib, model = eng.ctx, eng.ctx.lib, eng.model
+        PostProcInstErodedContourMap.bind(ctx)
+        P_in, P_out = int(self.patch_input_shape), int(self.patch_output_shape)
+        B = max(1, int(self.batch_size))
+        C = model.canvas_c
+        idx_dict = model.idx_dict
+        plan = eng.plan_for(B, P_in, P_in, P_out, P_out)
+        metas, total = [], 0
+        for name, img in named_images:
+            img = np.ascontiguousarray(img, dtype=np.uint8)
+            info_list, src_pos, _ = patch_grid(img.shape[0], img.shape[1], P_in, P_out,
+                                               self.patch_output_overlap)
+            in_tl = info_list[:, 0, 0, :]
+            _, first = np.unique(in_tl, axis=0, return_index=True)
+            order = np.sort(first)
+            hw = np.max(info_list[:, 1, 1, :], axis=0)
+            metas.append({"name": name, "img": img, "src_pos": src_pos, "first": total,
+                          "in_tl": np.ascontiguousarray(in_tl[order], dtype=np.int32),
+                          "out_tl": np.ascontiguousarray(info_list[order, 1, 0, :], dtype=np.int32),
+                          "canvas_hw": (int(hw[0]), int(hw[1]))})
+            total += len(order)
+        nb = (total + B - 1) // B
+        pbytes, cbytes = P_in * P_in * 3, P_out * P_out * C * 4
+        d_patches = self._dev("patches", nb * B * pbytes)
+        d_store = self._dev("store", nb * B * cbytes)
+        max_img = max(m["img"].nbytes for m in metas)
+        d_img = self._dev("img", max_img)
+        for m in metas:  # a1/a2: reflect pad + slicing on the device, into the batch buffer
+            img = m["img"]
+            _lib.check(lib.cerb_memcpy(ctx.handle, ctypes.c_void_p(d_img),
+                                       img.ctypes.data_as(ctypes.c_void_p), img.nbytes, 1), "image H2D")
+            _lib.check(lib.cerb_extract_patches(
+                ctx.handle, ctypes.c_void_p(d_img), img.shape[0], img.shape[1], int(m["src_pos"][0]),
+                int(m["src_pos"][1]), m["in_tl"].ctypes.data_as(ctypes.c_void_p), len(m["in_tl"]),
+                P_in, P_in, ctypes.c_void_p(d_patches + m["first"] * pbytes), 3), "cerb_extract_patches")
+            ctx.sync()  # d_img is reused by the next image
+        canvas_ptr = plan.tensor_ptr(plan.spec.canvas)
+        for b in range(nb):  # a3-a15
+            plan.run(device_ptr=d_patches + b * B * pbytes)
+            _lib.check(lib.cerb_memcpy(ctx.handle, ctypes.c_void_p(d_store + b * B * cbytes),
+                                       ctypes.c_void_p(canvas_ptr), B * cbytes, 3), "canvas -> store")
+        self.nr_patches_inferred = getattr(self, "nr_patches_inferred", 0) + total
+        return [self._finish_image(m, d_store + m["first"] * cbytes, P_out, C, idx_dict, to_host)
+                for m in metas]
+
+    def _finish_image(self, m, d_patch_canvas, P_out, C, idx_dict, to_host):
+        """a16-a20 for one image, device-resident: stitch, post-process, instance tables."""
+        ctx = self.engine.ctx
+        lib = ctx.lib
+        img = m["img"]
+        H, W = img.shape[:2]
+        n = len(m["out_tl"])
+        hw4 = H * W * 4
+        d_canvas = self._dev("canvas", H * W * C * 4)
+        _lib.check(lib.cerb_stitch(ctx.handle, ctypes.c_void_p(d_patch_canvas), n, P_out, P_out, C,
+                                   m["out_tl"].ctypes.data_as(ctypes.c_void_p), m["canvas_hw"][0],
+                                   m["canvas_hw"][1], int(m["src_pos"][0]), int(m["src_pos"][1]), H, W,
+                                   ctypes.c_void_p(d_canvas), 3), "cerb_stitch")
+        self.last_canvas_dev = (d_canvas, H, W, C)
+
+        def plane(ch, key):
+            """canvas[..., ch]: device plane (for the instance tables) + host copy (for the .mat)."""
+            d = self._dev(key, hw4)
+            _lib.check(lib.cerb_channel_plane(ctx.handle, ctypes.c_void_p(d_canvas), H, W, C, ch,
+                                              ctypes.c_void_p(d), 2), "cerb_channel_plane")
+            host = None
+            if to_host:
+                host = np.empty((H, W), dtype=np.float32)
+                _lib.check(lib.cerb_memcpy(ctx.handle, host.ctypes.data_as(ctypes.c_void_p),
+                                           ctypes.c_void_p(d), hw4, 2), "type plane D2H")
+            return d, host
+
+        inst_dev, inst_map_dict, type_map_dict, type_dev = {}, {}, {}, {}
+        pclass_map = None
+        d_flag = self._dev("any_fg", 256)
+        for tissue_code in self.postproc_list:
+            tissue_code = tissue_code.capitalize()
+            if tissue_code + "-INST" in self.decoder_dict.keys():
+                code = self.decoder_dict[tissue_code + "-INST"]
+                if code not in _postproc_func_dict:
+                    raise NotImplementedError("post-proc code %r is outside the hot path" % code)
+                lo, hi = idx_dict[tissue_code + "-INST"]
+                d_lab = self._dev("lab." + tissue_code, hw4)
+                any_fg = 1
+                if _postproc_func_dict[code] is PostProcInstErodedMap:
+                    if hi - lo != 1:
+                        raise ValueError("%s-INST must be a single channel for IP-ERODED-*" % tissue_code)
+                    _lib.check(lib.cerb_postproc_eroded_map(
+                        ctx.handle, ctypes.c_void_p(d_canvas), 1, H, W, C, lo,
+                        {"Gland": 0, "Lumen": 1, "Nuclei": 2}[tissue_code], ctypes.c_void_p(d_lab), 3),
+                        "cerb_postproc_eroded_map")
+                    as_float = True
+                elif tissue_code == "Nuclei":
+                    _lib.check(lib.cerb_postproc_nuclei(ctx.handle, ctypes.c_void_p(d_canvas), 1, H, W, C,
+                                                        lo, ctypes.c_void_p(d_lab),
+                                                        ctypes.c_void_p(d_flag), 3), "cerb_postproc_nuclei")
+                    flag = np.zeros(1, dtype=np.int32)
+                    _lib.check(lib.cerb_memcpy(ctx.handle, flag.ctypes.data_as(ctypes.c_void_p),
+                                               ctypes.c_void_p(d_flag), 4, 2), "any_fg D2H")
+                    any_fg = int(flag[0])
+                    as_float = False
+                else:
+                    _lib.check(lib.cerb_postproc_gland_lumen(
+                        ctx.handle, ctypes.c_void_p(d_canvas), 1, H, W, C, lo,
+                        0 if tissue_code == "Gland" else 1, 1.0, ctypes.c_void_p(d_lab), 3),
+                        "cerb_postproc_gland_lumen")
+                    as_float = True
+                inst_dev[tissue_code] = (d_lab, as_float, any_fg)
+                tkey = tissue_code + "-TYPE"
+                if tkey in idx_dict:
+                    type_dev[tissue_code], type_map_dict[tissue_code] = plane(idx_dict[tkey][0],
+                                                                             "type." + tissue_code)
+                else:
+                    type_dev[tissue_code], type_map_dict[tissue_code] = None, None
+            elif tissue_code == "Patch-class":
+                _, pclass_map = plane(idx_dict["Patch-Class"][0], "pclass")
+        if "lumen" in self.postproc_list and "gland" in self.postproc_list:  # tile.py:187-191
+            _lib.check(lib.cerb_mask_lumen(ctx.handle, ctypes.c_void_p(inst_dev["Lumen"][0]),
+                                           ctypes.c_void_p(inst_dev["Gland"][0]), H * W), "cerb_mask_lumen")
+        # tile.py:193-203: x2 nearest resize of the maps, then get_inst_info_dict; the device
+        # version addresses the upsampled image through up=2. Lumen inherits the previous
+        # tissue's type map (the reference's stale `pred_type_tmp`).
+        inst_info_dict = {}
+        type_tmp = None
+        for tissue_code in self.postproc_list:
+            tissue_code = tissue_code.capitalize()
+            if tissue_code == "Patch-class" or tissue_code not in inst_dev:
+                continue
+            d_lab, as_float, any_fg = inst_dev[tissue_code]
+            if tissue_code != "Lumen" and type_dev[tissue_code] is not None:
+                type_tmp = type_dev[tissue_code]
+            # keys carry the dtype of the reference's label map (np.unique keeps it)
+            kd = np.float64 if (as_float or not any_fg) else np.int32
+            inst_info_dict[tissue_code] = get_inst_info_dict(
+                d_lab, type_tmp, ctx=ctx, up=2, on_device=True, shape=(H, W), key_dtype=kd)
+            if to_host:
+                lab = np.empty((H, W), dtype=np.int32)
+                _lib.check(lib.cerb_memcpy(ctx.handle, lab.ctypes.data_as(ctypes.c_void_p),
+                                           ctypes.c_void_p(d_lab), hw4, 2), "labels D2H")
+                # reference dtypes: nuclei int32 (float64 zeros when the mask is empty,
+                # postproc.py:378-380), gland / lumen float64 (postproc.py:290,331)
+                inst_map_dict[tissue_code] = lab.astype(np.float64) if (as_float or not any_fg) else lab
+        return (m["name"], img, inst_map_dict, inst_info_dict, type_map_dict, pclass_map)
+
     def process_image(self, img, name="image"):
         """One RGB uint8 image -> the tuple _post_process_patches returns."""
+        return self.process_images([(name, img)])[0]
+
+    def process_image_host_plumbing(self, img, name="image"):
+        """The same through the reference-shaped host plumbing (`run_step` list of dicts ->
+        `_post_process_patches`): kept for API parity and as a cross-check of the device path."""
         PostProcInstErodedContourMap.bind(self.engine.ctx)
         info_list, src_pos, _ = patch_grid(img.shape[0], img.shape[1], self.patch_input_shape,
                                            self.patch_output_shape, self.patch_output_overlap)
-        # infer every distinct patch once (the reference's appended duplicate grid averages a
-        # patch with itself, which is exact)
         in_tl = info_list[:, 0, 0, :]
         uniq, first, inverse = np.unique(in_tl, axis=0, return_index=True, return_inverse=True)
         order = np.sort(first)
@@ -231,7 +412,10 @@ class InferManager(base.InferManager):
 
     def process_file_list(self, run_args):
         """Process image tiles < 5000x5000 (tile.py:218-429): same skip-if-done resume rule,
-        same outputs."""
+        same outputs. Files are cached into groups until more than 256 patches are pending
+        (tile.py:294-325) and each group goes through `process_images`; under
+        `torchrun` / `--gpu=0,1,..` (run_infer_tile.py) the sorted file list is sharded over the
+        ranks at file granularity, so stitching and post-processing stay rank-local."""
         for variable, value in run_args.items():
             self.__setattr__(variable, value)
         file_path_list_all = recur_find_ext(self.input_dir, [".png", ".jpg"])
@@ -246,6 +430,10 @@ class InferManager(base.InferManager):
                 file_path_list.append(file_path)
         file_path_list.sort()
         assert len(file_path_list) > 0, "Not Detected Any Files From Path"
+        rank, world = int(getattr(self, "rank", 0)), int(getattr(self, "world_size", 1))
+        if world > 1:
+            from ..dist import shard_units
+            file_path_list = [file_path_list[i] for i in shard_units(len(file_path_list), rank, world)]
         # The reference decodes images in DataLoader worker processes (--nr_inference_workers) and
         # post-processes / saves in a ProcessPoolExecutor (--nr_post_proc_workers). Here every GPU
         # call stays on this thread (a cerb_ctx is single-threaded); the same two flags size a
@@ -261,24 +449,37 @@ class InferManager(base.InferManager):
         pending_saves = []
         try:
             loads = {}
-            for i, file_path in enumerate(file_path_list):
-                if loaders is not None:
-                    for j in range(i, min(i + ahead, len(file_path_list))):
-                        if j not in loads:
-                            loads[j] = loaders.submit(self._load_rgb, file_path_list[j])
-                    img = loads.pop(i).result()
-                else:
-                    img = self._load_rgb(file_path)
-                results = self.process_image(img, pathlib.Path(file_path).stem)
-                if savers is not None:
-                    pending_saves.append((file_path, savers.submit(self._save, results, self.output_dir)))
-                    while len(pending_saves) > 4 * n_save:  # bound the results held in memory
-                        done_path, fut = pending_saves.pop(0)
-                        fut.result()
-                        print("Done Assembling %s" % done_path)
-                else:
-                    self._save(results, self.output_dir)
-                    print("Done Assembling %s" % file_path)
+            i = 0
+            while i < len(file_path_list):
+                # cache files until more than 256 patch-grid entries are pending (tile.py:322-323)
+                group, pending = [], 0
+                while i < len(file_path_list):
+                    file_path = file_path_list[i]
+                    if loaders is not None:
+                        for j in range(i, min(i + ahead, len(file_path_list))):
+                            if j not in loads:
+                                loads[j] = loaders.submit(self._load_rgb, file_path_list[j])
+                        img = loads.pop(i).result()
+                    else:
+                        img = self._load_rgb(file_path)
+                    i += 1
+                    group.append((file_path, img))
+                    info_list, _, _ = patch_grid(img.shape[0], img.shape[1], self.patch_input_shape,
+                                                 self.patch_output_shape, self.patch_output_overlap)
+                    pending += info_list.shape[0]
+                    if pending > 256:
+                        break
+                results = self.process_images([(pathlib.Path(fp).stem, im) for fp, im in group])
+                for (file_path, _), res in zip(group, results):
+                    if savers is not None:
+                        pending_saves.append((file_path, savers.submit(self._save, res, self.output_dir)))
+                        while len(pending_saves) > 4 * n_save:  # bound the results held in memory
+                            done_path, fut = pending_saves.pop(0)
+                            fut.result()
+                            print("Done Assembling %s" % done_path)
+                    else:
+                        self._save(res, self.output_dir)
+                        print("Done Assembling %s" % file_path)
             for done_path, fut in pending_saves:  # a failed write raises here: no silent crash
                 fut.result()
                 print("Done Assembling %s" % done_path)

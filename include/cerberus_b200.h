@@ -285,6 +285,12 @@ int cerb_region_half(cerb_ctx* ctx, const float* canvas_dev, int H, int W, int C
 int cerb_nearest_channel(cerb_ctx* ctx, const float* canvas_dev, int H, int W, int C, int ch,
                          double scale, float* out_host, int oh, int ow);
 
+/* canvas[..., ch] of a device-resident f32 [H,W,C] canvas as a contiguous [H,W] plane: the type /
+ * Patch-Class maps loader/postproc.py:401-405 and infer/tile.py:183-184 slice out of the stitched
+ * canvas. flags bit 1: `out` is device memory (queued on the ctx stream), else host (synchronous). */
+int cerb_channel_plane(cerb_ctx* ctx, const float* canvas_dev, int H, int W, int C, int ch,
+                       float* out, int flags);
+
 /* infer/tile.py:136-163: canvas[tl : tl + (oh,ow)] += patch (in list order), count likewise,
  * canvas / (count + 1e-8), crop [src_y : src_y + out_h, src_x : src_x + out_w].
  * patches: f32 [n,oh,ow,C]; tl_yx: HOST int32 [n][2] (output top-left in canvas coordinates);

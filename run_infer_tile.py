@@ -21,11 +21,20 @@ Options:
   --patch_output_shape=<n>    Shape of network output- Assume square shape. [default: 144]
 
 Same flags and defaults as the reference CLI (run_infer_tile.py:1-23); the work runs on the
-B200-native engine (cerberus_b200). The worker-count flags are accepted for compatibility:
-patch extraction, the network and the post-processing all run on the GPU, there are no
-loader / post-processing worker processes to size.
+B200-native engine (cerberus_b200). Differences a user should know:
+  * `--gpu=0,1,..` uses every listed GPU like the reference (nn.DataParallel over the visible
+    devices, infer/base.py:46) - as one process per GPU: the script re-launches itself under
+    `python -m torch.distributed.run --nproc-per-node N`, rank 0 packs the checkpoint and
+    NCCL-broadcasts it once, the sorted file list is sharded over the ranks (it can also be
+    started under torchrun directly);
+  * --nr_inference_workers / --nr_post_proc_workers size an image-decode and a file-writer
+    thread pool; patch extraction, the network and the post-processing run on the GPU;
+  * precision: environment variable CERB_PRECISION = f16x2 (default: parity mode, logits within
+    1e-3 of the fp32 reference) or f16 (throughput mode); see cerberus_b200/infer/base.py.
 """
 import os
+import subprocess
+import sys
 
 import yaml
 
@@ -34,7 +43,18 @@ from cerberus_b200.cli import parse_usage
 if __name__ == "__main__":
     args = parse_usage(__doc__, version="CoBi Gland Inference")
 
-    if args["--gpu"]:
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    gpu_ids = [g for g in (args["--gpu"] or "").split(",") if g.strip() != ""]
+    if world == 1 and len(gpu_ids) > 1:
+        # one process per listed GPU (the reference spreads over all visible GPUs in one process)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=",".join(gpu_ids))
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node", str(len(gpu_ids)), "--master-addr", "127.0.0.1",
+               "--master-port", os.environ.get("CERB_MASTER_PORT", "29533"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd, env=env))
+    if gpu_ids and world == 1:
         os.environ["CUDA_VISIBLE_DEVICES"] = args["--gpu"]
 
     input_dir = args["--input_dir"]
@@ -61,11 +81,21 @@ if __name__ == "__main__":
         "postproc_list": target_list,
     }
 
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
     from cerberus_b200.infer.tile import InferManager
 
     infer = InferManager(
         checkpoint_path=checkpoint_path,
         decoder_dict=run_paramset["dataset_kwargs"]["req_target_code"],
         model_args=run_paramset["model_kwargs"],
+        device=local_rank if world > 1 else 0,
     )
     infer.process_file_list(run_args)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()

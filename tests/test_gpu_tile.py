@@ -97,3 +97,76 @@ def test_process_image_end_to_end_vs_oracle(manager, six_head_sd):
         if sy1 > sy0 and sx1 > sx0:
             ref_pclass[sy0:sy1, sx0:sx1] = step[k]["Patch-Class"][sy0 - yy0:sy1 - yy0, sx0 - xx0:sx1 - xx0]
     assert (ref_pclass != pclass).mean() < 0.02
+
+
+def _read_dev(manager, ptr, shape, dtype):
+    import ctypes
+    out = np.empty(shape, dtype=dtype)
+    ctx = manager.engine.ctx
+    from cerberus_b200 import _lib
+    _lib.check(ctx.lib.cerb_memcpy(ctx.handle, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(ptr),
+                                   out.nbytes, 2), "D2H")
+    return out
+
+
+def _same_results(a, b):
+    _, _, inst_a, info_a, types_a, pc_a = a
+    _, _, inst_b, info_b, types_b, pc_b = b
+    assert inst_a.keys() == inst_b.keys()
+    for t in inst_a:
+        assert inst_a[t].dtype == inst_b[t].dtype, t
+        assert np.array_equal(inst_a[t], inst_b[t]), t
+        assert list(info_a[t].keys()) == list(info_b[t].keys()), t
+        assert [type(k) for k in info_a[t]] == [type(k) for k in info_b[t]], t
+        for k in info_a[t]:
+            for f in ("box", "centroid", "contour"):
+                assert np.array_equal(info_a[t][k][f], info_b[t][k][f]), (t, k, f)
+            assert info_a[t][k].get("type") == info_b[t][k].get("type"), (t, k)
+            assert info_a[t][k].get("type_prob") == info_b[t][k].get("type_prob"), (t, k)
+        if types_a[t] is None:
+            assert types_b[t] is None
+        else:
+            assert np.array_equal(types_a[t], types_b[t]), t
+    assert np.array_equal(pc_a, pc_b)
+
+
+def test_device_tile_path_equals_host_plumbing_and_oracle(manager):
+    """process_image (device-resident: extract -> plan -> stitch -> post-proc -> instance tables
+    without a host round trip) must equal (a) the reference-shaped host plumbing (run_step list of
+    dicts -> _post_process_patches) in every output, and (b) the ORACLE post-processing
+    (loader/postproc.py restated) applied to the device path's own stitched canvas, bit-exact."""
+    from oracle import postproc_oracle as po
+    img = synth.synthetic_tiles(1, 304, 384, seed=13)[0][:300, :380]
+    manager.patch_input_shape, manager.patch_output_shape = 448, 144
+    manager.patch_output_overlap, manager.batch_size = 0, 4
+    manager.postproc_list = ["gland", "lumen", "nuclei", "patch-class"]
+    dev = manager.process_image(img, "t")
+    d_canvas, H, W, C = manager.last_canvas_dev
+    canvas = _read_dev(manager, d_canvas, (H, W, C), np.float32)
+    host = manager.process_image_host_plumbing(img, "t")
+    _same_results(dev, host)
+    idx = manager.engine.model.idx_dict
+    ref = {t: po.post_process(canvas, idx, t, 1.0)[0] for t in ("Nuclei", "Gland", "Lumen")}
+    ref["Lumen"] = ref["Lumen"] * (ref["Gland"] > 0)
+    n_inst = 0
+    for t in ref:
+        assert np.array_equal(dev[2][t].astype(np.int64), ref[t].astype(np.int64)), t
+        n_inst += int(ref[t].max())
+    assert n_inst > 20  # the check is not vacuous
+
+
+def test_batches_are_filled_across_images(manager):
+    """infer/tile.py:294-325: patches of several files share batches. Three images of different
+    sizes through ONE process_images call with batch 7 == each image alone with batch 3."""
+    imgs = [synth.synthetic_tiles(1, 256, 256, seed=31)[0], synth.synthetic_tiles(1, 304, 384, seed=32)[0][:290, :333],
+            synth.synthetic_tiles(1, 160, 208, seed=33)[0][:150, :200]]
+    manager.patch_input_shape, manager.patch_output_shape = 448, 144
+    manager.patch_output_overlap = 0
+    manager.postproc_list = ["gland", "lumen", "nuclei", "patch-class"]
+    manager.batch_size = 7
+    manager.nr_patches_inferred = 0
+    together = manager.process_images([("a%d" % i, im) for i, im in enumerate(imgs)])
+    assert manager.nr_patches_inferred == 4 + 9 + 4  # unique patches: ceil(size / 144)^2 per image
+    manager.batch_size = 3
+    for i, im in enumerate(imgs):
+        _same_results(together[i], manager.process_image(im, "a%d" % i))

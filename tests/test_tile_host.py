@@ -122,11 +122,17 @@ def test_process_file_list_overlaps_loading_and_saving_with_threads(tmp_path, mo
     main = threading.get_ident()
     seen, saved = [], []
 
-    def fake_process(img, name="image"):
+    groups = []
+
+    def fake_process(named_images):
         assert threading.get_ident() == main      # device work never leaves the calling thread
-        assert img.shape == (8, 9, 3)
-        seen.append((name, int(img[0, 0, 0])))
-        return (name, img, {}, {}, {}, None)
+        groups.append(len(named_images))
+        out = []
+        for name, img in named_images:
+            assert img.shape == (8, 9, 3)
+            seen.append((name, int(img[0, 0, 0])))
+            out.append((name, img, {}, {}, {}, None))
+        return out
 
     def fake_save(results, root):
         if results[0] == "img5" and fail["on"]:
@@ -134,17 +140,52 @@ def test_process_file_list_overlaps_loading_and_saving_with_threads(tmp_path, mo
         saved.append((results[0], threading.get_ident() != main))
 
     fail = {"on": False}
-    monkeypatch.setattr(m, "process_image", fake_process, raising=False)
+    monkeypatch.setattr(m, "process_images", fake_process, raising=False)
     monkeypatch.setattr(tile_mod.InferManager, "_save", staticmethod(fake_save))
     for workers in (0, 2):
         seen.clear()
         saved.clear()
+        groups.clear()
         m.process_file_list({"input_dir": str(in_dir), "output_dir": str(out_dir), "postproc_list": ["gland"],
-                             "nr_inference_workers": workers, "nr_post_proc_workers": workers})
+                             "nr_inference_workers": workers, "nr_post_proc_workers": workers,
+                             "patch_input_shape": 16, "patch_output_shape": 4, "patch_output_overlap": 0})
+        # 8x9 px at 16/4: 2 x 3 grid, duplicated = 12 entries per file; files are cached until more
+        # than 256 entries are pending (infer/tile.py:322-323) -> all 7 files form one group
+        assert groups == [7]
         assert seen == [("img%d" % i, 10 * i) for i in range(7)]
         assert sorted(s[0] for s in saved) == ["img%d" % i for i in range(7)]
         assert all(s[1] == (workers > 0) for s in saved)
     fail["on"] = True
     with pytest.raises(RuntimeError):
         m.process_file_list({"input_dir": str(in_dir), "output_dir": str(out_dir), "postproc_list": ["gland"],
-                             "nr_inference_workers": 2, "nr_post_proc_workers": 2})
+                             "nr_inference_workers": 2, "nr_post_proc_workers": 2,
+                             "patch_input_shape": 16, "patch_output_shape": 4, "patch_output_overlap": 0})
+
+
+def test_process_file_list_groups_and_shards_files(tmp_path, monkeypatch):
+    """Cache groups close when more than 256 patch-grid entries are pending (infer/tile.py:322-323);
+    with world_size 2 the sorted file list is split rank-strided at file granularity."""
+    import cv2
+    from cerberus_b200.infer import tile as tile_mod
+    in_dir, out_dir = tmp_path / "in", tmp_path / "out"
+    in_dir.mkdir()
+    for i in range(9):  # 40x40 px at 16/4: 10 x 10 grid, duplicated = 200 entries per file
+        cv2.imwrite(str(in_dir / ("f%d.png" % i)), np.full((40, 40, 3), i, np.uint8))
+    monkeypatch.setattr(tile_mod.InferManager, "_save", staticmethod(lambda results, root: None))
+    for world in (1, 2):
+        names = []
+        for rank in range(world):
+            m = object.__new__(tile_mod.InferManager)
+            m.rank, m.world_size = rank, world
+            groups = []
+            monkeypatch.setattr(m, "process_images", lambda ni, g=groups: (
+                g.append([n for n, _ in ni]) or [(n, im, {}, {}, {}, None) for n, im in ni]), raising=False)
+            m.process_file_list({"input_dir": str(in_dir), "output_dir": str(out_dir), "postproc_list": ["gland"],
+                                 "nr_inference_workers": 0, "nr_post_proc_workers": 0,
+                                 "patch_input_shape": 16, "patch_output_shape": 4, "patch_output_overlap": 0})
+            assert all(len(g) == 2 for g in groups[:-1]) and 1 <= len(groups[-1]) <= 2
+            names.append([n for g in groups for n in g])
+        if world == 1:
+            assert names[0] == ["f%d" % i for i in range(9)]
+        else:
+            assert names[0] == ["f0", "f2", "f4", "f6", "f8"] and names[1] == ["f1", "f3", "f5", "f7"]
