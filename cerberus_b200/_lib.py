@@ -144,6 +144,8 @@ _SIGNATURES = {
                                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_int32)]),
     "cerb_inst_info_read": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_void_p] * 6),
+    "cerb_pickle_instances": (ctypes.c_int64, [ctypes.c_char_p] + [ctypes.c_void_p] * 6 + [ctypes.c_int64] +
+                              [ctypes.c_void_p] * 2 + [ctypes.c_int64]),
     "cerb_ellipse_rows": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32)]),
     "cerb_copy_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

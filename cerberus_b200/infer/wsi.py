@@ -117,10 +117,29 @@ class InferManager(base.InferManager):
         return None, 0, 1
 
     # ------------------------------------------------------------------ inference
+    @staticmethod
+    def _row_bands(patch_outputs, world):
+        """Splits the (row-major) patch list into `world` contiguous groups of whole patch ROWS,
+        balanced by patch count: [(p_lo, p_hi)] per rank. A rank's patches then cover a
+        horizontal band of the slide that no other rank writes."""
+        n = len(patch_outputs)
+        ys = patch_outputs[:, 1]
+        row_start = np.concatenate([[0], np.nonzero(np.diff(ys))[0] + 1, [n]])  # first patch of each row
+        bands, lo = [], 0
+        for r in range(world):
+            target = n * (r + 1) / world
+            k = int(np.argmin(np.abs(row_start - target)))  # nearest row boundary
+            hi = max(int(row_start[k]), lo) if r < world - 1 else n
+            bands.append((lo, hi))
+            lo = hi
+        return bands
+
     def _infer_slide(self, slide, patch_inputs, patch_outputs):
         """Raw prediction of every selected patch, merged into one device canvas [H, W, C]
-        (infer/wsi.py:585-621). Rank r of P handles batches r, r+P, ...; the canvases are then
-        summed (each pixel has exactly one writer)."""
+        (infer/wsi.py:585-621). With P ranks the patch rows are split into P contiguous bands
+        (balanced by patch count); a rank uploads only the slide rows its band reads, infers its
+        patches, and the bands are then exchanged by one NCCL broadcast per band - no arithmetic
+        and no pixel travels twice (each canvas pixel has exactly one writer)."""
         eng, ctx, lib = self.engine, self.engine.ctx, self.engine.ctx.lib
         dist, rank, world = self._dist()
         H, W = slide.img.shape[:2]
@@ -129,47 +148,56 @@ class InferManager(base.InferManager):
         B = int(self.batch_size)
         dev = torch.device("cuda", ctx.device)
         plan = eng.plan_for(B, pin, pin, pout, pout)
-        slide_dev = torch.from_numpy(np.array(slide.img, dtype=np.uint8, order="C")).to(dev)
+        bands = self._row_bands(patch_outputs, world)
+        p_lo, p_hi = bands[rank]
         canvas = torch.zeros((H, W, C), dtype=torch.float32, device=dev)
-        patch_buf = torch.empty((B, pin, pin, 3), dtype=torch.uint8, device=dev)
-        torch.cuda.synchronize(dev)
-        n = len(patch_inputs)
-        far = -4 * pin  # padding entries of the last batch read only zeros
-        for bi, start in enumerate(range(0, n, B)):
-            if bi % world != rank:
-                continue
-            k = min(B, n - start)
-            tl_in = np.full((B, 2), far, dtype=np.int32)
-            tl_in[:k, 0] = patch_inputs[start:start + k, 1]
-            tl_in[:k, 1] = patch_inputs[start:start + k, 0]
-            _lib.check(lib.cerb_extract_patches(ctx.handle, _ptr(slide_dev), H, W, 0, 0,
-                                                tl_in.ctypes.data_as(_lib.ctypes.c_void_p), B, pin,
-                                                pin, _ptr(patch_buf), 1 | 2 | 4),
-                       "cerb_extract_patches")
-            plan.run(device_ptr=patch_buf.data_ptr())
-            tl_out = np.ascontiguousarray(patch_outputs[start:start + k][:, [1, 0]], dtype=np.int32)
-            _lib.check(lib.cerb_scatter_patches(
-                ctx.handle, _lib.ctypes.c_void_p(plan.tensor_ptr(plan.spec.canvas)), k, pout, pout,
-                C, tl_out.ctypes.data_as(_lib.ctypes.c_void_p), _ptr(canvas), H, W),
-                "cerb_scatter_patches")
-            self.nr_patches_done += k
-        # extract / forward / scatter are queued asynchronously on the ctx stream (the loop above
-        # never waits for the GPU); torch must not touch or free these buffers before it is idle
-        _lib.check(lib.cerb_ctx_sync(ctx.handle), "cerb_ctx_sync")
-        if world > 1:
-            flat = canvas.view(-1)
-            step = 1 << 28  # 1 GiB of float32 per collective
-            for s in range(0, flat.numel(), step):
-                dist.all_reduce(flat[s:s + step])
+        if p_hi > p_lo:
+            # slide rows read by this band (zero padding applies only outside the slide itself)
+            r0 = max(int(patch_inputs[p_lo:p_hi, 1].min()), 0)
+            r1 = min(int(patch_inputs[p_lo:p_hi, 3].max()), H)
+            slide_dev = torch.from_numpy(np.array(slide.img[r0:r1], dtype=np.uint8, order="C")).to(dev)
+            patch_buf = torch.empty((B, pin, pin, 3), dtype=torch.uint8, device=dev)
             torch.cuda.synchronize(dev)
-        del slide_dev, patch_buf
+            far = -4 * pin  # padding entries of the last batch read only zeros
+            for start in range(p_lo, p_hi, B):
+                k = min(B, p_hi - start)
+                tl_in = np.full((B, 2), far, dtype=np.int32)
+                tl_in[:k, 0] = patch_inputs[start:start + k, 1] - r0
+                tl_in[:k, 1] = patch_inputs[start:start + k, 0]
+                _lib.check(lib.cerb_extract_patches(ctx.handle, _ptr(slide_dev), r1 - r0, W, 0, 0,
+                                                    tl_in.ctypes.data_as(_lib.ctypes.c_void_p), B, pin,
+                                                    pin, _ptr(patch_buf), 1 | 2 | 4),
+                           "cerb_extract_patches")
+                plan.run(device_ptr=patch_buf.data_ptr())
+                tl_out = np.ascontiguousarray(patch_outputs[start:start + k][:, [1, 0]], dtype=np.int32)
+                _lib.check(lib.cerb_scatter_patches(
+                    ctx.handle, _lib.ctypes.c_void_p(plan.tensor_ptr(plan.spec.canvas)), k, pout, pout,
+                    C, tl_out.ctypes.data_as(_lib.ctypes.c_void_p), _ptr(canvas), H, W),
+                    "cerb_scatter_patches")
+                self.nr_patches_done += k
+            # extract / forward / scatter are queued asynchronously on the ctx stream (the loop above
+            # never waits for the GPU); torch must not touch or free these buffers before it is idle
+            _lib.check(lib.cerb_ctx_sync(ctx.handle), "cerb_ctx_sync")
+            del slide_dev, patch_buf
+        if world > 1:
+            t0 = time.perf_counter()
+            for r, (lo, hi) in enumerate(bands):
+                if hi <= lo:
+                    continue
+                y0 = max(int(patch_outputs[lo:hi, 1].min()), 0)
+                y1 = min(int(patch_outputs[lo:hi, 3].max()), H)
+                dist.broadcast(canvas[y0:y1], src=r)  # rows are contiguous in [H, W, C]
+            torch.cuda.synchronize(dev)
+            self.t_exchange = time.perf_counter() - t0
         return canvas
 
     # ------------------------------------------------------------------ nuclei
     def _process_tile_predictions(self, canvas, tile_bounds, tile_flag, tile_mode, ref_boxes, margin):
         """infer/wsi.py:64-268 for one post-processing tile, on the device canvas. ref_boxes: [n,4]
         boxes of the instances accumulated so far (cross tiles replace some of them). Returns the
-        tile's instances keyed by fresh ids and the INDICES into ref_boxes it replaces."""
+        tile's surviving instances as COLUMNS (box, centroid, contour offsets, contour points,
+        prob, type - slide coordinates; see dat_writer.InstanceStore) or None, and the INDICES into
+        ref_boxes it replaces."""
         eng, ctx, lib = self.engine, self.engine.ctx, self.engine.ctx.lib
         idx = eng.model.idx_dict
         H, W, C = canvas.shape
@@ -178,7 +206,7 @@ class InferManager(base.InferManager):
         x0, y0 = int(tile_bounds[0]), int(tile_bounds[1])
         x1, y1 = min(int(tile_bounds[2]), W), min(int(tile_bounds[3]), H)  # numpy slicing clips
         if x1 <= x0 or y1 <= y0:
-            return {}, []
+            return None, []
         crop = canvas[y0:y1, x0:x1].contiguous()
         h, w = crop.shape[:2]
         # the label map of the tile stays in HBM: the device instance table is all the host needs
@@ -195,7 +223,7 @@ class InferManager(base.InferManager):
         self.t_dev += time.perf_counter() - t0
         del crop
         if not int(any_fg.item()):
-            return {}, []
+            return None, []
         t0 = time.perf_counter()
         table = inst_table(ctx, labels.data_ptr(), type_dev.data_ptr() if type_dev is not None else None,
                            on_device=True, shape=(h, w))
@@ -203,35 +231,61 @@ class InferManager(base.InferManager):
         rows = np.asarray(instinfo_rows(table), dtype=np.int64)
         if len(rows) == 0:
             self.t_host += time.perf_counter() - t0
-            return {}, []
+            return None, []
         inst_boxes = table.box[rows][:, [1, 0, 3, 2]]  # tile coordinates, [x0, y0, x1, y1]
         sel, sel_ref = select_tile_instances(inst_boxes, tile_bounds, tile_flag, tile_mode, margin,
                                              ref_boxes if tile_mode == 3 else None)
         keep = np.ones(len(rows), dtype=bool)
         keep[np.asarray(sel, dtype=np.int64)] = False
-        dicts = tiatoolbox_dicts(table, rows[keep], offset_xy=tile_tl, has_type=type_map_present)
-        new_inst_dict = dict(zip(_unique_ids(len(dicts)), dicts))
+        cols = self._table_columns(table, rows[keep], tile_tl, type_map_present)
         self.t_host += time.perf_counter() - t0
-        return new_inst_dict, sel_ref
+        return cols, sel_ref
+
+    @staticmethod
+    def _table_columns(table, rows, offset_xy, has_type):
+        """Rows of a device table as columns in slide coordinates - the arithmetic of
+        instinfo.tiatoolbox_dicts ((m10 / m00 + box origin) + offset in float64) without creating a
+        Python object per instance."""
+        rows = np.asarray(rows, dtype=np.int64)
+        off = np.asarray(offset_xy, dtype=np.int64)
+        box = table.box[rows][:, [1, 0, 3, 2]].astype(np.int64)          # x0, y0, x1, y1
+        m = table.moments[rows].astype(np.float64)
+        cen = np.stack([m[:, 1] / m[:, 0], m[:, 2] / m[:, 0]], axis=1)
+        cen = cen + box[:, :2]
+        if off.any():
+            cen = cen + off
+            box = box + np.concatenate([off, off])
+        starts, stops = table.contour_off[rows], table.contour_off[rows + 1]
+        lens = stops - starts
+        coff = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        src = np.repeat(starts - coff[:-1], lens) + np.arange(int(coff[-1]), dtype=np.int64)
+        xy = table.contour_xy[src].astype(np.int64) + off
+        if has_type:
+            typ = (table.type[rows, 0] / 4.0).astype(np.int64)  # int(np.float) truncates
+            prob = table.type[rows, 1] / (table.moments[rows, 0] + 1.0e-6)
+        else:
+            typ = prob = None
+        return (box, cen, coff, xy, prob, typ)
 
     def _postproc_nuclei(self, canvas, patch_outputs, pp_tile_shape, margin):
         """infer/wsi.py:640-686. With several ranks every rank holds the merged canvas; the tiles
-        of a set are strided over ranks (the reference's ProcessPoolExecutor), the per-tile results
-        are gathered and merged on rank 0 in the reference's tile order."""
+        of a set are strided over ranks (the reference's ProcessPoolExecutor); the per-tile tables
+        travel as a handful of arrays and rank 0 appends them in the reference's tile order.
+        Returns a dat_writer.InstanceStore (rank 0) / None."""
+        from .dat_writer import InstanceStore
         dist, rank, world = self._dist()
         H, W, _ = canvas.shape
         tile_sets = get_tile_info((W, H), pp_tile_shape, self.patch_output_shape, margin)
-        nuclei = {}
+        store = InstanceStore(has_type="Nuclei-TYPE" in self.engine.model.idx_dict)
         self.t_dev = self.t_host = 0.0
         for set_idx, (set_bounds, set_flags) in enumerate(tile_sets):
             todo = [i for i, tb in enumerate(set_bounds) if len(boxes_intersect(patch_outputs, tb)) > 0]
             # cross tiles (set 3) replace accumulated instances: every tile of the set sees the boxes
             # accumulated before the set started (the reference submits the whole set at once)
-            ref_uids, ref_boxes = None, None
+            ref_boxes = None
             if set_idx == 3:
                 if rank == 0:
-                    ref_uids = list(nuclei.keys())
-                    ref_boxes = np.array([nuclei[u]["box"] for u in ref_uids], dtype=np.int64).reshape(-1, 4)
+                    ref_boxes = store.boxes()
                 if world > 1:
                     obj = [ref_boxes]
                     dist.broadcast_object_list(obj, src=0)
@@ -239,15 +293,16 @@ class InferManager(base.InferManager):
             local = [(i, self._process_tile_predictions(canvas, set_bounds[i], set_flags[i], set_idx,
                                                         ref_boxes, margin)) for i in todo[rank::world]]
             if world > 1:
-                gathered = [None] * world
-                dist.all_gather_object(gathered, local)
-                local = sorted((x for part in gathered for x in part), key=lambda x: x[0])
+                gathered = [None] * world if rank == 0 else None
+                dist.gather_object(local, gathered, dst=0)
+                if rank == 0:
+                    local = sorted((x for part in gathered for x in part), key=lambda x: x[0])
             if rank == 0:
-                for _, (new_inst_dict, remove_idx_list) in local:
-                    nuclei.update(new_inst_dict)
-                    for j in remove_idx_list:
-                        nuclei.pop(ref_uids[j], None)
-        return nuclei
+                for _, (cols, remove_idx_list) in local:
+                    if cols is not None:
+                        store.append(*cols)
+                    store.remove(remove_idx_list)
+        return store if rank == 0 else None
 
     # ------------------------------------------------------------------ gland / lumen
     def _postproc_gland_lumen(self, canvas, wsi_mask, mask_downsample_ratio):
@@ -361,6 +416,8 @@ class InferManager(base.InferManager):
         dist, rank, world = self._dist()
         start = time.perf_counter()
         slide = ArraySlide.open(wsi_path, self.wsi_proc_mag)
+        if getattr(self, "warm_crop", None):  # tools/wsi_bench.py: untimed warm-up on a corner
+            slide.img = slide.img[:self.warm_crop, :self.warm_crop]
         self.wsi_proc_shape = slide.slide_dimensions(self.wsi_proc_mag)[::-1]  # YX
         self.wsi_base_mag = slide.mpp
         self.wsi_base_shape = np.array(slide.img.shape[:2])
@@ -390,13 +447,20 @@ class InferManager(base.InferManager):
         self.logger.info("Inference Time: %s (%d patches on this rank, %d selected)" % (
             time.perf_counter() - start, self.nr_patches_done, len(patch_inputs)))
         self.last_canvas = canvas if getattr(self, "keep_canvas", False) else None
+        if os.environ.get("CERB_WSI_CANVAS_SHA"):  # debugging aid: is the merged canvas reproducible?
+            import hashlib
+            hsh = hashlib.sha1()
+            for y in range(0, H, 512):
+                hsh.update(canvas[y:y + 512].cpu().numpy().tobytes())
+            self.logger.info("Canvas sha1: %s" % hsh.hexdigest())
+            print("rank %d canvas sha1 %s" % (rank, hsh.hexdigest()), flush=True)
         wsi_inst_info = {}
         start = time.perf_counter()
         # hard-coded in both IOSegmentorConfigs of the reference (infer/wsi.py:898,909), which
         # ignores --ambiguous_size; `_test_margin` is a test hook only
         margin = int(getattr(self, "_test_margin", 64))
-        wsi_inst_info["Nuclei"] = self._postproc_nuclei(canvas, patch_outputs,
-                                                        self.postproc_tile_shape, margin)
+        nuclei_store = self._postproc_nuclei(canvas, patch_outputs, self.postproc_tile_shape, margin)
+        wsi_inst_info["Nuclei"] = nuclei_store
         self.logger.info("Nuclei Post Proc Time: %s" % (time.perf_counter() - start))
         lib_, h_ = eng.ctx.lib, eng.ctx.handle
         self.logger.info("Nuclei watershed: %d large tiles, %d redone by the exact whole-tile emulation "
@@ -406,7 +470,9 @@ class InferManager(base.InferManager):
 
         start = time.perf_counter()
         idx = eng.model.idx_dict
-        if rank == 0 and "Patch-Class" in self.model_args["decoder_kwargs"].keys() and "Patch-Class" in idx:
+        # every rank holds the merged canvas: the tissue map is written by the LAST rank while rank 0
+        # is busy with the instance tables
+        if rank == world - 1 and "Patch-Class" in self.model_args["decoder_kwargs"].keys() and "Patch-Class" in idx:
             import scipy.io as sio
             ds = 0.25
             ph, pw = _cv_round(H * ds), _cv_round(W * ds)
@@ -433,7 +499,14 @@ class InferManager(base.InferManager):
         # for tens of thousands of small arrays; a protocol-5 pickle is what joblib.load reads back
         # identically (tests/test_gpu_wsi.py loads it with joblib) at a fraction of the time.
         t_out = time.perf_counter()
-        dump_dat(wsi_inst_info, "%s/dat/%s.dat" % (output_dir, wsi_basename))
+        from .dat_writer import InstanceStore, write_dat
+        write_dat(wsi_inst_info, "%s/dat/%s.dat" % (output_dir, wsi_basename))
+        self.n_nuclei = int(nuclei_store.alive().sum())
+        if getattr(self, "return_inst_dicts", True):
+            # API convenience (tests, notebooks): the reference's dict of dicts; the CLI turns it off -
+            # half a million Python dicts per slide are the serial tail this module is built to avoid
+            wsi_inst_info = {k: (v.to_dict() if isinstance(v, InstanceStore) else v)
+                             for k, v in wsi_inst_info.items()}
         # part of the reference's "Gland & Lumen Post Proc Time" (:853-856); logged on its own too
         self.logger.info("Output File Time: %s" % (time.perf_counter() - t_out))
         self.logger.info("Gland & Lumen Post Proc Time: %s" % (time.perf_counter() - start))

@@ -358,6 +358,21 @@ int cerb_inst_info(cerb_ctx* ctx, const int32_t* labels, int H, int W, const flo
 int cerb_inst_info_read(cerb_ctx* ctx, int32_t* ids, int32_t* box, int64_t* moments, int32_t* type,
                         int64_t* contour_off, int32_t* contour_xy);
 
+/* Host-only: the pickle stream (protocol-2 opcodes) of the dict items
+ *   uid -> {"box": int64[4], "centroid": float64[2], "contour": int64[k,2], "prob": float|None,
+ *           "type": int|None}
+ * of n instances held as arrays - the `.dat` instance table of infer/wsi.py:853 (joblib.dump of a
+ * dict of half a million small dicts per slide) written without creating a Python object per
+ * instance. uid_hex: n x 32 ASCII characters; contour_off: int64 [n+1] offsets into contour_xy
+ * (int64 [.,2]); prob / type: NULL writes None. memo: 11 pickle memo slots the caller's stream has
+ * defined for (_reconstruct, ndarray, (0,), b"b", dtype int64, dtype float64, "box", "centroid",
+ * "contour", "prob", "type") - see cerberus_b200/infer/dat_writer.py. Returns the stream length in
+ * bytes (written if out != NULL and out_cap suffices) or a negative value on bad input. */
+int64_t cerb_pickle_instances(const char* uid_hex, const int64_t* box, const double* centroid,
+                              const int64_t* contour_off, const int64_t* contour_xy,
+                              const double* prob, const int64_t* type, int64_t n,
+                              const uint8_t* memo, uint8_t* out, int64_t out_cap);
+
 /* cv2.getStructuringElement(MORPH_ELLIPSE, (k,k)) as row runs [j1[i], j2[i]) (1 <= k <= 32). */
 int cerb_ellipse_rows(int k, int32_t* j1, int32_t* j2);
 

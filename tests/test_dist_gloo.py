@@ -88,14 +88,29 @@ def _wsi_worker(rank, world, port, out_dir):
         boxes = np.concatenate([xy, xy + rng.randint(4, 12, (40, 2))], -1)
         sel, sel_ref = select_tile_instances(boxes, tb, tile_flag, tile_mode, margin,
                                              ref_boxes if tile_mode == 3 else None)
-        new = {"m%d_%d_%d_%d" % (tile_mode, tb[0], tb[1], k): {"box": b + np.concatenate([tb[:2]] * 2)}
-               for k, b in enumerate(boxes) if k not in set(sel)}
-        return new, sel_ref  # indices into ref_boxes, resolved to keys on rank 0
+        keep = np.array([k not in set(sel) for k in range(len(boxes))])
+        kb = boxes[keep] + np.concatenate([tb[:2]] * 2)
+        n = len(kb)
+        # columns of dat_writer.InstanceStore: box, centroid, contour offsets, contour points, prob, type
+        cols = (kb, kb[:, :2].astype(np.float64), np.arange(n + 1) * 2, np.repeat(kb[:, :2], 2, axis=0),
+                np.full(n, 0.5), np.full(n, tile_mode))
+        return cols, sel_ref  # indices into the rows accumulated so far
 
+    class _Model:
+        idx_dict = {"Nuclei-TYPE": [6, 7]}
+
+    class _Eng:
+        model = _Model()
+
+    m.engine = _Eng()
     m._process_tile_predictions = fake_tile
     _, pout = get_coordinates((1000, 700), [448, 448], [144, 144], [144, 144])
-    nuclei = m._postproc_nuclei(_FakeCanvas(), pout, [300, 300], 64)
-    torch.save({"keys": sorted(nuclei.keys()), "n_calls": len(calls)}, os.path.join(out_dir, "w%d_r%d.pt" % (world, rank)))
+    store = m._postproc_nuclei(_FakeCanvas(), pout, [300, 300], 64)
+    keys = []
+    if store is not None:
+        box, _, _, _, _, typ = store.columns()
+        keys = sorted("m%d_%s" % (t, "_".join(map(str, b))) for b, t in zip(box.tolist(), typ.tolist()))
+    torch.save({"keys": keys, "n_calls": len(calls)}, os.path.join(out_dir, "w%d_r%d.pt" % (world, rank)))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -161,3 +161,27 @@ def test_dat_writer_round_trips_like_a_plain_pickle(tmp_path):
         same(ref, loaded)
         loaded["Nuclei"]["k3"]["contour"] += 1  # writable, not a view of anything shared
         assert loaded["Nuclei"]["k3"]["contour"].flags.owndata
+
+
+def test_row_bands_split_whole_patch_rows_balanced():
+    """Multi-GPU WSI inference: contiguous bands of whole patch rows, balanced by patch count."""
+    from cerberus_b200.infer.wsi import InferManager
+    from cerberus_b200.infer.wsi_geometry import get_coordinates
+    _, pout = get_coordinates((3000, 2500), [448, 448], [144, 144], [144, 144])
+    rng = np.random.RandomState(0)
+    pout = pout[np.sort(rng.choice(len(pout), int(0.6 * len(pout)), replace=False))]  # mask-filtered
+    for world in (1, 2, 3, 8, 64):
+        bands = InferManager._row_bands(pout, world)
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == len(pout)
+        rows_seen = []
+        for (lo, hi), nxt in zip(bands, bands[1:] + [None]):
+            assert lo <= hi
+            if nxt is not None:
+                assert hi == nxt[0]
+            rows_seen.append(set(pout[lo:hi, 1].tolist()))
+        for a in range(world):
+            for b in range(a + 1, world):
+                assert not (rows_seen[a] & rows_seen[b])  # no patch row is shared between ranks
+        if world <= 8:
+            sizes = [hi - lo for lo, hi in bands]
+            assert max(sizes) - min(sizes) <= 2 * 21  # within two patch rows (21 patches wide)
