@@ -67,6 +67,9 @@ struct Step {
   bool split = false;
   // misc ops
   ActRef a, b, c;
+  // grouped UPADD (op.cout = G > 1): prev / out of every group; a = the shared skip
+  int up_groups = 0;
+  ActRef up_prev[8], up_out[8];
   const uint8_t* u8_in = nullptr;
   HeadParams head;
   PClassParams pclass;
@@ -1133,6 +1136,28 @@ int cerb::plan_create_impl(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n
         if ((rc = check_id(pl, op.in0, "upadd")) || (rc = check_id(pl, op.in1, "upadd")) ||
             (rc = check_id(pl, op.out, "upadd")))
           return bail(rc);
+        if (op.cout > 1) {
+          // grouped form: G = op.cout decoders share the skip tensor in0; their low-resolution
+          // inputs are the tensors in1, in1+1, .., in1+G-1 and their outputs out, .., out+G-1
+          if (op.cout > 8) return bail(fail(CERB_ERR_ARG, "op %d: UPADD groups > 8", i));
+          st.a = act_ref(pl->tensors[op.in0]);
+          st.up_groups = op.cout;
+          for (int d = 0; d < op.cout; ++d) {
+            if ((rc = check_id(pl, op.in1 + d, "upadd")) || (rc = check_id(pl, op.out + d, "upadd")))
+              return bail(rc);
+            ActRef pv = act_ref(pl->tensors[op.in1 + d]);
+            const ActRef ov = act_ref(pl->tensors[op.out + d]);
+            if (st.a.h != 2 * pv.h || st.a.w != 2 * pv.w || ov.h != st.a.h || ov.w != st.a.w ||
+                st.a.c != ov.c || st.a.c % 8 != 0 || op.in_coff % 8 != 0 || op.in_coff + st.a.c > pv.c ||
+                st.a.n != pv.n || st.a.n != ov.n)
+              return bail(fail(CERB_ERR_ARG, "op %d: UPADD (group %d) shape mismatch", i, d));
+            pv.hi += op.in_coff;
+            if (pv.lo) pv.lo += op.in_coff;
+            st.up_prev[d] = pv;
+            st.up_out[d] = ov;
+          }
+          break;
+        }
         st.a = act_ref(pl->tensors[op.in0]);  // skip
         st.b = act_ref(pl->tensors[op.in1]);  // prev (low res)
         st.c = act_ref(pl->tensors[op.out]);
@@ -1245,7 +1270,8 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
       e = launch_maxpool(st.a, st.b, s);
       break;
     case CERB_OP_UPADD:
-      e = launch_upadd(st.a, st.b, st.c, s);
+      e = st.up_groups > 1 ? launch_upadd_multi(st.a, st.up_prev, st.up_out, st.up_groups, s)
+                           : launch_upadd(st.a, st.b, st.c, s);
       break;
     case CERB_OP_HEAD:
       e = launch_head(st.head, s);

@@ -24,6 +24,9 @@ cudaError_t launch_maxpool(ActRef in, ActRef out, cudaStream_t s);
 // out = skip + bilinear_x2(prev), align_corners=False (models/utils/net_layers.py:45-46,
 // models/net_desc.py:185-188). skip/out: [N,2h,2w,C], prev: [N,h,w,C].
 cudaError_t launch_upadd(ActRef skip, ActRef prev, ActRef out, cudaStream_t s);
+// n_groups (prev[d], out[d]) pairs against ONE skip tensor, read once (fp16 mode; else one pass each)
+cudaError_t launch_upadd_multi(ActRef skip, const ActRef* prev, const ActRef* out, int n_groups,
+                               cudaStream_t s);
 
 struct HeadParams {
   ActRef in;            // [N,H,W,96] post-ReLU hidden layer of the classification head

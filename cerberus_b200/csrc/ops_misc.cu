@@ -276,6 +276,80 @@ __global__ void __launch_bounds__(288) upadd_f16_kernel(
   }
 }
 
+// Grouped form: G decoders add THEIR low-resolution tensor to the SAME skip tensor
+// (models/net_desc.py:183-188 runs per decoder; the skip x_k is shared). One launch; the blocks of
+// the G groups that read the same skip pixels are neighbours in launch order, so HBM delivers the
+// skip tensor once: at 256^2 and batch 32 five separate passes move 5 x 603 MB, this one 1943 MB.
+// (Keeping the skip pixels in registers across a per-thread loop over the groups was measured
+// at 2.3 TB/s - too few loads in flight per thread.)
+constexpr int kUpMaxGroups = 8;
+struct UpGroups {
+  const __half* prev[kUpMaxGroups];
+  __half* out[kUpMaxGroups];
+};
+
+__global__ void __launch_bounds__(288) upadd_f16_multi_kernel(
+    const __half* __restrict__ skip, int skip_c, UpGroups gr, int n_groups, int prev_c, int out_c,
+    int PH, int PW, int cg_shift, int ipb) {
+  // blockIdx.x = column block * n_groups + group: the n_groups blocks that need the same skip
+  // pixels are adjacent in launch order, so the skip lines come from HBM once and from L2 after
+  const int d = blockIdx.x % n_groups;
+  const int bx = blockIdx.x / n_groups;
+  const __half* __restrict__ prev = gr.prev[d];
+  __half* __restrict__ out = gr.out[d];
+  const int cg = 1 << cg_shift;
+  const int g = threadIdx.x & (cg - 1);
+  const int i = bx * ipb + (threadIdx.x >> cg_shift) - 1;  // pair column, -1 .. PW-1
+  if (i >= PW) return;
+  const int ph = PH + 1;
+  const int n = blockIdx.y / ph;
+  const int j = blockIdx.y - n * ph - 1;  // pair row, -1 .. PH-1
+  const int H = 2 * PH, W = 2 * PW;
+  const int x0 = max(i, 0), x1 = min(i + 1, PW - 1);
+  const int y0 = max(j, 0), y1 = min(j + 1, PH - 1);
+  const uint32_t pb = static_cast<uint32_t>(n) * PH;
+  const uint32_t gc = g * 8;
+  const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y0) * PW + x0) * prev_c + gc));
+  const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y0) * PW + x1) * prev_c + gc));
+  const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y1) * PW + x0) * prev_c + gc));
+  const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y1) * PW + x1) * prev_c + gc));
+  const int Y0 = 2 * j + 1, X0 = 2 * i + 1;
+  const bool oky[2] = {Y0 >= 0, Y0 + 1 < H};
+  const bool okx[2] = {X0 >= 0, X0 + 1 < W};
+  const uint32_t pix00 = (static_cast<uint32_t>(n) * H + Y0) * W + X0;  // may wrap; used only when valid
+  uint4 sk[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sk[k] = make_uint4(0, 0, 0, 0);
+    if (oky[k >> 1] && okx[k & 1])
+      sk[k] = __ldg(reinterpret_cast<const uint4*>(skip + (pix00 + (k >> 1) * W + (k & 1)) * skip_c + gc));
+  }
+  float p00[8], p01[8], p10[8], p11[8];
+  cvt8(q00, p00); cvt8(q01, p01); cvt8(q10, p10); cvt8(q11, p11);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dy = k >> 1, dx = k & 1;
+    if (!(oky[dy] && okx[dx])) continue;
+    const float ly = (j < 0) ? 0.0f : (dy == 0 ? 0.25f : 0.75f);
+    const float hy = 1.0f - ly;
+    const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
+    const float hx = 1.0f - lx;
+    float s[8];
+    cvt8(sk[k], s);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float u0 = hy * (hx * p00[2 * e] + lx * p01[2 * e]) + ly * (hx * p10[2 * e] + lx * p11[2 * e]);
+      const float u1 = hy * (hx * p00[2 * e + 1] + lx * p01[2 * e + 1]) +
+                       ly * (hx * p10[2 * e + 1] + lx * p11[2 * e + 1]);
+      const __half2 h = __floats2half2_rn(s[2 * e] + u0, s[2 * e + 1] + u1);
+      ow[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(out + (pix00 + dy * W + dx) * out_c + gc) = o;
+  }
+}
+
 // ------------------------------------------------------------------ head tail
 constexpr int kHeadIn = 96;
 constexpr int kHeadMaxC = 8;
@@ -463,6 +537,39 @@ cudaError_t launch_upadd(ActRef skip, ActRef prev, ActRef out, cudaStream_t s) {
   }
   const size_t total = static_cast<size_t>(out.n) * (prev.h + 1) * (prev.w + 1) * (out.c >> 3);
   upadd_kernel<<<grid_for(total, 256), 256, 0, s>>>(skip, prev, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upadd_multi(ActRef skip, const ActRef* prev, const ActRef* out, int n_groups,
+                               cudaStream_t s) {
+  const ActRef& o0 = out[0];
+  const ActRef& p0 = prev[0];
+  const int cg = o0.c >> 3;
+  const size_t out_elems = static_cast<size_t>(o0.n) * o0.h * o0.w * o0.c;
+  bool fast = skip.lo == nullptr && (cg & (cg - 1)) == 0 && cg <= 32 && out_elems < (1ull << 31) &&
+              o0.h == 2 * p0.h && o0.w == 2 * p0.w && n_groups <= kUpMaxGroups && skip.c == o0.c;
+  for (int d = 0; d < n_groups && fast; ++d)
+    fast = prev[d].lo == nullptr && out[d].lo == nullptr && prev[d].c == p0.c && out[d].c == o0.c;
+  if (!fast) {  // split-precision mode / odd shapes: one pass per group
+    for (int d = 0; d < n_groups; ++d) {
+      cudaError_t e = launch_upadd(skip, prev[d], out[d], s);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  UpGroups gr;
+  for (int d = 0; d < kUpMaxGroups; ++d) {
+    gr.prev[d] = d < n_groups ? prev[d].hi : nullptr;
+    gr.out[d] = d < n_groups ? out[d].hi : nullptr;
+  }
+  int cg_shift = 0;
+  while ((1 << cg_shift) < cg) ++cg_shift;
+  const int pw = p0.w + 1;
+  const int nblk = (pw * cg + 255) / 256;
+  const int ipb = (pw + nblk - 1) / nblk;
+  dim3 grid(nblk * n_groups, o0.n * (p0.h + 1));
+  upadd_f16_multi_kernel<<<grid, ipb * cg, 0, s>>>(skip.hi, skip.c, gr, n_groups, p0.c, o0.c, p0.h, p0.w,
+                                                   cg_shift, ipb);
   return cudaGetLastError();
 }
 

@@ -1349,8 +1349,10 @@ __global__ void __launch_bounds__(kThreads)
 k_gl_instance(const int* __restrict__ lab, const int* __restrict__ count,
               const int* __restrict__ has_bg, const int* __restrict__ bb,
               int* __restrict__ out, int H, int W, int max_inst, EllipseRows ell, int smem_words,
+              uint32_t* __restrict__ gpool, unsigned int gpool_words, unsigned int* __restrict__ gpool_top,
               int* __restrict__ err) {
   extern __shared__ uint32_t bitmem[];
+  __shared__ unsigned int s_goff;
   const int img = blockIdx.y;
   const int id = blockIdx.x + 1;
   if (id > count[img]) return;
@@ -1371,12 +1373,21 @@ k_gl_instance(const int* __restrict__ lab, const int* __restrict__ count,
   if (y2 + pad <= H - 1) y2 += pad;
   const int ch = y2 - y1, cw = x2 - x1;
   const int nw = (cw + 31) >> 5;
+  // Crops whose two bit planes do not fit in shared memory (merged glands of ~900 px and more)
+  // take a slice of a global-memory pool instead: same code, the planes just live in L2 / HBM.
+  uint32_t* planes = bitmem;
   if (2 * ch * nw > smem_words) {
-    if (threadIdx.x == 0) atomicExch(err, 11);
-    return;
+    const unsigned int need = 2u * static_cast<unsigned int>(ch) * static_cast<unsigned int>(nw);
+    if (threadIdx.x == 0) s_goff = atomicAdd(gpool_top, need);
+    __syncthreads();
+    if (gpool == nullptr || s_goff + need > gpool_words) {
+      if (threadIdx.x == 0) atomicExch(err, 11);
+      return;
+    }
+    planes = gpool + s_goff;
   }
-  uint32_t* A = bitmem;            // instance bits, later the "outside" flood
-  uint32_t* B = bitmem + ch * nw;  // dilated bits
+  uint32_t* A = planes;            // instance bits, later the "outside" flood
+  uint32_t* B = planes + ch * nw;  // dilated bits
   const int total = ch * nw;
   const uint32_t tail = (cw & 31) ? ((1u << (cw & 31)) - 1u) : 0xffffffffu;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -1825,8 +1836,15 @@ static int gl_pipeline(cerb_ctx* ctx, const char* what, const float* canvas, int
                                    200 * 1024));
     attr_set = true;
   }
+  // overflow pool for oversized crops: the connected-component parent plane (n * hw words, free by
+  // now) holds 16 n whole-image crops; its fill pointer is one of the watershed control words
+  unsigned int* pool_top = reinterpret_cast<unsigned int*>(ws->ctl);
+  CERB_CUDA(cudaMemsetAsync(pool_top, 0, sizeof(unsigned int), s));
+  const size_t pool_words = static_cast<size_t>(n) * hw;
   k_gl_instance<<<dim3(max_inst, n), kThreads, static_cast<size_t>(smem_words) * 4, s>>>(
       ws->lab, ws->count, ws->any_fg, ws->bb, out, H, W, max_inst, ell, smem_words,
+      reinterpret_cast<uint32_t*>(ws->L),
+      static_cast<unsigned int>(pool_words > 0xffffffffull ? 0xffffffffull : pool_words), pool_top,
       ctx->err_flag_dev + 1);
   ctx->launches += 3;
   return finish(ctx, out, labels_out, static_cast<size_t>(n) * hw, flags & 2);

@@ -94,8 +94,11 @@ class ForwardPlan:
             # cannot hide those round trips. Opt-in until the tail is software-pipelined.
             fuse_tail = (ctx.precision == "f16" and ctx.conv64_mode == 1
                          and os.environ.get("CERB_FUSE_TAIL", "0") == "1")
+            # CERB_LEVEL_SYNC=1: decoders level by level with one grouped UPADD per level (A/B switch;
+            # measured slower, see PlanSpec._decoders_level_sync)
             spec = PlanSpec(model, n, h, w, out_h, out_w, want_logits, fuse_upadd=fuse_up,
-                            fuse_tail=fuse_tail)
+                            fuse_tail=fuse_tail,
+                            level_sync=os.environ.get("CERB_LEVEL_SYNC", "0") == "1")
         self.spec = spec
         td, ops = self.spec.c_arrays()
         blob = model.blob

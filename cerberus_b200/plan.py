@@ -182,7 +182,7 @@ class PlanSpec:
     """Tensors + ops for one batch shape. Pure host data (testable without a GPU)."""
 
     def __init__(self, model, n, h, w, out_h, out_w, want_logits=False, fuse_head=True,
-                 fuse_upadd=False, fuse_tail=False):
+                 fuse_upadd=False, fuse_tail=False, level_sync=False):
         if h % 16 or w % 16:
             raise ValueError("input size must be a multiple of 16 (got %dx%d)" % (h, w))
         if out_h > h or out_w > w:
@@ -252,6 +252,10 @@ class PlanSpec:
             self._op(_lib.OP_UPADD, in0=x3, in1=f4, out=s3)
             u4a = T("u4a", n, hs[3], ws[3], 256 * D)
             self._conv(L["dec.first"], s3, u4a, relu=1)
+            if level_sync and fuse_head and not (fuse_upadd or fuse_tail):
+                self._decoders_level_sync(model, L, T, n, h, w, hs, ws, feats, u4a, canvas, want_logits)
+                D = 0  # handled
+        if D:
             u4b = T("u4b", n, hs[3], ws[3], 128)
             s2 = T("s2", n, hs[2], ws[2], 128)
             a2 = T("a2", n, hs[2], ws[2], 128)
@@ -310,6 +314,72 @@ class PlanSpec:
                              head_mode=mode, logits_out=lg, w_off=ho["w_off"], b_off=ho["b_off"])
         if model.has_pclass and want_logits:
             self.logit_tensors["Patch-Class"] = pclass_logits
+
+    def _decoders_level_sync(self, model, L, T, n, h, w, hs, ws, feats, u4a, canvas, want_logits):
+        """OPT-IN (level_sync=True / CERB_LEVEL_SYNC=1), measured and NOT faster on B200: with
+        five separate passes `upadd` already runs at 5.9 TB/s (0.102 ms per decoder at 256^2);
+        the grouped pass moves 36 % fewer bytes but is write-dominated (1.34 of 1.94 GB) and takes
+        0.545 ms for the five, and the step went from 6.12 to 6.21 ms (profiles/r2_level_sync_ab.txt).
+        The D decoders level by level instead of decoder by decoder: the skip tensor of a level
+        (x2 / x1 / x0) is the same for every decoder (models/net_desc.py:183-188), so ONE grouped
+        UPADD reads it once and writes the D sums (at 256^2, batch 32: 1.9 GB of traffic instead
+        of 3.0 GB); consecutive convolutions of a level are independent of each other, so each
+        one's prologue overlaps its predecessor's tail. Every decoder owns its tensors (ids of a
+        kind are consecutive: the grouped UPADD addresses them as first id + d)."""
+        x0, x1, x2 = feats[0], feats[1], feats[2]
+        D = len(model.seg_decoders)
+        decs = model.seg_decoders
+
+        def per_decoder(name, hh, ww, c):
+            return [T("%s.%d" % (name, d), n, hh, ww, c) for d in range(D)]
+
+        u4b = per_decoder("u4b", hs[3], ws[3], 128)
+        s2 = per_decoder("s2", hs[2], ws[2], 128)
+        a2 = per_decoder("a2", hs[2], ws[2], 128)
+        b2 = per_decoder("b2", hs[2], ws[2], 64)
+        s1 = per_decoder("s1", hs[1], ws[1], 64)
+        a1 = per_decoder("a1", hs[1], ws[1], 64)
+        b1 = per_decoder("b1", hs[1], ws[1], 64)
+        s0 = per_decoder("s0", h, w, 64)
+        a0 = per_decoder("a0", h, w, 64)
+        b0 = per_decoder("b0", h, w, 64)
+
+        def upadd(skip, prev, out):
+            if D > 1:
+                self._op(_lib.OP_UPADD, in0=skip, in1=prev[0], out=out[0], cout=D)
+            else:
+                self._op(_lib.OP_UPADD, in0=skip, in1=prev[0], out=out[0])
+
+        for di, d in enumerate(decs):
+            self._conv(L["dec.%s.0.1" % d], u4a, u4b[di], relu=1, in_coff=di * 256)
+        upadd(x2, u4b, s2)
+        for di, d in enumerate(decs):
+            self._conv(L["dec.%s.1.0" % d], s2[di], a2[di], relu=1)
+        for di, d in enumerate(decs):
+            self._conv(L["dec.%s.1.1" % d], a2[di], b2[di], relu=1)
+        upadd(x1, b2, s1)
+        for di, d in enumerate(decs):
+            self._conv(L["dec.%s.2.0" % d], s1[di], a1[di], relu=1)
+        for di, d in enumerate(decs):
+            self._conv(L["dec.%s.2.1" % d], a1[di], b1[di], relu=1)
+        upadd(x0, b1, s0)
+        for di, d in enumerate(decs):
+            self._conv(L["dec.%s.3.0" % d], s0[di], a0[di], relu=1)
+        for di, d in enumerate(decs):
+            self._conv(L["dec.%s.3.1" % d], a0[di], b0[di], relu=1)
+        for di, d in enumerate(decs):
+            ho = L["head.%s.out" % d]
+            key = HEAD_NAME_MAP[d]
+            lo, _ = model.idx_dict[key]
+            lg = -1
+            if want_logits:
+                lg = T("logits." + key, n, h, w, ho["classes"], _lib.CERB_F32)
+                self.logit_tensors[key] = lg
+            mode = _lib.HEAD_INST if ho["clf"] == "INST" else _lib.HEAD_TYPE
+            # 1x1 64->96 + BN + ReLU + 1x1 96->C + softmax/argmax/crop in ONE kernel
+            self._conv(L["head.%s.hidden" % d], b0[di], canvas, relu=1, out_coff=lo,
+                       aux_classes=ho["classes"], aux_w_off=ho["w_off"],
+                       aux_b_off=ho["b_off"], head_mode=mode, logits_out=lg)
 
     # -- helpers
     def _tensor(self, name, n, h, w, c, dtype=_lib.CERB_F16):

@@ -84,7 +84,9 @@ typedef struct cerb_op {
   int32_t in_coff;  /* CONV: first input channel read from in0; UPADD: first channel of in1 */
   int32_t in_c;     /* CONV: number of input channels (multiple of 64; stem: 8)         */
   int32_t out_coff; /* CONV/HEAD/PCLASS: first output channel written                   */
-  int32_t cout;     /* CONV: output channels; HEAD: classes C; PCLASS: classes          */
+  int32_t cout;     /* CONV: output channels; HEAD: classes C; PCLASS: classes; UPADD: G > 1 = grouped form:
+                       the G decoders' prev tensors in1 .. in1+G-1 are added to the ONE skip tensor in0
+                       (read once) into out .. out+G-1                                  */
   int32_t kh, kw, stride, pad;
   int32_t relu;
   int32_t stem;       /* CONV: 1 = 7x7 stem reading the PREP tensor                     */

@@ -265,3 +265,20 @@ def test_model_api_forward_equals_plan_api(built_lib, six_head_sd):
         assert got.shape == want.shape and np.array_equal(got, want)
     cm.close()
     eng.close()
+
+
+def test_level_sync_order_gives_the_same_canvas(built_lib, six_head_sd, monkeypatch):
+    """Opt-in decoder order (level by level, ONE grouped UPADD per level that reads the shared
+    skip tensor once): same arithmetic per output, so the canvas must be bit-identical."""
+    args = synth.model_args()
+    tiles = synth.synthetic_tiles(3, 256, 256, seed=17)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CERB_LEVEL_SYNC", flag)
+        eng = Engine(six_head_sd, args, precision="f16")
+        plan = eng.plan_for(3, 256, 256, 256, 256)
+        assert any(op["kind"] == 4 and op["cout"] > 1 for op in plan.spec.ops) == (flag == "1")
+        plan.run(tiles)
+        outs.append(plan.read_canvas().copy())
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])

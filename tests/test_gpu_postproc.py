@@ -200,3 +200,29 @@ def test_small_tile_marker_ties_fall_back_only_when_the_order_can_matter(ctx):
         ref = po.proc_nuclei(f)
         assert ref.max() == 10 and np.array_equal(got[0], ref), (order_matters, equal_pushes)
         assert after[0] - before[0] == 1 and after[1] - before[1] == expect, (order_matters, equal_pushes, before, after)
+
+
+def test_oversized_gland_crops_use_the_global_memory_path(ctx):
+    """A merged gland whose padded bounding box (~1300 x 1250 px) needs more bit-plane words than
+    fit in shared memory: the reference handles any size (loader/postproc.py:292-307), so must the
+    device (global-memory planes instead of the former error 11). Two such giants plus ordinary
+    glands with holes, at ds 1.0 and ds 0.5, bit-exact vs the oracle."""
+    H, W = 1500, 1400
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    rng = np.random.RandomState(3)
+    inner = np.zeros((H, W), np.float32)
+    # giant ring-shaped gland with lobes (bbox ~1250 x 1200) and a second big one nested in its lumen
+    r = np.hypot(yy - 760, xx - 690)
+    inner[(r < 600 + 25 * np.sin(xx / 40.0)) & (r > 420)] = 0.97
+    inner[np.hypot(yy - 760, xx - 690) < 330] = 0.93
+    for _ in range(40):  # holes that must be filled, small glands, specks below the size filter
+        cy, cx, rad = rng.randint(60, H - 60), rng.randint(60, W - 60), rng.randint(6, 28)
+        inner[np.hypot(yy - cy, xx - cx) < rad] = 0.0 if rng.rand() < 0.5 else 0.9
+    contour = np.zeros_like(inner)
+    field = np.stack([inner, contour], -1)
+    for tissue in ("Gland", "Lumen"):
+        for ds in (1.0, 0.5):
+            got, _ = post_process_batch(ctx, field[None], 0, tissue, ds)
+            ref = po.proc_gland_lumen(field, tissue, ds)
+            assert int(ref.max()) >= 3
+            assert np.array_equal(got[0].astype(np.int64), ref.astype(np.int64)), (tissue, ds)
