@@ -18,6 +18,7 @@
 
 #include "capi_internal.cuh"
 #include "conv3x3.cuh"
+#include "conv3x3c2.cuh"
 #include "conv64.cuh"
 #include "conv64x.cuh"
 #include "conv_tc.cuh"
@@ -59,6 +60,8 @@ struct Step {
   ConvKParams conv;
   Conv64Params c64;
   Conv3Params c3;
+  Conv3c2Params c3p;
+  bool use3p = false;  // CTA-pair kernel (csrc/conv3x3c2.cu)
   Conv64xParams c64x;
   bool use64x = false;
   bool use64 = false;
@@ -550,6 +553,88 @@ int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
   return CERB_OK;
 }
 
+// Wide 3x3 stride-1 layers with Cout % 256 == 0 on CTA pairs (csrc/conv3x3c2.cu).
+int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
+  cerb_ctx* ctx = pl->ctx;
+  const Tensor& in = pl->tensors[op.in0];
+  const Tensor& out = pl->tensors[op.out];
+  Conv3c2Params& p = st.c3p;
+  memset(&p, 0, sizeof(p));
+  st.use3p = true;
+  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  const size_t es = 2;
+  p.n_img = N;
+  p.H = H;
+  p.W = W;
+  p.n_chunks = op.in_c / 64;
+  p.BN = op.cout % 256 == 0 ? 256 : op.cout;  // 256, or the layer's 128 / 64
+  p.n_ntiles = op.cout / p.BN;
+  if (op.in_coff % 8 != 0 || op.in_coff + op.in_c > in.d.c || in.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv3x3c2: bad input channels");
+  if (op.out_coff % 8 != 0 || op.out_coff + op.cout > out.d.c || out.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv3x3c2: bad output channels");
+  {
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(op.in_c), static_cast<cuuint64_t>(W),
+                                static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * in.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * in.d.c * es};
+    const cuuint32_t box[4] = {64, 10, 18, 1};
+    int rc = encode_map(ctx, &p.in_map, static_cast<__half*>(in.plane[0]) + op.in_coff, 4, dims,
+                        strides, box);
+    if (rc) return rc;
+  }
+  const size_t k_total = static_cast<size_t>(9) * op.in_c;
+  if (op.w_off < 0 || op.w_off % 16 != 0 ||
+      static_cast<size_t>(op.w_off) + static_cast<size_t>(op.cout) * k_total * es > pl->blob_bytes)
+    return fail(CERB_ERR_ARG, "conv3x3c2: weight offset out of range");
+  {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(op.cout)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_total) * es};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.BN / 2)};
+    int rc = encode_map(ctx, &p.w_map, pl->blob + op.w_off, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (op.b_off >= 0) {
+    if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + op.cout * 4u > pl->blob_bytes)
+      return fail(CERB_ERR_ARG, "conv3x3c2: bias offset out of range");
+    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+  }
+  const cuuint64_t odims[4] = {static_cast<cuuint64_t>(op.cout), static_cast<cuuint64_t>(W),
+                               static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+  const cuuint32_t obox[4] = {64, 8, 16, 1};
+  {
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(out.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * out.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * out.d.c * es};
+    int rc = encode_map(ctx, &p.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, odims,
+                        strides, obox);
+    if (rc) return rc;
+  }
+  if (op.in1 >= 0) {
+    if (op.in1 >= static_cast<int>(pl->tensors.size()))
+      return fail(CERB_ERR_ARG, "conv3x3c2: residual id out of range");
+    const Tensor& res = pl->tensors[op.in1];
+    if (res.d.n != N || res.d.h != H || res.d.w != W || res.d.c < op.cout || res.d.c % 8 != 0 ||
+        res.d.dtype != CERB_F16)
+      return fail(CERB_ERR_ARG, "conv3x3c2: residual shape mismatch");
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(res.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * res.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * res.d.c * es};
+    int rc = encode_map(ctx, &p.res_map, res.plane[0], 4, odims, strides, obox);
+    if (rc) return rc;
+    p.has_res = 1;
+  }
+  p.relu = op.relu;
+  if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv3x3c2: w_shift out of range");
+  p.acc_scale = ldexpf(1.0f, -op.w_shift);
+  p.err_flag = ctx->err_flag_dev;
+  p.prof = ctx->prof_dev;
+  p.tile_counter = ctx->dyn_sched ? pl->cur_counter : nullptr;
+  conv3x3c2_plan(p);
+  return CERB_OK;
+}
+
 int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   cerb_ctx* ctx = pl->ctx;
   const int nt = static_cast<int>(pl->tensors.size());
@@ -607,6 +692,17 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
                         op.in_c % 64 == 0 && op.cout % 128 == 0 &&
                         (ctx->conv3_mode > 1 || op.cout <= 512) && in.d.h == H && in.d.w == W &&
                         op.in0 < nt && op.out < nt;
+  const bool conv3_shape = !split && !op.stem && !fused_head && ctx->conv3_mode > 0 && op.kh == 3 &&
+                           op.kw == 3 && op.stride == 1 && op.pad == 1 && op.in_c >= 128 &&
+                           op.in_c % 64 == 0 && in.d.h == H && in.d.w == W;
+  // conv3_pair 1 (default): the layers with Cout % 256 == 0 (layer3 / layer4), where the pair kernel
+  // measured faster (0.044 vs 0.048 ms at batch 32); 2: also Cout = 128 / 64, where it measured
+  // SLOWER than conv3x3.cu (0.063 vs 0.048 ms on 128->128 at 64x64: both kernels sit at the L2 -> SM
+  // delivery limit there and the pair kernel's items are half as long)
+  if (conv3_shape && ctx->conv3_pair > 0 &&
+      ((op.cout % 256 == 0 && (ctx->conv3_mode > 1 || op.cout <= 512)) ||
+       (ctx->conv3_pair > 1 && (op.cout == 64 || op.cout == 128))))
+    return build_conv3_pair(pl, op, st);
   if (conv3_ok) return build_conv3(pl, op, st);
   int bw = op.box_w > 0 ? op.box_w : pick_box_w(H, W);
   if (bw > 128 || (bw & (bw - 1)) != 0) return fail(CERB_ERR_ARG, "conv: bad box_w %d", bw);
@@ -892,6 +988,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
   if (strcmp(name, "conv64_mode") == 0) {
     if (value < -1 || value > 3) return fail(CERB_ERR_ARG, "conv64_mode must be -1, 0, 1, 2 or 3");
     ctx->conv64_mode = value;
+    return CERB_OK;
+  }
+  if (strcmp(name, "conv3_pair") == 0) {
+    ctx->conv3_pair = value;
     return CERB_OK;
   }
   if (strcmp(name, "conv3_mode") == 0) {
@@ -1263,6 +1363,7 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
     case CERB_OP_CONV:
       e = st.use64x ? conv64x_launch(st.c64x, ctx->conv_sms, s, ctx->use_pdl)
           : st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s, ctx->use_pdl)
+          : st.use3p ? conv3x3c2_launch(st.c3p, ctx->conv_sms, s, ctx->use_pdl)
           : st.use3 ? conv3x3_launch(st.c3, ctx->conv_sms, s, ctx->use_pdl)
                     : conv_tc_launch(st.conv, st.split, ctx->conv_sms, s, ctx->use_pdl);
       break;

@@ -179,3 +179,35 @@ def test_conv64_fused_upsample_add(shape, built_lib):
     ref = nchw_to_nhwc(ref.numpy())
     err = np.abs(outs[0] - ref)
     assert np.all(err <= 4e-3 * np.abs(ref) + 4e-3), err.max()
+
+
+PAIR_CASES = [
+    # n, h, w, cin, cout, k, stride, residual, relu  (3x3 stride 1, Cout % 256 == 0)
+    (2, 32, 32, 256, 256, 3, 1, False, True),     # layer3 body
+    (2, 28, 28, 256, 256, 3, 1, True, True),      # partial regions (448 input), residual
+    (3, 16, 16, 512, 512, 3, 1, True, True),      # layer4: two 256-channel tiles, K = 4608
+    (1, 16, 16, 128, 256, 3, 1, False, False),    # one region, 2 chunks, no ReLU
+    (37, 16, 16, 256, 256, 3, 1, True, True),     # an odd number of items
+    (5, 40, 24, 128, 512, 3, 1, True, False),     # partial regions in x and y
+    (80, 16, 16, 256, 256, 3, 1, False, True),    # more items than CTA pairs (dynamic scheduling)
+    (2, 64, 64, 128, 128, 3, 1, True, True),      # N = 128 per pair (64 weight rows per CTA): layer2 / u3
+    (5, 40, 24, 128, 128, 3, 1, True, False),
+    (40, 16, 16, 256, 128, 3, 1, False, True),    # decoder u4 second conv
+    (1, 48, 80, 128, 64, 3, 1, False, True),      # N = 64 per pair (32 weight rows per CTA): u3 second conv
+    (3, 64, 64, 128, 64, 3, 1, False, True),
+]
+
+
+@pytest.mark.parametrize("dyn", [1, 0])
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv3x3_cta_pair_kernel(case, dyn, built_lib, monkeypatch):
+    """Wide 3x3 layers on CTA pairs (tcgen05.mma.cta_group::2, csrc/conv3x3c2.cu): M = 256 x N = 256 /
+    128 / 64 MMAs whose operands and accumulator are split over the two CTAs of a cluster. Run with
+    the pair kernel forced on and compared with the fp64 convolution; the default-mode tests above
+    (test_conv_f16) cover whichever kernel the library picks."""
+    monkeypatch.setenv("CERB_CONV3_PAIR", "2")  # also the N = 128 / 64 variants (off by default: slower)
+    monkeypatch.setenv("CERB_DYN_SCHED", str(dyn))
+    got, ref = _run_case("f16", *case)
+    err = np.abs(got - ref)
+    tol = 2e-3 * np.abs(ref) + 2e-3
+    assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))
