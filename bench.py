@@ -745,7 +745,9 @@ def run_tile448(args):
     m = InferManager(checkpoint_path=tmp + "/model_all/weights.tar",
                      decoder_dict=st["dataset_kwargs"]["req_target_code"], model_args=st["model_kwargs"],
                      precision=args.precision, device=local_rank)
-    run_args = {"nr_inference_workers": 4, "nr_post_proc_workers": 4, "batch_size": args.batch,
+    nw = int(os.environ.get("CERB_TILE448_WORKERS", "4"))
+    m.time_stages = os.environ.get("CERB_TILE448_STAGES") == "1"
+    run_args = {"nr_inference_workers": nw, "nr_post_proc_workers": nw, "batch_size": args.batch,
                 "input_dir": tmp + "/in", "output_dir": tmp + "/out_warm", "patch_input_shape": 448,
                 "patch_output_shape": 144, "patch_output_overlap": 0,
                 "postproc_list": ["gland", "lumen", "nuclei", "patch-class"]}
@@ -757,6 +759,8 @@ def run_tile448(args):
         if world > 1:
             dist.barrier()
         m.nr_patches_inferred = 0
+        m.stage_seconds = {"extract": 0.0, "forward": 0.0, "finish": 0.0}
+        m.finish_seconds = {}
         run_args["output_dir"] = tmp + "/out"
         os.makedirs(run_args["output_dir"], exist_ok=True)
         l0 = m.engine.ctx.launch_count
@@ -790,7 +794,10 @@ def run_tile448(args):
                                        % (n_files, size, size, args.batch),
                            "files": n_files, "patches_448_inferred": int(patches),
                            "patches_per_s": patches / dt, "files_per_s": n_files / dt,
-                           "precision": args.precision, "mat_files_written": n_out},
+                           "precision": args.precision, "mat_files_written": n_out,
+                           "loader_and_writer_threads": nw,
+                           "rank0_stage_seconds": {k: round(v, 3) for k, v in m.stage_seconds.items()},
+                           "rank0_finish_seconds": {k: round(v, 3) for k, v in getattr(m, "finish_seconds", {}).items()}},
                 "e2e": {"value": px / 65536.0 / dt, "unit": "tiles/s",
                         "h2d_bytes_per_step": int(px * 3), "d2h_bytes_per_step": int(px * 4 * 6)},
                 "gpu_launches": int(m.engine.ctx.launch_count - l0),

@@ -208,13 +208,16 @@ class InferManager(base.InferManager):
         return out
 
     # ------------------------------------------------------------------ device-resident path
-    def _dev(self, key, nbytes):
-        """Grow-only device buffer owned by the manager."""
-        bufs = self.__dict__.setdefault("_dev_bufs", {})
+    def _dev(self, key, nbytes, ctx=None):
+        """Grow-only device buffer owned by the manager, one pool per context (the finishing
+        stage runs on its own context / thread and must not share buffers with the forward)."""
+        ctx = ctx if ctx is not None else self.engine.ctx
+        pools = self.__dict__.setdefault("_dev_bufs", {})
+        bufs = pools.setdefault(id(ctx), {"ctx": ctx})
         cur = bufs.get(key)
         if cur is None or cur[1] < nbytes:
-            ctx = self.engine.ctx
             if cur is not None:
+                ctx.sync()
                 ctx.lib.cerb_dev_free(ctx.handle, ctypes.c_void_p(cur[0]))
             p = ctx.lib.cerb_dev_alloc(ctx.handle, int(nbytes))
             if not p:
@@ -223,10 +226,35 @@ class InferManager(base.InferManager):
         return cur[0]
 
     def release_device_buffers(self):
-        ctx = self.engine.ctx
-        for p, _ in self.__dict__.get("_dev_bufs", {}).values():
-            ctx.lib.cerb_dev_free(ctx.handle, ctypes.c_void_p(p))
+        for bufs in self.__dict__.get("_dev_bufs", {}).values():
+            ctx = bufs["ctx"]
+            if getattr(ctx, "handle", None):
+                for k, v in bufs.items():
+                    if k != "ctx":
+                        ctx.lib.cerb_dev_free(ctx.handle, ctypes.c_void_p(v[0]))
         self._dev_bufs = {}
+        for fin in self.__dict__.pop("_finish_ctxs", []):
+            fin.close()
+        self.__dict__.pop("_finish_tl", None)
+
+    def _sync_forward(self):
+        self.engine.ctx.sync()
+
+    def _finisher_ctx(self):
+        """A context (own stream, own post-processing workspaces) for the finishing stage: one per
+        worker thread, created on first use."""
+        import threading
+        tl = self.__dict__.setdefault("_finish_tl", threading.local())
+        if getattr(tl, "ctx", None) is None:
+            from ..engine import Context
+            tl.ctx = Context(self.engine.ctx.device, self.engine.ctx.precision)
+            self.__dict__.setdefault("_finish_ctxs", []).append(tl.ctx)
+        return tl.ctx
+
+    def _finish_one(self, m, group, to_host=True):
+        """Worker-thread task: a16-a20 for one image of a forwarded group."""
+        return self._finish_image(m, group["store"] + m["first"] * group["cbytes"], group["P_out"],
+                                  group["C"], self.engine.model.idx_dict, to_host, self._finisher_ctx())
 
     def process_images(self, named_images, to_host=True):
         """A group of RGB uint8 images -> one result tuple per image (the tuple
@@ -240,13 +268,26 @@ class InferManager(base.InferManager):
         Per image the host receives the label maps, the type / Patch-Class planes and the
         instance tables, nothing else. Every distinct patch is inferred once: the duplicate grid
         the reference appends (tile.py:90-103) averages a patch with itself, which is exact."""
+        import time as _time
+        tm = self.__dict__.setdefault("stage_seconds", {"extract": 0.0, "forward": 0.0, "finish": 0.0})
+        group = self._forward_group(named_images, slot=0)
+        self.engine.ctx.sync()
+        t0 = _time.perf_counter()
+        out = self._finish_group(group, self.engine.ctx, to_host)
+        tm["finish"] += _time.perf_counter() - t0
+        return out
+
+    def _forward_group(self, named_images, slot=0):
+        """Stage 1 (forward context): upload, extract, forward; the per-patch canvases of the
+        group end up in the device store `slot`. Asynchronous - the caller synchronises."""
+        import time as _time
         eng = self.engine
         ctx, lib, model = eng.ctx, eng.ctx.lib, eng.model
-        PostProcInstErodedContourMap.bind(ctx)
+        tm = self.__dict__.setdefault("stage_seconds", {"extract": 0.0, "forward": 0.0, "finish": 0.0})
+        t_stage = _time.perf_counter()
         P_in, P_out = int(self.patch_input_shape), int(self.patch_output_shape)
         B = max(1, int(self.batch_size))
         C = model.canvas_c
-        idx_dict = model.idx_dict
         plan = eng.plan_for(B, P_in, P_in, P_out, P_out)
         metas, total = [], 0
         for name, img in named_images:
@@ -265,7 +306,7 @@ class InferManager(base.InferManager):
         nb = (total + B - 1) // B
         pbytes, cbytes = P_in * P_in * 3, P_out * P_out * C * 4
         d_patches = self._dev("patches", nb * B * pbytes)
-        d_store = self._dev("store", nb * B * cbytes)
+        d_store = self._dev("store%d" % slot, nb * B * cbytes)
         max_img = max(m["img"].nbytes for m in metas)
         d_img = self._dev("img", max_img)
         for m in metas:  # a1/a2: reflect pad + slicing on the device, into the batch buffer
@@ -277,33 +318,55 @@ class InferManager(base.InferManager):
                 int(m["src_pos"][1]), m["in_tl"].ctypes.data_as(ctypes.c_void_p), len(m["in_tl"]),
                 P_in, P_in, ctypes.c_void_p(d_patches + m["first"] * pbytes), 3), "cerb_extract_patches")
             ctx.sync()  # d_img is reused by the next image
+        tm["extract"] += _time.perf_counter() - t_stage
+        t_stage = _time.perf_counter()
         canvas_ptr = plan.tensor_ptr(plan.spec.canvas)
         for b in range(nb):  # a3-a15
             plan.run(device_ptr=d_patches + b * B * pbytes)
             _lib.check(lib.cerb_memcpy(ctx.handle, ctypes.c_void_p(d_store + b * B * cbytes),
                                        ctypes.c_void_p(canvas_ptr), B * cbytes, 3), "canvas -> store")
         self.nr_patches_inferred = getattr(self, "nr_patches_inferred", 0) + total
-        return [self._finish_image(m, d_store + m["first"] * cbytes, P_out, C, idx_dict, to_host)
-                for m in metas]
+        if getattr(self, "time_stages", False):
+            ctx.sync()
+        tm["forward"] += _time.perf_counter() - t_stage
+        return {"metas": metas, "store": d_store, "cbytes": cbytes, "P_out": P_out, "C": C}
 
-    def _finish_image(self, m, d_patch_canvas, P_out, C, idx_dict, to_host):
+    def _finish_group(self, group, ctx, to_host=True):
+        """Stage 2 (any context): a16-a20 for every image of a forwarded group."""
+        idx_dict = self.engine.model.idx_dict
+        return [self._finish_image(m, group["store"] + m["first"] * group["cbytes"], group["P_out"],
+                                   group["C"], idx_dict, to_host, ctx) for m in group["metas"]]
+
+    def _finish_image(self, m, d_patch_canvas, P_out, C, idx_dict, to_host, ctx=None):
         """a16-a20 for one image, device-resident: stitch, post-process, instance tables."""
-        ctx = self.engine.ctx
+        import time as _time
+        ctx = ctx if ctx is not None else self.engine.ctx
         lib = ctx.lib
         img = m["img"]
         H, W = img.shape[:2]
         n = len(m["out_tl"])
         hw4 = H * W * 4
-        d_canvas = self._dev("canvas", H * W * C * 4)
+        fine = self.__dict__.setdefault("finish_seconds", {}) if getattr(self, "time_stages", False) else None
+        t_ph = [_time.perf_counter()]
+
+        def phase(name):
+            if fine is not None:
+                ctx.sync()
+                now = _time.perf_counter()
+                fine[name] = fine.get(name, 0.0) + now - t_ph[0]
+                t_ph[0] = now
+
+        d_canvas = self._dev("canvas", H * W * C * 4, ctx)
         _lib.check(lib.cerb_stitch(ctx.handle, ctypes.c_void_p(d_patch_canvas), n, P_out, P_out, C,
                                    m["out_tl"].ctypes.data_as(ctypes.c_void_p), m["canvas_hw"][0],
                                    m["canvas_hw"][1], int(m["src_pos"][0]), int(m["src_pos"][1]), H, W,
                                    ctypes.c_void_p(d_canvas), 3), "cerb_stitch")
         self.last_canvas_dev = (d_canvas, H, W, C)
+        phase("stitch")
 
         def plane(ch, key):
             """canvas[..., ch]: device plane (for the instance tables) + host copy (for the .mat)."""
-            d = self._dev(key, hw4)
+            d = self._dev(key, hw4, ctx)
             _lib.check(lib.cerb_channel_plane(ctx.handle, ctypes.c_void_p(d_canvas), H, W, C, ch,
                                               ctypes.c_void_p(d), 2), "cerb_channel_plane")
             host = None
@@ -315,7 +378,7 @@ class InferManager(base.InferManager):
 
         inst_dev, inst_map_dict, type_map_dict, type_dev = {}, {}, {}, {}
         pclass_map = None
-        d_flag = self._dev("any_fg", 256)
+        d_flag = self._dev("any_fg", 256, ctx)
         for tissue_code in self.postproc_list:
             tissue_code = tissue_code.capitalize()
             if tissue_code + "-INST" in self.decoder_dict.keys():
@@ -323,7 +386,7 @@ class InferManager(base.InferManager):
                 if code not in _postproc_func_dict:
                     raise NotImplementedError("post-proc code %r is outside the hot path" % code)
                 lo, hi = idx_dict[tissue_code + "-INST"]
-                d_lab = self._dev("lab." + tissue_code, hw4)
+                d_lab = self._dev("lab." + tissue_code, hw4, ctx)
                 any_fg = 1
                 if _postproc_func_dict[code] is PostProcInstErodedMap:
                     if hi - lo != 1:
@@ -357,6 +420,7 @@ class InferManager(base.InferManager):
                     type_dev[tissue_code], type_map_dict[tissue_code] = None, None
             elif tissue_code == "Patch-class":
                 _, pclass_map = plane(idx_dict["Patch-Class"][0], "pclass")
+        phase("postproc+planes")
         if "lumen" in self.postproc_list and "gland" in self.postproc_list:  # tile.py:187-191
             _lib.check(lib.cerb_mask_lumen(ctx.handle, ctypes.c_void_p(inst_dev["Lumen"][0]),
                                            ctypes.c_void_p(inst_dev["Gland"][0]), H * W), "cerb_mask_lumen")
@@ -376,6 +440,7 @@ class InferManager(base.InferManager):
             kd = np.float64 if (as_float or not any_fg) else np.int32
             inst_info_dict[tissue_code] = get_inst_info_dict(
                 d_lab, type_tmp, ctx=ctx, up=2, on_device=True, shape=(H, W), key_dtype=kd)
+            phase("inst_info")
             if to_host:
                 lab = np.empty((H, W), dtype=np.int32)
                 _lib.check(lib.cerb_memcpy(ctx.handle, lab.ctypes.data_as(ctypes.c_void_p),
@@ -383,6 +448,7 @@ class InferManager(base.InferManager):
                 # reference dtypes: nuclei int32 (float64 zeros when the mask is empty,
                 # postproc.py:378-380), gland / lumen float64 (postproc.py:290,331)
                 inst_map_dict[tissue_code] = lab.astype(np.float64) if (as_float or not any_fg) else lab
+                phase("labels_d2h")
         return (m["name"], img, inst_map_dict, inst_info_dict, type_map_dict, pclass_map)
 
     def process_image(self, img, name="image"):
@@ -435,8 +501,9 @@ class InferManager(base.InferManager):
             from ..dist import shard_units
             file_path_list = [file_path_list[i] for i in shard_units(len(file_path_list), rank, world)]
         # The reference decodes images in DataLoader worker processes (--nr_inference_workers) and
-        # post-processes / saves in a ProcessPoolExecutor (--nr_post_proc_workers). Here every GPU
-        # call stays on this thread (a cerb_ctx is single-threaded); the same two flags size a
+        # post-processes / saves in a ProcessPoolExecutor (--nr_post_proc_workers). Here the forward
+        # stays on this thread and the finishing stage on worker threads with their own contexts (a
+        # cerb_ctx is single-threaded); the same two flags size a
         # loader thread pool (PNG decode of the next images) and a writer thread pool (overlay,
         # .mat files of the previous images), both of which spend their time inside OpenCV /
         # scipy.io with the GIL released. 0 workers = everything inline, as in the reference.
@@ -447,6 +514,27 @@ class InferManager(base.InferManager):
         savers = ThreadPoolExecutor(n_save) if n_save > 0 else None
         ahead = max(2 * n_load, 1)
         pending_saves = []
+        # finishing stage: --nr_post_proc_workers threads (1..4), each with its own context
+        finisher = ThreadPoolExecutor(max(1, min(n_save, 4)))
+        inflight, n_groups = None, 0
+
+        def deliver(group, futs):
+            import time as _time
+            t0 = _time.perf_counter()
+            results = [f.result() for f in futs]
+            tm = self.__dict__.setdefault("stage_seconds", {"extract": 0.0, "forward": 0.0, "finish": 0.0})
+            tm["finish"] += _time.perf_counter() - t0  # time the main thread WAITED for the finisher
+            for (file_path, _), res in zip(group, results):
+                if savers is not None:
+                    pending_saves.append((file_path, savers.submit(self._save, res, self.output_dir)))
+                    while len(pending_saves) > 4 * n_save:  # bound the results held in memory
+                        done_path, f2 = pending_saves.pop(0)
+                        f2.result()
+                        print("Done Assembling %s" % done_path)
+                else:
+                    self._save(res, self.output_dir)
+                    print("Done Assembling %s" % file_path)
+
         try:
             loads = {}
             i = 0
@@ -469,21 +557,24 @@ class InferManager(base.InferManager):
                     pending += info_list.shape[0]
                     if pending > 256:
                         break
-                results = self.process_images([(pathlib.Path(fp).stem, im) for fp, im in group])
-                for (file_path, _), res in zip(group, results):
-                    if savers is not None:
-                        pending_saves.append((file_path, savers.submit(self._save, res, self.output_dir)))
-                        while len(pending_saves) > 4 * n_save:  # bound the results held in memory
-                            done_path, fut = pending_saves.pop(0)
-                            fut.result()
-                            print("Done Assembling %s" % done_path)
-                    else:
-                        self._save(res, self.output_dir)
-                        print("Done Assembling %s" % file_path)
+                # Two-stage pipeline: the forward of THIS group runs on the engine's context while
+                # worker threads finish (stitch / post-processing / instance tables) the images of
+                # the PREVIOUS group on their own contexts - the finishing stage is many small
+                # kernels and host work, the forward keeps the GPU busy. Two device stores alternate.
+                fwd = self._forward_group([(pathlib.Path(fp).stem, im) for fp, im in group], slot=n_groups & 1)
+                n_groups += 1
+                self._sync_forward()
+                if inflight is not None:
+                    deliver(*inflight)
+                inflight = (group, [finisher.submit(self._finish_one, m, fwd) for m in fwd["metas"]])
+            if inflight is not None:
+                deliver(*inflight)
+                inflight = None
             for done_path, fut in pending_saves:  # a failed write raises here: no silent crash
                 fut.result()
                 print("Done Assembling %s" % done_path)
         finally:
+            finisher.shutdown(wait=True)
             for pool in (loaders, savers):
                 if pool is not None:
                     pool.shutdown(wait=True)

@@ -123,20 +123,31 @@ def get_inst_info_dict(inst_map, type_map, ds_factor=1.0, ctx=None, up=1, key_dt
         if up != 1 and key_dtype is np.int64:
             key_dtype = np.int32  # the cv2.resize this call folds in hands int64 maps back as int32
     has_type = bool(type_map) if on_device else type_map is not None
+    # All fields for all rows at once (a 1000 x 1000 tile holds ~1500 nuclei; a per-instance
+    # Python loop over numpy scalars costs 15 us each): same arithmetic and dtypes as the
+    # reference's loop - bbox int64 [[rmin, cmin], [rmax, cmax]], centroid float64 (m10 / m00 +
+    # cmin, m01 / m00 + rmin), contour = the device's int32 points, type int, type_prob float.
+    rows = np.asarray(_rows(table), dtype=np.int64)
     info = {}
-    m = table.moments.astype(np.float64)
-    for i in _rows(table):
-        rmin, cmin, rmax, cmax = (int(v) for v in table.box[i])
-        bbox = np.array([[rmin, cmin], [rmax, cmax]])
-        centroid = np.array([m[i, 1] / m[i, 0], m[i, 2] / m[i, 0]])
-        centroid[0] += cmin
-        centroid[1] += rmin
-        contour = table.contour_xy[table.contour_off[i]:table.contour_off[i + 1]].copy()
-        d = {"box": bbox, "centroid": centroid, "contour": contour}
+    if len(rows):
+        box = table.box[rows].astype(np.int64).reshape(-1, 2, 2)
+        m = table.moments[rows].astype(np.float64)
+        cen = np.stack([m[:, 1] / m[:, 0] + box[:, 0, 1], m[:, 2] / m[:, 0] + box[:, 0, 0]], axis=1)
+        starts, stops = table.contour_off[rows], table.contour_off[rows + 1]
+        if np.array_equal(stops[:-1], starts[1:]):
+            contours = np.split(table.contour_xy[starts[0]:stops[-1]], (stops[:-1] - starts[0]).tolist())
+        else:
+            contours = [table.contour_xy[a:b] for a, b in zip(starts.tolist(), stops.tolist())]
+        contours = [c.copy() for c in contours]  # own their data, like the reference's arrays
+        keys = [key_dtype(v) for v in table.ids[rows].tolist()]
         if has_type:
-            d["type"] = int(table.type[i, 0] / 4.0)  # int(np.float) truncates (postproc.py:69)
-            d["type_prob"] = float(table.type[i, 1] / (table.moments[i, 0] + 1.0e-6))
-        info[key_dtype(table.ids[i])] = d
+            types = (table.type[rows, 0] / 4.0).astype(np.int64).tolist()  # int(np.float) truncates (postproc.py:69)
+            probs = (table.type[rows, 1] / (table.moments[rows, 0] + 1.0e-6)).tolist()
+            for k, b, c, ct, ty, pr in zip(keys, list(box), list(cen), contours, types, probs):
+                info[k] = {"box": b, "centroid": c, "contour": ct, "type": ty, "type_prob": pr}
+        else:
+            for k, b, c, ct in zip(keys, list(box), list(cen), contours):
+                info[k] = {"box": b, "centroid": c, "contour": ct}
     if ds_factor != 1.0:
         for inst_id in list(info.keys()):
             d = info[inst_id]

@@ -122,17 +122,22 @@ def test_process_file_list_overlaps_loading_and_saving_with_threads(tmp_path, mo
     main = threading.get_ident()
     seen, saved = [], []
 
-    groups = []
+    groups, fin_threads = [], set()
 
-    def fake_process(named_images):
-        assert threading.get_ident() == main      # device work never leaves the calling thread
+    def fake_forward(named_images, slot=0):
+        assert threading.get_ident() == main      # the forward never leaves the calling thread
         groups.append(len(named_images))
-        out = []
-        for name, img in named_images:
-            assert img.shape == (8, 9, 3)
-            seen.append((name, int(img[0, 0, 0])))
-            out.append((name, img, {}, {}, {}, None))
-        return out
+        return list(named_images)
+
+    def fake_forward_wrapped(named_images, slot=0):
+        return {"metas": fake_forward(named_images, slot)}
+
+    def fake_finish(meta, group, to_host=True):
+        fin_threads.add(threading.get_ident())    # the finishing stage: worker threads
+        name, img = meta
+        assert img.shape == (8, 9, 3)
+        seen.append((name, int(img[0, 0, 0])))
+        return (name, img, {}, {}, {}, None)
 
     def fake_save(results, root):
         if results[0] == "img5" and fail["on"]:
@@ -140,7 +145,9 @@ def test_process_file_list_overlaps_loading_and_saving_with_threads(tmp_path, mo
         saved.append((results[0], threading.get_ident() != main))
 
     fail = {"on": False}
-    monkeypatch.setattr(m, "process_images", fake_process, raising=False)
+    monkeypatch.setattr(m, "_forward_group", fake_forward_wrapped, raising=False)
+    monkeypatch.setattr(m, "_finish_one", fake_finish, raising=False)
+    monkeypatch.setattr(m, "_sync_forward", lambda: None, raising=False)
     monkeypatch.setattr(tile_mod.InferManager, "_save", staticmethod(fake_save))
     for workers in (0, 2):
         seen.clear()
@@ -152,7 +159,9 @@ def test_process_file_list_overlaps_loading_and_saving_with_threads(tmp_path, mo
         # 8x9 px at 16/4: 2 x 3 grid, duplicated = 12 entries per file; files are cached until more
         # than 256 entries are pending (infer/tile.py:322-323) -> all 7 files form one group
         assert groups == [7]
-        assert seen == [("img%d" % i, 10 * i) for i in range(7)]
+        assert 1 <= len(fin_threads) <= max(1, workers) and main not in fin_threads
+        fin_threads.clear()
+        assert sorted(seen) == [("img%d" % i, 10 * i) for i in range(7)]
         assert sorted(s[0] for s in saved) == ["img%d" % i for i in range(7)]
         assert all(s[1] == (workers > 0) for s in saved)
     fail["on"] = True
@@ -178,8 +187,11 @@ def test_process_file_list_groups_and_shards_files(tmp_path, monkeypatch):
             m = object.__new__(tile_mod.InferManager)
             m.rank, m.world_size = rank, world
             groups = []
-            monkeypatch.setattr(m, "process_images", lambda ni, g=groups: (
-                g.append([n for n, _ in ni]) or [(n, im, {}, {}, {}, None) for n, im in ni]), raising=False)
+            monkeypatch.setattr(m, "_forward_group", lambda ni, slot=0, g=groups: (
+                g.append([n for n, _ in ni]) or {"metas": list(ni)}), raising=False)
+            monkeypatch.setattr(m, "_finish_one", lambda meta, grp, to_host=True: (
+                meta[0], meta[1], {}, {}, {}, None), raising=False)
+            monkeypatch.setattr(m, "_sync_forward", lambda: None, raising=False)
             m.process_file_list({"input_dir": str(in_dir), "output_dir": str(out_dir), "postproc_list": ["gland"],
                                  "nr_inference_workers": 0, "nr_post_proc_workers": 0,
                                  "patch_input_shape": 16, "patch_output_shape": 4, "patch_output_overlap": 0})
