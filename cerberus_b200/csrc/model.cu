@@ -21,7 +21,8 @@ using namespace cerb;
 
 namespace {
 
-constexpr int kBlocks[4] = {3, 4, 6, 3};          // resnet34 (models/backbone/resnet.py:301-303)
+// BasicBlock encoders (models/backbone/resnet.py:292-313): resnet34 has 3, 4, 6, 3 blocks per stage,
+// resnet18 2, 2, 2, 2 - the builder takes the count from the layer table (consecutive block indices)
 constexpr int kFilters[5] = {64, 64, 128, 256, 512};
 
 struct Spec {
@@ -125,7 +126,10 @@ int build_spec(const cerb_model_desc& d, const cerb_layer* layers, int n_layers,
     const int o_t = b.T(n, hs[li], ws[li], c);
     const int ds = li > 1 ? b.T(n, hs[li], ws[li], c) : -1;
     const int pair0 = li == 1 ? pool : ds, pair1 = o_t;
-    for (int bi = 0; bi < kBlocks[li - 1]; ++bi) {
+    int n_blocks = 0;
+    while (b.find(CERB_L_BLOCK_CONV1, li, n_blocks) != nullptr) ++n_blocks;
+    if (n_blocks == 0) return fail(CERB_ERR_ARG, "cerb_model: layer table lacks encoder stage %d", li);
+    for (int bi = 0; bi < n_blocks; ++bi) {
       const int stride = (li > 1 && bi == 0) ? 2 : 1;
       NEED(c1, CERB_L_BLOCK_CONV1, li, bi);
       NEED(c2, CERB_L_BLOCK_CONV2, li, bi);

@@ -25,7 +25,8 @@ def broadcast_packed_model(model, margs, rank, world, device):
         blob_t = torch.from_numpy(model.blob).to(device)
         meta = [{"layers": model.layers, "idx": model.idx_dict, "canvas_c": model.canvas_c,
                  "seg": model.seg_decoders, "pc": model.has_pclass,
-                 "dk": model.decoder_kwargs, "tasks": model.considered_tasks}]
+                 "dk": model.decoder_kwargs, "tasks": model.considered_tasks,
+                 "blocks": getattr(model, "blocks", [3, 4, 6, 3]), "backbone": getattr(model, "backbone", "resnet34")}]
     else:
         blob_t = torch.empty(int(nbytes.item()), dtype=torch.uint8, device=device)
         meta = [None]
@@ -37,6 +38,7 @@ def broadcast_packed_model(model, margs, rank, world, device):
         model.decoder_kwargs, model.considered_tasks = m["dk"], m["tasks"]
         model.layers, model.idx_dict, model.canvas_c = m["layers"], m["idx"], m["canvas_c"]
         model.seg_decoders, model.has_pclass = m["seg"], m["pc"]
+        model.blocks, model.backbone = m["blocks"], m["backbone"]
         model.blob = np.ascontiguousarray(blob_t.cpu().numpy())
     return model
 

@@ -17,8 +17,11 @@ import numpy as np
 from . import _lib
 from .pack import BlobBuilder, _np, bn_of, fold_bn, pack_conv, pack_stem, strip_module_prefix
 
-RESNET34_BLOCKS = [3, 4, 6, 3]
-RESNET34_FILTERS = [64, 64, 128, 256, 512]  # models/backbone/__init__.py resnet34 row
+# BasicBlock encoders of models/backbone/resnet.py:292-313 (same block type, same decoder filters:
+# models/backbone/__init__.py:27-28); resnet50 (Bottleneck) and the other families are outside the path
+RESNET_BLOCKS = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3]}
+RESNET34_BLOCKS = RESNET_BLOCKS["resnet34"]
+RESNET34_FILTERS = [64, 64, 128, 256, 512]  # models/backbone/__init__.py resnet18 / resnet34 rows
 
 # models/run_desc.py:472-479
 HEAD_NAME_MAP = {
@@ -51,9 +54,11 @@ class PackedModel:
 
     def __init__(self, state_dict, model_args):
         name = model_args.get("encoder_backbone_name")
-        if name != "resnet34":
-            raise ValueError("cerberus_b200 implements the resnet34 encoder only (got %r); the "
+        if name not in RESNET_BLOCKS:
+            raise ValueError("cerberus_b200 implements the resnet34 / resnet18 encoders only (got %r); the "
                              "other backbones are outside the hot path (SURVEY.md section 2)" % (name,))
+        self.backbone = name
+        self.blocks = RESNET_BLOCKS[name]
         self.decoder_kwargs = OrderedDict(
             (k, OrderedDict(v)) for k, v in model_args["decoder_kwargs"].items())
         self.considered_tasks = list(model_args["considered_tasks"])
@@ -74,7 +79,7 @@ class PackedModel:
         # encoder (models/backbone/resnet.py)
         w, b = fold_bn(_np(sd["backbone.conv1.weight"]), None, bn_of(sd, "backbone.bn1"))
         L["stem"] = pack_stem(blob, w, b)
-        for li, nblocks in enumerate(RESNET34_BLOCKS, start=1):
+        for li, nblocks in enumerate(self.blocks, start=1):
             for bi in range(nblocks):
                 p = "backbone.layer%d.%d" % (li, bi)
                 conv_bn(p + ".conv1", p + ".conv1.weight", p + ".bn1")
@@ -142,7 +147,7 @@ def c_model_tables(model):
                                layer.get("b_off", -1)))
 
     add(_lib.L_STEM, L["stem"])
-    for li, nblocks in enumerate(RESNET34_BLOCKS, start=1):
+    for li, nblocks in enumerate(getattr(model, "blocks", RESNET34_BLOCKS), start=1):
         for bi in range(nblocks):
             p = "backbone.layer%d.%d" % (li, bi)
             add(_lib.L_BLOCK_CONV1, L[p + ".conv1"], li, bi)
@@ -208,7 +213,7 @@ class PlanSpec:
         self._op(_lib.OP_MAXPOOL, in0=x0, out=pool)
         feats = [x0]
         cur = pool
-        for li, nblocks in enumerate(RESNET34_BLOCKS, start=1):
+        for li, nblocks in enumerate(getattr(model, "blocks", RESNET34_BLOCKS), start=1):
             c = F[li]
             mid = T("l%d.mid" % li, n, hs[li], ws[li], c)
             o = T("l%d.o" % li, n, hs[li], ws[li], c)

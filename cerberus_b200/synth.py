@@ -33,14 +33,15 @@ DEFAULT_REQ_TARGET_CODE = OrderedDict([
     ("Patch-Class", "PC"),
 ])
 BLOCKS = [3, 4, 6, 3]
+BACKBONE_BLOCKS = {"resnet34": [3, 4, 6, 3], "resnet18": [2, 2, 2, 2]}
 FILTERS = [64, 64, 128, 256, 512]
 # share of pixels whose (inner + contour) probability exceeds 0.5 on the calibration tiles
 FOREGROUND_FRACTION = {"Nuclei": 0.35, "Gland": 0.35, "Lumen": 0.08}
 
 
-def model_args(considered_tasks=None, decoder_kwargs=None):
+def model_args(considered_tasks=None, decoder_kwargs=None, backbone="resnet34"):
     return {
-        "encoder_backbone_name": "resnet34",
+        "encoder_backbone_name": backbone,
         "decoder_kwargs": decoder_kwargs if decoder_kwargs is not None else DEFAULT_DECODER_KWARGS,
         "considered_tasks": list(considered_tasks) if considered_tasks is not None
         else list(DEFAULT_CONSIDERED_TASKS),
@@ -108,7 +109,7 @@ class _Gen:
 
 
 def make_state_dict(considered_tasks=None, decoder_kwargs=None, seed=0, calib_tiles=None,
-                    logit_std=1.5):
+                    logit_std=1.5, backbone="resnet34"):
     """Seeded, BN-calibrated checkpoint (CPU, fp32). ~2 s for the six-head model."""
     args = model_args(considered_tasks, decoder_kwargs)
     dk, tasks = args["decoder_kwargs"], args["considered_tasks"]
@@ -146,7 +147,7 @@ def make_state_dict(considered_tasks=None, decoder_kwargs=None, seed=0, calib_ti
         x0 = F.relu(bn_calibrated("backbone.bn1", t, 64))
         cur = F.max_pool2d(x0, 3, 2, 1)
         feats = [x0]
-        for li, nb in enumerate(BLOCKS, start=1):
+        for li, nb in enumerate(BACKBONE_BLOCKS[backbone], start=1):
             c = FILTERS[li]
             for bi in range(nb):
                 p = "backbone.layer%d.%d" % (li, bi)
@@ -238,19 +239,20 @@ def make_state_dict(considered_tasks=None, decoder_kwargs=None, seed=0, calib_ti
     return sd
 
 
-def write_model_dir(path, considered_tasks=None, decoder_kwargs=None, seed=0, state_dict=None):
+def write_model_dir(path, considered_tasks=None, decoder_kwargs=None, seed=0, state_dict=None,
+                    backbone="resnet34"):
     """Writes <path>/weights.tar and <path>/settings.yml (the plugin surface)."""
     import yaml
     os.makedirs(path, exist_ok=True)
     args = model_args(considered_tasks, decoder_kwargs)
     if state_dict is None:
-        state_dict = make_state_dict(args["considered_tasks"], args["decoder_kwargs"], seed)
+        state_dict = make_state_dict(args["considered_tasks"], args["decoder_kwargs"], seed, backbone=backbone)
     torch.save({"desc": state_dict}, os.path.join(path, "weights.tar"))
     settings = {
         "dataset_kwargs": {"input_shape": 448, "output_shape": 448, "class_input_shape": 144,
                            "req_target_code": dict(DEFAULT_REQ_TARGET_CODE)},
         "model_kwargs": {
-            "encoder_backbone_name": "resnet34",
+            "encoder_backbone_name": backbone,
             "decoder_kwargs": {k: dict(v) for k, v in args["decoder_kwargs"].items()},
             "considered_tasks": list(args["considered_tasks"]),
         },

@@ -26,6 +26,8 @@ FORWARD_CASES = [
     ("six_256", None, 2, 256, 256, 7),
     ("six_448", None, 1, 448, 144, 8),
     ("nuclei_256", ["Nuclei"], 1, 256, 256, 9),
+    # resnet18 encoder (same BasicBlock family, models/backbone/resnet.py:292-302): name carries the backbone
+    ("r18_256", ["Nuclei", "Gland#TYPE", "Patch-Class"], 1, 256, 256, 10),
 ]
 
 
@@ -36,9 +38,13 @@ def gen_forward():
     from models.net_desc import create_model
     from models.run_desc import infer_step
 
+    only = [a[len("forward:"):] for a in sys.argv[1:] if a.startswith("forward:")]
     for name, tasks, n, size, out, tseed in FORWARD_CASES:
-        args = synth.model_args(tasks)
-        sd = synth.make_state_dict(args["considered_tasks"], seed=0)
+        if only and name not in only:
+            continue
+        backbone = "resnet18" if name.startswith("r18") else "resnet34"
+        args = synth.model_args(tasks, backbone=backbone)
+        sd = synth.make_state_dict(args["considered_tasks"], seed=0, backbone=backbone)
         net = create_model(**args)
         net.load_state_dict(sd, strict=True)
         net.eval()
@@ -46,9 +52,9 @@ def gen_forward():
         with torch.no_grad():
             logits = net(torch.from_numpy(tiles).float().permute(0, 3, 1, 2).contiguous())
         step = infer_step(torch.from_numpy(tiles), net, out, args["considered_tasks"])
-        rec = {"n": n, "size": size, "out": out, "tile_seed": tseed, "ckpt_seed": 0,
+        rec = {"n": n, "size": size, "out": out, "tile_seed": tseed, "ckpt_seed": 0, "backbone": np.array(backbone),
                "tasks": np.array(args["considered_tasks"]),
-               "sd_check": np.array([float(sd["backbone.layer4.2.bn2.running_var"].double().sum()),
+               "sd_check": np.array([float(sd["backbone.layer4.%d.bn2.running_var" % (synth.BACKBONE_BLOCKS[backbone][3] - 1)].double().sum()),
                                      float(sd["backbone.layer1.0.bn1.running_mean"].double().sum())])}
         for k, v in logits.items():
             v = v.numpy()
@@ -352,7 +358,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["forward", "patching", "postproc", "postproc_eroded", "stitch", "instinfo"]
     for w in which:
-        fn = globals().get("gen_" + w)
+        fn = globals().get("gen_" + w.split(":")[0])  # "forward:r18_256" regenerates one forward case
         if fn is None:
             print("skip (not implemented):", w)
             continue

@@ -88,7 +88,10 @@ def _forward(sd, imgs_nchw_f32, decoder_kwargs, considered_tasks, return_feats, 
         x0 = x = F.relu(_bn(x, sd, "backbone.bn1"))
         x = F.max_pool2d(x, 3, 2, 1)  # resnet.py:201
         feats = [x0]
-        for li, nb in enumerate(BLOCKS, start=1):
+        for li in range(1, 5):  # blocks per stage from the checkpoint (resnet34: 3,4,6,3; resnet18: 2,2,2,2)
+            nb = 0
+            while ("backbone.layer%d.%d.conv1.weight" % (li, nb)) in sd:
+                nb += 1
             for bi in range(nb):
                 p = "backbone.layer%d.%d" % (li, bi)
                 stride = 2 if (li > 1 and bi == 0) else 1

@@ -26,12 +26,13 @@ def _oracle_logits(sd, args, tiles):
     return {k: v.permute(0, 2, 3, 1).contiguous().numpy() for k, v in out.items()}
 
 
-@pytest.mark.parametrize("name", ["six_256", "six_448", "nuclei_256"])
+@pytest.mark.parametrize("name", ["six_256", "six_448", "nuclei_256", "r18_256"])
 def test_logits_match_reference_golden_f16x2(name, built_lib):
     g = np.load(os.path.join(GOLD, "forward_%s.npz" % name))
     tasks = [str(t) for t in g["tasks"]]
-    args = synth.model_args(tasks)
-    sd = synth.make_state_dict(tasks, seed=int(g["ckpt_seed"]))
+    backbone = str(g["backbone"]) if "backbone" in g else "resnet34"  # r18_*: resnet18 encoder
+    args = synth.model_args(tasks, backbone=backbone)
+    sd = synth.make_state_dict(tasks, seed=int(g["ckpt_seed"]), backbone=backbone)
     n, size, out = int(g["n"]), int(g["size"]), int(g["out"])
     tiles = synth.synthetic_tiles(n, size, size, seed=int(g["tile_seed"]))
     eng = Engine(sd, args, precision="f16x2")

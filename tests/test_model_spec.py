@@ -69,3 +69,26 @@ def test_spec_rejects_bad_shapes(models, built_lib):
     rc = built_lib.cerb_model_spec(ctypes.byref(desc), layers, len(layers) - 1, 1, 256, 256, 256, 256, 0,
                                    None, ctypes.byref(n_t), None, ctypes.byref(n_o), None, None)
     assert rc == -2 and b"layer table lacks" in built_lib.cerb_last_error()
+
+
+def test_resnet18_graph_equals_python_graph(built_lib):
+    """The resnet18 encoder (2, 2, 2, 2 BasicBlocks; models/backbone/resnet.py:292-302): the library
+    takes the block count per stage from the layer table."""
+    args = synth.model_args(["Nuclei", "Gland#TYPE", "Patch-Class"], backbone="resnet18")
+    model = PackedModel(synth.make_state_dict(args["considered_tasks"], seed=0, backbone="resnet18"), args)
+    assert model.blocks == [2, 2, 2, 2]
+    spec = PlanSpec(model, 2, 256, 256, 256, 256, want_logits=True)
+    td_py, ops_py = spec.c_arrays()
+    desc, layers = c_model_tables(model)
+    cap_t, cap_o = ctypes.c_int(256), ctypes.c_int(512)
+    td = (_lib.TensorDesc * 256)()
+    ops = (_lib.Op * 512)()
+    _lib.check(built_lib.cerb_model_spec(ctypes.byref(desc), layers, len(layers), 2, 256, 256, 256, 256, 1,
+                                         td, ctypes.byref(cap_t), ops, ctypes.byref(cap_o), None, None),
+               "cerb_model_spec")
+    assert cap_t.value == len(td_py) and cap_o.value == len(ops_py)
+    n_conv = sum(1 for o in ops_py if o.kind == _lib.OP_CONV)
+    assert n_conv == 1 + 2 * 8 + 3 + 1 + 1 + 2 * 7 + 2  # stem, 8 blocks, 3 downsamples, conv_map, first, 2 x 7 decoder convs, 2 heads
+    for i in range(len(ops_py)):
+        for f, _ in _lib.Op._fields_:
+            assert getattr(ops[i], f) == getattr(ops_py[i], f), ("op", i, f)

@@ -13,13 +13,14 @@ from oracle import net_oracle
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("name", ["six_256", "six_448", "nuclei_256"])
+@pytest.mark.parametrize("name", ["six_256", "six_448", "nuclei_256", "r18_256"])
 def test_oracle_matches_reference_golden(name):
     g = np.load(os.path.join(GOLD, "forward_%s.npz" % name))
     tasks = [str(t) for t in g["tasks"]]
-    args = synth.model_args(tasks)
-    sd = synth.make_state_dict(tasks, seed=int(g["ckpt_seed"]))
-    chk = np.array([float(sd["backbone.layer4.2.bn2.running_var"].double().sum()),
+    backbone = str(g["backbone"]) if "backbone" in g else "resnet34"  # r18_*: resnet18 encoder
+    args = synth.model_args(tasks, backbone=backbone)
+    sd = synth.make_state_dict(tasks, seed=int(g["ckpt_seed"]), backbone=backbone)
+    chk = np.array([float(sd["backbone.layer4.%d.bn2.running_var" % (synth.BACKBONE_BLOCKS[backbone][3] - 1)].double().sum()),
                     float(sd["backbone.layer1.0.bn1.running_mean"].double().sum())])
     assert np.allclose(chk, g["sd_check"], rtol=1e-4), "synthetic checkpoint drifted"
     n, size, out = int(g["n"]), int(g["size"]), int(g["out"])
