@@ -20,6 +20,7 @@
 #include "conv3x3.cuh"
 #include "conv3x3c2.cuh"
 #include "conv64.cuh"
+#include "conv64s.cuh"
 #include "conv64x.cuh"
 #include "conv_tc.cuh"
 #include "ops.cuh"
@@ -61,6 +62,8 @@ struct Step {
   Conv64Params c64;
   Conv3Params c3;
   Conv3c2Params c3p;
+  Conv64sParams c64s;
+  bool use64s = false;  // split-precision 64->64 kernel (csrc/conv64s.cu)
   bool use3p = false;  // CTA-pair kernel (csrc/conv3x3c2.cu)
   Conv64xParams c64x;
   bool use64x = false;
@@ -553,6 +556,76 @@ int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
   return CERB_OK;
 }
 
+// 64->64 3x3 stride-1 in the split-precision mode: halo reuse + resident hi weights (csrc/conv64s.cu).
+int build_conv64s(cerb_plan* pl, const cerb_op& op, Step& st) {
+  cerb_ctx* ctx = pl->ctx;
+  const Tensor& in = pl->tensors[op.in0];
+  const Tensor& out = pl->tensors[op.out];
+  Conv64sParams& p = st.c64s;
+  memset(&p, 0, sizeof(p));
+  st.use64s = true;
+  const int H = out.d.h, W = out.d.w, N = out.d.n;
+  const size_t es = 2;
+  p.n_img = N;
+  p.H = H;
+  p.W = W;
+  if (!in.plane[1] || !out.plane[1]) return fail(CERB_ERR_ARG, "conv64s: tensors lack a lo plane");
+  if (op.in_coff % 8 != 0 || op.in_coff + 64 > in.d.c || in.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv64s: bad input channels");
+  if (op.out_coff % 8 != 0 || op.out_coff + 64 > out.d.c || out.d.c % 8 != 0)
+    return fail(CERB_ERR_ARG, "conv64s: bad output channels");
+  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                              static_cast<cuuint64_t>(N)};
+  auto act_map = [&](CUtensorMap* m, const Tensor& t, int plane, int coff, const cuuint32_t* box) {
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(t.d.c) * es,
+                                   static_cast<cuuint64_t>(W) * t.d.c * es,
+                                   static_cast<cuuint64_t>(H) * W * t.d.c * es};
+    return encode_map(ctx, m, static_cast<__half*>(t.plane[plane]) + coff, 4, dims, strides, box);
+  };
+  const cuuint32_t halo_box[4] = {64, 10, 18, 1};
+  const cuuint32_t tile_box[4] = {64, 8, 16, 1};
+  int rc;
+  if ((rc = act_map(&p.in_hi, in, 0, op.in_coff, halo_box))) return rc;
+  if ((rc = act_map(&p.in_lo, in, 1, op.in_coff, halo_box))) return rc;
+  if ((rc = act_map(&p.out_hi, out, 0, op.out_coff, tile_box))) return rc;
+  if ((rc = act_map(&p.out_lo, out, 1, op.out_coff, tile_box))) return rc;
+  const size_t wbytes = 64u * 576u * es;
+  if (op.w_off < 0 || op.w_off % 16 != 0 || static_cast<size_t>(op.w_off) + wbytes > pl->blob_bytes ||
+      op.w_lo_off < 0 || op.w_lo_off % 16 != 0 || static_cast<size_t>(op.w_lo_off) + wbytes > pl->blob_bytes)
+    return fail(CERB_ERR_ARG, "conv64s: weight offsets out of range");
+  {
+    const cuuint64_t wd[2] = {576, 64};
+    const cuuint64_t ws[1] = {576 * es};
+    const cuuint32_t wb[2] = {64, 64};
+    if ((rc = encode_map(ctx, &p.w_hi, pl->blob + op.w_off, 2, wd, ws, wb))) return rc;
+    if ((rc = encode_map(ctx, &p.w_lo, pl->blob + op.w_lo_off, 2, wd, ws, wb))) return rc;
+  }
+  if (op.b_off >= 0) {
+    if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + 64 * 4u > pl->blob_bytes)
+      return fail(CERB_ERR_ARG, "conv64s: bias offset out of range");
+    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+  }
+  if (op.in1 >= 0) {
+    if (op.in1 >= static_cast<int>(pl->tensors.size()))
+      return fail(CERB_ERR_ARG, "conv64s: residual id out of range");
+    const Tensor& res = pl->tensors[op.in1];
+    if (res.d.n != N || res.d.h != H || res.d.w != W || res.d.c < 64 || res.d.c % 8 != 0 ||
+        res.d.dtype != CERB_F16 || !res.plane[1])
+      return fail(CERB_ERR_ARG, "conv64s: residual shape mismatch");
+    if ((rc = act_map(&p.res_hi, res, 0, 0, tile_box))) return rc;
+    if ((rc = act_map(&p.res_lo, res, 1, 0, tile_box))) return rc;
+    p.has_res = 1;
+  }
+  p.relu = op.relu;
+  if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64s: w_shift out of range");
+  p.acc_scale = ldexpf(1.0f, -op.w_shift);
+  p.err_flag = ctx->err_flag_dev;
+  p.prof = ctx->prof_dev;
+  p.tile_counter = ctx->dyn_sched ? pl->cur_counter : nullptr;
+  conv64s_plan(p);
+  return CERB_OK;
+}
+
 // Wide 3x3 stride-1 layers with Cout % 256 == 0 on CTA pairs (csrc/conv3x3c2.cu).
 int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
   cerb_ctx* ctx = pl->ctx;
@@ -675,6 +748,10 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
                 op.out_coff, out.d.c);
   }
 
+  if (split && ctx->conv64s && !op.stem && !fused_head && op.kh == 3 && op.kw == 3 && op.stride == 1 &&
+      op.pad == 1 && op.in_c == 64 && op.cout == 64 && op.up_prev1 <= 0 && in.d.dtype == CERB_F16 &&
+      out.d.dtype == CERB_F16 && in.d.h == out.d.h && in.d.w == out.d.w && in.d.n == out.d.n)
+    return build_conv64s(pl, op, st);
   const bool conv64_ok = !split && !op.stem && !fused_head && ctx->conv64_mode >= 0 && op.kh == 3 &&
                          op.kw == 3 && op.stride == 1 && op.pad == 1 && op.in_c == 64 &&
                          op.cout == 64 && in.d.h == H && in.d.w == W;
@@ -988,6 +1065,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
   if (strcmp(name, "conv64_mode") == 0) {
     if (value < -1 || value > 3) return fail(CERB_ERR_ARG, "conv64_mode must be -1, 0, 1, 2 or 3");
     ctx->conv64_mode = value;
+    return CERB_OK;
+  }
+  if (strcmp(name, "conv64s") == 0) {
+    ctx->conv64s = value != 0;
     return CERB_OK;
   }
   if (strcmp(name, "conv3_pair") == 0) {
@@ -1363,6 +1444,7 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
     case CERB_OP_CONV:
       e = st.use64x ? conv64x_launch(st.c64x, ctx->conv_sms, s, ctx->use_pdl)
           : st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s, ctx->use_pdl)
+          : st.use64s ? conv64s_launch(st.c64s, ctx->conv_sms, s, ctx->use_pdl)
           : st.use3p ? conv3x3c2_launch(st.c3p, ctx->conv_sms, s, ctx->use_pdl)
           : st.use3 ? conv3x3_launch(st.c3, ctx->conv_sms, s, ctx->use_pdl)
                     : conv_tc_launch(st.conv, st.split, ctx->conv_sms, s, ctx->use_pdl);

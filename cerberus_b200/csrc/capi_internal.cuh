@@ -37,6 +37,7 @@ struct cerb_ctx {
   bool dyn_sched = true;  // dynamic tile scheduling in the persistent conv kernels
   int stem_mode = 1;    // 1: 7x7 stem on conv64.cu (mode 4); 0: generic kernel
   int k_rotate = 1;     // per-CTA rotated K walk in conv3x3.cu (de-synchronises weight-slab reads)
+  bool conv64s = true;  // split-precision mode: 64->64 3x3 layers on csrc/conv64s.cu (0: generic kernel)
   int conv3_pair = 1;  // wide 3x3 stride-1 layers on CTA pairs (csrc/conv3x3c2.cu): 0 never, 1 Cout % 256 == 0, 2 also Cout 128 / 64
   int conv3_mode = 1;   // 0: generic kernel for the wide 3x3 layers; 1: conv3x3.cu (cout <= 512); 2: always
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout

@@ -35,6 +35,8 @@ class Context:
         # conv64.cu (tools/conv64_modes.py); -1 = generic kernel
         self.conv64_mode = int(os.environ.get("CERB_CONV64_MODE", "3"))
         self.set_option("conv64_mode", self.conv64_mode)
+        if os.environ.get("CERB_CONV64S") is not None:  # split-precision 64->64 kernel (A/B switch)
+            self.set_option("conv64s", int(os.environ["CERB_CONV64S"]))
         if os.environ.get("CERB_CONV3_PAIR") is not None:  # CTA-pair kernel for the wide 3x3 layers
             self.set_option("conv3_pair", int(os.environ["CERB_CONV3_PAIR"]))
         if os.environ.get("CERB_DYN_SCHED") is not None:

@@ -211,3 +211,26 @@ def test_conv3x3_cta_pair_kernel(case, dyn, built_lib, monkeypatch):
     err = np.abs(got - ref)
     tol = 2e-3 * np.abs(ref) + 2e-3
     assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+SPLIT64_CASES = [
+    # n, h, w, cin, cout, k, stride, residual, relu   (64 -> 64 3x3 stride 1, split-precision mode)
+    (2, 32, 32, 64, 64, 3, 1, False, True),
+    (1, 128, 128, 64, 64, 3, 1, True, True),
+    (2, 50, 36, 64, 64, 3, 1, True, True),       # partial tiles in x and y, residual
+    (1, 16, 8, 64, 64, 3, 1, False, False),      # a single tile
+    (3, 40, 24, 64, 64, 3, 1, True, False),
+    (40, 16, 16, 64, 64, 3, 1, False, True),     # more tiles than SMs
+]
+
+
+@pytest.mark.parametrize("kernel", [1, 0])
+@pytest.mark.parametrize("case", SPLIT64_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv64_split_precision_kernel(case, kernel, built_lib, monkeypatch):
+    """Split-precision 64->64 3x3: the halo-reuse kernel (csrc/conv64s.cu, default) and the generic
+    kernel against the fp64 convolution at the parity-mode tolerance."""
+    monkeypatch.setenv("CERB_CONV64S", str(kernel))
+    got, ref = _run_case("f16x2", *case)
+    err = np.abs(got - ref)
+    tol = 5e-5 * np.abs(ref) + 1e-4
+    assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))

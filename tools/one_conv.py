@@ -43,7 +43,8 @@ def main():
                    aux_b_off=blob.add(b2), head_mode=L_.HEAD_INST)
     else:
         spec._conv(layer, ti, to, relu=1, residual=tr)
-    ctx = Context(0, "f16")
+    prec = os.environ.get("CERB_ONE_PREC", "f16")
+    ctx = Context(0, prec)
     ctx.set_option("kernel_prof", 1)
     ctx.set_option("use_graphs", 0)
     for kv in os.environ.get("CERB_OPTS", "").split(","):
@@ -51,6 +52,8 @@ def main():
             ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     plan = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
     plan.write(ti, rng.standard_normal((n, h, w, cin)).astype(np.float16))
+    if prec == "f16x2":
+        plan.write(ti, (rng.standard_normal((n, h, w, cin)) * 1e-4).astype(np.float16), plane=1)
     if res:
         plan.write(tr, rng.standard_normal((n, h, w, cout)).astype(np.float16))
     for _ in range(3):
