@@ -220,9 +220,24 @@ __device__ __forceinline__ void cvt8(const uint4& u, float (&v)[8]) {
   }
 }
 
+// SPLIT: every tensor is a hi + lo fp16 pair (CERB_PREC_F16X2); values are hi + lo in fp32, the
+// result is split again (hi = fp16(v), lo = fp16(v - hi)).
+__device__ __forceinline__ void cvt8_pair(const uint4& hi, const uint4& lo, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 a = __half22float2(h[e]), b = __half22float2(l[e]);
+    v[2 * e] = a.x + b.x;
+    v[2 * e + 1] = a.y + b.y;
+  }
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(288) upadd_f16_kernel(
-    const __half* __restrict__ skip, int skip_c, const __half* __restrict__ prev, int prev_c,
-    __half* __restrict__ out, int out_c, int PH, int PW, int cg_shift, int ipb) {
+    const __half* __restrict__ skip, const __half* __restrict__ skip_lo, int skip_c,
+    const __half* __restrict__ prev, const __half* __restrict__ prev_lo, int prev_c,
+    __half* __restrict__ out, __half* __restrict__ out_lo, int out_c, int PH, int PW, int cg_shift, int ipb) {
   const int cg = 1 << cg_shift;
   const int g = threadIdx.x & (cg - 1);
   const int i = blockIdx.x * ipb + (threadIdx.x >> cg_shift) - 1;  // pair column, -1 .. PW-1
@@ -235,23 +250,40 @@ __global__ void __launch_bounds__(288) upadd_f16_kernel(
   const int y0 = max(j, 0), y1 = min(j + 1, PH - 1);
   const uint32_t pb = static_cast<uint32_t>(n) * PH;
   const uint32_t gc = g * 8;
-  const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y0) * PW + x0) * prev_c + gc));
-  const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y0) * PW + x1) * prev_c + gc));
-  const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y1) * PW + x0) * prev_c + gc));
-  const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(prev + ((pb + y1) * PW + x1) * prev_c + gc));
+  const uint32_t o00 = ((pb + y0) * PW + x0) * prev_c + gc, o01 = ((pb + y0) * PW + x1) * prev_c + gc;
+  const uint32_t o10 = ((pb + y1) * PW + x0) * prev_c + gc, o11 = ((pb + y1) * PW + x1) * prev_c + gc;
+  const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(prev + o00));
+  const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(prev + o01));
+  const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(prev + o10));
+  const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(prev + o11));
+  uint4 l00, l01, l10, l11;
+  if (SPLIT) {
+    l00 = __ldg(reinterpret_cast<const uint4*>(prev_lo + o00));
+    l01 = __ldg(reinterpret_cast<const uint4*>(prev_lo + o01));
+    l10 = __ldg(reinterpret_cast<const uint4*>(prev_lo + o10));
+    l11 = __ldg(reinterpret_cast<const uint4*>(prev_lo + o11));
+  }
   const int Y0 = 2 * j + 1, X0 = 2 * i + 1;
   const bool oky[2] = {Y0 >= 0, Y0 + 1 < H};
   const bool okx[2] = {X0 >= 0, X0 + 1 < W};
   const uint32_t pix00 = (static_cast<uint32_t>(n) * H + Y0) * W + X0;  // may wrap; used only when valid
-  uint4 sk[4];
+  uint4 sk[4], skl[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     sk[k] = make_uint4(0, 0, 0, 0);
-    if (oky[k >> 1] && okx[k & 1])
-      sk[k] = __ldg(reinterpret_cast<const uint4*>(skip + (pix00 + (k >> 1) * W + (k & 1)) * skip_c + gc));
+    skl[k] = make_uint4(0, 0, 0, 0);
+    if (oky[k >> 1] && okx[k & 1]) {
+      const uint32_t so = (pix00 + (k >> 1) * W + (k & 1)) * skip_c + gc;
+      sk[k] = __ldg(reinterpret_cast<const uint4*>(skip + so));
+      if (SPLIT) skl[k] = __ldg(reinterpret_cast<const uint4*>(skip_lo + so));
+    }
   }
   float p00[8], p01[8], p10[8], p11[8];
-  cvt8(q00, p00); cvt8(q01, p01); cvt8(q10, p10); cvt8(q11, p11);
+  if (SPLIT) {
+    cvt8_pair(q00, l00, p00); cvt8_pair(q01, l01, p01); cvt8_pair(q10, l10, p10); cvt8_pair(q11, l11, p11);
+  } else {
+    cvt8(q00, p00); cvt8(q01, p01); cvt8(q10, p10); cvt8(q11, p11);
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int dy = k >> 1, dx = k & 1;
@@ -261,18 +293,28 @@ __global__ void __launch_bounds__(288) upadd_f16_kernel(
     const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
     const float hx = 1.0f - lx;
     float s[8];
-    cvt8(sk[k], s);
-    uint4 o;
+    if (SPLIT) cvt8_pair(sk[k], skl[k], s);
+    else cvt8(sk[k], s);
+    uint4 o, ol;
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    uint32_t* olw = reinterpret_cast<uint32_t*>(&ol);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float u0 = hy * (hx * p00[2 * e] + lx * p01[2 * e]) + ly * (hx * p10[2 * e] + lx * p11[2 * e]);
       const float u1 = hy * (hx * p00[2 * e + 1] + lx * p01[2 * e + 1]) +
                        ly * (hx * p10[2 * e + 1] + lx * p11[2 * e + 1]);
-      const __half2 h = __floats2half2_rn(s[2 * e] + u0, s[2 * e + 1] + u1);
+      const float a = s[2 * e] + u0, b = s[2 * e + 1] + u1;
+      const __half2 h = __floats2half2_rn(a, b);
       ow[e] = *reinterpret_cast<const uint32_t*>(&h);
+      if (SPLIT) {
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        olw[e] = *reinterpret_cast<const uint32_t*>(&l);
+      }
     }
-    *reinterpret_cast<uint4*>(out + (pix00 + dy * W + dx) * out_c + gc) = o;
+    const uint32_t oo = (pix00 + dy * W + dx) * out_c + gc;
+    *reinterpret_cast<uint4*>(out + oo) = o;
+    if (SPLIT) *reinterpret_cast<uint4*>(out_lo + oo) = ol;
   }
 }
 
@@ -523,7 +565,9 @@ cudaError_t launch_upadd(ActRef skip, ActRef prev, ActRef out, cudaStream_t s) {
   const int cg = out.c >> 3;
   const size_t out_elems = static_cast<size_t>(out.n) * out.h * out.w * out.c;
   const size_t skip_elems = static_cast<size_t>(out.n) * out.h * out.w * skip.c;
-  if (skip.lo == nullptr && prev.lo == nullptr && out.lo == nullptr && (cg & (cg - 1)) == 0 && cg <= 32 &&
+  const bool all_lo = skip.lo != nullptr && prev.lo != nullptr && out.lo != nullptr;
+  const bool no_lo = skip.lo == nullptr && prev.lo == nullptr && out.lo == nullptr;
+  if ((all_lo || no_lo) && (cg & (cg - 1)) == 0 && cg <= 32 &&
       out_elems < (1ull << 31) && skip_elems < (1ull << 31) && out.h == 2 * prev.h && out.w == 2 * prev.w) {
     int cg_shift = 0;
     while ((1 << cg_shift) < cg) ++cg_shift;
@@ -531,8 +575,12 @@ cudaError_t launch_upadd(ActRef skip, ActRef prev, ActRef out, cudaStream_t s) {
     const int nblk = (pw * cg + 255) / 256;
     const int ipb = (pw + nblk - 1) / nblk;  // pair columns per block; ipb * cg <= 256 + cg
     dim3 grid(nblk, out.n * (prev.h + 1));
-    upadd_f16_kernel<<<grid, ipb * cg, 0, s>>>(skip.hi, skip.c, prev.hi, prev.c, out.hi, out.c, prev.h,
-                                               prev.w, cg_shift, ipb);
+    if (all_lo)
+      upadd_f16_kernel<true><<<grid, ipb * cg, 0, s>>>(skip.hi, skip.lo, skip.c, prev.hi, prev.lo, prev.c,
+                                                       out.hi, out.lo, out.c, prev.h, prev.w, cg_shift, ipb);
+    else
+      upadd_f16_kernel<false><<<grid, ipb * cg, 0, s>>>(skip.hi, nullptr, skip.c, prev.hi, nullptr, prev.c,
+                                                        out.hi, nullptr, out.c, prev.h, prev.w, cg_shift, ipb);
     return cudaGetLastError();
   }
   const size_t total = static_cast<size_t>(out.n) * (prev.h + 1) * (prev.w + 1) * (out.c >> 3);

@@ -234,3 +234,41 @@ def test_conv64_split_precision_kernel(case, kernel, built_lib, monkeypatch):
     err = np.abs(got - ref)
     tol = 5e-5 * np.abs(ref) + 1e-4
     assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+@pytest.mark.parametrize("precision", ["f16", "f16x2"])
+@pytest.mark.parametrize("shape", [(2, 16, 24, 64), (1, 14, 14, 256), (3, 32, 32, 128), (2, 5, 7, 40)])
+def test_upadd_matches_torch_bilinear(shape, precision, built_lib):
+    """out = skip + bilinear_x2(prev), align_corners=False (models/utils/net_layers.py:45-46,
+    models/net_desc.py:185-188), both precision modes (40 channels: the generic fallback kernel)."""
+    n, ph, pw, c = shape
+    rng = np.random.RandomState(5)
+    prev = rng.standard_normal((n, ph, pw, c)).astype(np.float32)
+    skip = rng.standard_normal((n, 2 * ph, 2 * pw, c)).astype(np.float32)
+    if precision == "f16":
+        prev, skip = f16(prev).astype(np.float32), f16(skip).astype(np.float32)
+    spec = MiniSpec()
+    t_skip = spec._tensor("skip", n, 2 * ph, 2 * pw, c)
+    t_prev = spec._tensor("prev", n, ph, pw, c)
+    t_out = spec._tensor("out", n, 2 * ph, 2 * pw, c)
+    spec._op(_lib.OP_UPADD, in0=t_skip, in1=t_prev, out=t_out)
+    ctx = Context(0, precision)
+    plan = ForwardPlan(ctx, MiniModel(BlobBuilder()), 0, 0, 0, 0, 0, spec=spec)
+
+    def put(tid, a):
+        hi = a.astype(np.float16)
+        plan.write(tid, hi, 0)
+        if precision == "f16x2":
+            plan.write(tid, (a - hi.astype(np.float32)).astype(np.float16), 1)
+
+    put(t_skip, skip)
+    put(t_prev, prev)
+    plan.run()
+    got = plan.read(t_out).astype(np.float32)
+    up = F.interpolate(torch.from_numpy(nhwc_to_nchw(prev)).double(), scale_factor=2, mode="bilinear",
+                       align_corners=False)
+    ref = nchw_to_nhwc((torch.from_numpy(nhwc_to_nchw(skip)).double() + up).numpy())
+    tol = (2e-3 * np.abs(ref) + 2e-3) if precision == "f16" else (2e-6 * np.abs(ref) + 2e-6)
+    assert np.all(np.abs(got - ref) <= tol), float(np.abs(got - ref).max())
+    plan.close()
+    ctx.close()
