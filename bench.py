@@ -344,12 +344,16 @@ def conv_roofline(arm, dev_ptr, peaks):
     flops = spec.conv_flops()
     achieved = dom_fl / (dom_ms * 1e-3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     kname = "conv64x_kernel" if ctx.conv64_mode == 3 else "conv64_kernel"
-    if os.path.exists(tpath) and B == 32 and arm.precision == "f16":
-        tj = json.load(open(tpath)).get("%s 256x256 64->64 3x3 batch 32" % kname)
-        if tj:
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    tsrc = None
+    for tf in ("r2_traffic.json", "r1_traffic.json"):  # ncu --set full captures, newest first
+        tpath = os.path.join(ROOT, "profiles", tf)
+        if os.path.exists(tpath) and B == 32 and arm.precision == "f16":
+            tj = json.load(open(tpath)).get("%s 256x256 64->64 3x3 batch 32" % kname)
+            if tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                tsrc = tf
+                break
     agg = flops / (all_ms * 1e-3) / 1e12
     enc = enc_fl / (enc_ms * 1e-3) / 1e12 if enc_ms > 0 else None
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor_burst"],
@@ -360,8 +364,8 @@ def conv_roofline(arm, dev_ptr, peaks):
             "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json bf16_tflops): "
                                              "the kernel is timed alone by per-op events",
             "frac_of_sustained": achieved / peaks["tensor_sustained"],
-            "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r1_traffic.json); "
-                            "algorithmic bytes 536.9 MB (fp16 in + out)",
+            "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/%s); "
+                            "algorithmic bytes 536.9 MB (fp16 in + out)" % tsrc,
             "all_convs": {"achieved": agg, "frac": agg / peaks["tensor_burst"],
                           "launches_per_step": n_conv, "ms_per_step": all_ms,
                           "gflop_per_step": flops / 1e9},

@@ -36,6 +36,12 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// max(x, 0) fused into the fp32 -> fp16x2 conversion (one instruction instead of two FMNMX + F2FP)
+__device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 
 template <bool SPLIT, int MAX_THREADS>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
@@ -315,18 +321,21 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
             v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z);
             v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w);
           }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
-          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int cj = (j >> 3) + i;  // 16-byte chunk index inside the 96-channel row
             uint4 u;
-            u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
-            u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
-            u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
-            u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+            if (p.relu) {  // ReLU rides on the conversion
+              u.x = pack_half2_relu(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_half2_relu(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_half2_relu(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_half2_relu(v[8 * i + 6], v[8 * i + 7]);
+            } else {
+              u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+            }
             *reinterpret_cast<uint4*>(a2 + (cj >> 3) * kATileBytes + m * 128 + (((cj & 7) ^ sw) << 4)) = u;
           }
         }
