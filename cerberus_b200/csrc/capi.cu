@@ -906,6 +906,11 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
     p.head_b = reinterpret_cast<const float*>(pl->blob + op.aux_b_off);
     p.head_classes = op.aux_classes;
     p.head_mode = op.head_mode;
+    if (op.cout == 96 && op.b_off >= 0) {  // biases as kernel parameters (see conv_tc.cuh)
+      CERB_CUDA(cudaMemcpy(p.head_hbias, pl->blob + op.b_off, 96 * sizeof(float), cudaMemcpyDeviceToHost));
+      CERB_CUDA(cudaMemcpy(p.head_obias, pl->blob + op.aux_b_off, op.aux_classes * sizeof(float),
+                           cudaMemcpyDeviceToHost));
+    }
     p.canvas = static_cast<float*>(out.plane[0]);
     p.oh = out.d.h;
     p.ow = out.d.w;

@@ -311,16 +311,10 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
           ptx::tmem_ld32(taddr + j, r);
           ptx::tmem_ld_wait();
           float v[32];
-          const float4* b4 = reinterpret_cast<const float4*>(s_head_w + j);
           const float sc = p.acc_scale;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = b4[i];
-            v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), sc, b.x);
-            v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), sc, b.y);
-            v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z);
-            v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w);
-          }
+          for (int i = 0; i < 32; ++i)  // j and i are compile-time: the bias is a constant-bank operand
+            v[i] = fmaf(__uint_as_float(r[i]), sc, p.head_hbias[j + i]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int cj = (j >> 3) + i;  // 16-byte chunk index inside the 96-channel row
@@ -375,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
           float hacc[kHeadMaxC];
 #pragma unroll
           for (int c = 0; c < kHeadMaxC; ++c)
-            hacc[c] = c < p.head_classes ? __uint_as_float(r8[c]) + s_head_w[96 + c] : 0.0f;
+            hacc[c] = c < p.head_classes ? __uint_as_float(r8[c]) + p.head_obias[c] : 0.0f;
           const int y_off = static_cast<int>((p.H - p.oh) * 0.5), x_off = static_cast<int>((p.W - p.ow) * 0.5);
           const int cy = oy - y_off, cx = ox - x_off;
           float* dst = nullptr;

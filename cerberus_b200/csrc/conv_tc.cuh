@@ -56,6 +56,11 @@ struct ConvKParams {
   const float* head_w;   // [C][96] fp32
   const float* head_b;   // [C]
   int head_classes, head_mode;
+  // MMA-tail head: the hidden layer's 96 biases and the C head biases travel in the kernel
+  // parameters (constant bank): the epilogue's FMAs read them as constant operands instead of
+  // 24 broadcast LDS.128 per pixel, which cost 38 % of the kernel's shared-memory wavefronts
+  float head_hbias[96];
+  float head_obias[8];
   float* canvas;         // [N, oh, ow, canvas_c]
   float* logits;         // optional [N, H, W, C]
   int oh, ow, canvas_c, canvas_coff;

@@ -235,26 +235,36 @@ class InferManager(base.InferManager):
         self._dev_bufs = {}
         for fin in self.__dict__.pop("_finish_ctxs", []):
             fin.close()
-        self.__dict__.pop("_finish_tl", None)
+        self.__dict__.pop("_finish_pool", None)
 
     def _sync_forward(self):
         self.engine.ctx.sync()
 
     def _finisher_ctx(self):
-        """A context (own stream, own post-processing workspaces) for the finishing stage: one per
-        worker thread, created on first use."""
-        import threading
-        tl = self.__dict__.setdefault("_finish_tl", threading.local())
-        if getattr(tl, "ctx", None) is None:
+        """Borrows a context (own stream, own post-processing workspaces) for one finishing task;
+        give it back with `_release_finisher_ctx`. Contexts are created on demand and reused
+        across `process_file_list` calls (at most one per concurrently running finishing thread)."""
+        import queue
+        pool = self.__dict__.setdefault("_finish_pool", queue.SimpleQueue())
+        try:
+            return pool.get_nowait()
+        except queue.Empty:
             from ..engine import Context
-            tl.ctx = Context(self.engine.ctx.device, self.engine.ctx.precision)
-            self.__dict__.setdefault("_finish_ctxs", []).append(tl.ctx)
-        return tl.ctx
+            ctx = Context(self.engine.ctx.device, self.engine.ctx.precision)
+            self.__dict__.setdefault("_finish_ctxs", []).append(ctx)
+            return ctx
+
+    def _release_finisher_ctx(self, ctx):
+        self._finish_pool.put(ctx)
 
     def _finish_one(self, m, group, to_host=True):
         """Worker-thread task: a16-a20 for one image of a forwarded group."""
-        return self._finish_image(m, group["store"] + m["first"] * group["cbytes"], group["P_out"],
-                                  group["C"], self.engine.model.idx_dict, to_host, self._finisher_ctx())
+        ctx = self._finisher_ctx()
+        try:
+            return self._finish_image(m, group["store"] + m["first"] * group["cbytes"], group["P_out"],
+                                      group["C"], self.engine.model.idx_dict, to_host, ctx)
+        finally:
+            self._release_finisher_ctx(ctx)
 
     def process_images(self, named_images, to_host=True):
         """A group of RGB uint8 images -> one result tuple per image (the tuple
