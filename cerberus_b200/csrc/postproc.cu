@@ -814,12 +814,17 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
     for (int k = tid; k < ncomp; k += kWcThreads) {
       uint64_t* hp = pool + c_off[k];
       int n = c_cnt[k];
+      // The queue is a 4-ARY heap: within a component every (value, age) key is unique except
+      // between tied marker entries, whose relative order is either proven irrelevant or sends the
+      // tile to the exact emulation - so ANY correct priority queue pops in the reference's order,
+      // and a 4-ary sift-down reads four children at once (one shared-memory latency per level,
+      // half as many levels as the binary heap the exact kernels must emulate).
       for (int j = 1; j < n; ++j) {  // in-place build by successive pushes
         const uint64_t e = hp[j];
         const uint64_t ek = e >> 16;
         int c = j;
         while (c > 0) {
-          const int parent = (c - 1) >> 1;
+          const int parent = (c - 1) >> 2;
           const uint64_t pe = hp[parent];
           if (!(ek < (pe >> 16))) break;
           hp[c] = pe;
@@ -881,15 +886,18 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
           const uint64_t xk = xe >> 16;
           int i = 0;
           for (;;) {
-            const int l = 2 * i + 1;
-            if (l >= n) break;
-            const uint64_t le = hp[l];
-            const uint64_t re = (l + 1 < n) ? hp[l + 1] : ~0ull;
-            int sidx = i;
-            uint64_t sk = xk, se = xe;
-            if ((le >> 16) < sk) { sidx = l; sk = le >> 16; se = le; }
-            if ((re >> 16) < sk) { sidx = l + 1; sk = re >> 16; se = re; }
-            if (sidx == i) break;
+            const int c0 = 4 * i + 1;
+            if (c0 >= n) break;
+            const uint64_t e0 = hp[c0];
+            const uint64_t e1 = (c0 + 1 < n) ? hp[c0 + 1] : ~0ull;
+            const uint64_t e2 = (c0 + 2 < n) ? hp[c0 + 2] : ~0ull;
+            const uint64_t e3 = (c0 + 3 < n) ? hp[c0 + 3] : ~0ull;
+            int sidx = c0;
+            uint64_t se = e0;
+            if ((e1 >> 16) < (se >> 16)) { sidx = c0 + 1; se = e1; }
+            if ((e2 >> 16) < (se >> 16)) { sidx = c0 + 2; se = e2; }
+            if ((e3 >> 16) < (se >> 16)) { sidx = c0 + 3; se = e3; }
+            if (!((se >> 16) < xk)) break;
             hp[i] = se;
             i = sidx;
           }
@@ -906,7 +914,7 @@ k_watershed_comp(const float* __restrict__ val, const uint8_t* __restrict__ msk,
           const uint64_t ek = e >> 16;                                  \
           int c = n++;                                                  \
           while (c > 0) {                                               \
-            const int parent = (c - 1) >> 1;                            \
+            const int parent = (c - 1) >> 2;                            \
             const uint64_t pe = hp[parent];                             \
             if (!(ek < (pe >> 16))) break;                              \
             hp[c] = pe;                                                 \
@@ -1008,18 +1016,24 @@ __global__ void k_wsg_seed(const float* __restrict__ val, const uint8_t* __restr
 // entries with bit-equal values surface in a component whose markers carry different labels.
 // CERT = true (k_wsg_certify): the age field of the marker entries holds an explicit rank, pushed
 // entries get ages above every rank, every labelled pixel is appended to `log`.
+#ifndef CERB_WSG_ARITY
+#define CERB_WSG_ARITY 4
+#endif
+constexpr int kWsgArity = CERB_WSG_ARITY;  // children per node of the global-memory flood queues
+
 template <bool CERT>
 __device__ __forceinline__ bool wsg_flood_component(const float* __restrict__ v,
                                                     const uint8_t* __restrict__ m, int* __restrict__ o,
                                                     int W, int hw, unsigned long long* __restrict__ k,
                                                     int* __restrict__ ix, int n, bool multi,
                                                     uint32_t age, int* __restrict__ log, int& nlog) {
+  // 4-ary heap (see k_watershed_comp: any correct priority queue gives the reference's order here)
   for (int j = 1; j < n; ++j) {  // in-place heap build by successive pushes
     const unsigned long long ek = k[j];
     const int ei = ix[j];
     int cidx = j;
     while (cidx > 0) {
-      const int parent = (cidx - 1) >> 1;
+      const int parent = (cidx - 1) / kWsgArity;
       if (!(ek < k[parent])) break;
       k[cidx] = k[parent];
       ix[cidx] = ix[parent];
@@ -1054,18 +1068,21 @@ __device__ __forceinline__ bool wsg_flood_component(const float* __restrict__ v,
     }
     unsigned e_mask = 0;
     --n;
-    if (n > 0) {  // move the last entry to the root and sift down (left child preferred)
+    if (n > 0) {  // move the last entry to the root and sift down
       const unsigned long long xk = k[n];
       const int xi = ix[n];
       int i = 0;
       for (;;) {
-        const int l = 2 * i + 1;
-        if (l >= n) break;
-        int sidx = i;
-        unsigned long long sk = xk;
-        if (k[l] < sk) { sidx = l; sk = k[l]; }
-        if (l + 1 < n && k[l + 1] < sk) { sidx = l + 1; sk = k[l + 1]; }
-        if (sidx == i) break;
+        const int c0 = kWsgArity * i + 1;
+        if (c0 >= n) break;
+        int sidx = c0;
+        unsigned long long sk = k[c0];
+#pragma unroll
+        for (int d = 1; d < kWsgArity; ++d) {
+          const unsigned long long kd = (c0 + d < n) ? k[c0 + d] : ~0ull;
+          if (kd < sk) { sidx = c0 + d; sk = kd; }
+        }
+        if (!(sk < xk)) break;
         k[i] = sk;
         ix[i] = ix[sidx];
         i = sidx;
@@ -1086,7 +1103,7 @@ __device__ __forceinline__ bool wsg_flood_component(const float* __restrict__ v,
         const unsigned long long ek = wsg_key(v[q], age);                \
         int cidx = n++;                                                  \
         while (cidx > 0) {                                               \
-          const int parent = (cidx - 1) >> 1;                            \
+          const int parent = (cidx - 1) / kWsgArity;                     \
           if (!(ek < k[parent])) break;                                  \
           k[cidx] = k[parent];                                           \
           ix[cidx] = ix[parent];                                         \
