@@ -65,6 +65,8 @@ struct Step {
   Conv64sParams c64s;
   bool use64s = false;  // split-precision 64->64 kernel (csrc/conv64s.cu)
   bool use3p = false;  // CTA-pair kernel (csrc/conv3x3c2.cu)
+  int chain_len = 0;     // > 1: this launch also runs the next chain_len - 1 steps (Conv3c2Params::layers)
+  bool chained = false;  // executed by the launch of an earlier step of its chain
   Conv64xParams c64x;
   bool use64x = false;
   bool use64 = false;
@@ -107,6 +109,9 @@ struct cerb_plan {
   int runs = 0;
   int* cur_counter = nullptr;    // counter of the op being built
   int* tile_counters = nullptr;  // one per op (dynamic tile scheduling), zeroed at the start of a run
+  size_t n_counters = 0;         // ... followed by the per-image completion counters of layer chains
+  std::vector<void*> chain_tables;  // device layer tables of the chains
+  int n_launches = 0;            // kernel launches of one run (chained steps do not launch)
 };
 
 namespace {
@@ -641,7 +646,6 @@ int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
   p.W = W;
   p.n_chunks = op.in_c / 64;
   p.BN = op.cout % 256 == 0 ? 256 : op.cout;  // 256, or the layer's 128 / 64
-  p.n_ntiles = op.cout / p.BN;
   if (op.in_coff % 8 != 0 || op.in_coff + op.in_c > in.d.c || in.d.c % 8 != 0)
     return fail(CERB_ERR_ARG, "conv3x3c2: bad input channels");
   if (op.out_coff % 8 != 0 || op.out_coff + op.cout > out.d.c || out.d.c % 8 != 0)
@@ -653,7 +657,7 @@ int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
                                    static_cast<cuuint64_t>(W) * in.d.c * es,
                                    static_cast<cuuint64_t>(H) * W * in.d.c * es};
     const cuuint32_t box[4] = {64, 10, 18, 1};
-    int rc = encode_map(ctx, &p.in_map, static_cast<__half*>(in.plane[0]) + op.in_coff, 4, dims,
+    int rc = encode_map(ctx, &p.l0.in_map, static_cast<__half*>(in.plane[0]) + op.in_coff, 4, dims,
                         strides, box);
     if (rc) return rc;
   }
@@ -665,13 +669,13 @@ int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(op.cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_total) * es};
     const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.BN / 2)};
-    int rc = encode_map(ctx, &p.w_map, pl->blob + op.w_off, 2, dims, strides, box);
+    int rc = encode_map(ctx, &p.l0.w_map, pl->blob + op.w_off, 2, dims, strides, box);
     if (rc) return rc;
   }
   if (op.b_off >= 0) {
     if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + op.cout * 4u > pl->blob_bytes)
       return fail(CERB_ERR_ARG, "conv3x3c2: bias offset out of range");
-    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+    p.l0.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
   }
   const cuuint64_t odims[4] = {static_cast<cuuint64_t>(op.cout), static_cast<cuuint64_t>(W),
                                static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
@@ -680,7 +684,7 @@ int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(out.d.c) * es,
                                    static_cast<cuuint64_t>(W) * out.d.c * es,
                                    static_cast<cuuint64_t>(H) * W * out.d.c * es};
-    int rc = encode_map(ctx, &p.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, odims,
+    int rc = encode_map(ctx, &p.l0.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, odims,
                         strides, obox);
     if (rc) return rc;
   }
@@ -694,13 +698,13 @@ int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(res.d.c) * es,
                                    static_cast<cuuint64_t>(W) * res.d.c * es,
                                    static_cast<cuuint64_t>(H) * W * res.d.c * es};
-    int rc = encode_map(ctx, &p.res_map, res.plane[0], 4, odims, strides, obox);
+    int rc = encode_map(ctx, &p.l0.res_map, res.plane[0], 4, odims, strides, obox);
     if (rc) return rc;
-    p.has_res = 1;
+    p.l0.has_res = 1;
   }
-  p.relu = op.relu;
+  p.l0.relu = op.relu;
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv3x3c2: w_shift out of range");
-  p.acc_scale = ldexpf(1.0f, -op.w_shift);
+  p.l0.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
   p.prof = ctx->prof_dev;
   p.tile_counter = ctx->dyn_sched ? pl->cur_counter : nullptr;
@@ -1080,6 +1084,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     ctx->conv3_pair = value;
     return CERB_OK;
   }
+  if (strcmp(name, "conv3_chain") == 0) {
+    ctx->conv3_chain = value != 0;  // consecutive pair-kernel layers of one geometry in one launch
+    return CERB_OK;
+  }
   if (strcmp(name, "conv3_mode") == 0) {
     if (value < 0 || value > 2) return fail(CERB_ERR_ARG, "conv3_mode must be 0, 1 or 2");
     ctx->conv3_mode = value;
@@ -1218,6 +1226,58 @@ extern "C" int64_t cerb_ctx_launch_count(cerb_ctx* ctx) { return ctx ? ctx->laun
 extern "C" void* cerb_ctx_stream(cerb_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 
 // ------------------------------------------------------------------------ plan
+namespace {
+// Runs of consecutive CTA-pair convolutions of identical geometry, each reading the output of the
+// one before (the bodies of encoder layer3 / layer4), become ONE launch: see Conv3c2Params::layers.
+// A residual may be any tensor written before the step that consumes it (the chain's dependency
+// rule - layer l of an image starts when layer l - 1 of that image is stored - orders it too).
+int link_chains(cerb_plan* pl, const cerb_op* ops, int n_ops) {
+  cerb_ctx* ctx = pl->ctx;
+  pl->n_launches = n_ops;
+  if (!ctx->conv3_chain || !ctx->dyn_sched) return CERB_OK;
+  int* done_next = pl->tile_counters + n_ops;
+  for (int i = 0; i < n_ops;) {
+    Step& first = pl->steps[i];
+    if (first.kind != CERB_OP_CONV || !first.use3p || first.side) { ++i; continue; }
+    const Conv3c2Params& a = first.c3p;
+    int j = i + 1;
+    while (j < n_ops) {
+      const Step& st = pl->steps[j];
+      const Conv3c2Params& b = st.c3p;
+      if (st.kind != CERB_OP_CONV || !st.use3p || st.side || ops[j].in0 != ops[j - 1].out ||
+          ops[j].in_coff != ops[j - 1].out_coff || ops[j].out == ops[j].in0 ||
+          b.n_img != a.n_img || b.H != a.H || b.W != a.W || b.n_chunks != a.n_chunks || b.BN != a.BN ||
+          b.n_ntiles != a.n_ntiles || b.n_bstages != a.n_bstages)
+        break;
+      ++j;
+    }
+    const int len = j - i;
+    if (len > 1) {
+      std::vector<Conv3c2Layer> table(static_cast<size_t>(len));
+      for (int k = 0; k < len; ++k) table[k] = pl->steps[i + k].c3p.l0;
+      void* dev = nullptr;
+      const size_t bytes = sizeof(Conv3c2Layer) * table.size();
+      if (cudaMalloc(&dev, bytes) != cudaSuccess ||
+          cudaMemcpy(dev, table.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(CERB_ERR_CUDA, "layer table of a convolution chain: %s",
+                    cudaGetErrorString(cudaGetLastError()));
+      pl->chain_tables.push_back(dev);
+      Conv3c2Params& p = first.c3p;
+      p.layers = static_cast<const Conv3c2Layer*>(dev);
+      p.n_layers = len;
+      p.done = done_next;
+      done_next += static_cast<size_t>(len) * p.n_img;
+      conv3x3c2_plan(p);
+      first.chain_len = len;
+      for (int k = 1; k < len; ++k) pl->steps[i + k].chained = true;
+      pl->n_launches -= len - 1;
+    }
+    i = j;
+  }
+  return CERB_OK;
+}
+}  // namespace
+
 extern "C" void cerb_plan_destroy(cerb_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->ctx->device);
@@ -1227,6 +1287,7 @@ extern "C" void cerb_plan_destroy(cerb_plan* pl) {
   }
   if (pl->blob && pl->owns_blob) cudaFree(pl->blob);
   if (pl->tile_counters) cudaFree(pl->tile_counters);
+  for (void* t : pl->chain_tables) cudaFree(t);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   delete pl;
 }
@@ -1279,7 +1340,10 @@ int cerb::plan_create_impl(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n
       cudaMemsetAsync(t.plane[pnum], 0, t.bytes, ctx->stream);
     }
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&pl->tile_counters), sizeof(int) * n_ops) != cudaSuccess)
+  int max_n = 1;
+  for (const Tensor& t : pl->tensors) max_n = t.d.n > max_n ? t.d.n : max_n;
+  pl->n_counters = static_cast<size_t>(n_ops) * (1 + static_cast<size_t>(max_n));
+  if (cudaMalloc(reinterpret_cast<void**>(&pl->tile_counters), sizeof(int) * pl->n_counters) != cudaSuccess)
     return bail(fail(CERB_ERR_CUDA, "cudaMalloc for the tile counters failed"));
   pl->steps.resize(n_ops);
   for (int i = 0; i < n_ops; ++i) {
@@ -1429,6 +1493,7 @@ int cerb::plan_create_impl(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n
         return bail(fail(CERB_ERR_ARG, "op %d: unknown kind %d", i, op.kind));
     }
   }
+  if ((rc = link_chains(pl, ops, n_ops))) return bail(rc);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return bail(fail(CERB_ERR_CUDA, "plan init: %s", cudaGetErrorString(e)));
   *out = pl;
@@ -1447,6 +1512,7 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
       }
       break;
     case CERB_OP_CONV:
+      if (st.chained) break;  // part of the launch of an earlier step
       e = st.use64x ? conv64x_launch(st.c64x, ctx->conv_sms, s, ctx->use_pdl)
           : st.use64  ? conv64_launch(st.c64, ctx->conv_sms, s, ctx->use_pdl)
           : st.use64s ? conv64s_launch(st.c64s, ctx->conv_sms, s, ctx->use_pdl)
@@ -1486,12 +1552,12 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
   }
   if (pl->graph_exec != nullptr) {
     CERB_CUDA(cudaGraphLaunch(pl->graph_exec, s));
-    ctx->launches += static_cast<int64_t>(pl->steps.size());
+    ctx->launches += static_cast<int64_t>(pl->n_launches);
     return CERB_OK;
   }
   const bool capture = ctx->use_graphs && pl->runs >= 1;
   if (capture) CERB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  CERB_CUDA(cudaMemsetAsync(pl->tile_counters, 0, sizeof(int) * pl->steps.size(), s));
+  CERB_CUDA(cudaMemsetAsync(pl->tile_counters, 0, sizeof(int) * pl->n_counters, s));
   bool forked = false;
   for (Step& st : pl->steps) {
     cudaStream_t ls = s;
@@ -1511,7 +1577,7 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
       }
       return fail(CERB_ERR_CUDA, "launch of op kind %d failed: %s", st.kind, cudaGetErrorString(e));
     }
-    if (!capture) ctx->launches += 1;
+    if (!capture && !st.chained) ctx->launches += 1;
   }
   pl->runs += 1;
   if (capture) {
@@ -1528,7 +1594,7 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
       return fail(CERB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
     }
     CERB_CUDA(cudaGraphLaunch(pl->graph_exec, s));
-    ctx->launches += static_cast<int64_t>(pl->steps.size());
+    ctx->launches += static_cast<int64_t>(pl->n_launches);
   }
   return CERB_OK;
 }
@@ -1546,13 +1612,13 @@ extern "C" int cerb_plan_profile(cerb_plan* pl, int reps, float* ms_per_op, int3
   for (cudaEvent_t& e : ev) CERB_CUDA(cudaEventCreate(&e));
   for (int r = 0; r < reps; ++r) {
     cudaEvent_t* e = ev.data() + static_cast<size_t>(r) * (n + 1);
-    CERB_CUDA(cudaMemsetAsync(pl->tile_counters, 0, sizeof(int) * n, s));
+    CERB_CUDA(cudaMemsetAsync(pl->tile_counters, 0, sizeof(int) * pl->n_counters, s));
     CERB_CUDA(cudaEventRecord(e[0], s));
     for (size_t i = 0; i < n; ++i) {
       cudaError_t le = launch_step(ctx, pl->steps[i], s);
       if (le != cudaSuccess)
         return fail(CERB_ERR_CUDA, "profile: launch of op %zu failed: %s", i, cudaGetErrorString(le));
-      ctx->launches += 1;
+      if (!pl->steps[i].chained) ctx->launches += 1;
       CERB_CUDA(cudaEventRecord(e[i + 1], s));
     }
   }
@@ -1568,6 +1634,14 @@ extern "C" int cerb_plan_profile(cerb_plan* pl, int reps, float* ms_per_op, int3
     }
     ms_per_op[i] = static_cast<float>(acc / reps);
     if (kinds) kinds[i] = pl->steps[i].kind;
+  }
+  // a layer chain is one launch: its time is spread evenly over its (identically shaped) layers
+  for (size_t i = 0; i < n; ++i) {
+    const int len = pl->steps[i].chain_len;
+    if (len <= 1) continue;
+    double tot = 0.0;
+    for (int k = 0; k < len; ++k) tot += ms_per_op[i + k];
+    for (int k = 0; k < len; ++k) ms_per_op[i + k] = static_cast<float>(tot / len);
   }
   for (cudaEvent_t& e : ev) cudaEventDestroy(e);
   return CERB_OK;

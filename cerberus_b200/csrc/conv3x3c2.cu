@@ -74,11 +74,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 
 struct Item {
-  int nt, rx, ry, img;
+  int layer, nt, rx, ry, img;
 };
 
 __device__ __forceinline__ Item decode(const Conv3c2Params& p, int item) {
   Item it;
+  it.layer = item / p.n_items_layer;  // chains number their items layer-major
+  item -= it.layer * p.n_items_layer;
   it.nt = item % p.n_ntiles;
   const int rg = item / p.n_ntiles;
   it.rx = rg % p.regions_x;
@@ -86,6 +88,40 @@ __device__ __forceinline__ Item decode(const Conv3c2Params& p, int item) {
   it.ry = t % p.regions_y;
   it.img = t / p.regions_y;
   return it;
+}
+
+__device__ __forceinline__ const Conv3c2Layer& layer_of(const Conv3c2Params& p, int layer) {
+  return p.layers != nullptr ? p.layers[layer] : p.l0;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// Chain dependency: every item of `layer - 1` on image `img` has been stored (both CTAs of its pair).
+// Non-blocking form: false if not yet. One lane calls it; the TMA loads of the item are its own.
+__device__ __forceinline__ bool layer_done(const Conv3c2Params& p, int layer, int img, bool block) {
+  const int* cnt = p.done + (layer - 1) * p.n_img + img;
+  const int need = 2 * p.items_per_img;
+  if (ld_acquire_gpu(cnt) < need) {
+    if (!block) return false;
+    const uint64_t t0 = ptx::global_timer_ns();
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(cnt) < need) {
+      if ((++spins & 0x3FF) == 0 && ptx::global_timer_ns() - t0 > 2000000000ull) {
+        if (p.err_flag) atomicExch(p.err_flag, 69);
+        __threadfence_system();
+        asm volatile("trap;");
+      }
+    }
+  }
+  fence_proxy_async_all();  // the TMA loads that follow read what other CTAs' TMA stores wrote
+  return true;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3c2Threads, 1)
@@ -119,10 +155,12 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
   volatile int* s_ring = reinterpret_cast<volatile int*>(tmem_holder + 2);
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&p.in_map);
-    ptx::prefetch_tmap(&p.w_map);
-    ptx::prefetch_tmap(&p.out_map);
-    if (p.has_res) ptx::prefetch_tmap(&p.res_map);
+    if (p.layers == nullptr) {
+      ptx::prefetch_tmap(&p.l0.in_map);
+      ptx::prefetch_tmap(&p.l0.w_map);
+      ptx::prefetch_tmap(&p.l0.out_map);
+      if (p.l0.has_res) ptx::prefetch_tmap(&p.l0.res_map);
+    }
     for (int s = 0; s < kAStages; ++s) {
       ptx::mbar_init(&a_full[s], 1);   // leader's producer (expect_tx of both CTAs)
       ptx::mbar_init(&a_empty[s], 1);  // multicast commit
@@ -190,27 +228,41 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
     // tap 4 of the current pair is being queued, i.e. as soon as its stage can have been released.
     // (A decoupled halo stream polling for free stages on every tap, with two or three stages,
     // measured slower: 0.048-0.050 ms against 0.044 ms on 256->256 at 32x32, batch 32.)
-    auto issue_a = [&](int item, int c) {
+    // Chains: the first halo of an item of layer > 0 may only be requested once the previous layer
+    // of its image is stored. `block` = false while loads of the CURRENT item are still to be
+    // issued: a producer that blocked there could hold back the very items others wait for
+    // (its own included); the caller then retries after the tap loop.
+    auto issue_a = [&](int item, int c, bool block) -> bool {
       const Item it = decode(p, item);
+      if (c == 0 && it.layer > 0) {
+        int ok = 1;
+        if (leader_lane_p) ok = layer_done(p, it.layer, it.img, block) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, elected);
+        if (!ok) return false;
+      }
       const int st = a_issued % kAStages;
       const uint32_t ph = (a_issued / kAStages) & 1;
       ptx::mbar_wait(&a_empty[st], ph ^ 1, p.err_flag, 62);
       if (leader_lane_p) {
         if (is_leader) ptx::mbar_arrive_expect_tx(&a_full[st], 2 * kATxBytes);
-        ptx::tma_load_4d_2sm(sA + st * kAStageBytes, &p.in_map, a_full_l0 + 8u * st, c * 64,
+        ptx::tma_load_4d_2sm(sA + st * kAStageBytes, &layer_of(p, it.layer).in_map, a_full_l0 + 8u * st, c * 64,
                              it.rx * kRegion + 8 * static_cast<int>(rank) - 1, it.ry * kRegion - 1, it.img);
       }
       __syncwarp();
       ++a_issued;
+      return true;
     };
     int cur_item = fetch(), cur_c = 0;
-    if (cur_item >= 0) issue_a(cur_item, 0);
+    if (cur_item >= 0) issue_a(cur_item, 0, true);
     int nxt_item = cur_item, nxt_c = 1;
     if (cur_item >= 0 && nxt_c == n_chunks) { nxt_c = 0; nxt_item = fetch(); }
     while (cur_item >= 0) {
-      const int nt = cur_item % p.n_ntiles;
+      const Item cur = decode(p, cur_item);
+      const int nt = cur.nt;
+      const CUtensorMap* w_map = &layer_of(p, cur.layer).w_map;
+      bool a_deferred = false;
       for (int t = 0; t < 9; ++t) {
-        if (t == 4 && nxt_item >= 0) issue_a(nxt_item, nxt_c);
+        if (t == 4 && nxt_item >= 0) a_deferred = !issue_a(nxt_item, nxt_c, false);
         const int bs = b_cnt % n_bstages;
         const uint32_t bph = (b_cnt / n_bstages) & 1;
         CERB_PROF_T0(t_p);
@@ -218,12 +270,13 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
         CERB_PROF_ADD(prof_a, t_p);
         if (leader_lane_p) {
           if (is_leader) ptx::mbar_arrive_expect_tx(&b_full[bs], 2 * b_stage_bytes);
-          ptx::tma_load_2d_2sm(sB + bs * b_stage_bytes, &p.w_map, b_full_l0 + 8u * bs, (t * n_chunks + cur_c) * 64,
+          ptx::tma_load_2d_2sm(sB + bs * b_stage_bytes, w_map, b_full_l0 + 8u * bs, (t * n_chunks + cur_c) * 64,
                                nt * BN + (BN >> 1) * static_cast<int>(rank));
         }
         __syncwarp();
         ++b_cnt;
       }
+      if (a_deferred) issue_a(nxt_item, nxt_c, true);
       cur_item = nxt_item;
       cur_c = nxt_c;
       if (nxt_item >= 0 && ++nxt_c == n_chunks) { nxt_c = 0; nxt_item = fetch(); }
@@ -316,6 +369,7 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
     const uint32_t tempty_l1 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[1]), 0);
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
     int sidx = 0, it = 0;
+    uint32_t res_phase = 0;  // bit b: parity of the next residual arrival in slab buffer b
     for (;; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -326,6 +380,10 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
       if (item < 0) break;
       ptx::tc_fence_after();
       const Item im = decode(p, item);
+      const Conv3c2Layer& L = layer_of(p, im.layer);
+      const int has_res = L.has_res, relu = L.relu;
+      const float acc_scale = L.acc_scale;
+      const float* bias = L.bias;
       const int x0 = im.rx * kRegion + 8 * static_cast<int>(rank), y0 = im.ry * kRegion;
       const int n0 = im.nt * BN;
       const int n_slabs = BN >> 6;
@@ -336,9 +394,9 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
         uint64_t* rbar = &res_bar[buf];
         if (store_warp && ptx::elect_one()) {
           ptx::bulk_wait_read<1>();  // the store that last used this slab buffer has drained it
-          if (p.has_res) {
+          if (has_res) {
             ptx::mbar_arrive_expect_tx(rbar, kSlabBytes);
-            ptx::tma_load_4d(sO, &p.res_map, rbar, n0 + slab * 64, x0, y0, im.img);
+            ptx::tma_load_4d(sO, &L.res_map, rbar, n0 + slab * 64, x0, y0, im.img);
           }
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + slab * 64;
@@ -352,8 +410,9 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
           if (lane == 0) ptx::mbar_arrive_cluster(acc == 0 ? tempty_l0 : tempty_l1);
         }
         CERB_PROF_T0(t_e1);
-        if (p.has_res) {
-          ptx::mbar_wait(rbar, (sidx >> 1) & 1, p.err_flag, 68);
+        if (has_res) {
+          ptx::mbar_wait(rbar, (res_phase >> buf) & 1, p.err_flag, 68);
+          res_phase ^= 1u << buf;
         } else {
           ptx::named_bar_sync(1, 128);  // the elected lane has seen the slab buffer drained
         }
@@ -364,16 +423,16 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            v[i] = __uint_as_float(half == 0 ? r0[i] : r1[i]) * p.acc_scale;
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + slab * 64 + half * 32);
+            v[i] = __uint_as_float(half == 0 ? r0[i] : r1[i]) * acc_scale;
+          if (bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + slab * 64 + half * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 b = __ldg(b4 + i);
               v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
-          if (p.has_res) {
+          if (has_res) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint4 u = *reinterpret_cast<const uint4*>(my_row + (((half * 4 + i) ^ sw) << 4));
@@ -385,7 +444,7 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
               }
             }
           }
-          if (p.relu) {
+          if (relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
           }
@@ -404,8 +463,15 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
         ptx::fence_proxy_async_smem();
         ptx::named_bar_sync(1, 128);
         if (store_warp && ptx::elect_one()) {
-          ptx::tma_store_4d(&p.out_map, sO, n0 + slab * 64, x0, y0, im.img);
+          ptx::tma_store_4d(&L.out_map, sO, n0 + slab * 64, x0, y0, im.img);
           ptx::bulk_commit_group();
+          if (slab == n_slabs - 1 && im.layer + 1 < p.n_layers) {
+            // chain: this CTA's half of the item is in global memory -> release it to the next layer
+            ptx::bulk_wait_all<0>();
+            fence_proxy_async_all();
+            __threadfence();
+            atomicAdd(p.done + im.layer * p.n_img + im.img, 1);
+          }
         }
         CERB_PROF_ADD(prof_d, t_e3);
       }
@@ -436,7 +502,10 @@ void conv3x3c2_plan(Conv3c2Params& p) {
   p.n_bstages = n;
   p.regions_x = (p.W + kRegion - 1) / kRegion;
   p.regions_y = (p.H + kRegion - 1) / kRegion;
-  p.n_items = p.n_img * p.regions_x * p.regions_y * p.n_ntiles;
+  p.items_per_img = p.regions_x * p.regions_y * p.n_ntiles;
+  p.n_items_layer = p.n_img * p.items_per_img;
+  if (p.n_layers < 1) p.n_layers = 1;
+  p.n_items = p.n_layers * p.n_items_layer;
 }
 
 size_t conv3x3c2_smem_bytes(const Conv3c2Params& p) {

@@ -39,6 +39,8 @@ class Context:
             self.set_option("conv64s", int(os.environ["CERB_CONV64S"]))
         if os.environ.get("CERB_CONV3_PAIR") is not None:  # CTA-pair kernel for the wide 3x3 layers
             self.set_option("conv3_pair", int(os.environ["CERB_CONV3_PAIR"]))
+        if os.environ.get("CERB_CONV3_CHAIN") is not None:  # layer chains of the pair kernel (A/B switch)
+            self.set_option("conv3_chain", int(os.environ["CERB_CONV3_CHAIN"]))
         if os.environ.get("CERB_DYN_SCHED") is not None:
             self.set_option("dyn_sched", int(os.environ["CERB_DYN_SCHED"]))
         if os.environ.get("CERB_USE_PDL") is not None:  # A/B switch for the PDL launches

@@ -213,6 +213,76 @@ def test_conv3x3_cta_pair_kernel(case, dyn, built_lib, monkeypatch):
     assert np.all(err <= tol), "max err %g at %r" % (err.max(), np.unravel_index(err.argmax(), err.shape))
 
 
+CHAIN_CASES = [
+    # n, h, w, channels, layers
+    (3, 32, 32, 256, 5),     # layer3 body: 4 regions per image
+    (5, 40, 24, 256, 4),     # partial regions in x and y
+    (37, 16, 16, 512, 5),    # layer4 body: two 256-channel tiles per region, K = 4608
+    (1, 16, 16, 256, 6),     # ONE item per layer: every item waits for the one before it
+    (2, 16, 16, 256, 3),     # fewer items than layers x pairs
+    (160, 16, 16, 256, 3),   # more items per layer than CTA pairs
+]
+
+
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv3x3_layer_chain_is_one_launch_with_identical_results(case, built_lib, monkeypatch):
+    """Consecutive pair-kernel layers of one geometry run as ONE persistent launch whose items wait
+    for the previous layer of their image (Conv3c2Params::layers; encoder layer3 / layer4 bodies,
+    models/backbone/resnet.py:203-211 with BasicBlock residuals). Same bits as layer-by-layer
+    launches, fewer launches, and the last layer within fp16 tolerance of the fp64 chain."""
+    n, h, w, ch, n_layers = case
+    rng = np.random.RandomState(11)
+    x = f16(rng.standard_normal((n, h, w, ch)).astype(np.float32)).astype(np.float32)
+    wts = [f16((rng.standard_normal((ch, ch, 3, 3)) * (1.0 / np.sqrt(ch * 9))).astype(np.float32)).astype(np.float32)
+           for _ in range(n_layers)]
+    bs = [rng.uniform(-0.5, 0.5, ch).astype(np.float32) for _ in range(n_layers)]
+
+    def run(chain):
+        monkeypatch.setenv("CERB_CONV3_CHAIN", str(chain))
+        blob = BlobBuilder()
+        layers = [pack_conv(blob, wt.astype(np.float64), b.astype(np.float64)) for wt, b in zip(wts, bs)]
+        spec = MiniSpec()
+        tids = [spec._tensor("t%d" % i, n, h, w, ch) for i in range(n_layers + 1)]
+        for i, layer in enumerate(layers):
+            # BasicBlock pattern: every second conv adds the tensor two steps back; the last has no ReLU
+            res = tids[i - 1] if i % 2 == 1 else -1
+            spec._conv(layer, tids[i], tids[i + 1], relu=int(i != n_layers - 1), stride=1, residual=res)
+        ctx = Context(0, "f16")
+        plan = ForwardPlan(ctx, MiniModel(blob), 0, 0, 0, 0, 0, spec=spec)
+        plan.write(tids[0], x.astype(np.float16), 0)
+        outs = []
+        for rep in range(3):  # eager, graph capture, graph replay
+            before = ctx.launch_count
+            plan.run()
+            ctx.sync()
+            launches = ctx.launch_count - before
+            outs.append([plan.read(t) for t in tids[1:]])
+        plan.close()
+        ctx.close()
+        for o in outs[1:]:
+            for a, b in zip(o, outs[0]):
+                assert np.array_equal(a, b)
+        return outs[0], launches
+
+    chained, l1 = run(1)
+    single, l0 = run(0)
+    assert l0 == n_layers and l1 == 1, (l0, l1)
+    for i, (a, b) in enumerate(zip(chained, single)):
+        assert np.array_equal(a, b), "layer %d differs between the chained and the layer-by-layer launch" % i
+    # fp64 chain on the device's own fp16 intermediates (each layer checked on its actual input)
+    prev = [x] + [a.astype(np.float32) for a in chained]
+    for i in range(n_layers):
+        ref = F.conv2d(torch.from_numpy(nhwc_to_nchw(prev[i])).double(), torch.from_numpy(wts[i]).double(),
+                       torch.from_numpy(bs[i]).double(), padding=1)
+        if i % 2 == 1:
+            ref = ref + torch.from_numpy(nhwc_to_nchw(prev[i - 1])).double()
+        if i != n_layers - 1:
+            ref = F.relu(ref)
+        ref = nchw_to_nhwc(ref.numpy())
+        err = np.abs(prev[i + 1] - ref)
+        assert np.all(err <= 2e-3 * np.abs(ref) + 2e-3), (i, err.max())
+
+
 SPLIT64_CASES = [
     # n, h, w, cin, cout, k, stride, residual, relu   (64 -> 64 3x3 stride 1, split-precision mode)
     (2, 32, 32, 64, 64, 3, 1, False, True),
