@@ -646,6 +646,7 @@ int build_conv3_pair(cerb_plan* pl, const cerb_op& op, Step& st) {
   p.W = W;
   p.n_chunks = op.in_c / 64;
   p.BN = op.cout % 256 == 0 ? 256 : op.cout;  // 256, or the layer's 128 / 64
+  p.n_ntiles = op.cout / p.BN;
   if (op.in_coff % 8 != 0 || op.in_coff + op.in_c > in.d.c || in.d.c % 8 != 0)
     return fail(CERB_ERR_ARG, "conv3x3c2: bad input channels");
   if (op.out_coff % 8 != 0 || op.out_coff + op.cout > out.d.c || out.d.c % 8 != 0)
@@ -1575,7 +1576,10 @@ extern "C" int cerb_plan_run(cerb_plan* pl, const uint8_t* input_u8, int input_o
         cudaStreamEndCapture(s, &g);
         if (g) cudaGraphDestroy(g);
       }
-      return fail(CERB_ERR_CUDA, "launch of op kind %d failed: %s", st.kind, cudaGetErrorString(e));
+      return fail(CERB_ERR_CUDA, "launch of op %d (kind %d%s) failed: %s",
+                  static_cast<int>(&st - pl->steps.data()), st.kind,
+                  st.use3p ? ", pair kernel" : st.use3 ? ", conv3x3" : st.use64x ? ", conv64x" : "",
+                  cudaGetErrorString(e));
     }
     if (!capture && !st.chained) ctx->launches += 1;
   }

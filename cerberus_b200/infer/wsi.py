@@ -197,7 +197,14 @@ class InferManager(base.InferManager):
         boxes of the instances accumulated so far (cross tiles replace some of them). Returns the
         tile's surviving instances as COLUMNS (box, centroid, contour offsets, contour points,
         prob, type - slide coordinates; see dat_writer.InstanceStore) or None, and the INDICES into
-        ref_boxes it replaces."""
+        ref_boxes it replaces. (Both halves on the main context, one after the other.)"""
+        labelled = self._tile_labels(canvas, tile_bounds)
+        return self._tile_tables(self.engine.ctx, labelled, tile_bounds, tile_flag, tile_mode,
+                                 ref_boxes, margin)
+
+    def _tile_labels(self, canvas, tile_bounds):
+        """First half of a post-processing tile (infer/wsi.py:64-135): nuclei label map of the tile
+        crop, left in HBM. None when the tile is empty."""
         eng, ctx, lib = self.engine, self.engine.ctx, self.engine.ctx.lib
         idx = eng.model.idx_dict
         H, W, C = canvas.shape
@@ -206,7 +213,7 @@ class InferManager(base.InferManager):
         x0, y0 = int(tile_bounds[0]), int(tile_bounds[1])
         x1, y1 = min(int(tile_bounds[2]), W), min(int(tile_bounds[3]), H)  # numpy slicing clips
         if x1 <= x0 or y1 <= y0:
-            return None, []
+            return None
         crop = canvas[y0:y1, x0:x1].contiguous()
         h, w = crop.shape[:2]
         # the label map of the tile stays in HBM: the device instance table is all the host needs
@@ -214,7 +221,9 @@ class InferManager(base.InferManager):
         type_dev = crop[..., idx["Nuclei-TYPE"][0]].contiguous() if type_map_present else None
         labels = torch.empty((h, w), dtype=torch.int32, device=canvas.device)
         any_fg = torch.zeros(1, dtype=torch.int32, device=canvas.device)
-        torch.cuda.synchronize(canvas.device)
+        # torch's stream only (crop / type plane are ready); a device-wide synchronisation would
+        # also wait for the table thread's kernels of the previous tile
+        torch.cuda.current_stream(canvas.device).synchronize()
         t0 = time.perf_counter()
         _lib.check(lib.cerb_postproc_nuclei(ctx.handle, _ptr(crop), 1, h, w, C,
                                             idx["Nuclei-INST"][0], _ptr(labels), _ptr(any_fg), 1 | 2),
@@ -223,11 +232,22 @@ class InferManager(base.InferManager):
         self.t_dev += time.perf_counter() - t0
         del crop
         if not int(any_fg.item()):
+            return None
+        return labels, type_dev, (h, w), type_map_present
+
+    def _tile_tables(self, ctx, labelled, tile_bounds, tile_flag, tile_mode, ref_boxes, margin):
+        """Second half of a post-processing tile (infer/wsi.py:137-268): instance table of the label
+        map (device pass on `ctx` - a context of its own, so that it overlaps the watershed of the
+        next tile on the main context) and the boundary de-duplication."""
+        if labelled is None:
             return None, []
+        labels, type_dev, (h, w), type_map_present = labelled
+        tile_bounds = np.asarray(tile_bounds, dtype=np.int64)
+        tile_tl = tile_bounds[:2]
         t0 = time.perf_counter()
         table = inst_table(ctx, labels.data_ptr(), type_dev.data_ptr() if type_dev is not None else None,
                            on_device=True, shape=(h, w))
-        del labels, type_dev
+        del labels, type_dev, labelled
         rows = np.asarray(instinfo_rows(table), dtype=np.int64)
         if len(rows) == 0:
             self.t_host += time.perf_counter() - t0
@@ -278,6 +298,23 @@ class InferManager(base.InferManager):
         tile_sets = get_tile_info((W, H), pp_tile_shape, self.patch_output_shape, margin)
         store = InstanceStore(has_type="Nuclei-TYPE" in self.engine.model.idx_dict)
         self.t_dev = self.t_host = 0.0
+        from concurrent.futures import ThreadPoolExecutor
+        table_ctx = self._table_ctx()
+        with ThreadPoolExecutor(max_workers=1) as table_pool:
+            self._nuclei_tile_sets(tile_sets, canvas, patch_outputs, margin, store, table_pool, table_ctx)
+        return store if rank == 0 else None
+
+    def _table_ctx(self):
+        """Context (own stream and instance-table workspace) of the table thread; kept for the life
+        of the manager."""
+        ctx = self.__dict__.get("_tbl_ctx")
+        if ctx is None:
+            from ..engine import Context
+            ctx = self._tbl_ctx = Context(self.engine.ctx.device, self.engine.ctx.precision)
+        return ctx
+
+    def _nuclei_tile_sets(self, tile_sets, canvas, patch_outputs, margin, store, table_pool, table_ctx):
+        dist, rank, world = self._dist()
         for set_idx, (set_bounds, set_flags) in enumerate(tile_sets):
             todo = [i for i, tb in enumerate(set_bounds) if len(boxes_intersect(patch_outputs, tb)) > 0]
             # cross tiles (set 3) replace accumulated instances: every tile of the set sees the boxes
@@ -290,8 +327,19 @@ class InferManager(base.InferManager):
                     obj = [ref_boxes]
                     dist.broadcast_object_list(obj, src=0)
                     ref_boxes = obj[0]
-            local = [(i, self._process_tile_predictions(canvas, set_bounds[i], set_flags[i], set_idx,
-                                                        ref_boxes, margin)) for i in todo[rank::world]]
+            # two-stage pipeline over the tiles of this rank: the watershed of tile k + 1 (main
+            # context) runs while a worker thread builds the instance table of tile k on a context
+            # of its own; at most two label maps wait in HBM
+            futs = []
+            for i in todo[rank::world]:
+                if len(futs) >= 2:
+                    futs[-2][1].result()
+                labelled = self._tile_labels(canvas, set_bounds[i])
+                futs.append((i, table_pool.submit(self._tile_tables, table_ctx, labelled, set_bounds[i],
+                                                  set_flags[i], set_idx, ref_boxes, margin)))
+                del labelled
+            local = [(i, f.result()) for i, f in futs]
+            del futs
             if world > 1:
                 gathered = [None] * world if rank == 0 else None
                 dist.gather_object(local, gathered, dst=0)
@@ -302,7 +350,6 @@ class InferManager(base.InferManager):
                     if cols is not None:
                         store.append(*cols)
                     store.remove(remove_idx_list)
-        return store if rank == 0 else None
 
     # ------------------------------------------------------------------ gland / lumen
     def _postproc_gland_lumen(self, canvas, wsi_mask, mask_downsample_ratio):

@@ -103,7 +103,11 @@ def _wsi_worker(rank, world, port, out_dir):
         model = _Model()
 
     m.engine = _Eng()
-    m._process_tile_predictions = fake_tile
+    # the two halves of a post-processing tile (watershed on the main context / instance table on
+    # the table thread's context) and the table context itself are replaced
+    m._tile_labels = lambda canvas, tb: tb
+    m._tile_tables = lambda ctx, labelled, tb, flag, mode, ref, margin: fake_tile(None, tb, flag, mode, ref, margin)
+    m._table_ctx = lambda: None
     _, pout = get_coordinates((1000, 700), [448, 448], [144, 144], [144, 144])
     store = m._postproc_nuclei(_FakeCanvas(), pout, [300, 300], 64)
     keys = []
