@@ -500,7 +500,7 @@ int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
                                    static_cast<cuuint64_t>(W) * in.d.c * es,
                                    static_cast<cuuint64_t>(H) * W * in.d.c * es};
     const cuuint32_t box[4] = {64, 18, 18, 1};
-    int rc = encode_map(ctx, &p.in_map, static_cast<__half*>(in.plane[0]) + op.in_coff, 4, dims,
+    int rc = encode_map(ctx, &p.l0.in_map, static_cast<__half*>(in.plane[0]) + op.in_coff, 4, dims,
                         strides, box);
     if (rc) return rc;
   }
@@ -512,13 +512,13 @@ int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(op.cout)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_total) * es};
     const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.BN)};
-    int rc = encode_map(ctx, &p.w_map, pl->blob + op.w_off, 2, dims, strides, box);
+    int rc = encode_map(ctx, &p.l0.w_map, pl->blob + op.w_off, 2, dims, strides, box);
     if (rc) return rc;
   }
   if (op.b_off >= 0) {
     if (op.b_off % 16 != 0 || static_cast<size_t>(op.b_off) + op.cout * 4u > pl->blob_bytes)
       return fail(CERB_ERR_ARG, "conv3x3: bias offset out of range");
-    p.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
+    p.l0.bias = reinterpret_cast<const float*>(pl->blob + op.b_off);
   }
   {
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(op.cout), static_cast<cuuint64_t>(W),
@@ -527,7 +527,7 @@ int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
                                    static_cast<cuuint64_t>(W) * out.d.c * es,
                                    static_cast<cuuint64_t>(H) * W * out.d.c * es};
     const cuuint32_t box[4] = {64, 8, 16, 1};
-    int rc = encode_map(ctx, &p.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, dims,
+    int rc = encode_map(ctx, &p.l0.out_map, static_cast<__half*>(out.plane[0]) + op.out_coff, 4, dims,
                         strides, box);
     if (rc) return rc;
   }
@@ -544,13 +544,13 @@ int build_conv3(cerb_plan* pl, const cerb_op& op, Step& st) {
                                    static_cast<cuuint64_t>(W) * res.d.c * es,
                                    static_cast<cuuint64_t>(H) * W * res.d.c * es};
     const cuuint32_t box[4] = {64, 8, 16, 1};
-    int rc = encode_map(ctx, &p.res_map, res.plane[0], 4, dims, strides, box);
+    int rc = encode_map(ctx, &p.l0.res_map, res.plane[0], 4, dims, strides, box);
     if (rc) return rc;
-    p.has_res = 1;
+    p.l0.has_res = 1;
   }
-  p.relu = op.relu;
+  p.l0.relu = op.relu;
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv3x3: w_shift out of range");
-  p.acc_scale = ldexpf(1.0f, -op.w_shift);
+  p.l0.acc_scale = ldexpf(1.0f, -op.w_shift);
   p.err_flag = ctx->err_flag_dev;
   p.prof = ctx->prof_dev;
   p.tile_counter = ctx->dyn_sched ? pl->cur_counter : nullptr;
@@ -1228,10 +1228,34 @@ extern "C" void* cerb_ctx_stream(cerb_ctx* ctx) { return ctx ? ctx->stream : nul
 
 // ------------------------------------------------------------------------ plan
 namespace {
-// Runs of consecutive CTA-pair convolutions of identical geometry, each reading the output of the
-// one before (the bodies of encoder layer3 / layer4), become ONE launch: see Conv3c2Params::layers.
+// Runs of consecutive wide 3x3 convolutions of identical geometry on one kernel (CTA-pair kernel or
+// conv3x3.cu), each reading the output of the one before (the bodies of encoder layer2 / layer3 /
+// layer4), become ONE launch: see conv_chain.cuh.
 // A residual may be any tensor written before the step that consumes it (the chain's dependency
 // rule - layer l of an image starts when layer l - 1 of that image is stored - orders it too).
+// Geometry of a pair-kernel / conv3x3.cu step as far as chaining is concerned.
+struct ChainGeom {
+  int kernel, n_img, H, W, n_chunks, BN, n_ntiles, n_bstages;
+  bool operator==(const ChainGeom& o) const {
+    return kernel == o.kernel && n_img == o.n_img && H == o.H && W == o.W && n_chunks == o.n_chunks &&
+           BN == o.BN && n_ntiles == o.n_ntiles && n_bstages == o.n_bstages;
+  }
+};
+bool chain_geom(const Step& st, ChainGeom& g) {
+  if (st.kind != CERB_OP_CONV || st.side) return false;
+  if (st.use3p) {
+    const Conv3c2Params& p = st.c3p;
+    g = {1, p.n_img, p.H, p.W, p.n_chunks, p.BN, p.n_ntiles, p.n_bstages};
+    return true;
+  }
+  if (st.use3 && !st.c3.rotate) {
+    const Conv3Params& p = st.c3;
+    g = {2, p.n_img, p.H, p.W, p.n_chunks, p.BN, p.n_ntiles, p.n_bstages};
+    return true;
+  }
+  return false;
+}
+
 int link_chains(cerb_plan* pl, const cerb_op* ops, int n_ops) {
   cerb_ctx* ctx = pl->ctx;
   pl->n_launches = n_ops;
@@ -1239,36 +1263,42 @@ int link_chains(cerb_plan* pl, const cerb_op* ops, int n_ops) {
   int* done_next = pl->tile_counters + n_ops;
   for (int i = 0; i < n_ops;) {
     Step& first = pl->steps[i];
-    if (first.kind != CERB_OP_CONV || !first.use3p || first.side) { ++i; continue; }
-    const Conv3c2Params& a = first.c3p;
+    ChainGeom a;
+    if (!chain_geom(first, a)) { ++i; continue; }
     int j = i + 1;
     while (j < n_ops) {
-      const Step& st = pl->steps[j];
-      const Conv3c2Params& b = st.c3p;
-      if (st.kind != CERB_OP_CONV || !st.use3p || st.side || ops[j].in0 != ops[j - 1].out ||
-          ops[j].in_coff != ops[j - 1].out_coff || ops[j].out == ops[j].in0 ||
-          b.n_img != a.n_img || b.H != a.H || b.W != a.W || b.n_chunks != a.n_chunks || b.BN != a.BN ||
-          b.n_ntiles != a.n_ntiles || b.n_bstages != a.n_bstages)
+      ChainGeom b;
+      if (!chain_geom(pl->steps[j], b) || !(b == a) || ops[j].in0 != ops[j - 1].out ||
+          ops[j].in_coff != ops[j - 1].out_coff || ops[j].out == ops[j].in0)
         break;
       ++j;
     }
     const int len = j - i;
     if (len > 1) {
-      std::vector<Conv3c2Layer> table(static_cast<size_t>(len));
-      for (int k = 0; k < len; ++k) table[k] = pl->steps[i + k].c3p.l0;
+      std::vector<ConvChainLayer> table(static_cast<size_t>(len));
+      for (int k = 0; k < len; ++k)
+        table[k] = a.kernel == 1 ? pl->steps[i + k].c3p.l0 : pl->steps[i + k].c3.l0;
       void* dev = nullptr;
-      const size_t bytes = sizeof(Conv3c2Layer) * table.size();
+      const size_t bytes = sizeof(ConvChainLayer) * table.size();
       if (cudaMalloc(&dev, bytes) != cudaSuccess ||
           cudaMemcpy(dev, table.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(CERB_ERR_CUDA, "layer table of a convolution chain: %s",
                     cudaGetErrorString(cudaGetLastError()));
       pl->chain_tables.push_back(dev);
-      Conv3c2Params& p = first.c3p;
-      p.layers = static_cast<const Conv3c2Layer*>(dev);
-      p.n_layers = len;
-      p.done = done_next;
-      done_next += static_cast<size_t>(len) * p.n_img;
-      conv3x3c2_plan(p);
+      if (a.kernel == 1) {
+        Conv3c2Params& p = first.c3p;
+        p.layers = static_cast<const ConvChainLayer*>(dev);
+        p.n_layers = len;
+        p.done = done_next;
+        conv3x3c2_plan(p);
+      } else {
+        Conv3Params& p = first.c3;
+        p.layers = static_cast<const ConvChainLayer*>(dev);
+        p.n_layers = len;
+        p.done = done_next;
+        conv3x3_plan(p);
+      }
+      done_next += static_cast<size_t>(len) * a.n_img;
       first.chain_len = len;
       for (int k = 1; k < len; ++k) pl->steps[i + k].chained = true;
       pl->n_launches -= len - 1;

@@ -39,11 +39,13 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 struct Item {
-  int nt, rx, ry, img;
+  int layer, nt, rx, ry, img;
 };
 
 __device__ __forceinline__ Item decode(const Conv3Params& p, int item) {
   Item it;
+  it.layer = item / p.n_items_layer;  // chains number their items layer-major
+  item -= it.layer * p.n_items_layer;
   it.nt = item % p.n_ntiles;
   const int rg = item / p.n_ntiles;
   it.rx = rg % p.regions_x;
@@ -51,6 +53,10 @@ __device__ __forceinline__ Item decode(const Conv3Params& p, int item) {
   it.ry = t % p.regions_y;
   it.img = t / p.regions_y;
   return it;
+}
+
+__device__ __forceinline__ const ConvChainLayer& layer_of(const Conv3Params& p, int layer) {
+  return p.layers != nullptr ? p.layers[layer] : p.l0;
 }
 
 __global__ void __launch_bounds__(kConv3Threads, 1)
@@ -79,10 +85,12 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
   volatile int* s_ring = reinterpret_cast<volatile int*>(tmem_holder + 2);
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&p.in_map);
-    ptx::prefetch_tmap(&p.w_map);
-    ptx::prefetch_tmap(&p.out_map);
-    if (p.has_res) ptx::prefetch_tmap(&p.res_map);
+    if (p.layers == nullptr) {
+      ptx::prefetch_tmap(&p.l0.in_map);
+      ptx::prefetch_tmap(&p.l0.w_map);
+      ptx::prefetch_tmap(&p.l0.out_map);
+      if (p.l0.has_res) ptx::prefetch_tmap(&p.l0.res_map);
+    }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&a_full[s], 1);
       ptx::mbar_init(&a_empty[s], 1);
@@ -123,21 +131,34 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
     const bool leader = ptx::elect_one() != 0;
     long long prof_a = 0;
     int a_issued = 0, b_cnt = 0;
-    auto issue_a = [&](int item, int c_seq) {
+    const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
+    // Chains (conv_chain.cuh): the first halo of an item of layer > 0 waits for the previous layer
+    // of its image. `block` = false while loads of the CURRENT item are still to be issued (a
+    // producer blocked there could hold back the very items others wait for); the caller retries
+    // after the tap loop.
+    auto issue_a = [&](int item, int c_seq, bool block) -> bool {
       const int c = (c_seq + rot_c) % n_chunks;
       const Item it = decode(p, item);
+      if (c_seq == 0 && it.layer > 0) {
+        int ok = 1;
+        if (leader)
+          ok = chain::wait_count(p.done + (it.layer - 1) * p.n_img + it.img, 2 * p.items_per_img, block,
+                                 p.err_flag, 39) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, leader_lane);
+        if (!ok) return false;
+      }
       const int st = a_issued & 1;
       const uint32_t ph = (a_issued >> 1) & 1;
       ptx::mbar_wait(&a_empty[st], ph ^ 1, p.err_flag, 31);
       if (leader) {
         ptx::mbar_arrive_expect_tx(&a_full[st], kATxBytes);
-        ptx::tma_load_4d(sA + st * kAStageBytes, &p.in_map, &a_full[st], c * 64, it.rx * kRegion - 1,
-                         it.ry * kRegion - 1, it.img);
+        ptx::tma_load_4d(sA + st * kAStageBytes, &layer_of(p, it.layer).in_map, &a_full[st], c * 64,
+                         it.rx * kRegion - 1, it.ry * kRegion - 1, it.img);
       }
       __syncwarp();
       ++a_issued;
+      return true;
     };
-    const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
     int n_fetched = 0;
     auto fetch = [&]() -> int {
       int item = 0;
@@ -153,13 +174,16 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
       return item;
     };
     int cur_item = fetch(), cur_c = 0;
-    if (cur_item >= 0) issue_a(cur_item, 0);
+    if (cur_item >= 0) issue_a(cur_item, 0, true);
     int nxt_item = cur_item, nxt_c = 1;
     if (cur_item >= 0 && nxt_c == n_chunks) { nxt_c = 0; nxt_item = fetch(); }
     while (cur_item >= 0) {
-      const int nt = cur_item % p.n_ntiles;
+      const Item cur = decode(p, cur_item);
+      const int nt = cur.nt;
+      const CUtensorMap* w_map = &layer_of(p, cur.layer).w_map;
+      bool a_deferred = false;
       for (int t = 0; t < 9; ++t) {
-        if (t == 4 && nxt_item >= 0) issue_a(nxt_item, nxt_c);
+        if (t == 4 && nxt_item >= 0) a_deferred = !issue_a(nxt_item, nxt_c, false);
         const int bs = b_cnt % n_bstages;
         const uint32_t bph = (b_cnt / n_bstages) & 1;
         CERB_PROF_T0(t_p);
@@ -168,12 +192,13 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
         if (leader) {
           ptx::mbar_arrive_expect_tx(&b_full[bs], b_stage_bytes);
           const int tap = (t + rot_t) % 9, chunk = (cur_c + rot_c) % n_chunks;
-          ptx::tma_load_2d(sB + bs * b_stage_bytes, &p.w_map, &b_full[bs], (tap * n_chunks + chunk) * 64,
+          ptx::tma_load_2d(sB + bs * b_stage_bytes, w_map, &b_full[bs], (tap * n_chunks + chunk) * 64,
                            nt * p.BN);
         }
         __syncwarp();
         ++b_cnt;
       }
+      if (a_deferred) issue_a(nxt_item, nxt_c, true);
       cur_item = nxt_item;
       cur_c = nxt_c;
       if (nxt_item >= 0 && ++nxt_c == n_chunks) { nxt_c = 0; nxt_item = fetch(); }
@@ -271,6 +296,7 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
     const int n_slabs = p.BN >> 6;
     long long prof_a = 0, prof_b = 0, prof_c = 0, prof_d = 0;
     int sidx = 0, it = 0;
+    uint32_t res_phase = 0;  // bit b: parity of the next residual arrival in slab buffer b of this group
     for (;; ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -281,6 +307,10 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
       if (item < 0) break;
       ptx::tc_fence_after();
       const Item im = decode(p, item);
+      const ConvChainLayer& L = layer_of(p, im.layer);
+      const int has_res = L.has_res, relu = L.relu;
+      const float acc_scale = L.acc_scale;
+      const float* bias = L.bias;
       const int x0 = im.rx * kRegion + 8 * g, y0 = im.ry * kRegion;
       const int n0 = im.nt * p.BN;
       for (int slab = 0; slab < n_slabs; ++slab, ++sidx) {
@@ -290,9 +320,9 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
         uint64_t* rbar = &res_bar[g * 2 + buf];
         if (store_warp && ptx::elect_one()) {
           ptx::bulk_wait_read<1>();  // the store that last used this slab buffer has drained it
-          if (p.has_res) {
+          if (has_res) {
             ptx::mbar_arrive_expect_tx(rbar, kSlabBytes);
-            ptx::tma_load_4d(sO, &p.res_map, rbar, n0 + slab * 64, x0, y0, im.img);
+            ptx::tma_load_4d(sO, &L.res_map, rbar, n0 + slab * 64, x0, y0, im.img);
           }
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + g * 128 + slab * 64;
@@ -306,8 +336,9 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
         }
         CERB_PROF_T0(t_e1);
-        if (p.has_res) {
-          ptx::mbar_wait(rbar, (sidx >> 1) & 1, p.err_flag, 37);
+        if (has_res) {
+          ptx::mbar_wait(rbar, (res_phase >> buf) & 1, p.err_flag, 37);
+          res_phase ^= 1u << buf;
         } else {
           ptx::named_bar_sync(1 + g, 128);  // thread 0 has seen the slab buffer drained
         }
@@ -318,16 +349,16 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            v[i] = __uint_as_float(half == 0 ? r0[i] : r1[i]) * p.acc_scale;
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + slab * 64 + half * 32);
+            v[i] = __uint_as_float(half == 0 ? r0[i] : r1[i]) * acc_scale;
+          if (bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + slab * 64 + half * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 b = __ldg(b4 + i);
               v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
             }
           }
-          if (p.has_res) {
+          if (has_res) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint4 u = *reinterpret_cast<const uint4*>(my_row + (((half * 4 + i) ^ sw) << 4));
@@ -339,7 +370,7 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
               }
             }
           }
-          if (p.relu) {
+          if (relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
           }
@@ -358,8 +389,11 @@ conv3x3_kernel(const __grid_constant__ Conv3Params p) {
         ptx::fence_proxy_async_smem();
         ptx::named_bar_sync(1 + g, 128);
         if (store_warp && ptx::elect_one()) {
-          ptx::tma_store_4d(&p.out_map, sO, n0 + slab * 64, x0, y0, im.img);
+          ptx::tma_store_4d(&L.out_map, sO, n0 + slab * 64, x0, y0, im.img);
           ptx::bulk_commit_group();
+          // chain: this group's half of the item is in global memory -> release it to the next layer
+          if (slab == n_slabs - 1 && im.layer + 1 < p.n_layers)
+            chain::signal_stored(p.done + im.layer * p.n_img + im.img);
         }
         CERB_PROF_ADD(prof_d, t_e3);
       }
@@ -389,7 +423,10 @@ void conv3x3_plan(Conv3Params& p) {
   p.n_bstages = n;
   p.regions_x = (p.W + kRegion - 1) / kRegion;
   p.regions_y = (p.H + kRegion - 1) / kRegion;
-  p.n_items = p.n_img * p.regions_x * p.regions_y * p.n_ntiles;
+  p.items_per_img = p.regions_x * p.regions_y * p.n_ntiles;
+  p.n_items_layer = p.n_img * p.items_per_img;
+  if (p.n_layers < 1) p.n_layers = 1;
+  p.n_items = p.n_layers * p.n_items_layer;
 }
 
 size_t conv3x3_smem_bytes(const Conv3Params& p) {

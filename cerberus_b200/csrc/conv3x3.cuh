@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "conv_chain.cuh"
+
 namespace cerb {
 
 // warp 0: TMA producer, warp 1: MMA issuer + TMEM allocator, warps 2-5 / 6-9: epilogue of the
@@ -13,11 +15,14 @@ namespace cerb {
 constexpr int kConv3Threads = 320;
 
 struct Conv3Params {
-  CUtensorMap in_map;   // [Cin, W, H, N], box {64, 18, 18, 1}: halo of a 16x16 region, one 64-channel chunk
-  CUtensorMap w_map;    // [9*Cin, Cout], box {64, BN}
-  CUtensorMap out_map;  // [Cout, W, H, N], box {64, 8, 16, 1} (TMA store of one 64-channel slab)
-  CUtensorMap res_map;  // residual, same geometry as out_map
-  int has_res;
+  // l0 maps: in [Cin, W, H, N], box {64, 18, 18, 1} (halo of a 16x16 region, one 64-channel chunk);
+  // w [9*Cin, Cout], box {64, BN}; out / res [Cout, W, H, N], box {64, 8, 16, 1}
+  ConvChainLayer l0;             // the layer of a single-layer launch
+  const ConvChainLayer* layers;  // chain of n_layers > 1 layers (conv_chain.cuh), table in global memory
+  int n_layers;        // 1 = single layer (l0)
+  int n_items_layer;   // work items per layer; n_items = n_layers * n_items_layer
+  int items_per_img;   // regions_x * regions_y * n_ntiles
+  int* done;           // [n_layers * n_img], zeroed before the launch; += 1 per epilogue group and item
   int n_img, H, W;
   int n_chunks;  // Cin / 64
   int BN;        // output channels per work item: 64 or 128
@@ -25,9 +30,6 @@ struct Conv3Params {
   int regions_x, regions_y, n_items;
   int n_bstages;  // weight-tile pipeline depth
   int rotate;     // 1: each CTA starts its K walk at a different (tap, chunk)
-  const float* bias;  // [Cout] fp32 (BN folded), may be null
-  float acc_scale;    // 2^-w_shift
-  int relu;
   int* tile_counter;  // zeroed before the launch: dynamic work-item scheduling; null = static split
   int* err_flag;
   long long* prof;

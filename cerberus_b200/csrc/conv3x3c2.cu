@@ -94,36 +94,6 @@ __device__ __forceinline__ const Conv3c2Layer& layer_of(const Conv3c2Params& p, 
   return p.layers != nullptr ? p.layers[layer] : p.l0;
 }
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_proxy_async_all() {
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
-
-// Chain dependency: every item of `layer - 1` on image `img` has been stored (both CTAs of its pair).
-// Non-blocking form: false if not yet. One lane calls it; the TMA loads of the item are its own.
-__device__ __forceinline__ bool layer_done(const Conv3c2Params& p, int layer, int img, bool block) {
-  const int* cnt = p.done + (layer - 1) * p.n_img + img;
-  const int need = 2 * p.items_per_img;
-  if (ld_acquire_gpu(cnt) < need) {
-    if (!block) return false;
-    const uint64_t t0 = ptx::global_timer_ns();
-    uint32_t spins = 0;
-    while (ld_acquire_gpu(cnt) < need) {
-      if ((++spins & 0x3FF) == 0 && ptx::global_timer_ns() - t0 > 2000000000ull) {
-        if (p.err_flag) atomicExch(p.err_flag, 69);
-        __threadfence_system();
-        asm volatile("trap;");
-      }
-    }
-  }
-  fence_proxy_async_all();  // the TMA loads that follow read what other CTAs' TMA stores wrote
-  return true;
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConv3c2Threads, 1)
 conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -236,7 +206,9 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
       const Item it = decode(p, item);
       if (c == 0 && it.layer > 0) {
         int ok = 1;
-        if (leader_lane_p) ok = layer_done(p, it.layer, it.img, block) ? 1 : 0;
+        if (leader_lane_p)
+          ok = chain::wait_count(p.done + (it.layer - 1) * p.n_img + it.img, 2 * p.items_per_img, block,
+                                 p.err_flag, 69) ? 1 : 0;
         ok = __shfl_sync(0xffffffffu, ok, elected);
         if (!ok) return false;
       }
@@ -467,10 +439,7 @@ conv3x3c2_kernel(const __grid_constant__ Conv3c2Params p) {
           ptx::bulk_commit_group();
           if (slab == n_slabs - 1 && im.layer + 1 < p.n_layers) {
             // chain: this CTA's half of the item is in global memory -> release it to the next layer
-            ptx::bulk_wait_all<0>();
-            fence_proxy_async_all();
-            __threadfence();
-            atomicAdd(p.done + im.layer * p.n_img + im.img, 1);
+            chain::signal_stored(p.done + im.layer * p.n_img + im.img);
           }
         }
         CERB_PROF_ADD(prof_d, t_e3);

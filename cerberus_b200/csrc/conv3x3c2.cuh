@@ -6,24 +6,14 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "conv_chain.cuh"
+
 namespace cerb {
 
 // per CTA - warp 0: TMA producer, warp 1: MMA issuer (leader CTA) + TMEM allocator, warps 2-5: epilogue
 constexpr int kConv3c2Threads = 192;
 
-// What differs between the layers of a chain (see Conv3c2Params::layers).
-struct Conv3c2Layer {
-  CUtensorMap in_map;   // [Cin, W, H, N], box {64, 10, 18, 1}: halo of one 16x8 half region, one 64-channel chunk
-  CUtensorMap w_map;    // [9*Cin, Cout], box {64, BN / 2}: the half of a weight slab one CTA holds
-  CUtensorMap out_map;  // [Cout, W, H, N], box {64, 8, 16, 1}
-  CUtensorMap res_map;  // residual, same geometry as out_map
-  const float* bias;    // [Cout] fp32 (BN folded), may be null
-  float acc_scale;      // 2^-w_shift
-  int has_res;
-  int relu;
-  int pad_[11];
-};
-static_assert(sizeof(Conv3c2Layer) % 64 == 0, "tensor maps of a layer table must stay 64-byte aligned");
+using Conv3c2Layer = ConvChainLayer;
 
 struct Conv3c2Params {
   Conv3c2Layer l0;  // the layer of a single-layer launch (kernel parameter space)

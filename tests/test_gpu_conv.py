@@ -221,6 +221,10 @@ CHAIN_CASES = [
     (1, 16, 16, 256, 6),     # ONE item per layer: every item waits for the one before it
     (2, 16, 16, 256, 3),     # fewer items than layers x pairs
     (160, 16, 16, 256, 3),   # more items per layer than CTA pairs
+    (2, 64, 64, 128, 4),     # layer2 body: the single-CTA kernel (conv3x3.cu) chains the same way
+    (5, 40, 24, 128, 3),
+    (1, 16, 16, 128, 5),     # one item per layer
+    (200, 16, 16, 128, 3),   # more items per layer than SMs
 ]
 
 
