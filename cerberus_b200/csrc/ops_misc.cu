@@ -72,6 +72,41 @@ __global__ void prep_kernel(const uint8_t* __restrict__ in, __half* __restrict__
 // ------------------------------------------------------------------ maxpool
 // fp16 throughput mode: the maximum of fp16 values is exact, so the nine taps are loaded as raw
 // 16-byte words (all issued before the first compare) and reduced with packed __hmax2.
+// 64-channel fp16 fast path (the only max-pool of the network, resnet.py:201): a block owns an
+// 8 x 4 tile of output pixels (x 8 channel groups of 16 bytes), so the 17 x 9 input pixels it reads
+// are shared through L1 between its warps (612 B of L2 traffic per output pixel instead of 864
+// with one output row per block), and the small register footprint lets 4 blocks (instead of 2) share an SM.
+__global__ void __launch_bounds__(256, 4)
+maxpool64_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int ih, int iw, int oh, int ow) {
+  const int g = threadIdx.x & 7;
+  const int ox = blockIdx.x * 8 + ((threadIdx.x >> 3) & 7);
+  const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int n = blockIdx.z;
+  if (ox >= ow || oy >= oh) return;
+  const __half* src = in + static_cast<size_t>(n) * ih * iw * 64 + g * 8;
+  uint4 tap[9];
+  bool ok[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int y = 2 * oy + k / 3 - 1, x = 2 * ox + k % 3 - 1;
+    ok[k] = y >= 0 && y < ih && x >= 0 && x < iw;
+    if (ok[k]) tap[k] = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(y) * iw + x) * 64));
+  }
+  __half2 best[4];  // the centre tap (k = 4) is always inside the image
+  const __half2* c4 = reinterpret_cast<const __half2*>(&tap[4]);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) best[e] = c4[e];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (k == 4 || !ok[k]) continue;
+    const __half2* h = reinterpret_cast<const __half2*>(&tap[k]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) best[e] = __hmax2(best[e], h[e]);
+  }
+  *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * oh + oy) * ow + ox) * 64 + g * 8) =
+      *reinterpret_cast<const uint4*>(best);
+}
+
 __global__ void __launch_bounds__(256, 2) maxpool_kernel(ActRef in, ActRef out) {
   const int cg = out.c >> 3;
   const size_t total = static_cast<size_t>(out.n) * out.h * out.w * cg;
@@ -557,6 +592,12 @@ cudaError_t launch_prep(const uint8_t* in_u8, __half* out, int n, int h, int w, 
 
 cudaError_t launch_maxpool(ActRef in, ActRef out, cudaStream_t s) {
   const size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.c >> 3);
+  if (in.lo == nullptr && out.lo == nullptr && in.c == 64 && out.c == 64 && out.n <= 65535 &&
+      (out.h + 3) / 4 <= 65535) {
+    const dim3 grid((out.w + 7) / 8, (out.h + 3) / 4, out.n);
+    maxpool64_f16_kernel<<<grid, 256, 0, s>>>(in.hi, out.hi, in.h, in.w, out.h, out.w);
+    return cudaGetLastError();
+  }
   maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
   return cudaGetLastError();
 }

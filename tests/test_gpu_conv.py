@@ -346,3 +346,35 @@ def test_upadd_matches_torch_bilinear(shape, precision, built_lib):
     assert np.all(np.abs(got - ref) <= tol), float(np.abs(got - ref).max())
     plan.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("precision", ["f16", "f16x2"])
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 30, 50, 64), (3, 17, 23, 64), (33, 8, 8, 64), (2, 16, 16, 128)])
+def test_maxpool_matches_torch(shape, precision, built_lib):
+    """3x3 stride-2 pad-1 max-pool (models/backbone/resnet.py:201), exact in both precision modes:
+    64 channels = the tiled fp16 fast path, 128 channels / split mode = the generic kernel."""
+    n, h, w, c = shape
+    oh, ow = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    rng = np.random.RandomState(9)
+    x = rng.standard_normal((n, h, w, c)).astype(np.float32)
+    if precision == "f16":
+        x = f16(x).astype(np.float32)
+    spec = MiniSpec()
+    t_in = spec._tensor("in", n, h, w, c)
+    t_out = spec._tensor("out", n, oh, ow, c)
+    spec._op(_lib.OP_MAXPOOL, in0=t_in, out=t_out)
+    ctx = Context(0, precision)
+    plan = ForwardPlan(ctx, MiniModel(BlobBuilder()), 0, 0, 0, 0, 0, spec=spec)
+    hi = x.astype(np.float16)
+    plan.write(t_in, hi, 0)
+    if precision == "f16x2":
+        plan.write(t_in, (x - hi.astype(np.float32)).astype(np.float16), 1)
+    plan.run()
+    got = plan.read(t_out).astype(np.float32)  # hi + lo in split mode
+    ref = nchw_to_nhwc(F.max_pool2d(torch.from_numpy(nhwc_to_nchw(x)), 3, 2, 1).numpy())
+    if precision == "f16":
+        assert np.array_equal(got, ref)
+    else:
+        assert np.all(np.abs(got - ref) <= 2e-6 * np.abs(ref) + 2e-6)
+    plan.close()
+    ctx.close()
