@@ -828,6 +828,7 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
       if (rc) return rc;
     }
     k_total = 7 * 64;
+    p.a_lo_zero = split ? 1 : 0;  // PREP writes integers 0..255 (exact in fp16) and zeroes the lo plane
   } else {
     const int s = op.stride;
     if (s != 1 && s != 2) return fail(CERB_ERR_ARG, "conv: stride must be 1 or 2");

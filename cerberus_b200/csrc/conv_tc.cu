@@ -28,8 +28,11 @@ constexpr int kMaxAcc = 4;  // accumulator stages (= epilogue warp groups): 512 
 // |acc| per instruction; keeping the small cross terms (lo*hi + hi*lo) out of the big hi*hi
 // accumulator and alternating hi*hi between two accumulators cuts that error ~6x. The
 // epilogue adds the three in fp32 (round-to-nearest).
-constexpr int kSplitMain1 = 128;
-constexpr int kSplitCross = 256;
+// split mode: three accumulators per tile (hi*hi of even / odd k-steps, cross terms). One stage
+// of 3 x 128 columns, or - tiles of at most 64 output channels - two stages of 3 x 64 columns so
+// that the epilogue of a tile overlaps the MMAs of the next (the 7-k-step stem, 128 -> 64).
+__device__ __forceinline__ int split_main1(int n_acc) { return n_acc == 2 ? 64 : 128; }
+__device__ __forceinline__ int split_cross(int n_acc) { return n_acc == 2 ? 128 : 256; }
 constexpr int kHeadA2Bytes = 2 * kATileBytes;  // hidden tile of one epilogue group: 2 slabs x 16 KB
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -125,8 +128,9 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   ptx::grid_dep_launch();
   ptx::grid_dep_wait();  // prologue above overlaps the previous kernel's tail (PDL)
 
-  const int kAccStages = SPLIT ? 1 : p.n_acc;
-  const int kAccStride = SPLIT ? 512 : 512 / p.n_acc;
+  const int kAccStages = p.n_acc;  // split mode: 1, or 2 for BN <= 64 (conv_tc_plan_pipeline)
+  const int kAccStride = 512 / p.n_acc;
+  const int kSplitMain1 = split_main1(p.n_acc), kSplitCross = split_cross(p.n_acc);
   const int n_ksteps = p.n_taps * p.n_chunks;
   const int bw_mask = (1 << p.bw_log2) - 1;
   const int BW = 1 << p.bw_log2;
@@ -140,7 +144,9 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     const bool leader = ptx::elect_one() != 0;
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = (SPLIT ? 2u : 1u) * (kATileBytes + b_tile_bytes);
+    const bool a_lo_zero = SPLIT && p.a_lo_zero != 0;
+    const uint32_t tx_bytes =
+        (SPLIT ? 2u : 1u) * (kATileBytes + b_tile_bytes) - (a_lo_zero ? static_cast<uint32_t>(kATileBytes) : 0u);
     long long prof_a = 0;
     const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
     for (int it = 0;; ++it) {
@@ -183,8 +189,9 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
             ptx::tma_load_2d(sB, &p.w_hi, &full_bar[stage], (t * p.n_chunks + c) * 64,
                              nt * p.BN);
             if (SPLIT) {
-              ptx::tma_load_4d(sA + kATileBytes, &p.in_lo[tap.map], &full_bar[stage], c * 64,
-                               x0 + tap.dx, y0 + tap.dy, img);
+              if (!a_lo_zero)
+                ptx::tma_load_4d(sA + kATileBytes, &p.in_lo[tap.map], &full_bar[stage], c * 64,
+                                 x0 + tap.dx, y0 + tap.dy, img);
               ptx::tma_load_2d(sB + b_tile_bytes, &p.w_lo, &full_bar[stage],
                                (t * p.n_chunks + c) * 64, nt * p.BN);
             }
@@ -248,8 +255,10 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
             } else {
               ptx::umma_f16(tmem_d + ((k & 1) ? kSplitMain1 : 0), a0 + 2 * k, b0 + 2 * k, idesc,
                             (ks != 0) || (k >= 2));
-              ptx::umma_f16(tmem_d + kSplitCross, a0 + lo_a_u + 2 * k, b0 + 2 * k, idesc, (ks | k) != 0);
-              ptx::umma_f16(tmem_d + kSplitCross, a0 + 2 * k, b0 + lo_b_u + 2 * k, idesc, 1);
+              if (!p.a_lo_zero)
+                ptx::umma_f16(tmem_d + kSplitCross, a0 + lo_a_u + 2 * k, b0 + 2 * k, idesc, (ks | k) != 0);
+              ptx::umma_f16(tmem_d + kSplitCross, a0 + 2 * k, b0 + lo_b_u + 2 * k, idesc,
+                            p.a_lo_zero ? static_cast<int>((ks | k) != 0) : 1);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once the MMAs retire
@@ -527,7 +536,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
 void conv_tc_plan_pipeline(ConvKParams& p, bool split) {
   // epilogue-bound layers (one or two K steps per tile) get four accumulator stages / epilogue
   // groups when the tile is narrow enough for 4 x BN TMEM columns
-  p.n_acc = (!split && p.BN <= 128 && p.n_taps * p.n_chunks <= 2) ? 4 : 2;
+  p.n_acc = split ? (p.BN <= 64 ? 2 : 1) : ((p.BN <= 128 && p.n_taps * p.n_chunks <= 2) ? 4 : 2);
   p.stage_bytes = (split ? 2 : 1) * (kATileBytes + p.BN * 128);
   int budget = 192 * 1024;
   p.mma_tail = (!split && p.head_classes > 0 && p.n_acc == 4 && p.BN == 96) ? 1 : 0;
@@ -549,9 +558,10 @@ size_t conv_tc_smem_bytes(const ConvKParams& p) {
 }
 
 cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaStream_t stream, bool pdl) {
-  static bool attr_set[3] = {false, false, false};
-  const int variant = split ? 2 : (p.n_acc == 4 ? 1 : 0);
-  void (*kern)(ConvKParams) = variant == 2   ? conv_tc_kernel<true, 192>
+  static bool attr_set[4] = {false, false, false, false};
+  const int variant = split ? (p.n_acc == 2 ? 3 : 2) : (p.n_acc == 4 ? 1 : 0);
+  void (*kern)(ConvKParams) = variant == 3   ? conv_tc_kernel<true, 320>
+                              : variant == 2 ? conv_tc_kernel<true, 192>
                               : variant == 1 ? conv_tc_kernel<false, 576>
                                              : conv_tc_kernel<false, 320>;
   if (!attr_set[variant]) {
@@ -561,7 +571,7 @@ cudaError_t conv_tc_launch(const ConvKParams& p, bool split, int num_sms, cudaSt
     attr_set[variant] = true;
   }
   const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-  const int threads = 64 + 128 * (split ? 1 : p.n_acc);
+  const int threads = 64 + 128 * p.n_acc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(threads);

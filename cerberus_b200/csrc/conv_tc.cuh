@@ -65,9 +65,11 @@ struct ConvKParams {
   float* logits;         // optional [N, H, W, C]
   int oh, ow, canvas_c, canvas_coff;
   // pipeline
-  int n_acc;  // accumulator stages = epilogue groups (2 or 4; split mode always 1)
+  int n_acc;  // accumulator stages = epilogue groups (2 or 4; split mode: 1, or 2 when BN <= 64)
   int n_stages;
   int stage_bytes;
+  int a_lo_zero;  // split mode: the lo plane of the input is all zeros (stem: uint8 pixels are exact
+                  // in fp16) - its loads and the lo x hi products are skipped
   int mma_tail;  // fused head: 1x1 96 -> C on the tensor core (fp16 mode), else fp32 FMAs
   int* tile_counter;  // zeroed before the launch: dynamic tile scheduling; null = static split
   int* err_flag;

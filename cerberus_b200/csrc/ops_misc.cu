@@ -107,6 +107,51 @@ maxpool64_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, in
       *reinterpret_cast<const uint4*>(best);
 }
 
+// Split-precision twin of maxpool64_f16_kernel: every value is a (hi, lo) fp16 pair whose order is
+// lexicographic (hi = round(value)); the winning pair is copied verbatim. Same tiling; the 18 loads
+// of a thread are issued before the first compare.
+__global__ void __launch_bounds__(256, 2)
+maxpool64_split_kernel(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+                       __half* __restrict__ out_hi, __half* __restrict__ out_lo, int ih, int iw, int oh, int ow) {
+  const int g = threadIdx.x & 7;
+  const int ox = blockIdx.x * 8 + ((threadIdx.x >> 3) & 7);
+  const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int n = blockIdx.z;
+  if (ox >= ow || oy >= oh) return;
+  const size_t base = static_cast<size_t>(n) * ih * iw * 64 + g * 8;
+  uint4 th[9], tl[9];
+  bool ok[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int y = 2 * oy + k / 3 - 1, x = 2 * ox + k % 3 - 1;
+    ok[k] = y >= 0 && y < ih && x >= 0 && x < iw;
+    if (ok[k]) {
+      const size_t off = base + (static_cast<size_t>(y) * iw + x) * 64;
+      th[k] = __ldg(reinterpret_cast<const uint4*>(in_hi + off));
+      tl[k] = __ldg(reinterpret_cast<const uint4*>(in_lo + off));
+    }
+  }
+  // the centre tap (k = 4) is always inside the image
+  uint4 bh = th[4], bl = tl[4];
+  __half* bhp = reinterpret_cast<__half*>(&bh);
+  __half* blp = reinterpret_cast<__half*>(&bl);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (k == 4 || !ok[k]) continue;
+    const __half* h = reinterpret_cast<const __half*>(&th[k]);
+    const __half* l = reinterpret_cast<const __half*>(&tl[k]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float vh = __half2float(h[e]), vl = __half2float(l[e]);
+      const float ch = __half2float(bhp[e]), cl = __half2float(blp[e]);
+      if (vh > ch || (vh == ch && vl > cl)) { bhp[e] = h[e]; blp[e] = l[e]; }
+    }
+  }
+  const size_t ooff = ((static_cast<size_t>(n) * oh + oy) * ow + ox) * 64 + g * 8;
+  *reinterpret_cast<uint4*>(out_hi + ooff) = bh;
+  *reinterpret_cast<uint4*>(out_lo + ooff) = bl;
+}
+
 __global__ void __launch_bounds__(256, 2) maxpool_kernel(ActRef in, ActRef out) {
   const int cg = out.c >> 3;
   const size_t total = static_cast<size_t>(out.n) * out.h * out.w * cg;
@@ -592,10 +637,13 @@ cudaError_t launch_prep(const uint8_t* in_u8, __half* out, int n, int h, int w, 
 
 cudaError_t launch_maxpool(ActRef in, ActRef out, cudaStream_t s) {
   const size_t total = static_cast<size_t>(out.n) * out.h * out.w * (out.c >> 3);
-  if (in.lo == nullptr && out.lo == nullptr && in.c == 64 && out.c == 64 && out.n <= 65535 &&
-      (out.h + 3) / 4 <= 65535) {
+  if (in.c == 64 && out.c == 64 && out.n <= 65535 && (out.h + 3) / 4 <= 65535 &&
+      (in.lo == nullptr) == (out.lo == nullptr)) {
     const dim3 grid((out.w + 7) / 8, (out.h + 3) / 4, out.n);
-    maxpool64_f16_kernel<<<grid, 256, 0, s>>>(in.hi, out.hi, in.h, in.w, out.h, out.w);
+    if (in.lo == nullptr)
+      maxpool64_f16_kernel<<<grid, 256, 0, s>>>(in.hi, out.hi, in.h, in.w, out.h, out.w);
+    else
+      maxpool64_split_kernel<<<grid, 256, 0, s>>>(in.hi, in.lo, out.hi, out.lo, in.h, in.w, out.h, out.w);
     return cudaGetLastError();
   }
   maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out);
