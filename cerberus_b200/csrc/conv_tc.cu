@@ -28,10 +28,13 @@ constexpr int kMaxAcc = 4;  // accumulator stages (= epilogue warp groups): 512 
 // |acc| per instruction; keeping the small cross terms (lo*hi + hi*lo) out of the big hi*hi
 // accumulator and alternating hi*hi between two accumulators cuts that error ~6x. The
 // epilogue adds the three in fp32 (round-to-nearest).
-// split mode: three accumulators per tile (hi*hi of even / odd k-steps, cross terms). One stage
-// of 3 x 128 columns, or - tiles of at most 64 output channels - two stages of 3 x 64 columns so
-// that the epilogue of a tile overlaps the MMAs of the next (the 7-k-step stem, 128 -> 64).
-__device__ __forceinline__ int split_main1(int n_acc) { return n_acc == 2 ? 64 : 128; }
+// split mode: three accumulators per tile (hi*hi of even / odd k16 steps, cross terms). One stage
+// of 3 x 128 columns, or two stages of 256 columns so that the epilogue of a tile overlaps the
+// MMAs of the next: 3 x 64 columns for tiles of at most 64 output channels (the 7-k-step stem,
+// 128 -> 64), or - wider tiles with at most two k-steps, i.e. the heads' 64 -> 96 - ONE hi*hi
+// accumulator + the cross terms (with four to eight k16 products the even / odd split buys
+// nothing).
+__device__ __forceinline__ int split_main1(int n_acc, int bn) { return n_acc == 2 ? (bn > 64 ? 0 : 64) : 128; }
 __device__ __forceinline__ int split_cross(int n_acc) { return n_acc == 2 ? 128 : 256; }
 constexpr int kHeadA2Bytes = 2 * kATileBytes;  // hidden tile of one epilogue group: 2 slabs x 16 KB
 
@@ -130,7 +133,8 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
 
   const int kAccStages = p.n_acc;  // split mode: 1, or 2 for BN <= 64 (conv_tc_plan_pipeline)
   const int kAccStride = 512 / p.n_acc;
-  const int kSplitMain1 = split_main1(p.n_acc), kSplitCross = split_cross(p.n_acc);
+  const int kSplitMain1 = split_main1(p.n_acc, p.BN), kSplitCross = split_cross(p.n_acc);
+  const bool split_merged = SPLIT && kSplitMain1 == 0;  // one hi*hi accumulator
   const int n_ksteps = p.n_taps * p.n_chunks;
   const int bw_mask = (1 << p.bw_log2) - 1;
   const int BW = 1 << p.bw_log2;
@@ -254,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
               ptx::umma_f16(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc, (ks | k) != 0);
             } else {
               ptx::umma_f16(tmem_d + ((k & 1) ? kSplitMain1 : 0), a0 + 2 * k, b0 + 2 * k, idesc,
-                            (ks != 0) || (k >= 2));
+                            (ks != 0) || (k >= (split_merged ? 1 : 2)));
               if (!p.a_lo_zero)
                 ptx::umma_f16(tmem_d + kSplitCross, a0 + lo_a_u + 2 * k, b0 + 2 * k, idesc, (ks | k) != 0);
               ptx::umma_f16(tmem_d + kSplitCross, a0 + 2 * k, b0 + lo_b_u + 2 * k, idesc,
@@ -400,13 +404,14 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
         ptx::tmem_ld_wait();
         if (SPLIT) {
           uint32_t r1[32], r2[32];
-          ptx::tmem_ld32(taddr + kSplitMain1 + j, r1);
+          if (!split_merged) ptx::tmem_ld32(taddr + kSplitMain1 + j, r1);
           ptx::tmem_ld32(taddr + kSplitCross + j, r2);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            v[i] = ((__uint_as_float(r[i]) + __uint_as_float(r1[i])) + __uint_as_float(r2[i])) *
-                   p.acc_scale;
+          for (int i = 0; i < 32; ++i) {
+            const float main1 = split_merged ? 0.0f : __uint_as_float(r1[i]);
+            v[i] = ((__uint_as_float(r[i]) + main1) + __uint_as_float(r2[i])) * p.acc_scale;
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.acc_scale;
@@ -536,7 +541,8 @@ conv_tc_kernel(const __grid_constant__ ConvKParams p) {
 void conv_tc_plan_pipeline(ConvKParams& p, bool split) {
   // epilogue-bound layers (one or two K steps per tile) get four accumulator stages / epilogue
   // groups when the tile is narrow enough for 4 x BN TMEM columns
-  p.n_acc = split ? (p.BN <= 64 ? 2 : 1) : ((p.BN <= 128 && p.n_taps * p.n_chunks <= 2) ? 4 : 2);
+  const bool short_k = p.n_taps * p.n_chunks <= 2;
+  p.n_acc = split ? ((p.BN <= 64 || (p.BN <= 128 && short_k)) ? 2 : 1) : ((p.BN <= 128 && short_k) ? 4 : 2);
   p.stage_bytes = (split ? 2 : 1) * (kATileBytes + p.BN * 128);
   int budget = 192 * 1024;
   p.mma_tail = (!split && p.head_classes > 0 && p.n_acc == 4 && p.BN == 96) ? 1 : 0;
