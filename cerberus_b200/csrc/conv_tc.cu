@@ -28,12 +28,13 @@ constexpr int kMaxAcc = 4;  // accumulator stages (= epilogue warp groups): 512 
 // |acc| per instruction; keeping the small cross terms (lo*hi + hi*lo) out of the big hi*hi
 // accumulator and alternating hi*hi between two accumulators cuts that error ~6x. The
 // epilogue adds the three in fp32 (round-to-nearest).
-// split mode: three accumulators per tile (hi*hi of even / odd k16 steps, cross terms). One stage
-// of 3 x 128 columns, or two stages of 256 columns so that the epilogue of a tile overlaps the
-// MMAs of the next: 3 x 64 columns for tiles of at most 64 output channels (the 7-k-step stem,
-// 128 -> 64), or - wider tiles with at most two k-steps, i.e. the heads' 64 -> 96 - ONE hi*hi
-// accumulator + the cross terms (with four to eight k16 products the even / odd split buys
-// nothing).
+// split mode: the hi*hi products and the cross terms (hi*lo + lo*hi) accumulate separately (the lo
+// weights carry their own power-of-two scale), and the hi*hi products of even / odd k16 steps go to
+// two accumulators (halves the accumulation error, see conv_tc_plan_pipeline). Layouts: one stage
+// of 3 x 128 columns (wide tiles, long K); or two stages of 256 columns so that the epilogue of a
+// tile overlaps the MMAs of the next - 3 x 64 columns for tiles of at most 64 output channels
+// (the 7-k-step stem, 128 -> 64), or ONE hi*hi accumulator + cross terms for wide tiles with at
+// most two k-steps (the heads' 64 -> 96: four k16 products per accumulator either way).
 __device__ __forceinline__ int split_main1(int n_acc, int bn) { return n_acc == 2 ? (bn > 64 ? 0 : 64) : 128; }
 __device__ __forceinline__ int split_cross(int n_acc) { return n_acc == 2 ? 128 : 256; }
 constexpr int kHeadA2Bytes = 2 * kATileBytes;  // hidden tile of one epilogue group: 2 slabs x 16 KB
@@ -542,6 +543,11 @@ void conv_tc_plan_pipeline(ConvKParams& p, bool split) {
   // epilogue-bound layers (one or two K steps per tile) get four accumulator stages / epilogue
   // groups when the tile is narrow enough for 4 x BN TMEM columns
   const bool short_k = p.n_taps * p.n_chunks <= 2;
+  // split mode: two stages of 256 TMEM columns for narrow tiles and for wide tiles with a short K
+  // loop. Long-K wide tiles keep ONE stage with the even / odd hi*hi accumulators: merging them
+  // made the parity mode 3.4 % faster (15.70 -> 15.17 ms) but doubled its logit error (3.3e-4 ->
+  // 6.5e-4 max-abs against the 1e-3 gate) - the tensor core's fp32 accumulation error grows with
+  // the number of products per accumulator, and it is the dominant error of this mode.
   p.n_acc = split ? ((p.BN <= 64 || (p.BN <= 128 && short_k)) ? 2 : 1) : ((p.BN <= 128 && short_k) ? 4 : 2);
   p.stage_bytes = (split ? 2 : 1) * (kATileBytes + p.BN * 128);
   int budget = 192 * 1024;
