@@ -37,7 +37,6 @@ constexpr int kHaloH = 18, kHaloW = 10;            // halo of a 16 (rows) x 8 (c
 constexpr int kATxBytes = kHaloH * kHaloW * 128;   // 23040
 constexpr int kAStageBytes = 23 * 1024;            // padded to the swizzle period
 constexpr int kAStages = 2;                        // halo pipeline depth
-constexpr int kMaxBStageBytes = 128 * 128;         // BN / 2 = 128 output channels x 64 fp16
 constexpr int kSlabBytes = 128 * 128;              // staging: 128 pixels x 64 fp16 channels
 constexpr int kMaxBStages = 8;
 constexpr int kTmemCols = 512;                     // 2 accumulator stages x 256 columns

@@ -444,66 +444,6 @@ __device__ __forceinline__ uint64_t ws_entry(float v, uint32_t age, int pix) {
          static_cast<uint32_t>(pix);
 }
 
-struct Heap64 {
-  uint64_t* s;
-  uint64_t* g;
-  __device__ __forceinline__ uint64_t get(int i) const { return i < kWsHeapSmem ? s[i] : g[i]; }
-  __device__ __forceinline__ uint64_t get_or_max(int i, int n) const {
-    return i < n ? get(i) : ~0ull;
-  }
-  __device__ __forceinline__ void set(int i, uint64_t e) const {
-    if (i < kWsHeapSmem) s[i] = e; else g[i] = e;
-  }
-  __device__ __forceinline__ void push(int& n, uint64_t e) const {
-    int c = n++;
-    const uint64_t k = e >> 16;
-    while (c > 0) {
-      const int parent = (c - 1) >> 1;
-      const uint64_t pe = get(parent);
-      if (!(k < (pe >> 16))) break;
-      set(c, pe);
-      c = parent;
-    }
-    set(c, e);
-  }
-  // removes the root (the caller has already read it)
-  __device__ __forceinline__ void remove_top(int& n) const {
-    --n;
-    if (n == 0) return;
-    const uint64_t x = get(n);
-    const uint64_t xk = x >> 16;
-    int i = 0;
-    for (;;) {
-      const int l = 2 * i + 1;
-      if (l >= n) break;
-      const uint64_t c0 = get(l), c1 = get_or_max(l + 1, n);
-      const int gl = 2 * l + 1;
-      const uint64_t g0 = get_or_max(gl, n), g1 = get_or_max(gl + 1, n);
-      const uint64_t g2 = get_or_max(gl + 2, n), g3 = get_or_max(gl + 3, n);
-      // level 1: smallest of (x, left, right); x wins ties, left wins over right
-      int s1 = -1;
-      uint64_t sk = xk;
-      if ((c0 >> 16) < sk) { s1 = 0; sk = c0 >> 16; }
-      if ((c1 >> 16) < sk) { s1 = 1; sk = c1 >> 16; }
-      if (s1 < 0) break;
-      set(i, s1 ? c1 : c0);
-      i = l + s1;
-      // level 2 with the grandchildren already in registers
-      const int l2 = 2 * i + 1;
-      if (l2 >= n) break;
-      const uint64_t d0 = s1 ? g2 : g0, d1 = s1 ? g3 : g1;
-      int s2 = -1;
-      sk = xk;
-      if ((d0 >> 16) < sk) { s2 = 0; sk = d0 >> 16; }
-      if ((d1 >> 16) < sk) { s2 = 1; sk = d1 >> 16; }
-      if (s2 < 0) break;
-      set(i, s2 ? d1 : d0);
-      i = l2 + s2;
-    }
-    set(i, x);
-  }
-};
-
 // Warp-cooperative version of the same heap (same array layout after every operation). One
 // GPU thread retires roughly one dependent instruction every 4-6 cycles, so the sequential
 // sift loops above cost ~2000 cycles per queue operation. Here warp 0 owns the heap:

@@ -126,7 +126,11 @@ int cerb_ctx_sync(cerb_ctx* ctx);
 /* Tuning knobs applied to plans created afterwards. "conv64_mode": -1 = generic kernel for every
  * convolution, 0/1/2 = halo layout of the 64->64 3x3 kernel (csrc/conv64.cu). "conv3_mode": 0 =
  * generic kernel for the wide 3x3 stride-1 layers, 1 (default) = halo kernel csrc/conv3x3.cu for
- * Cout <= 512, 2 = for every Cout. "use_graphs", "ws_mode", "kernel_prof": see capi.cu. */
+ * Cout <= 512, 2 = for every Cout. "conv3_pair": 0 = never, 1 (default) = layers with Cout % 256
+ * == 0 on the CTA-pair kernel (csrc/conv3x3c2.cu), 2 = also Cout 128 / 64. "conv3_chain": 1
+ * (default) = consecutive wide 3x3 layers of one geometry run as ONE launch (csrc/conv_chain.cuh;
+ * needs "dyn_sched" = 1, the default), 0 = one launch per layer. "cerb_plan_profile" spreads a
+ * chain's time evenly over its layers. "use_graphs", "ws_mode", "kernel_prof": see capi.cu. */
 int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value);
 /* Attribution evidence (option "kernel_prof" = 1 before creating the plan): the 64->64 3x3 kernel
  * stores, per CTA, 16 counters of clock cycles each role spent waiting (layout in csrc/conv64.cu;
