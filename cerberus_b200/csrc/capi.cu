@@ -464,6 +464,25 @@ int build_conv64x(cerb_plan* pl, const cerb_op& op, Step& st) {
     if (rc) return rc;
     p.has_res = 1;
   }
+  if (op.up_prev1 > 0) {
+    // input = skip (in0) + bilinear_x2(low): the halo fix-up of conv64x.cu
+    const int pid = op.up_prev1 - 1;
+    if (pid >= static_cast<int>(pl->tensors.size()))
+      return fail(CERB_ERR_ARG, "conv64x: up_prev id out of range");
+    const Tensor& pv = pl->tensors[pid];
+    if (pv.d.dtype != CERB_F16 || pv.d.n != N || pv.d.h * 2 != H || pv.d.w * 2 != W || pv.d.c < 64 ||
+        pv.d.c % 8 != 0)
+      return fail(CERB_ERR_ARG, "conv64x: fused upsample+add shape mismatch");
+    const cuuint64_t ldims[4] = {64, static_cast<cuuint64_t>(pv.d.w), static_cast<cuuint64_t>(pv.d.h),
+                                 static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pv.d.c) * es,
+                                   static_cast<cuuint64_t>(pv.d.w) * pv.d.c * es,
+                                   static_cast<cuuint64_t>(pv.d.h) * pv.d.w * pv.d.c * es};
+    const cuuint32_t box[4] = {64, 10, 10, 1};
+    int rc = encode_map(ctx, &p.low_map, pv.plane[0], 4, ldims, strides, box);
+    if (rc) return rc;
+    p.fuse_up = 1;
+  }
   p.relu = op.relu;
   if (op.w_shift < -60 || op.w_shift > 60) return fail(CERB_ERR_ARG, "conv64x: w_shift out of range");
   p.acc_scale = ldexpf(1.0f, -op.w_shift);
@@ -760,13 +779,13 @@ int build_conv(cerb_plan* pl, const cerb_op& op, Step& st) {
   const bool conv64_ok = !split && !op.stem && !fused_head && ctx->conv64_mode >= 0 && op.kh == 3 &&
                          op.kw == 3 && op.stride == 1 && op.pad == 1 && op.in_c == 64 &&
                          op.cout == 64 && in.d.h == H && in.d.w == W;
-  if (op.up_prev1 > 0 && !(conv64_ok && ctx->conv64_mode == 1))
-    return fail(CERB_ERR_ARG, "conv: fused upsample+add needs the 64->64 3x3 kernel (conv64_mode 1, "
+  if (op.up_prev1 > 0 && !(conv64_ok && (ctx->conv64_mode == 1 || ctx->conv64_mode == 3)))
+    return fail(CERB_ERR_ARG, "conv: fused upsample+add needs the 64->64 3x3 kernel (conv64_mode 1 or 3, "
                 "CERB_PREC_F16)");
   if (op.stem && !split && !fused_head && ctx->conv64_mode >= 1 && ctx->stem_mode == 1 &&
       in.d.dtype == CERB_F16 && out.d.dtype == CERB_F16)
     return build_stem64(pl, op, st);
-  if (conv64_ok && ctx->conv64_mode == 3 && op.up_prev1 <= 0) return build_conv64x(pl, op, st);
+  if (conv64_ok && ctx->conv64_mode == 3) return build_conv64x(pl, op, st);
   if (conv64_ok) return build_conv64(pl, op, st);
   // wide 3x3 stride-1 layers: halo reuse + two M tiles per weight slab (csrc/conv3x3.cu)
   const bool conv3_ok = !split && !op.stem && !fused_head && ctx->conv3_mode > 0 && op.kh == 3 &&
@@ -1086,6 +1105,10 @@ extern "C" int cerb_ctx_set_option(cerb_ctx* ctx, const char* name, int value) {
     ctx->conv3_pair = value;
     return CERB_OK;
   }
+  if (strcmp(name, "fuse_upadd") == 0) {
+    ctx->fuse_upadd = value != 0;  // fold skip + bilinear_x2(low) into the 64->64 convolution that reads it
+    return CERB_OK;
+  }
   if (strcmp(name, "conv3_chain") == 0) {
     ctx->conv3_chain = value != 0;  // consecutive pair-kernel layers of one geometry in one launch
     return CERB_OK;
@@ -1234,6 +1257,48 @@ namespace {
 // layer4), become ONE launch: see conv_chain.cuh.
 // A residual may be any tensor written before the step that consumes it (the chain's dependency
 // rule - layer l of an image starts when layer l - 1 of that image is stored - orders it too).
+// out = skip + bilinear_x2(low) followed by the 64->64 3x3 convolution that is its ONLY reader
+// (decoder levels u2 / u1, models/net_desc.py:183-189): the convolution reads the skip tensor
+// itself and its fix-up warps add the upsampled tensor inside the halo (csrc/conv64x.cu), so the
+// sum never travels through HBM. fp16 mode, default 64->64 kernel (conv64_mode 3) only.
+void fuse_upadd_ops(const cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n_tensors,
+                    std::vector<cerb_op>& ops, std::vector<char>& folded) {
+  if (!ctx->fuse_upadd || ctx->precision != CERB_PREC_F16 || ctx->conv64_mode != 3) return;
+  const int n = static_cast<int>(ops.size());
+  auto valid = [&](int t) { return t >= 0 && t < n_tensors; };
+  for (int i = 0; i + 1 < n; ++i) {
+    const cerb_op& u = ops[i];
+    cerb_op& c = ops[i + 1];
+    if (u.kind != CERB_OP_UPADD || u.cout > 1 || c.kind != CERB_OP_CONV || u.side || c.side) continue;
+    if (!valid(u.in0) || !valid(u.in1) || !valid(u.out) || !valid(c.out)) continue;
+    if (c.in0 != u.out || c.in_coff != 0 || c.in_c != 64 || c.cout != 64 || c.kh != 3 || c.kw != 3 ||
+        c.stride != 1 || c.pad != 1 || c.stem || c.aux_classes > 0 || c.up_prev1 > 0 || c.in1 == u.out ||
+        c.out == u.in0 || c.out == u.in1)
+      continue;
+    const cerb_tensor_desc& sk = tensors[u.in0];
+    const cerb_tensor_desc& lo = tensors[u.in1];
+    const cerb_tensor_desc& su = tensors[u.out];
+    if (sk.dtype != CERB_F16 || lo.dtype != CERB_F16 || su.dtype != CERB_F16 || sk.c != 64 || lo.c != 64 ||
+        su.c != 64 || sk.h != su.h || sk.w != su.w || sk.n != su.n || lo.n != su.n || lo.h * 2 != su.h ||
+        lo.w * 2 != su.w)
+      continue;
+    // does anything else read THIS sum? (the tensor may be reused: scan up to its next writer)
+    bool other_reader = false;
+    for (int k = i + 2; k < n; ++k) {
+      const cerb_op& o = ops[k];
+      if (o.in0 == u.out || o.in1 == u.out || o.up_prev1 - 1 == u.out) {
+        other_reader = true;
+        break;
+      }
+      if (o.out == u.out) break;
+    }
+    if (other_reader) continue;
+    c.in0 = u.in0;
+    c.up_prev1 = u.in1 + 1;
+    folded[i] = 1;
+  }
+}
+
 // Geometry of a pair-kernel / conv3x3.cu step as far as chaining is concerned.
 struct ChainGeom {
   int kernel, n_img, H, W, n_chunks, BN, n_ntiles, n_bstages;
@@ -1259,7 +1324,8 @@ bool chain_geom(const Step& st, ChainGeom& g) {
 
 int link_chains(cerb_plan* pl, const cerb_op* ops, int n_ops) {
   cerb_ctx* ctx = pl->ctx;
-  pl->n_launches = n_ops;
+  pl->n_launches = 0;
+  for (const Step& st : pl->steps) pl->n_launches += st.chained ? 0 : 1;
   if (!ctx->conv3_chain || !ctx->dyn_sched) return CERB_OK;
   int* done_next = pl->tile_counters + n_ops;
   for (int i = 0; i < n_ops;) {
@@ -1331,11 +1397,17 @@ extern "C" int cerb_plan_create(cerb_ctx* ctx, const cerb_tensor_desc* tensors, 
 }
 
 int cerb::plan_create_impl(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n_tensors,
-                           const cerb_op* ops, int n_ops, const void* weight_blob, size_t blob_bytes,
+                           const cerb_op* ops_in, int n_ops, const void* weight_blob, size_t blob_bytes,
                            uint8_t* shared_dev_blob, cerb_plan** out) {
-  if (!ctx || !tensors || !ops || !out || n_tensors <= 0 || n_ops <= 0)
+  if (!ctx || !tensors || !ops_in || !out || n_tensors <= 0 || n_ops <= 0)
     return fail(CERB_ERR_ARG, "cerb_plan_create: bad arguments");
   *out = nullptr;
+  // the op list as executed: UPADD ops whose only reader is an eligible 64->64 convolution are
+  // folded into that convolution (fuse_upadd_ops)
+  std::vector<cerb_op> opv(ops_in, ops_in + n_ops);
+  std::vector<char> folded(static_cast<size_t>(n_ops), 0);
+  fuse_upadd_ops(ctx, tensors, n_tensors, opv, folded);
+  const cerb_op* ops = opv.data();
   CERB_CUDA(cudaSetDevice(ctx->device));
   cerb_plan* pl = new cerb_plan();
   pl->ctx = ctx;
@@ -1384,6 +1456,10 @@ int cerb::plan_create_impl(cerb_ctx* ctx, const cerb_tensor_desc* tensors, int n
     pl->cur_counter = pl->tile_counters + i;
     st.kind = op.kind;
     st.side = op.side != 0;
+    if (folded[i]) {  // an UPADD executed by the producer of the convolution that follows
+      st.chained = true;
+      continue;
+    }
     switch (op.kind) {
       case CERB_OP_PREP: {
         if ((rc = check_id(pl, op.in0, "prep")) || (rc = check_id(pl, op.out, "prep")))
@@ -1556,6 +1632,7 @@ cudaError_t launch_step(cerb_ctx* ctx, Step& st, cudaStream_t s) {
       e = launch_maxpool(st.a, st.b, s);
       break;
     case CERB_OP_UPADD:
+      if (st.chained) break;  // folded into the next convolution
       e = st.up_groups > 1 ? launch_upadd_multi(st.a, st.up_prev, st.up_out, st.up_groups, s)
                            : launch_upadd(st.a, st.b, st.c, s);
       break;

@@ -39,6 +39,7 @@ struct cerb_ctx {
   int k_rotate = 1;     // per-CTA rotated K walk in conv3x3.cu (de-synchronises weight-slab reads)
   bool conv64s = true;  // split-precision mode: 64->64 3x3 layers on csrc/conv64s.cu (0: generic kernel)
   int conv3_pair = 1;  // wide 3x3 stride-1 layers on CTA pairs (csrc/conv3x3c2.cu): 0 never, 1 Cout % 256 == 0, 2 also Cout 128 / 64
+  bool fuse_upadd = true;   // fp16 mode: UPADD ops read only by a 64->64 3x3 convolution run inside its producer (conv64x.cu)
   bool conv3_chain = true;  // consecutive pair-kernel layers of one geometry run as ONE launch (layer chains)
   int conv3_mode = 1;   // 0: generic kernel for the wide 3x3 layers; 1: conv3x3.cu (cout <= 512); 2: always
   int conv64_mode = -1;  // -1: generic kernel for every conv; 0/1/2: conv64.cu halo layout

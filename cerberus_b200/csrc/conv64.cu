@@ -19,6 +19,7 @@
 #include "conv64.cuh"
 #include "head_tail.cuh"
 #include "ptx.cuh"
+#include "upadd_math.cuh"
 
 namespace cerb {
 
@@ -269,26 +270,13 @@ conv64_kernel(const __grid_constant__ Conv64Params p) {
           const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f);
           const int py0 = static_cast<int>(sy), px0 = static_cast<int>(sx);
           const int py1 = min(py0 + 1, PH - 1), px1 = min(px0 + 1, PW - 1);
-          const float ly = sy - py0, lx = sx - px0, hy_ = 1.0f - ly, hx_ = 1.0f - lx;
+          const float ly = sy - py0, lx = sx - px0;
           const uint4 sk = *reinterpret_cast<const uint4*>(stS + t * 16);
           const uint4 q00 = *reinterpret_cast<const uint4*>(stP + (((py0 - pby) * 6 + (px0 - pbx)) * 8 + c) * 16);
           const uint4 q01 = *reinterpret_cast<const uint4*>(stP + (((py0 - pby) * 6 + (px1 - pbx)) * 8 + c) * 16);
           const uint4 q10 = *reinterpret_cast<const uint4*>(stP + (((py1 - pby) * 6 + (px0 - pbx)) * 8 + c) * 16);
           const uint4 q11 = *reinterpret_cast<const uint4*>(stP + (((py1 - pby) * 6 + (px1 - pbx)) * 8 + c) * 16);
-          const __half2* s2 = reinterpret_cast<const __half2*>(&sk);
-          const __half2* a2 = reinterpret_cast<const __half2*>(&q00);
-          const __half2* b2 = reinterpret_cast<const __half2*>(&q01);
-          const __half2* c2 = reinterpret_cast<const __half2*>(&q10);
-          const __half2* d2 = reinterpret_cast<const __half2*>(&q11);
-          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 sv = __half22float2(s2[e]), av = __half22float2(a2[e]), bv = __half22float2(b2[e]);
-            const float2 cv = __half22float2(c2[e]), dv = __half22float2(d2[e]);
-            const float ux = hy_ * (hx_ * av.x + lx * bv.x) + ly * (hx_ * cv.x + lx * dv.x);
-            const float uy = hy_ * (hx_ * av.y + lx * bv.y) + ly * (hx_ * cv.y + lx * dv.y);
-            ow[e] = pack_half2(sv.x + ux, sv.y + uy);
-          }
+          o = upadd_pixel8_h2(q00, q01, q10, q11, sk, ly, lx);  // the arithmetic of the stand-alone pass
         }
         // 128-byte swizzle: 16-byte chunk c of row h lives at chunk (c ^ (h & 7))
         *reinterpret_cast<uint4*>(dst + h * 128 + ((c ^ (h & 7)) << 4)) = o;

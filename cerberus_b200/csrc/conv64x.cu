@@ -20,6 +20,7 @@
 // one TMA store per region (which also clips partial regions); the residual arrives by TMA.
 #include "conv64x.cuh"
 #include "ptx.cuh"
+#include "upadd_math.cuh"
 
 namespace cerb {
 
@@ -38,13 +39,21 @@ constexpr int kStageBytes = 2 * kPlaneBytes;   // odd plane | even plane
 constexpr int kOutBytes = 256 * 128;           // staging: 16 x 16 pixels x 64 fp16 channels
 constexpr int kAccStages = 3;                  // accumulator stages of 128 columns
 constexpr int kTmemCols = 512;                 // power of two >= 3 x 128
+// fused upsample+add: the 10 x 10 low-resolution pixels under a halo (one buffer: the fix-up of a
+// region is over long before the next halo can be requested)
+constexpr int kLowPx = 10;
+constexpr int kLowTx = kLowPx * kLowPx * 128;  // 12800
+constexpr int kLowBytes = 13 * 1024;
+constexpr int kFixWarps = 6;
+constexpr int kFixItems = 9 * 9 * 8;           // 2x2-pixel blocks of the 18 x 18 halo x 8 channel groups
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kConv64xThreads, 1)
+template <bool FUSE>
+__global__ void __launch_bounds__(FUSE ? kConv64xFuseThreads : kConv64xThreads, 1)
 conv64x_kernel(const __grid_constant__ Conv64xParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -56,13 +65,16 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
   uint8_t* sW = smem;                   // tile (r, q): sW + (2r + q) * 16 KB; q = 0: [W(r,1); W(r,0)], q = 1: [W(r,2); W(r,1)]
   uint8_t* sOut = sW + kWBytes;         // output / residual staging
   uint8_t* sA = sOut + kOutBytes;       // halo stages
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + n_stages * kStageBytes);
+  uint8_t* sLow = sA + n_stages * kStageBytes;  // FUSE only
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sLow + (FUSE ? kLowBytes : 0));
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* tfull_bar = empty_bar + 4;
   uint64_t* tempty_bar = tfull_bar + kAccStages;
   uint64_t* w_bar = tempty_bar + kAccStages;
   uint64_t* res_bar = w_bar + 1;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 1);
+  uint64_t* fixed_bar = res_bar + 1;   // FUSE: "halo stage s holds skip + up(low)" (one arrival per fix-up warp)
+  uint64_t* low_empty = fixed_bar + 4;  // FUSE: the fix-up warps are done with the low buffer
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(low_empty + 1);
   // region ids handed from the producer to the MMA / epilogue warps (dynamic scheduling)
   volatile int* s_ring = reinterpret_cast<volatile int*>(tmem_holder + 2);
 
@@ -71,10 +83,13 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
     ptx::prefetch_tmap(&p.w_map);
     ptx::prefetch_tmap(&p.out_map);
     if (p.has_res) ptx::prefetch_tmap(&p.res_map);
+    if (FUSE) ptx::prefetch_tmap(&p.low_map);
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&fixed_bar[s], kFixWarps);
     }
+    ptx::mbar_init(low_empty, kFixWarps);
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
       ptx::mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
@@ -113,7 +128,7 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
     ptx::grid_dep_wait();  // weights do not depend on the previous kernel, activations do
     long long prof_a = 0;
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, low_phase = 0;
     const int leader_lane = __ffs(__ballot_sync(0xffffffffu, leader)) - 1;
     // Region ids come from a global counter (dynamic scheduling): a CTA that starts late - its SM
     // was busy with a block of another stream - simply finds less work, instead of forcing a
@@ -134,6 +149,10 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
       const int x0 = rx * 16, y0 = ry * 16 - 1;
       CERB_PROF_T0(t_p);
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 41);
+      if (FUSE) {
+        ptx::mbar_wait(low_empty, low_phase ^ 1, p.err_flag, 48);
+        low_phase ^= 1;
+      }
       CERB_PROF_ADD(prof_a, t_p);
       if (leader) {
         s_ring[i & 7] = done ? -1 : rg;
@@ -141,9 +160,10 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
           ptx::mbar_arrive(&full_bar[stage]);
         } else {
           uint8_t* dst = sA + stage * kStageBytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kPlaneTx);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kPlaneTx + (FUSE ? kLowTx : 0));
           ptx::tma_load_4d(dst, &p.in_map, &full_bar[stage], 0, x0 - 1, y0, img);            // odd columns
           ptx::tma_load_4d(dst + kPlaneBytes, &p.in_map, &full_bar[stage], 0, x0, y0, img);  // even columns
+          if (FUSE) ptx::tma_load_4d(sLow, &p.low_map, &full_bar[stage], 0, (x0 >> 1) - 1, ry * 8 - 1, img);
         }
       }
       __syncwarp();
@@ -172,7 +192,7 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err_flag, 43);
       CERB_PROF_ADD(prof_a, t_m0);
       CERB_PROF_T0(t_m1);
-      ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 44);
+      ptx::mbar_wait(FUSE ? &fixed_bar[stage] : &full_bar[stage], phase, p.err_flag, 44);
       CERB_PROF_ADD(prof_b, t_m1);
       if (s_ring[i & 7] < 0) {  // no more regions: pass the end marker on to the epilogue
         if (leader) ptx::mbar_arrive(&tfull_bar[acc]);
@@ -225,6 +245,77 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
     if (p.prof != nullptr && lane == 0) {
       long long* o = p.prof + blockIdx.x * 16;
       o[1] = prof_a; o[2] = prof_b; o[3] = prof_c; o[8] = clock64() - t_all;
+    }
+  } else if (FUSE && warp >= 10) {
+    // ------------------------------------------------------------------ halo fix-up (warps 10-15)
+    // The planes hold the SKIP halo; add bilinear_x2(low) in place. A work item is a 2x2 block of
+    // halo pixels (rows 2 bj, 2 bj + 1; columns 2 bi = odd plane column bi, 2 bi + 1 = even plane
+    // column bi) x one 16-byte channel group: exactly the block below / right of low pixel (j, i)
+    // of the stand-alone pass (ops_misc.cu), whose arithmetic is shared (upadd_math.cuh). Pixels
+    // outside the image stay zero (TMA fill = the convolution's padding).
+    const int tid_f = (warp - 10) * 32 + lane;
+    const int PH = p.H >> 1, PW = p.W >> 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0;; ++it) {
+      ptx::mbar_wait(&full_bar[stage], phase, p.err_flag, 47);
+      const int rg = s_ring[it & 7];
+      if (rg < 0) {  // pass the end marker on to the MMA warp
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&fixed_bar[stage]);
+        break;
+      }
+      const int img = rg / regions_per_img;
+      const int rem = rg - img * regions_per_img;
+      const int ry = rem / p.regions_x, rx = rem - ry * p.regions_x;
+      const int j0 = ry * 8 - 1, i0 = rx * 8 - 1;  // low pixel of block (0, 0) = origin of the low box
+      uint8_t* plane0 = sA + stage * kStageBytes;  // odd columns | even columns
+      for (int idx = tid_f; idx < kFixItems; idx += kFixWarps * 32) {
+        const int g = idx & 7;
+        const int blk = idx >> 3;
+        const int bj = blk / 9, bi = blk - bj * 9;
+        const int j = j0 + bj, i = i0 + bi;
+        const int Y = 2 * j + 1, X = 2 * i + 1;  // top-left output pixel of the block
+        const bool oky[2] = {Y >= 0 && Y < p.H, Y + 1 < p.H};
+        const bool okx[2] = {X >= 0 && X < p.W, X + 1 < p.W};
+        if (!((oky[0] || oky[1]) && (okx[0] || okx[1]))) continue;
+        const int by0 = max(j, 0) - j0, by1 = min(j + 1, PH - 1) - j0;
+        const int bx0 = max(i, 0) - i0, bx1 = min(i + 1, PW - 1) - i0;
+        // all eight loads first: the four stores below would otherwise order every later load
+        // behind them (the compiler cannot tell the cells apart)
+        const int q00 = by0 * kLowPx + bx0, q01 = by0 * kLowPx + bx1;
+        const int q10 = by1 * kLowPx + bx0, q11 = by1 * kLowPx + bx1;
+        const uint4 l00 = *reinterpret_cast<const uint4*>(sLow + q00 * 128 + ((g ^ (q00 & 7)) << 4));
+        const uint4 l01 = *reinterpret_cast<const uint4*>(sLow + q01 * 128 + ((g ^ (q01 & 7)) << 4));
+        const uint4 l10 = *reinterpret_cast<const uint4*>(sLow + q10 * 128 + ((g ^ (q10 & 7)) << 4));
+        const uint4 l11 = *reinterpret_cast<const uint4*>(sLow + q11 * 128 + ((g ^ (q11 & 7)) << 4));
+        uint4* cell[4];
+        uint4 sk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int pix = (2 * bj + (k >> 1)) * 9 + bi;
+          cell[k] = reinterpret_cast<uint4*>(plane0 + (k & 1) * kPlaneBytes + pix * 128 + ((g ^ (pix & 7)) << 4));
+          sk[k] = *cell[k];
+        }
+        uint4 o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int dy = k >> 1, dx = k & 1;
+          const float ly = (j < 0) ? 0.0f : (dy == 0 ? 0.25f : 0.75f);
+          const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
+          o[k] = upadd_pixel8_h2(l00, l01, l10, l11, sk[k], ly, lx);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (oky[k >> 1] && okx[k & 1]) *cell[k] = o[k];
+      }
+      ptx::fence_proxy_async_smem();  // the tensor core reads these planes through the async proxy
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&fixed_bar[stage]);
+        ptx::mbar_arrive(low_empty);
+      }
+      if (++stage == n_stages) { stage = 0; phase ^= 1; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2-9)
@@ -359,28 +450,30 @@ void conv64x_plan(Conv64xParams& p) {
   p.regions_x = (p.W + 15) / 16;
   p.regions_y = (p.H + 15) / 16;
   p.n_regions = p.n_img * p.regions_x * p.regions_y;
-  int n = (224 * 1024 - kWBytes - kOutBytes - 1024) / kStageBytes;
+  int n = (224 * 1024 - kWBytes - kOutBytes - 1024 - (p.fuse_up ? kLowBytes : 0)) / kStageBytes;
   if (n > 4) n = 4;
   if (n < 2) n = 2;
   p.n_stages = n;
 }
 
 size_t conv64x_smem_bytes(const Conv64xParams& p) {
-  return static_cast<size_t>(kWBytes) + kOutBytes + static_cast<size_t>(p.n_stages) * kStageBytes + 256 + 1024;
+  return static_cast<size_t>(kWBytes) + kOutBytes + static_cast<size_t>(p.n_stages) * kStageBytes +
+         (p.fuse_up ? kLowBytes : 0) + 256 + 1024;
 }
 
 cudaError_t conv64x_launch(const Conv64xParams& p, int num_sms, cudaStream_t stream, bool pdl) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv64x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+  static bool attr_set[2] = {false, false};
+  const int fuse = p.fuse_up ? 1 : 0;
+  void (*kern)(Conv64xParams) = fuse ? conv64x_kernel<true> : conv64x_kernel<false>;
+  if (!attr_set[fuse]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[fuse] = true;
   }
   const int grid = p.n_regions < num_sms ? p.n_regions : num_sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kConv64xThreads);
+  cfg.blockDim = dim3(fuse ? kConv64xFuseThreads : kConv64xThreads);
   cfg.dynamicSmemBytes = conv64x_smem_bytes(p);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -388,7 +481,7 @@ cudaError_t conv64x_launch(const Conv64xParams& p, int num_sms, cudaStream_t str
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv64x_kernel, p);
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 }  // namespace cerb

@@ -12,6 +12,9 @@ namespace cerb {
 // warp 0: TMA producer, warp 1: MMA issuer + TMEM allocator, warps 2-5 / 6-9: epilogue of the
 // even / odd pixel of every lane
 constexpr int kConv64xThreads = 320;
+// fused upsample+add (Conv64xParams::fuse_up): warps 10-15 add bilinear_x2(low) to the skip halo
+// in shared memory before the MMA warp may read it
+constexpr int kConv64xFuseThreads = 512;
 
 struct Conv64xParams {
   CUtensorMap in_map;   // [64 ch, W, H, N], box {64, 18 (element stride 2 -> 9 columns), 18, 1}
@@ -20,6 +23,11 @@ struct Conv64xParams {
                         // of the even-pixel / odd-pixel plane of a region
   CUtensorMap res_map;  // residual, same geometry
   int has_res;
+  // fuse_up: the input of the convolution is skip + bilinear_x2(low), align_corners=False
+  // (models/net_desc.py:185-188): in_map addresses the SKIP tensor, low_map the half-resolution
+  // tensor [64 ch, W/2, H/2, N], box {64, 10, 10, 1} = the low pixels under an 18x18 halo
+  CUtensorMap low_map;
+  int fuse_up;
   int n_img, H, W;
   int regions_x, regions_y, n_regions;
   const float* bias;

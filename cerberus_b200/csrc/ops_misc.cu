@@ -2,6 +2,7 @@
 // bilinear-x2 + skip add, classification-head tail and the Patch-Class branch.
 // All activations are NHWC fp16 (optionally hi+lo pairs); arithmetic is fp32.
 #include "ops.cuh"
+#include "upadd_math.cuh"
 
 #include <cfloat>
 
@@ -375,6 +376,11 @@ __global__ void __launch_bounds__(288) upadd_f16_kernel(
     float s[8];
     if (SPLIT) cvt8_pair(sk[k], skl[k], s);
     else cvt8(sk[k], s);
+    const uint32_t oo = (pix00 + dy * W + dx) * out_c + gc;
+    if (!SPLIT) {  // the arithmetic conv64x.cu's fused producer shares (upadd_math.cuh)
+      *reinterpret_cast<uint4*>(out + oo) = upadd_pixel8_h2(q00, q01, q10, q11, sk[k], ly, lx);
+      continue;
+    }
     uint4 o, ol;
     uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
     uint32_t* olw = reinterpret_cast<uint32_t*>(&ol);
@@ -392,7 +398,6 @@ __global__ void __launch_bounds__(288) upadd_f16_kernel(
         olw[e] = *reinterpret_cast<const uint32_t*>(&l);
       }
     }
-    const uint32_t oo = (pix00 + dy * W + dx) * out_c + gc;
     *reinterpret_cast<uint4*>(out + oo) = o;
     if (SPLIT) *reinterpret_cast<uint4*>(out_lo + oo) = ol;
   }
@@ -446,29 +451,14 @@ __global__ void __launch_bounds__(288) upadd_f16_multi_kernel(
     if (oky[k >> 1] && okx[k & 1])
       sk[k] = __ldg(reinterpret_cast<const uint4*>(skip + (pix00 + (k >> 1) * W + (k & 1)) * skip_c + gc));
   }
-  float p00[8], p01[8], p10[8], p11[8];
-  cvt8(q00, p00); cvt8(q01, p01); cvt8(q10, p10); cvt8(q11, p11);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int dy = k >> 1, dx = k & 1;
     if (!(oky[dy] && okx[dx])) continue;
     const float ly = (j < 0) ? 0.0f : (dy == 0 ? 0.25f : 0.75f);
-    const float hy = 1.0f - ly;
     const float lx = (i < 0) ? 0.0f : (dx == 0 ? 0.25f : 0.75f);
-    const float hx = 1.0f - lx;
-    float s[8];
-    cvt8(sk[k], s);
-    uint4 o;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float u0 = hy * (hx * p00[2 * e] + lx * p01[2 * e]) + ly * (hx * p10[2 * e] + lx * p11[2 * e]);
-      const float u1 = hy * (hx * p00[2 * e + 1] + lx * p01[2 * e + 1]) +
-                       ly * (hx * p10[2 * e + 1] + lx * p11[2 * e + 1]);
-      const __half2 h = __floats2half2_rn(s[2 * e] + u0, s[2 * e + 1] + u1);
-      ow[e] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(out + (pix00 + dy * W + dx) * out_c + gc) = o;
+    *reinterpret_cast<uint4*>(out + (pix00 + dy * W + dx) * out_c + gc) =
+        upadd_pixel8_h2(q00, q01, q10, q11, sk[k], ly, lx);
   }
 }
 

@@ -39,6 +39,8 @@ class Context:
             self.set_option("conv64s", int(os.environ["CERB_CONV64S"]))
         if os.environ.get("CERB_CONV3_PAIR") is not None:  # CTA-pair kernel for the wide 3x3 layers
             self.set_option("conv3_pair", int(os.environ["CERB_CONV3_PAIR"]))
+        if os.environ.get("CERB_FUSE_UPADD") is not None:  # default on with the conv64x kernel (A/B switch)
+            self.set_option("fuse_upadd", int(os.environ["CERB_FUSE_UPADD"]))
         if os.environ.get("CERB_CONV3_CHAIN") is not None:  # layer chains of the pair kernel (A/B switch)
             self.set_option("conv3_chain", int(os.environ["CERB_CONV3_CHAIN"]))
         if os.environ.get("CERB_DYN_SCHED") is not None:
@@ -91,6 +93,9 @@ class ForwardPlan:
             # The upsample+add fusion (fp16 64->64 kernel, conv64_mode 1) is exact but measured
             # SLOWER than upadd_kernel + conv64 on B200 (0.38 vs 0.34 ms per 256^2 layer: its eight
             # producer warps are instruction-bound), so it is opt-in.
+            # With the default kernel (conv64_mode 3, csrc/conv64x.cu) the LIBRARY folds those UPADD ops
+            # into the convolution (option fuse_upadd, default on: fix-up warps add the upsampled
+            # tensor to the TMA-loaded skip halo) - nothing to do in the op list.
             fuse_up = (ctx.precision == "f16" and ctx.conv64_mode == 1
                        and os.environ.get("CERB_FUSE_UPADD", "0") == "1")
             # Last decoder conv + output head in one kernel (csrc/conv64.cu, fp16 mode only): exact
