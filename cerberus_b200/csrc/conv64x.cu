@@ -147,6 +147,14 @@ conv64x_kernel(const __grid_constant__ Conv64xParams p) {
       const int rem = rg - img * regions_per_img;
       const int ry = rem / p.regions_x, rx = rem - ry * p.regions_x;
       const int x0 = rx * 16, y0 = ry * 16 - 1;
+      // The stage this halo will land in is still being read by the MMAs of the region before
+      // last: ask L2 for the boxes now, so that the load issued after the wait below is an L2 hit
+      // (with two stages the region period is load latency (+ fix-up), not MMA time).
+      if (leader && !done) {
+        ptx::tma_prefetch_4d(&p.in_map, 0, x0 - 1, y0, img);
+        ptx::tma_prefetch_4d(&p.in_map, 0, x0, y0, img);
+        if (FUSE) ptx::tma_prefetch_4d(&p.low_map, 0, (x0 >> 1) - 1, ry * 8 - 1, img);
+      }
       CERB_PROF_T0(t_p);
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 41);
       if (FUSE) {
