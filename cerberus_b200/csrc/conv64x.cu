@@ -18,6 +18,16 @@
 // shared memory from per-tap TMA boxes and stay resident. Epilogue: a thread owns two adjacent
 // pixels = 256 contiguous bytes of the NHWC output; rows go through a swizzled staging tile and
 // one TMA store per region (which also clips partial regions); the residual arrives by TMA.
+//
+// conv64x_kernel<true> (Conv64xParams::fuse_up): the input is skip + bilinear_x2(low)
+// (models/net_desc.py:185-188). The halo planes are loaded from the SKIP tensor, a third TMA box
+// brings the 10 x 10 low-resolution pixels under the halo, and six extra warps add the
+// interpolated term to the planes in shared memory before the MMA warp may read them
+// (upadd_math.cuh: the arithmetic of the stand-alone pass, so both round identically).
+//
+// Both variants: while the stage a halo will land in is still busy, the producer asks L2 for its
+// boxes (cp.async.bulk.prefetch.tensor) - with two stages the region period of a latency-bound
+// launch is load latency (+ fix-up), and the later load then hits L2.
 #include "conv64x.cuh"
 #include "ptx.cuh"
 #include "upadd_math.cuh"
