@@ -31,7 +31,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"],
+                    help="reference = the reference's CPU path (the driver's second arm); torch-gpu = EXTRA CONTEXT "
+                         "only: the unmodified reference network run by PyTorch / cuDNN on cuda:0 (fp16, "
+                         "channels_last), forward only")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--precision", default="f16", choices=["f16", "f16x2"])
     ap.add_argument("--no-postproc", action="store_true")
@@ -840,9 +843,52 @@ def run_tile448(args):
         dist.destroy_process_group()
 
 
+def run_torch_gpu(args):
+    """EXTRA CONTEXT ("second baseline"; not an arm the driver runs): the
+    UNMODIFIED reference network (oracle/_ref: models.net_desc.create_model, random-init synthetic
+    checkpoint) executed by PyTorch / cuDNN on cuda:0 - `.half()`, channels_last,
+    cudnn.benchmark - forward only on the bench batch, timed with CUDA events. Compare with
+    `forward_only` of the default line. Nothing of this repository's engine is on this path."""
+    import torch
+    from cerberus_b200 import synth
+    from oracle import ref_runner
+    if not ref_runner.available():
+        print(json.dumps({"impl": "torch_gpu_context", "unavailable": "oracle/_ref is not staged"}))
+        return
+    margs = synth.model_args()
+    ref = ref_runner.ReferenceTilePath(synth.make_state_dict(seed=0), margs)
+    torch.backends.cudnn.benchmark = True
+    net = ref.net.half().cuda().to(memory_format=torch.channels_last)
+    tiles = synth.synthetic_tiles(args.batch, TILE, TILE, seed=123)
+    x = torch.from_numpy(tiles).cuda().permute(0, 3, 1, 2).half().contiguous(memory_format=torch.channels_last)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            net(x)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            net(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({
+        "impl": "torch_gpu_context", "metric": "tiles/sec (256x256x3) forward only",
+        "value": args.batch / (ms * 1e-3), "unit": "tiles/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "dtype": "f16",
+        "data": "synthetic",
+        "config": {"workload": "batch=%d synthetic 256x256x3 tiles, forward of the unmodified reference "
+                               "network (six heads) under PyTorch %s / cuDNN: net.half(), channels_last, "
+                               "cudnn.benchmark, no post-processing; the reference's own forward syncs once "
+                               "per call (net_desc.py:171)" % (args.batch, torch.__version__)},
+        "note": "context only: compare with `forward_only.ms_per_step` of the default bench line"}))
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.impl == "torch-gpu":
+        run_torch_gpu(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.config == "1":
         run_config1(args)
