@@ -83,6 +83,8 @@ _SIGNATURES = {
                                              ctypes.c_void_p, ctypes.c_size_t]),
     "cerb_plan_write_tensor": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_void_p, ctypes.c_size_t]),
+    "cerb_plan_preview_folding": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(TensorDesc), ctypes.c_int,
+                                                 ctypes.POINTER(Op), ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]),
     "cerb_model_spec": (ctypes.c_int, [ctypes.POINTER(ModelDesc), ctypes.POINTER(Layer), ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.POINTER(TensorDesc), ctypes.POINTER(ctypes.c_int),

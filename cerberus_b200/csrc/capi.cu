@@ -1376,6 +1376,20 @@ int link_chains(cerb_plan* pl, const cerb_op* ops, int n_ops) {
 }
 }  // namespace
 
+extern "C" int cerb_plan_preview_folding(int precision, const cerb_tensor_desc* tensors, int n_tensors,
+                                         const cerb_op* ops, int n_ops, int32_t* folded) {
+  if (!tensors || !ops || !folded || n_tensors <= 0 || n_ops <= 0)
+    return fail(CERB_ERR_ARG, "cerb_plan_preview_folding: bad arguments");
+  cerb_ctx defaults;  // option defaults of a fresh context; never touches a device
+  defaults.precision = precision;
+  defaults.conv64_mode = 3;
+  std::vector<cerb_op> opv(ops, ops + n_ops);
+  std::vector<char> f(static_cast<size_t>(n_ops), 0);
+  fuse_upadd_ops(&defaults, tensors, n_tensors, opv, f);
+  for (int i = 0; i < n_ops; ++i) folded[i] = f[i];
+  return CERB_OK;
+}
+
 extern "C" void cerb_plan_destroy(cerb_plan* pl) {
   if (!pl) return;
   cudaSetDevice(pl->ctx->device);

@@ -221,6 +221,13 @@ int cerb_model_spec(const cerb_model_desc* desc, const cerb_layer* layers, int n
                     int w, int out_h, int out_w, int want_logits, cerb_tensor_desc* tensors,
                     int* n_tensors, cerb_op* ops, int* n_ops, int32_t* canvas_tensor,
                     int32_t* logit_tensors);
+/* Which UPADD ops of an op list cerb_plan_create folds into the 64->64 3x3 convolution that follows
+ * them (option "fuse_upadd", fp16 mode, default 64->64 kernel): folded[i] = 1 for every such op.
+ * Pure host code (no device): introspection and the CPU-side test of the folding rule - an UPADD
+ * is folded iff the next op is that convolution reading its output and nothing else reads that
+ * output before the tensor is written again. precision: cerb_precision. */
+int cerb_plan_preview_folding(int precision, const cerb_tensor_desc* tensors, int n_tensors,
+                              const cerb_op* ops, int n_ops, int32_t* folded);
 /* Uploads the blob once (shared by every plan of the model). weight_blob may be NULL when the
  * weights will arrive by cerb_bcast_weights. */
 int cerb_model_create(cerb_ctx* ctx, const cerb_model_desc* desc, const cerb_layer* layers,

@@ -92,3 +92,42 @@ def test_resnet18_graph_equals_python_graph(built_lib):
     for i in range(len(ops_py)):
         for f, _ in _lib.Op._fields_:
             assert getattr(ops[i], f) == getattr(ops_py[i], f), ("op", i, f)
+
+
+def _folding(built_lib, spec, precision=_lib.CERB_PREC_F16):
+    td, ops = spec.c_arrays()
+    folded = (ctypes.c_int32 * len(ops))()
+    _lib.check(built_lib.cerb_plan_preview_folding(precision, td, len(td), ops, len(ops), folded),
+               "cerb_plan_preview_folding")
+    return [int(v) for v in folded]
+
+
+def test_upadd_folding_rule(models, built_lib):
+    """cerb_plan_create folds an UPADD into the 64->64 3x3 convolution that follows it (conv64x.cu's
+    fused producer) iff that convolution is the only reader of the sum - decided by pure host code,
+    checked here without a device. Six-head model: the 128^2 and 256^2 levels of every segmentation
+    decoder (2 x 5), not the 128 / 256-channel levels; the sum tensors are REUSED by the decoders,
+    which must not count as a second reader; nothing is folded in the split-precision mode."""
+    model = models[None]
+    spec = PlanSpec(model, 2, 256, 256, 256, 256)
+    folded = _folding(built_lib, spec)
+    ups = [i for i, op in enumerate(spec.ops) if op["kind"] == _lib.OP_UPADD]
+    assert len(ups) == 1 + 3 * 5
+    n_dec = len(model.seg_decoders)
+    assert sum(folded) == 2 * n_dec
+    for i in ups:
+        _, _, h, w, c, _ = spec.tensors[spec.ops[i]["out"]]
+        assert folded[i] == int(c == 64), (i, h, w, c)
+        if folded[i]:
+            nxt = spec.ops[i + 1]
+            assert nxt["kind"] == _lib.OP_CONV and nxt["in0"] == spec.ops[i]["out"] and nxt["cout"] == 64
+    assert all(f == 0 for i, f in enumerate(folded) if i not in ups)
+    assert sum(_folding(built_lib, spec, _lib.CERB_PREC_F16X2)) == 0
+    # a second reader of the sum (here: a later op made to read it) keeps the stand-alone pass
+    i0 = next(i for i in ups if folded[i])
+    spec2 = PlanSpec(model, 2, 256, 256, 256, 256)
+    victim = next(k for k in range(i0 + 2, len(spec2.ops)) if spec2.ops[k]["kind"] == _lib.OP_CONV
+                  and spec2.ops[k]["in1"] < 0 and spec2.ops[k]["out"] != spec2.ops[i0]["out"])
+    spec2.ops[victim]["in1"] = spec2.ops[i0]["out"]
+    folded2 = _folding(built_lib, spec2)
+    assert folded2[i0] == 0 and sum(folded2) == 2 * n_dec - 1
